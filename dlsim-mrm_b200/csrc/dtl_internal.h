@@ -1,0 +1,183 @@
+// Internal device data layout and kernel launchers of the B200 DTALite engine.
+// Everything here is structure-of-arrays in HBM; see DESIGN.md "Data layout".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/dtalite_b200.h"
+
+#define DTL_MAX_LABEL_COST 1.0e15  // unreachable label, reference DTA.h:11
+#define DTL_NO_PRED (-9999)        // reference routing.h:683-685
+#define DTL_FIX_SCALE 4294967296.0 // Q31.32 fixed point for link volumes
+#define DTL_SPEED_SLOTS 300        // MAX_TIMEINTERVAL_PerDay, reference DTA.h:24
+
+namespace dtl {
+
+// One forward-star edge: everything a relaxation needs in a single 16-byte load.
+// `to` carries the node seq no; bit 31 is set when the link has an outgoing-connector zone tag
+// (reference routing.h:779-786), in which case link_tag[link] must equal the origin zone.
+struct __align__(16) Edge {
+    double cost;
+    int to;
+    int link;
+};
+
+// SSSP work-queue entry: node, the label it was pushed with, and the link that produced it.
+struct __align__(16) QEntry {
+    double lab;
+    int node;
+    int link;
+};
+
+// forward star of one (agent type, period): reference NetworkForSP::BuildNetwork, routing.h:257-352
+struct ForwardStar {
+    int n_edges = 0;
+    int* row_ptr = nullptr;   // [N+1]
+    Edge* edges = nullptr;    // [E] forward-star order == reference scan order
+    int* in_ptr = nullptr;    // [N+1] reverse star (tie verification only)
+    int2* in_edges = nullptr; // [E] {from node, forward edge index}
+    int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
+    double delta = 1.0;       // current label window of the near/far SSSP
+    std::vector<int> h_row_ptr;
+};
+
+struct VdfParams { // [T*L] each, reference CPeriod_VDF (VDF.h:369-466)
+    double *fftt, *cap, *alpha, *beta, *vf, *vc, *nlanes, *cap_lane, *qdf, *preload, *penalty;
+    double *Q_alpha, *Q_beta, *Q_cd, *Q_n, *Q_cp, *Q_s, *t2, *L_h, *start_h, *end_h, *plf;
+    float *cycle_length, *red_time, *sat_flow;
+    int* vdf_type;
+};
+
+struct LinkState { // [T*L] each
+    unsigned long long* pce_fix;    // Q31.32 PCE volume sums (all-reduced across GPUs)
+    unsigned long long* person_fix; // [T*(1+AT)*L]: slot 0 person volume, slot 1+at per agent type
+    double *tt, *link_volume, *doc, *voc, *P, *vt2;
+    // detail outputs, filled by the DETAIL variant of the VDF kernel
+    double *avg_queue_speed, *avg_speed_bpr, *Q_mu, *Q_gamma, *t0, *t3, *severe_P;
+};
+
+struct ColumnPool {     // column CSR with fixed slots per OD cell
+    int n_od = 0;       // OD cells owned by this rank
+    int cap = 0;        // column slots per OD cell
+    int* count;         // [n_od]
+    int* node_sum;      // [n_od*cap]
+    int* n_links;       // [n_od*cap]
+    int* n_nodes;       // [n_od*cap]
+    long long* offset;  // [n_od*cap] first path link in the arena
+    double* volume;     // [n_od*cap]
+    double* cost;       // [n_od*cap] path_gradient_cost
+    double* time;       // [n_od*cap] path_travel_time
+    int* arena;         // path links, origin -> destination order
+    long long arena_cap = 0;
+    unsigned long long* arena_used; // device bump pointer
+};
+
+struct SsspStats { // accumulated on device
+    unsigned long long relaxations, pops, rounds, tie_candidates, counted_edges, overflow, tied_origins, replayed;
+};
+
+// ------------------------------------------------------------------ kernel launchers
+struct VdfLaunch {
+    int T, L, AT;
+    VdfParams p;
+    LinkState s;
+    const double *toll, *lr_price; // [T*AT*L]
+    const float* vot;              // [AT]
+    int** link_edge;               // device array [AT*T] of link->edge maps
+    Edge** edges;                  // device array [AT*T]
+    double* block_sums;            // [n_blocks] partial sums of tt*link_volume
+    double* sys_tt;                // device scalar
+    const double* volume_override; // non-null: use this volume instead of pce+preload (KAT entry)
+    bool detail;
+    bool write_cost;
+};
+void launch_vdf(const VdfLaunch& a, cudaStream_t st);
+void launch_model_speed(int T, int L, int tau, const VdfParams& p, const LinkState& s, int first_slot, int n_slots,
+                        float* out, cudaStream_t st);
+int vdf_blocks(int n);
+
+struct SsspLaunch {
+    int N;
+    const int* row_ptr;
+    const Edge* edges;
+    const int* in_ptr;
+    const int2* in_edges;
+    const int* link_tag;
+    const int* link_from;
+    int n_tasks;             // tasks in this batch
+    const int* task_origin;  // [n_tasks] origin centroid node
+    const int* task_zone;    // [n_tasks] origin zone seq no
+    unsigned long long* labels; // [n_tasks][N] FP64 bit patterns
+    int* pred_link;          // [n_tasks][N]
+    int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes)
+    double delta;
+    // per-CTA workspace
+    QEntry* ws;              // [grid][ws_stride]
+    size_t ws_stride;
+    int cap_near, cap_far;
+    int* tie_cand;           // [grid][tie_cap]
+    int tie_cap;
+    int* task_counter;       // device int, zeroed before launch
+    SsspStats* stats;
+    int grid, block;
+};
+void launch_sssp(const SsspLaunch& a, cudaStream_t st);
+// exact serial emulation of the reference deque for origins whose tree has tied predecessors
+void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
+                        cudaStream_t st);
+void launch_count_edges(const SsspLaunch& a, cudaStream_t st);
+void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);
+
+struct ColumnLaunch {
+    int N, L, T, AT;
+    ColumnPool pool;
+    // OD cells of this rank (local index space)
+    const int *od_dest_node, *od_at, *od_tau, *od_task; // [n_od]
+    const double* od_vol;
+    const int* link_from;
+    // trees of the current batch
+    const unsigned long long* labels;
+    const int* pred_link;
+    int task_first, task_count;        // batch range in local task numbering
+    const int* batch_cells;            // OD cells (local) belonging to the batch tasks
+    int n_batch_cells;
+    const unsigned char* task_skip_backtrace; // [n_tasks] origin has no physical out-link (routing.h:428)
+    int k;
+    double* least_contrib;             // [n_od]
+    int* error_flag;                   // bit0 arena overflow, bit1 column slots exhausted
+    unsigned long long* path_nodes;    // counter
+};
+void launch_backtrace(const ColumnLaunch& a, cudaStream_t st);
+
+struct ScatterLaunch {
+    int L, T, AT;
+    ColumnPool pool;
+    const int *od_at, *od_tau;
+    const double *pce, *occ; // [T*AT*L]
+    unsigned long long* pce_fix;
+    unsigned long long* person_fix; // may be null (skipped inside the CG loop)
+    int decay_k;                    // <0: none
+    unsigned long long* link_refs;  // counter
+};
+void launch_scatter(const ScatterLaunch& a, cudaStream_t st);
+
+struct PoolUpdateLaunch {
+    int L, T, AT;
+    ColumnPool pool;
+    const int *od_at, *od_tau;
+    const double* od_vol;
+    const double* tt;      // [T*L]
+    const double* penalty; // [T*L]
+    const double* toll;    // [T*AT*L]
+    const float* vot;
+    int n;                 // column-pool iteration index
+    double* od_sums;       // [n_od][4]: gap, cost, time, demand contributions
+};
+void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st);
+
+// deterministic sum of n doubles with stride `stride` starting at `in` -> out[0]
+void launch_sum(const double* in, long long n, int stride, double* out, cudaStream_t st);
+
+} // namespace dtl

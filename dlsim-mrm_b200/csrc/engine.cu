@@ -1,0 +1,1129 @@
+// Host side of the engine API (include/dtalite_b200.h, level B): owns the device image of the network,
+// the column pool and the shortest-path-tree batches, and sequences the kernels of one assignment
+// iteration on one CUDA stream.  Replaces the stage-1/2 loops of network_assignment
+// (reference main_api.cpp:589-759).  No CPU compute path exists here: every entry point launches
+// kernels and fails when CUDA is unavailable.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+#include "dtl_internal.h"
+
+using namespace dtl;
+
+namespace {
+
+thread_local std::string g_err;
+void set_err(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return -1;                                                                                     \
+        }                                                                                                  \
+    } while (0)
+
+// ---- NCCL through dlopen: single-GPU users never need libnccl -------------------------------------
+struct Nccl {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (h) return true;
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { set_err("cannot load libnccl.so.2: %s", dlerror()); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_err("libnccl lacks a required symbol"); return false; }
+        return true;
+    }
+} g_nccl;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+};
+
+} // namespace
+
+struct dtl_engine {
+    int dev = 0, sm_count = 148;
+    cudaStream_t st = nullptr;
+    int N = 0, L = 0, Z = 0, AT = 1, T = 1, B = 1;
+    int rank = 0, world = 1;
+    dtl_options opt{};
+    float total_demand = 0;
+    size_t dev_bytes = 0;
+    std::vector<void*> allocs;
+
+    // host copies
+    std::vector<int> h_link_from, h_link_to, h_link_tag, h_node_zone, h_zone_centroid;
+    std::vector<float> h_vot;
+    // tasks owned by this rank, canonical (at, tau, zone) order
+    std::vector<int> task_at, task_tau, task_zone;
+    std::vector<int> task_cell_ptr; // [n_tasks+1] into d_task_cells
+    int *d_task_origin = nullptr, *d_task_zone = nullptr, *d_task_cells = nullptr;
+    unsigned char* d_task_skip = nullptr;
+    // OD cells owned by this rank
+    std::vector<int> cell_global; // local -> global OD index
+    int n_cells = 0;
+    int *d_od_dest = nullptr, *d_od_at = nullptr, *d_od_tau = nullptr, *d_od_task = nullptr;
+    double* d_od_vol = nullptr;
+
+    std::vector<ForwardStar> fs; // [AT*T], index at*T+tau
+    int** d_link_edge_ptrs = nullptr;
+    Edge** d_edges_ptrs = nullptr;
+    int *d_link_tag = nullptr, *d_link_from = nullptr;
+    VdfParams vp{};
+    LinkState ls{};
+    double *d_pce = nullptr, *d_occ = nullptr, *d_toll = nullptr, *d_lr = nullptr;
+    float* d_vot = nullptr;
+    double *d_block_sums = nullptr, *d_scalars = nullptr, *d_volume_tmp = nullptr;
+    double* h_scalars = nullptr; // pinned [16]
+    ColumnPool pool{};
+    int* d_error_flag = nullptr;
+    double *d_least = nullptr, *d_od_sums = nullptr;
+
+    // tree batch
+    int batch_tasks = 0;
+    unsigned long long* d_labels = nullptr;
+    int* d_pred = nullptr;
+    int* d_tie_nodes = nullptr;
+    std::vector<int> h_tie_nodes;
+    // keep_trees: trees of the whole last iteration
+    unsigned long long* d_keep_labels = nullptr;
+    int* d_keep_pred = nullptr;
+    bool trees_valid = false;
+    // sssp workspace
+    int sssp_block = 256, sssp_grid = 0;
+    QEntry* d_ws = nullptr;
+    size_t ws_stride = 0;
+    int cap_near = 0, cap_far = 0, tie_cap = 4096;
+    int* d_tie_cand = nullptr;
+    int* d_task_counter = nullptr;
+    SsspStats* d_stats = nullptr;
+    unsigned long long* d_counters = nullptr; // [0] link refs, [1] path nodes
+    int *d_replay_tasks = nullptr, *d_replay_status = nullptr, *d_replay_next = nullptr;
+    int replay_cap = 0;
+    double counted_edges_cached = -1;
+
+    // timing
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> free_events;
+    double ms[8] = { 0 };
+    long long launches[8] = { 0 };
+    double ctr_base[8] = { 0 };
+    double tasks_done = 0;
+
+    ncclComm_t comm = nullptr;
+
+    template <class T>
+    int alloc(T** p, size_t n)
+    {
+        size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) {
+            set_err("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return -1;
+        }
+        allocs.push_back(q);
+        dev_bytes += bytes;
+        *p = (T*)q;
+        return 0;
+    }
+    template <class T>
+    int upload(T** p, const T* src, size_t n)
+    {
+        if (alloc(p, n)) return -1;
+        if (n) CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    cudaEvent_t get_event()
+    {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    int phase_begin(int cls)
+    {
+        cudaEvent_t a = get_event(), b = get_event();
+        cudaEventRecord(a, st);
+        pending.push_back({ cls, { a, b } });
+        return (int)pending.size() - 1;
+    }
+    void phase_end(int handle, int n_launches = 1)
+    {
+        cudaEventRecord(pending[handle].second.second, st);
+        launches[pending[handle].first] += n_launches;
+    }
+    void resolve_timing()
+    {
+        for (auto& p : pending) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, p.second.first, p.second.second) == cudaSuccess) ms[p.first] += t;
+            free_events.push_back(p.second.first);
+            free_events.push_back(p.second.second);
+        }
+        pending.clear();
+    }
+};
+
+namespace {
+
+int fs_index(const dtl_engine* e, int at, int tau) { return at * e->T + tau; }
+
+// Work partition of the reference (g_assign_computing_tasks_to_memory_blocks, main_api.cpp:201-275, and the
+// loop nest main_api.cpp:667-697): which (agent type, period, zone) triples get a shortest-path tree.
+void build_task_list(const dtl_problem* p, std::vector<int>& at_out, std::vector<int>& tau_out, std::vector<int>& zone_out)
+{
+    const int Z = p->n_zones, AT = p->n_agent_types, T = p->n_periods, B = std::max(1, p->memory_blocks);
+    struct Net { int at, tau; std::vector<int> zones; };
+    std::vector<Net> nets;
+    for (int at = 0; at < AT; ++at)
+        for (int tau = 0; tau < T; ++tau) {
+            const size_t base = nets.size();
+            for (int z = 0; z < Z; ++z) {
+                if (z < B) nets.push_back(Net{ at, tau, { z } });                        // one network per block
+                else if (p->origin_demand[z] > 0.001) nets[base + z % B].zones.push_back(z); // later zones only with demand
+            }
+        }
+    const int n_nets = (int)nets.size();
+    const int n_blocks = std::min(n_nets, B);
+    std::vector<unsigned char> visited((size_t)AT * T * Z + 1, 0);
+    for (int pid = 0; pid < n_blocks; ++pid)
+        for (int blk = 0; blk < AT * T; ++blk) {
+            const int ni = blk * B + pid;
+            if (ni >= n_nets) continue;
+            for (int z : nets[ni].zones) visited[((size_t)nets[ni].at * T + nets[ni].tau) * Z + z] = 1;
+        }
+    for (int at = 0; at < AT; ++at)
+        for (int tau = 0; tau < T; ++tau)
+            for (int z = 0; z < Z; ++z)
+                if (visited[((size_t)at * T + tau) * Z + z]) { at_out.push_back(at); tau_out.push_back(tau); zone_out.push_back(z); }
+}
+
+int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
+{
+    ForwardStar& f = e->fs[fs_index(e, at, tau)];
+    const int N = e->N, L = e->L;
+    const unsigned char* allowed = p->allowed + ((size_t)tau * e->AT + at) * L;
+    std::vector<int> row(N + 1, 0), link_edge(L, -1);
+    for (int l = 0; l < L; ++l)
+        if (allowed[l]) row[p->link_from[l] + 1]++;
+    for (int i = 0; i < N; ++i) row[i + 1] += row[i];
+    const int E = row[N];
+    std::vector<Edge> edges(std::max(E, 1));
+    std::vector<int> cur(row.begin(), row.end() - 1);
+    double cost_sum = 0;
+    long long cost_n = 0;
+    for (int l = 0; l < L; ++l) // out-links of a node in insertion order == ascending link seq no
+        if (allowed[l]) {
+            const int ei = cur[p->link_from[l]]++;
+            edges[ei].to = p->link_to[l] | (p->link_tag[l] >= 0 ? 0x80000000 : 0);
+            edges[ei].link = l;
+            edges[ei].cost = 0.0;
+            link_edge[l] = ei;
+            const double c = p->fftt[(size_t)tau * L + l];
+            if (c > 1e-3) { cost_sum += c; ++cost_n; }
+        }
+    std::vector<int> in_ptr(N + 1, 0);
+    for (int ei = 0; ei < E; ++ei) in_ptr[(edges[ei].to & 0x7fffffff) + 1]++;
+    for (int i = 0; i < N; ++i) in_ptr[i + 1] += in_ptr[i];
+    std::vector<int2> in_edges(std::max(E, 1));
+    std::vector<int> icur(in_ptr.begin(), in_ptr.end() - 1);
+    for (int u = 0; u < N; ++u)
+        for (int ei = row[u]; ei < row[u + 1]; ++ei) in_edges[icur[edges[ei].to & 0x7fffffff]++] = make_int2(u, ei);
+    f.n_edges = E;
+    f.h_row_ptr = row;
+    const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
+    f.delta = factor * (cost_n ? cost_sum / (double)cost_n : 1.0);
+    if (e->upload(&f.row_ptr, row.data(), row.size())) return -1;
+    if (e->upload(&f.edges, edges.data(), edges.size())) return -1;
+    if (e->upload(&f.in_ptr, in_ptr.data(), in_ptr.size())) return -1;
+    if (e->upload(&f.in_edges, in_edges.data(), in_edges.size())) return -1;
+    if (e->upload(&f.link_edge, link_edge.data(), link_edge.size())) return -1;
+    return 0;
+}
+
+int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt)
+{
+    if (e->world <= 1) return 0;
+    if (!e->comm) { set_err("world_size > 1 but dtl_comm_init was not called"); return -1; }
+    const int ph = e->phase_begin(6);
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, ncclSum, e->comm, e->st);
+    e->phase_end(ph);
+    if (r != ncclSuccess) { set_err("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return -1; }
+    return 0;
+}
+
+int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_override)
+{
+    VdfLaunch a{};
+    a.T = e->T; a.L = e->L; a.AT = e->AT;
+    a.p = e->vp; a.s = e->ls;
+    a.toll = e->d_toll; a.lr_price = e->d_lr; a.vot = e->d_vot;
+    a.link_edge = e->d_link_edge_ptrs; a.edges = e->d_edges_ptrs;
+    a.block_sums = e->d_block_sums; a.sys_tt = e->d_scalars + 0;
+    a.volume_override = volume_override;
+    a.detail = detail; a.write_cost = write_cost;
+    const int ph = e->phase_begin(0);
+    launch_vdf(a, e->st);
+    e->phase_end(ph, 2);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int do_scatter(dtl_engine* e, int decay_k, bool person)
+{
+    const size_t TL = (size_t)e->T * e->L;
+    const int ph = e->phase_begin(1);
+    CK(cudaMemsetAsync(e->ls.pce_fix, 0, TL * sizeof(unsigned long long), e->st));
+    if (person) CK(cudaMemsetAsync(e->ls.person_fix, 0, TL * (1 + e->AT) * sizeof(unsigned long long), e->st));
+    ScatterLaunch a{};
+    a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
+    a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.pce = e->d_pce; a.occ = e->d_occ;
+    a.pce_fix = e->ls.pce_fix; a.person_fix = person ? e->ls.person_fix : nullptr;
+    a.decay_k = decay_k; a.link_refs = e->d_counters + 0;
+    launch_scatter(a, e->st);
+    e->phase_end(ph, 1);
+    CK(cudaGetLastError());
+    if (all_reduce(e, e->ls.pce_fix, TL, ncclUint64)) return -1;
+    if (person && all_reduce(e, e->ls.person_fix, TL * (1 + e->AT), ncclUint64)) return -1;
+    return 0;
+}
+
+SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone,
+                            int tree_off)
+{
+    SsspLaunch a{};
+    a.N = e->N; a.row_ptr = f.row_ptr; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges;
+    a.link_tag = e->d_link_tag; a.link_from = e->d_link_from;
+    a.n_tasks = n_tasks; a.task_origin = d_origin; a.task_zone = d_zone;
+    a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;
+    a.tie_nodes = e->d_tie_nodes;
+    a.delta = f.delta;
+    a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_near = e->cap_near; a.cap_far = e->cap_far;
+    a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
+    a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
+    return a;
+}
+
+// run the SSSP kernel for one batch (trees land in d_labels/d_pred), replay tied origins
+int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, bool count_edges,
+                   int tree_off = 0)
+{
+    SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
+    const int ph = e->phase_begin(2);
+    CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
+    launch_sssp(a, e->st);
+    e->phase_end(ph, 1);
+    CK(cudaGetLastError());
+    e->h_tie_nodes.resize(n_tasks);
+    CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    std::vector<int> replay;
+    for (int i = 0; i < n_tasks; ++i)
+        if (e->h_tie_nodes[i] > 0) replay.push_back(i);
+    for (size_t done = 0; done < replay.size();) {
+        if (!e->d_replay_tasks) {
+            e->replay_cap = 64;
+            if (e->alloc(&e->d_replay_tasks, e->replay_cap)) return -1;
+            if (e->alloc(&e->d_replay_status, (size_t)e->replay_cap * e->N)) return -1;
+            if (e->alloc(&e->d_replay_next, (size_t)e->replay_cap * e->N)) return -1;
+        }
+        const int n = (int)std::min<size_t>(e->replay_cap, replay.size() - done);
+        CK(cudaMemcpyAsync(e->d_replay_tasks, replay.data() + done, sizeof(int) * n, cudaMemcpyHostToDevice, e->st));
+        const int ph3 = e->phase_begin(3);
+        launch_sssp_replay(a, e->d_replay_tasks, n, e->d_replay_status, e->d_replay_next, e->st);
+        e->phase_end(ph3, 1);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->st));
+        done += n;
+    }
+    if (count_edges) {
+        launch_count_edges(a, e->st);
+        CK(cudaGetLastError());
+    }
+    e->tasks_done += n_tasks;
+    return 0;
+}
+
+int check_flags(dtl_engine* e)
+{
+    int flag = 0;
+    SsspStats s{};
+    CK(cudaMemcpyAsync(&flag, e->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    if (flag & 1) { set_err("column arena exhausted (%lld path links): raise dtl_options.column_arena_bytes", e->pool.arena_cap); return -1; }
+    if (flag & 2) { set_err("an OD cell needs more than %d columns: raise dtl_options.max_columns_per_od", e->pool.cap); return -1; }
+    if (s.overflow) { set_err("SSSP work queue overflow (internal capacity bound violated)"); return -1; }
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* dtl_last_error(void) { return g_err.c_str(); }
+const char* dtl_version(void) { return "dtalite_b200 0.1 (sm_100a)"; }
+
+void dtl_default_options(dtl_options* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->device = -1;
+    o->max_columns_per_od = 24;
+    o->rank = 0;
+    o->world_size = 1;
+    o->sssp_delta_factor = 0;
+    o->sssp_block_threads = 0;
+    o->sssp_ctas_per_sm = 0;
+    o->tree_batch_bytes = 0;
+    o->column_arena_bytes = 0;
+    o->keep_trees = 0;
+}
+
+void dtl_destroy(dtl_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->dev);
+    if (e->st) cudaStreamSynchronize(e->st);
+    e->resolve_timing();
+    for (cudaEvent_t ev : e->free_events) cudaEventDestroy(ev);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->h_scalars) cudaFreeHost(e->h_scalars);
+    if (e->st) cudaStreamDestroy(e->st);
+    delete e;
+}
+
+static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* opt)
+{
+    dtl_options o;
+    if (opt) o = *opt; else dtl_default_options(&o);
+    e->opt = o;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        set_err("no CUDA device available (%s): this engine has no CPU fallback", cudaGetErrorString(ce));
+        return -1;
+    }
+    if (o.device >= 0) CK(cudaSetDevice(o.device));
+    CK(cudaGetDevice(&e->dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, e->dev));
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    CK(cudaMallocHost(&e->h_scalars, 16 * sizeof(double)));
+
+    e->N = p->n_nodes; e->L = p->n_links; e->Z = p->n_zones; e->AT = p->n_agent_types; e->T = p->n_periods;
+    e->B = std::max(1, p->memory_blocks);
+    e->rank = o.rank; e->world = std::max(1, o.world_size);
+    e->total_demand = p->total_demand_volume;
+    const int N = e->N, L = e->L, Z = e->Z, AT = e->AT, T = e->T;
+    if (N <= 0 || L < 0 || Z <= 0 || AT <= 0 || T <= 0) { set_err("empty problem"); return -1; }
+    if (e->rank < 0 || e->rank >= e->world) { set_err("rank %d outside world of %d", e->rank, e->world); return -1; }
+    e->h_link_from.assign(p->link_from, p->link_from + L);
+    e->h_link_to.assign(p->link_to, p->link_to + L);
+    e->h_link_tag.assign(p->link_tag, p->link_tag + L);
+    e->h_node_zone.assign(p->node_zone, p->node_zone + N);
+    e->h_zone_centroid.assign(p->zone_centroid, p->zone_centroid + Z);
+    e->h_vot.assign(p->vot, p->vot + AT);
+    for (int l = 0; l < L; ++l)
+        if (p->link_from[l] < 0 || p->link_from[l] >= N || p->link_to[l] < 0 || p->link_to[l] >= N) {
+            set_err("link %d has an endpoint outside [0, %d)", l, N);
+            return -1;
+        }
+
+    // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
+    std::vector<int> g_at, g_tau, g_zone;
+    build_task_list(p, g_at, g_tau, g_zone);
+    std::map<long long, int> task_of; // (at,tau,zone) -> local task
+    for (size_t i = 0; i < g_at.size(); ++i)
+        if (g_zone[i] % e->world == e->rank) {
+            task_of[((long long)g_at[i] * T + g_tau[i]) * Z + g_zone[i]] = (int)e->task_at.size();
+            e->task_at.push_back(g_at[i]); e->task_tau.push_back(g_tau[i]); e->task_zone.push_back(g_zone[i]);
+        }
+    const int n_tasks = (int)e->task_at.size();
+    std::vector<int> origin(n_tasks);
+    std::vector<unsigned char> skip(n_tasks, 0);
+    std::vector<int> n_out(N, 0);
+    for (int l = 0; l < L; ++l) n_out[p->link_from[l]]++;
+    for (int i = 0; i < n_tasks; ++i) {
+        origin[i] = p->zone_centroid[e->task_zone[i]];
+        skip[i] = n_out[origin[i]] == 0; // routing.h:428
+    }
+    if (e->upload(&e->d_task_origin, origin.data(), n_tasks)) return -1;
+    if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
+    if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
+
+    // ---- OD cells of this rank (cells whose origin has no task never get columns in the reference either) ----
+    std::vector<int> od_dest, od_at, od_tau, od_task;
+    std::vector<double> od_vol;
+    std::vector<std::vector<int>> cells_of_task(n_tasks);
+    for (int i = 0; i < p->n_od; ++i) {
+        if (p->od_o[i] % e->world != e->rank) continue;
+        auto it = task_of.find(((long long)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]);
+        if (it == task_of.end()) continue;
+        const int c = (int)e->cell_global.size();
+        e->cell_global.push_back(i);
+        od_dest.push_back(p->zone_centroid[p->od_d[i]]);
+        od_at.push_back(p->od_at[i]); od_tau.push_back(p->od_tau[i]); od_task.push_back(it->second);
+        od_vol.push_back(p->od_vol[i]);
+        cells_of_task[it->second].push_back(c);
+    }
+    e->n_cells = (int)e->cell_global.size();
+    std::vector<int> task_cells;
+    e->task_cell_ptr.assign(n_tasks + 1, 0);
+    for (int t = 0; t < n_tasks; ++t) {
+        task_cells.insert(task_cells.end(), cells_of_task[t].begin(), cells_of_task[t].end());
+        e->task_cell_ptr[t + 1] = (int)task_cells.size();
+    }
+    if (e->upload(&e->d_od_dest, od_dest.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_at, od_at.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_tau, od_tau.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
+
+    // ---- network image ----
+    if (e->upload(&e->d_link_tag, p->link_tag, L)) return -1;
+    if (e->upload(&e->d_link_from, p->link_from, L)) return -1;
+    const size_t TL = (size_t)T * L, TAL = (size_t)T * AT * L;
+#define UPV(field) if (e->upload(&e->vp.field, p->field, TL)) return -1
+    UPV(fftt); UPV(cap); UPV(alpha); UPV(beta); UPV(vf); UPV(vc); UPV(nlanes); UPV(cap_lane); UPV(qdf); UPV(preload);
+    UPV(penalty); UPV(Q_alpha); UPV(Q_beta); UPV(Q_cd); UPV(Q_n); UPV(Q_cp); UPV(Q_s); UPV(t2); UPV(L_h); UPV(start_h);
+    UPV(end_h); UPV(plf); UPV(cycle_length); UPV(red_time); UPV(sat_flow); UPV(vdf_type);
+#undef UPV
+    if (e->upload(&e->d_pce, p->pce, TAL)) return -1;
+    if (e->upload(&e->d_occ, p->occ, TAL)) return -1;
+    if (e->upload(&e->d_toll, p->toll, TAL)) return -1;
+    if (e->upload(&e->d_lr, p->lr_price, TAL)) return -1;
+    if (e->upload(&e->d_vot, p->vot, AT)) return -1;
+    if (e->alloc(&e->ls.pce_fix, TL)) return -1;
+    if (e->alloc(&e->ls.person_fix, TL * (1 + AT))) return -1;
+    double** st_fields[] = { &e->ls.tt, &e->ls.link_volume, &e->ls.doc, &e->ls.voc, &e->ls.P, &e->ls.vt2,
+                             &e->ls.avg_queue_speed, &e->ls.avg_speed_bpr, &e->ls.Q_mu, &e->ls.Q_gamma, &e->ls.t0,
+                             &e->ls.t3, &e->ls.severe_P };
+    for (double** f : st_fields) {
+        if (e->alloc(f, TL)) return -1;
+        CK(cudaMemset(*f, 0, TL * sizeof(double)));
+    }
+    CK(cudaMemset(e->ls.pce_fix, 0, TL * 8));
+    CK(cudaMemset(e->ls.person_fix, 0, TL * (1 + AT) * 8));
+    if (e->alloc(&e->d_block_sums, vdf_blocks((int)TL) + 1)) return -1;
+    if (e->alloc(&e->d_scalars, 16)) return -1;
+    if (e->alloc(&e->d_volume_tmp, TL)) return -1;
+
+    e->fs.resize((size_t)AT * T);
+    int maxE = 0;
+    for (int at = 0; at < AT; ++at)
+        for (int tau = 0; tau < T; ++tau) {
+            if (build_forward_star(e, p, at, tau)) return -1;
+            maxE = std::max(maxE, e->fs[fs_index(e, at, tau)].n_edges);
+        }
+    std::vector<int*> le(AT * T);
+    std::vector<Edge*> ed(AT * T);
+    for (int i = 0; i < AT * T; ++i) { le[i] = e->fs[i].link_edge; ed[i] = e->fs[i].edges; }
+    if (e->upload(&e->d_link_edge_ptrs, le.data(), le.size())) return -1;
+    if (e->upload(&e->d_edges_ptrs, ed.data(), ed.size())) return -1;
+
+    // ---- column pool ----
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    e->pool.n_od = e->n_cells;
+    e->pool.cap = std::max(1, o.max_columns_per_od);
+    const size_t slots = (size_t)e->n_cells * e->pool.cap;
+    if (e->alloc(&e->pool.count, e->n_cells)) return -1;
+    CK(cudaMemset(e->pool.count, 0, sizeof(int) * std::max(1, e->n_cells)));
+    if (e->alloc(&e->pool.node_sum, slots)) return -1;
+    if (e->alloc(&e->pool.n_links, slots)) return -1;
+    if (e->alloc(&e->pool.n_nodes, slots)) return -1;
+    if (e->alloc(&e->pool.offset, slots)) return -1;
+    if (e->alloc(&e->pool.volume, slots)) return -1;
+    if (e->alloc(&e->pool.cost, slots)) return -1;
+    if (e->alloc(&e->pool.time, slots)) return -1;
+    if (e->alloc(&e->pool.arena_used, 1)) return -1;
+    CK(cudaMemset(e->pool.arena_used, 0, 8));
+    if (e->alloc(&e->d_error_flag, 1)) return -1;
+    CK(cudaMemset(e->d_error_flag, 0, 4));
+    if (e->alloc(&e->d_least, e->n_cells)) return -1;
+    CK(cudaMemset(e->d_least, 0, sizeof(double) * std::max(1, e->n_cells)));
+    if (e->alloc(&e->d_od_sums, (size_t)e->n_cells * 4)) return -1;
+    if (e->alloc(&e->d_stats, 1)) return -1;
+    CK(cudaMemset(e->d_stats, 0, sizeof(SsspStats)));
+    if (e->alloc(&e->d_counters, 4)) return -1;
+    CK(cudaMemset(e->d_counters, 0, 32));
+    if (e->alloc(&e->d_task_counter, 1)) return -1;
+
+    // ---- tree batch + SSSP workspace ----
+    const size_t per_tree = (size_t)N * 12;
+    size_t tree_budget = o.tree_batch_bytes ? o.tree_batch_bytes : std::min<size_t>((size_t)24 << 30, free_b / 6);
+    e->batch_tasks = (int)std::max<size_t>(1, std::min<size_t>(std::max(1, n_tasks), tree_budget / per_tree));
+    if (o.keep_trees) e->batch_tasks = std::max(1, n_tasks);
+    if (e->alloc(&e->d_labels, (size_t)e->batch_tasks * N)) return -1;
+    if (e->alloc(&e->d_pred, (size_t)e->batch_tasks * N)) return -1;
+    if (e->alloc(&e->d_tie_nodes, e->batch_tasks)) return -1;
+    e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 256;
+    if (e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 256;
+    int occ = 0, regs = 0;
+    sssp_occupancy(e->sssp_block, &occ, &regs);
+    if (occ <= 0) { set_err("SSSP kernel cannot be resident on this device (built for sm_100a)"); return -1; }
+    int per_sm = o.sssp_ctas_per_sm > 0 ? std::min(o.sssp_ctas_per_sm, occ) : occ;
+    e->cap_near = std::max(N, maxE) + 32;
+    e->cap_far = N + maxE + 32;
+    e->ws_stride = 2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far;
+    const size_t ws_budget = std::min<size_t>((size_t)48 << 30, free_b / 3);
+    int grid = e->sm_count * per_sm;
+    grid = (int)std::min<size_t>(grid, std::max<size_t>(1, ws_budget / (e->ws_stride * sizeof(QEntry))));
+    grid = std::min(grid, std::max(1, e->batch_tasks));
+    e->sssp_grid = std::max(1, grid);
+    if (e->alloc(&e->d_ws, (size_t)e->sssp_grid * e->ws_stride)) return -1;
+    if (e->alloc(&e->d_tie_cand, (size_t)e->sssp_grid * e->tie_cap)) return -1;
+
+    // ---- path-link arena: what is left, bounded by the option ----
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t arena_bytes = o.column_arena_bytes ? o.column_arena_bytes : std::min<size_t>((size_t)32 << 30, free_b / 2);
+    // a column never has more links than nodes: enough for every slot is an upper bound worth respecting on small inputs
+    const size_t hard = (slots + 1) * (size_t)(((size_t)N + 3) & ~(size_t)3) * sizeof(int);
+    arena_bytes = std::min(arena_bytes, hard);
+    e->pool.arena_cap = (long long)(arena_bytes / sizeof(int));
+    if (e->alloc(&e->pool.arena, (size_t)e->pool.arena_cap)) return -1;
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+dtl_engine* dtl_create(const dtl_problem* p, const dtl_options* opt)
+{
+    if (!p) { set_err("null problem"); return nullptr; }
+    dtl_engine* e = new dtl_engine();
+    if (create_impl(e, p, opt)) {
+        std::string keep = g_err;
+        dtl_destroy(e);
+        g_err = keep;
+        return nullptr;
+    }
+    return e;
+}
+
+size_t dtl_device_bytes(const dtl_engine* e) { return e ? e->dev_bytes : 0; }
+int dtl_num_tasks(const dtl_engine* e) { return (int)e->task_at.size(); }
+int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone)
+{
+    const size_t n = e->task_at.size();
+    if (at) memcpy(at, e->task_at.data(), n * sizeof(int));
+    if (tau) memcpy(tau, e->task_tau.data(), n * sizeof(int));
+    if (zone) memcpy(zone, e->task_zone.data(), n * sizeof(int));
+    return 0;
+}
+
+int dtl_comm_get_unique_id(unsigned char id128[128])
+{
+    if (!g_nccl.load()) return -1;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { set_err("ncclGetUniqueId failed"); return -1; }
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int dtl_comm_init(dtl_engine* e, const unsigned char id128[128])
+{
+    if (e->world <= 1) return 0;
+    if (!g_nccl.load()) return -1;
+    CK(cudaSetDevice(e->dev));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&e->comm, e->world, id, e->rank);
+    if (r != ncclSuccess) { set_err("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return -1; }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int trees_and_columns(dtl_engine* e, int k, bool want_count)
+{
+    const int n_tasks = (int)e->task_at.size();
+    int t0 = 0;
+    while (t0 < n_tasks) {
+        // a batch never spans two forward stars
+        const int fsi = fs_index(e, e->task_at[t0], e->task_tau[t0]);
+        int t1 = t0;
+        while (t1 < n_tasks && t1 - t0 < e->batch_tasks && fs_index(e, e->task_at[t1], e->task_tau[t1]) == fsi) ++t1;
+        const int nb = t1 - t0;
+        const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
+        if (run_sssp_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, want_count, tree_off)) return -1;
+        ColumnLaunch c{};
+        c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
+        c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
+        c.od_vol = e->d_od_vol; c.link_from = e->d_link_from;
+        c.labels = e->d_labels + (size_t)tree_off * e->N; c.pred_link = e->d_pred + (size_t)tree_off * e->N;
+        c.task_first = t0; c.task_count = nb;
+        c.batch_cells = e->d_task_cells + e->task_cell_ptr[t0];
+        c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
+        c.task_skip_backtrace = e->d_task_skip;
+        c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
+        const int ph = e->phase_begin(4);
+        launch_backtrace(c, e->st);
+        e->phase_end(ph, 1);
+        CK(cudaGetLastError());
+        t0 = t1;
+    }
+    e->trees_valid = e->opt.keep_trees != 0;
+    return 0;
+}
+
+int dtl_iteration(dtl_engine* e, int k, double row[5])
+{
+    CK(cudaSetDevice(e->dev));
+    const int ph7 = e->phase_begin(7);
+    if (do_vdf(e, false, true, nullptr)) return -1;                    // main_api.cpp:606
+    if (do_scatter(e, k, false)) return -1;                            // main_api.cpp:618
+    const bool want_count = e->counted_edges_cached < 0;
+    unsigned long long before = 0;
+    if (want_count) CK(cudaMemsetAsync(&e->d_stats->counted_edges, 0, 8, e->st));
+    (void)before;
+    if (trees_and_columns(e, k, want_count)) return -1;                // main_api.cpp:647-699
+    launch_sum(e->d_least, e->n_cells, 1, e->d_scalars + 1, e->st);
+    CK(cudaGetLastError());
+    if (all_reduce(e, e->d_scalars + 1, 1, ncclFloat64)) return -1;
+    if (want_count) {
+        // counted edges: reachability does not change between iterations, so count once
+        unsigned long long ce = 0;
+        CK(cudaMemcpyAsync(&ce, &e->d_stats->counted_edges, 8, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        e->h_scalars[8] = (double)ce;
+        CK(cudaMemcpyAsync(e->d_scalars + 2, e->h_scalars + 8, 8, cudaMemcpyHostToDevice, e->st));
+        if (all_reduce(e, e->d_scalars + 2, 1, ncclFloat64)) return -1;
+        CK(cudaMemcpyAsync(e->h_scalars + 8, e->d_scalars + 2, 8, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        e->counted_edges_cached = e->h_scalars[8];
+    }
+    CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    e->phase_end(ph7, 0);
+    if (check_flags(e)) return -1;
+    e->resolve_timing();
+    const double sysTT = e->h_scalars[0], least = e->h_scalars[1];
+    if (row) {
+        row[0] = sysTT;
+        row[1] = least;
+        row[2] = (sysTT - least) / std::max(0.00001, least);           // main_api.cpp:711
+        const float denom = 1 > e->total_demand ? (float)1 : e->total_demand; // main_api.cpp:716
+        row[3] = sysTT / denom;
+        row[4] = e->counted_edges_cached;
+    }
+    return 0;
+}
+
+int dtl_column_update(dtl_engine* e, int n, double row[4])
+{
+    CK(cudaSetDevice(e->dev));
+    const int ph7 = e->phase_begin(7);
+    if (do_scatter(e, -1, false)) return -1;                           // assignment.h:575
+    if (do_vdf(e, false, true, nullptr)) return -1;                    // assignment.h:593
+    PoolUpdateLaunch a{};
+    a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
+    a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.od_vol = e->d_od_vol;
+    a.tt = e->ls.tt; a.penalty = e->vp.penalty; a.toll = e->d_toll; a.vot = e->d_vot; a.n = n; a.od_sums = e->d_od_sums;
+    const int ph5 = e->phase_begin(5);
+    launch_pool_update(a, e->st);
+    for (int j = 0; j < 4; ++j) launch_sum(e->d_od_sums + j, e->n_cells, 4, e->d_scalars + 4 + j, e->st);
+    e->phase_end(ph5, 5);
+    CK(cudaGetLastError());
+    if (all_reduce(e, e->d_scalars + 4, 4, ncclFloat64)) return -1;
+    CK(cudaMemcpyAsync(e->h_scalars + 4, e->d_scalars + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    e->phase_end(ph7, 0);
+    CK(cudaStreamSynchronize(e->st));
+    e->resolve_timing();
+    if (row) {
+        const double gap = e->h_scalars[4], cost = e->h_scalars[5], time = e->h_scalars[6], dem = e->h_scalars[7];
+        row[0] = time / std::max(0.001, dem);                          // assignment.h:907
+        row[1] = gap;
+        row[2] = gap * 100.0 / std::max(0.00001, cost);                // assignment.h:911
+        row[3] = dem;
+    }
+    return 0;
+}
+
+int dtl_finalize(dtl_engine* e, int K, double* sys_tt)
+{
+    (void)K;
+    CK(cudaSetDevice(e->dev));
+    if (do_scatter(e, -1, true)) return -1;                            // main_api.cpp:752
+    if (do_vdf(e, true, true, nullptr)) return -1;                     // main_api.cpp:759
+    CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    e->resolve_timing();
+    if (sys_tt) *sys_tt = e->h_scalars[0];
+    return 0;
+}
+
+int dtl_run_assignment(dtl_engine* e, int K, int CU, double* iter_rows, double* cu_rows)
+{
+    for (int k = 0; k < K; ++k) {
+        double row[5];
+        if (dtl_iteration(e, k, row)) return -1;
+        if (iter_rows) memcpy(iter_rows + (size_t)k * 5, row, sizeof(row));
+    }
+    for (int n = 0; n < CU; ++n) {
+        double row[4];
+        if (dtl_column_update(e, n, row)) return -1;
+        if (cu_rows) memcpy(cu_rows + (size_t)n * 4, row, sizeof(row));
+    }
+    return dtl_finalize(e, K, nullptr);
+}
+
+// -------------------------------------------------------------------------------------------------
+static int fetch(dtl_engine* e, double* dst, const double* src, int tau)
+{
+    if (!dst) return 0;
+    CK(cudaMemcpyAsync(dst, src + (size_t)tau * e->L, sizeof(double) * e->L, cudaMemcpyDeviceToHost, e->st));
+    return 0;
+}
+
+static int fetch_fixed(dtl_engine* e, double* dst, const unsigned long long* src)
+{
+    std::vector<long long> tmp(e->L);
+    CK(cudaMemcpyAsync(tmp.data(), src, sizeof(long long) * e->L, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    for (int l = 0; l < e->L; ++l) dst[l] = (double)tmp[l] * (1.0 / DTL_FIX_SCALE);
+    return 0;
+}
+
+int dtl_get_link_state(dtl_engine* e, int tau, double* tt, double* pce_volume, double* person_volume, double* link_volume,
+                       double* doc, double* voc, double* P, double* vt2)
+{
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    if (fetch(e, tt, e->ls.tt, tau) || fetch(e, link_volume, e->ls.link_volume, tau) || fetch(e, doc, e->ls.doc, tau) ||
+        fetch(e, voc, e->ls.voc, tau) || fetch(e, P, e->ls.P, tau) || fetch(e, vt2, e->ls.vt2, tau))
+        return -1;
+    CK(cudaStreamSynchronize(e->st));
+    if (pce_volume && fetch_fixed(e, pce_volume, e->ls.pce_fix + (size_t)tau * e->L)) return -1;
+    if (person_volume && fetch_fixed(e, person_volume, e->ls.person_fix + (size_t)tau * (1 + e->AT) * e->L)) return -1;
+    return 0;
+}
+
+int dtl_get_volume_fixed(dtl_engine* e, int tau, long long* q)
+{
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    CK(cudaMemcpyAsync(q, e->ls.pce_fix + (size_t)tau * e->L, sizeof(long long) * e->L, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int dtl_get_person_volume_at(dtl_engine* e, int tau, int at, double* out)
+{
+    if (tau < 0 || tau >= e->T || at < 0 || at >= e->AT) { set_err("index out of range"); return -1; }
+    CK(cudaSetDevice(e->dev));
+    return fetch_fixed(e, out, e->ls.person_fix + ((size_t)tau * (1 + e->AT) + 1 + at) * e->L);
+}
+
+int dtl_get_link_detail(dtl_engine* e, int tau, double* avg_queue_speed, double* avg_speed_bpr, double* Q_mu, double* Q_gamma,
+                        double* t0, double* t3, double* severe)
+{
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    if (fetch(e, avg_queue_speed, e->ls.avg_queue_speed, tau) || fetch(e, avg_speed_bpr, e->ls.avg_speed_bpr, tau) ||
+        fetch(e, Q_mu, e->ls.Q_mu, tau) || fetch(e, Q_gamma, e->ls.Q_gamma, tau) || fetch(e, t0, e->ls.t0, tau) ||
+        fetch(e, t3, e->ls.t3, tau) || fetch(e, severe, e->ls.severe_P, tau))
+        return -1;
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int dtl_get_model_speed(dtl_engine* e, int tau, int first_slot, int n_slots, float* speed)
+{
+    if (tau < 0 || tau >= e->T || n_slots <= 0) { set_err("bad arguments"); return -1; }
+    CK(cudaSetDevice(e->dev));
+    float* d = nullptr;
+    const size_t n = (size_t)e->L * n_slots;
+    CK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(float)));
+    cudaMemsetAsync(d, 0, n * sizeof(float), e->st);
+    launch_model_speed(e->T, e->L, tau, e->vp, e->ls, first_slot, n_slots, d, e->st);
+    cudaError_t ce = cudaMemcpyAsync(speed, d, n * sizeof(float), cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    cudaFree(d);
+    CK(ce);
+    return 0;
+}
+
+int dtl_get_gen_cost(dtl_engine* e, int at, int tau, double* cost)
+{
+    if (tau < 0 || tau >= e->T || at < 0 || at >= e->AT) { set_err("index out of range"); return -1; }
+    CK(cudaSetDevice(e->dev));
+    const ForwardStar& f = e->fs[fs_index(e, at, tau)];
+    std::vector<Edge> ed(std::max(1, f.n_edges));
+    CK(cudaMemcpyAsync(ed.data(), f.edges, sizeof(Edge) * f.n_edges, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    for (int l = 0; l < e->L; ++l) cost[l] = 0.0;
+    for (int i = 0; i < f.n_edges; ++i) cost[ed[i].link] = ed[i].cost;
+    return 0;
+}
+
+// ---- column pool read-back ---------------------------------------------------------------------
+struct PoolHost {
+    std::vector<int> count, node_sum, n_links, n_nodes;
+    std::vector<long long> offset;
+    std::vector<double> volume, cost, time;
+};
+static int pool_to_host(dtl_engine* e, PoolHost& h)
+{
+    const size_t n = e->n_cells, s = n * e->pool.cap;
+    h.count.resize(n); h.node_sum.resize(s); h.n_links.resize(s); h.n_nodes.resize(s); h.offset.resize(s);
+    h.volume.resize(s); h.cost.resize(s); h.time.resize(s);
+    if (!n) return 0;
+    CK(cudaMemcpyAsync(h.count.data(), e->pool.count, n * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.node_sum.data(), e->pool.node_sum, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.n_links.data(), e->pool.n_links, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.n_nodes.data(), e->pool.n_nodes, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.offset.data(), e->pool.offset, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.volume.data(), e->pool.volume, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.cost.data(), e->pool.cost, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.time.data(), e->pool.time, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+long long dtl_num_columns(dtl_engine* e)
+{
+    if (cudaSetDevice(e->dev) != cudaSuccess) return -1;
+    std::vector<int> cnt(std::max(1, e->n_cells));
+    if (cudaMemcpy(cnt.data(), e->pool.count, sizeof(int) * e->n_cells, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    long long n = 0;
+    for (int i = 0; i < e->n_cells; ++i) n += cnt[i];
+    return n;
+}
+
+long long dtl_num_column_links(dtl_engine* e)
+{
+    PoolHost h;
+    if (cudaSetDevice(e->dev) != cudaSuccess || pool_to_host(e, h)) return -1;
+    long long n = 0;
+    for (int c = 0; c < e->n_cells; ++c)
+        for (int j = 0; j < h.count[c]; ++j) n += h.n_links[(size_t)c * e->pool.cap + j];
+    return n;
+}
+
+int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, int* n_links, int* n_nodes, double* volume,
+                    double* cost, double* time, int* links)
+{
+    CK(cudaSetDevice(e->dev));
+    PoolHost h;
+    if (pool_to_host(e, h)) return -1;
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, e->pool.arena_used, 8, cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (unsigned long long)e->pool.arena_cap);
+    std::vector<int> arena;
+    if (links) {
+        arena.resize(std::max<size_t>(1, (size_t)used));
+        CK(cudaMemcpy(arena.data(), e->pool.arena, sizeof(int) * (size_t)used, cudaMemcpyDeviceToHost));
+    }
+    long long c_out = 0, l_out = 0;
+    std::vector<int> order;
+    for (int c = 0; c < e->n_cells; ++c) {
+        const size_t base = (size_t)c * e->pool.cap;
+        order.resize(h.count[c]);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return h.node_sum[base + x] < h.node_sum[base + y]; });
+        for (int j : order) { // std::map order of the reference: ascending node_sum
+            if (od_index) od_index[c_out] = e->cell_global[c];
+            if (node_sum) node_sum[c_out] = h.node_sum[base + j];
+            if (seq_no) seq_no[c_out] = j; // slots are filled in insertion order == path_seq_no
+            if (n_links) n_links[c_out] = h.n_links[base + j];
+            if (n_nodes) n_nodes[c_out] = h.n_nodes[base + j];
+            if (volume) volume[c_out] = h.volume[base + j];
+            if (cost) cost[c_out] = h.cost[base + j];
+            if (time) time[c_out] = h.time[base + j];
+            if (links) {
+                memcpy(links + l_out, arena.data() + h.offset[base + j], sizeof(int) * h.n_links[base + j]);
+                l_out += h.n_links[base + j];
+            }
+            ++c_out;
+        }
+    }
+    return 0;
+}
+
+// ---- kernel-level entry points -----------------------------------------------------------------
+int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int* zones, int n, double* labels, int* pred_node,
+                   int* pred_link, int* tie_nodes, double stats[6])
+{
+    if (tau < 0 || tau >= e->T || at < 0 || at >= e->AT) { set_err("index out of range"); return -1; }
+    CK(cudaSetDevice(e->dev));
+    ForwardStar& f = e->fs[fs_index(e, at, tau)];
+    const int N = e->N;
+    if (cost) { // known-answer mode: caller-supplied generalized costs
+        std::vector<Edge> ed(std::max(1, f.n_edges));
+        CK(cudaMemcpy(ed.data(), f.edges, sizeof(Edge) * f.n_edges, cudaMemcpyDeviceToHost));
+        double sum = 0;
+        long long cnt = 0;
+        for (int i = 0; i < f.n_edges; ++i) {
+            ed[i].cost = cost[ed[i].link];
+            if (ed[i].cost > 1e-3) { sum += ed[i].cost; ++cnt; }
+        }
+        CK(cudaMemcpy(f.edges, ed.data(), sizeof(Edge) * f.n_edges, cudaMemcpyHostToDevice));
+        const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
+        f.delta = factor * (cnt ? sum / (double)cnt : 1.0);
+    }
+    std::vector<int> origin(n);
+    for (int i = 0; i < n; ++i) {
+        if (zones[i] < 0 || zones[i] >= e->Z) { set_err("zone %d out of range", zones[i]); return -1; }
+        origin[i] = e->h_zone_centroid[zones[i]];
+    }
+    int *d_origin = nullptr, *d_zone = nullptr;
+    CK(cudaMalloc(&d_origin, sizeof(int) * std::max(1, n)));
+    CK(cudaMalloc(&d_zone, sizeof(int) * std::max(1, n)));
+    int rc = 0;
+    SsspStats s0{}, s1{};
+    cudaMemcpy(&s0, e->d_stats, sizeof(s0), cudaMemcpyDeviceToHost);
+    float total_ms = 0;
+    std::vector<unsigned long long> hl;
+    std::vector<int> hp;
+    for (int b0 = 0; b0 < n && rc == 0; b0 += e->batch_tasks) {
+        const int nb = std::min(e->batch_tasks, n - b0);
+        cudaMemcpy(d_origin, origin.data() + b0, sizeof(int) * nb, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_zone, zones + b0, sizeof(int) * nb, cudaMemcpyHostToDevice);
+        cudaEvent_t ea = e->get_event(), eb = e->get_event();
+        cudaEventRecord(ea, e->st);
+        rc = run_sssp_batch(e, f, nb, d_origin, d_zone, true);
+        cudaEventRecord(eb, e->st);
+        if (rc) break;
+        if (cudaStreamSynchronize(e->st) != cudaSuccess) { set_err("SSSP batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; break; }
+        float t = 0;
+        cudaEventElapsedTime(&t, ea, eb);
+        total_ms += t;
+        e->free_events.push_back(ea); e->free_events.push_back(eb);
+        if (tie_nodes) memcpy(tie_nodes + b0, e->h_tie_nodes.data(), sizeof(int) * nb);
+        if (labels) cudaMemcpy(labels + (size_t)b0 * N, e->d_labels, sizeof(double) * (size_t)nb * N, cudaMemcpyDeviceToHost);
+        if (pred_link || pred_node) {
+            hp.resize((size_t)nb * N);
+            cudaMemcpy(hp.data(), e->d_pred, sizeof(int) * (size_t)nb * N, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < (size_t)nb * N; ++i) {
+                const int pl = hp[i];
+                if (pred_link) pred_link[(size_t)b0 * N + i] = pl;
+                if (pred_node) pred_node[(size_t)b0 * N + i] = pl >= 0 ? e->h_link_from[pl] : DTL_NO_PRED;
+            }
+        }
+    }
+    cudaFree(d_origin);
+    cudaFree(d_zone);
+    if (rc) return rc;
+    if (check_flags(e)) return -1;
+    e->resolve_timing();
+    cudaMemcpy(&s1, e->d_stats, sizeof(s1), cudaMemcpyDeviceToHost);
+    if (stats) {
+        stats[0] = total_ms;
+        stats[1] = (double)(s1.counted_edges - s0.counted_edges);
+        stats[2] = (double)(s1.relaxations - s0.relaxations);
+        stats[3] = (double)(s1.pops - s0.pops);
+        stats[4] = (double)(s1.rounds - s0.rounds);
+        stats[5] = (double)(s1.replayed - s0.replayed);
+    }
+    e->trees_valid = false;
+    return 0;
+}
+
+int dtl_vdf(dtl_engine* e, int tau, const double* volume, double* tt, double* doc, double* voc, double* P, double* vt2)
+{
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    // volumes of the other periods: keep the current link volumes
+    CK(cudaMemcpyAsync(e->d_volume_tmp, e->ls.link_volume, sizeof(double) * (size_t)e->T * e->L, cudaMemcpyDeviceToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_volume_tmp + (size_t)tau * e->L, volume, sizeof(double) * e->L, cudaMemcpyHostToDevice, e->st));
+    if (do_vdf(e, true, false, e->d_volume_tmp)) return -1;
+    CK(cudaStreamSynchronize(e->st));
+    e->resolve_timing();
+    return dtl_get_link_state(e, tau, tt, nullptr, nullptr, nullptr, doc, voc, P, vt2);
+}
+
+int dtl_scatter(dtl_engine* e, int decay_k)
+{
+    CK(cudaSetDevice(e->dev));
+    if (do_scatter(e, decay_k, true)) return -1;
+    CK(cudaStreamSynchronize(e->st));
+    e->resolve_timing();
+    return 0;
+}
+
+int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pred_link)
+{
+    if (!e->trees_valid) { set_err("trees are not kept: set dtl_options.keep_trees and run dtl_iteration first"); return -1; }
+    if (task < 0 || task >= (int)e->task_at.size()) { set_err("task %d out of range", task); return -1; }
+    CK(cudaSetDevice(e->dev));
+    const int N = e->N;
+    if (label) CK(cudaMemcpy(label, e->d_labels + (size_t)task * N, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    if (pred_node || pred_link) {
+        std::vector<int> hp(N);
+        CK(cudaMemcpy(hp.data(), e->d_pred + (size_t)task * N, sizeof(int) * N, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; ++i) {
+            if (pred_link) pred_link[i] = hp[i];
+            if (pred_node) pred_node[i] = hp[i] >= 0 ? e->h_link_from[hp[i]] : DTL_NO_PRED;
+        }
+    }
+    return 0;
+}
+
+int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset)
+{
+    CK(cudaSetDevice(e->dev));
+    CK(cudaStreamSynchronize(e->st));
+    e->resolve_timing();
+    if (ms) memcpy(ms, e->ms, sizeof(e->ms));
+    if (counts) memcpy(counts, e->launches, sizeof(e->launches));
+    if (reset) { memset(e->ms, 0, sizeof(e->ms)); memset(e->launches, 0, sizeof(e->launches)); }
+    return 0;
+}
+
+int dtl_get_counters(dtl_engine* e, double c[8], int reset)
+{
+    CK(cudaSetDevice(e->dev));
+    CK(cudaStreamSynchronize(e->st));
+    SsspStats s{};
+    unsigned long long ctr[4] = { 0 };
+    CK(cudaMemcpy(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost));
+    const double now[8] = { e->counted_edges_cached < 0 ? 0.0 : e->counted_edges_cached, (double)s.relaxations, (double)s.pops,
+                            (double)s.rounds, e->tasks_done, (double)s.replayed, (double)ctr[0], (double)ctr[1] };
+    if (c) {
+        for (int i = 0; i < 8; ++i) c[i] = now[i] - e->ctr_base[i];
+        c[0] = now[0]; // counted edges per iteration (static property of the trees), not cumulative
+    }
+    if (reset) memcpy(e->ctr_base, now, sizeof(now));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,247 @@
+// K2a  tree -> column builder        (NetworkForSP::backtrace_shortest_path_tree, reference routing.h:413-629)
+// K3   column -> link volume scatter (g_reset_and_update_link_volume_based_on_columns, assignment.h:53-195)
+// K2b  column-pool gradient projection (g_update_gradient_cost_and_assigned_flow_in_column_pool,
+//      assignment.h:565-928)
+//
+// The column pool is a CSR of columns: fixed slots per OD cell (count, node_sum, n_links, offset, volume)
+// and one int32 arena of path links in origin->destination order.  All three kernels are HBM/L2 bound
+// gather/scatter work; algorithmic bytes per unit are listed in DESIGN.md.  Compiled with -fmad=false.
+#include "dtl_internal.h"
+
+namespace dtl {
+
+__device__ __forceinline__ double mxd(double a, double b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// K2a: one thread per OD cell of the batch.  Walks the predecessor chain destination -> origin twice:
+// first to form the reference's column key node_sum = sum(node + pred_link) (int32 wrap-around,
+// routing.h:536) and the path length, then -- only when the key is new for the cell -- to store the
+// links reversed (DTA.h:551-559).  Adds od_volume/(k+1) to the column (routing.h:435,502,619) and
+// writes the cell's share of the least system travel time (routing.h:517-520).
+__global__ void __launch_bounds__(128) backtrace_kernel(ColumnLaunch a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_batch_cells) return;
+    const int cell = a.batch_cells[t];
+    const int task = a.od_task[cell];
+    a.least_contrib[cell] = 0.0;
+    if (a.task_skip_backtrace[task]) return; // routing.h:428
+    const int lt = task - a.task_first;      // tree index inside the batch
+    const int N = a.N, L = a.L;
+    const unsigned long long* lab = a.labels + (size_t)lt * N;
+    const int* pred = a.pred_link + (size_t)lt * N;
+    const double od_volume = a.od_vol[cell];
+    if (!(od_volume > 0.000001)) return;     // routing.h:505
+    const int dest = a.od_dest_node[cell];
+    const float kp = (float)1 / (float)(a.k + 1); // routing.h:435
+    const double volume = od_volume * kp;    // routing.h:502
+
+    int pl = pred[dest];
+    if (pl >= 0) a.least_contrib[cell] = od_volume * __longlong_as_double((long long)lab[dest]); // :517-520
+    unsigned node_sum = 0;
+    int n_nodes = 0, n_links = 0;
+    int cur = dest;
+    while (cur >= 0 && cur < N) {            // routing.h:522-572
+        ++n_nodes;
+        pl = pred[cur];
+        node_sum += (unsigned)cur + (unsigned)pl;
+        if (pl >= 0 && pl < L) { ++n_links; cur = a.link_from[pl]; }
+        else cur = -1;
+    }
+    atomicAdd(a.path_nodes, (unsigned long long)n_nodes);
+    if (n_nodes < 2) return;                 // routing.h:584
+    const int key = (int)node_sum;
+    const ColumnPool& P = a.pool;
+    const size_t base = (size_t)cell * P.cap;
+    int cnt = P.count[cell];
+    int slot = -1;
+    for (int j = 0; j < cnt; ++j)
+        if (P.node_sum[base + j] == key) { slot = j; break; }
+    if (slot < 0) {                          // routing.h:595-617 insert a new column
+        if (cnt >= P.cap) { atomicOr(a.error_flag, 2); return; }
+        const long long need = (n_links + 3) & ~3; // keep every column 16-byte aligned
+        const long long off = (long long)atomicAdd(P.arena_used, (unsigned long long)need);
+        if (off + need > P.arena_cap) { atomicOr(a.error_flag, 1); return; }
+        slot = cnt;
+        P.node_sum[base + slot] = key;
+        P.n_links[base + slot] = n_links;
+        P.n_nodes[base + slot] = n_nodes;
+        P.offset[base + slot] = off;
+        P.volume[base + slot] = 0.0;
+        P.cost[base + slot] = 0.0;
+        P.time[base + slot] = 0.0;
+        int* out = P.arena + off;
+        int w = n_links;
+        cur = dest;
+        while (cur >= 0 && cur < N) {
+            pl = pred[cur];
+            if (pl >= 0 && pl < L) { out[--w] = pl; cur = a.link_from[pl]; }
+            else cur = -1;
+        }
+        for (int q = n_links; q < need; ++q) out[q] = -1;
+        P.count[cell] = cnt + 1;
+    }
+    P.volume[base + slot] += volume;         // routing.h:619
+}
+
+void launch_backtrace(const ColumnLaunch& a, cudaStream_t st)
+{
+    if (a.n_batch_cells == 0) return;
+    backtrace_kernel<<<(a.n_batch_cells + 127) / 128, 128, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one warp per OD cell; lanes stride over a column's links (coalesced 128-byte gathers from the
+// arena) and add the column's PCE volume to the per-link Q31.32 accumulators with integer atomics, so
+// the sums do not depend on the order columns are visited in -- across warps, launches or GPUs.
+// The addend is the reference's own  (double)(float)path_volume * pce  (assignment.h:87,127,140)
+// rounded once to 2^-32.
+template <bool PERSON>
+__global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.pool.n_od) return;
+    const int cell = warp;
+    const ColumnPool& P = a.pool;
+    const int cnt = P.count[cell];
+    if (cnt == 0) return;
+    const int at = a.od_at[cell], tau = a.od_tau[cell];
+    const double* pce = a.pce + ((size_t)tau * a.AT + at) * a.L;
+    const double* occ = a.occ + ((size_t)tau * a.AT + at) * a.L;
+    unsigned long long* acc = a.pce_fix + (size_t)tau * a.L;
+    unsigned long long* per = PERSON ? a.person_fix + (size_t)tau * (1 + a.AT) * a.L : nullptr;
+    unsigned long long* per_at = PERSON ? per + (size_t)(1 + at) * a.L : nullptr;
+    const size_t base = (size_t)cell * P.cap;
+    unsigned long long refs = 0;
+    for (int j = 0; j < cnt; ++j) {
+        const double vol = P.volume[base + j];
+        const float f = (float)vol;                                  // assignment.h:87,127
+        const int n = P.n_links[base + j];
+        const int* links = P.arena + P.offset[base + j];
+        if (f != 0.0f) {
+            for (int q = lane; q < n; q += 32) {
+                const int l = __ldg(&links[q]);
+                const double x = f * __ldg(&pce[l]);                 // assignment.h:140
+                atomicAdd(&acc[l], (unsigned long long)__double2ll_rn(x * DTL_FIX_SCALE));
+                if (PERSON) {
+                    const unsigned long long y = (unsigned long long)__double2ll_rn(f * __ldg(&occ[l]) * DTL_FIX_SCALE);
+                    atomicAdd(&per[l], y);                           // assignment.h:141
+                    atomicAdd(&per_at[l], y);                        // assignment.h:142
+                }
+            }
+        }
+        refs += n;
+        if (a.decay_k >= 0 && lane == 0)                             // assignment.h:182-186 MSA self-reduction
+            P.volume[base + j] = vol * ((double)a.decay_k / (double)(a.decay_k + 1));
+    }
+    if (lane == 0) atomicAdd(a.link_refs, refs);
+}
+
+void launch_scatter(const ScatterLaunch& a, cudaStream_t st)
+{
+    if (a.pool.n_od == 0) return;
+    const int blocks = (a.pool.n_od + 7) / 8;
+    if (a.person_fix) scatter_kernel<true><<<blocks, 256, 0, st>>>(a);
+    else scatter_kernel<false><<<blocks, 256, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: one thread per OD cell.  Path costs are left-to-right FP64 sums in path order exactly like the
+// reference (DTA.h:1154-1164, assignment.h:723-736), so the arg-min ("first strict minimum in ascending
+// node_sum order", assignment.h:757) and the flow shifts reproduce the reference's decisions.
+__global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.pool.n_od) return;
+    const ColumnPool& P = a.pool;
+    const int cnt = P.count[cell];
+    double* sums = a.od_sums + (size_t)cell * 4;
+    double s_gap = 0, s_cost = 0, s_time = 0, s_dem = 0;
+    if (cnt > 0) {
+        const int at = a.od_at[cell], tau = a.od_tau[cell];
+        const double* tt = a.tt + (size_t)tau * a.L;
+        const double* pen = a.penalty + (size_t)tau * a.L;
+        const double* toll = a.toll + ((size_t)tau * a.AT + at) * a.L;
+        const float vot = a.vot[at];
+        const size_t base = (size_t)cell * P.cap;
+        const double od_volume = a.od_vol[cell];
+        // pass 1: path cost / time of every column
+        for (int j = 0; j < cnt; ++j) {
+            const int n = P.n_links[base + j];
+            const int4* links = reinterpret_cast<const int4*>(P.arena + P.offset[base + j]);
+            double path_cost = 0, path_time = 0;
+            for (int q = 0; q < n; q += 4) {
+                const int4 v = __ldg(&links[q >> 2]);
+                const int ls[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (q + r < n) {
+                        const int l = ls[r];
+                        const double t = __ldg(&tt[l]);
+                        path_time += t;
+                        path_cost += t + __ldg(&pen[l]) + __ldg(&toll[l]) / vot * 60; // DTA.h:1157
+                    }
+                }
+            }
+            P.cost[base + j] = path_cost;
+            P.time[base + j] = path_time;
+        }
+        // pass 2: arg-min in ascending node_sum order with strict '<' (std::map order, assignment.h:686-767)
+        double least_cost = 999999;
+        int least = -1, least_key = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const double c = P.cost[base + j];
+            const double v = P.volume[base + j];
+            const int key = P.node_sum[base + j];
+            s_time += P.time[base + j] * v;                              // :746
+            s_dem += v;                                                  // :747
+            if (cnt == 1) s_cost += c * v;                               // :750-754
+            if (c < 999999 && (least < 0 || c < least_cost || (c == least_cost && key < least_key))) {
+                least_cost = c; least = j; least_key = key;
+            }
+        }
+        if (cnt >= 2) {                                                  // :769
+            double switched = 0;
+            // the reference walks the std::map, i.e. ascending node_sum: keep that order for the FP sums
+            int prev_key = 0;
+            bool first = true;
+            for (int step = 0; step < cnt; ++step) {
+                int j = -1, key = 0;
+                for (int c2 = 0; c2 < cnt; ++c2) { // next column in ascending key order (cnt is small)
+                    const int k2 = P.node_sum[base + c2];
+                    if ((first || k2 > prev_key) && (j < 0 || k2 < key)) { j = c2; key = k2; }
+                }
+                prev_key = key; first = false;
+                if (j == least) continue;                                // :775
+                const double c = P.cost[base + j];
+                const double v = P.volume[base + j];
+                const double diff = c - least_cost;
+                const double rel = diff / mxd(0.0001, least_cost);       // :781
+                s_gap += diff * v;                                       // :786
+                s_cost += c * v;                                         // :787
+                const double stepsz = 1.0 / (a.n + 2) * od_volume;       // :802
+                double shift = stepsz * mxd(0.0000, rel);                // :808
+                if (rel > 3 * 60) shift = v;                             // :811
+                if (shift > v) shift = v;                                // :816
+                const double nv = mxd(0.0, v - shift);                   // :851
+                P.volume[base + j] = nv;
+                switched += (v - nv);                                    // :859
+            }
+            if (least >= 0) {                                            // :869-886
+                const double nv = P.volume[base + least] + switched;
+                P.volume[base + least] = nv;
+                s_cost += P.cost[base + least] * nv;
+            }
+        }
+    }
+    sums[0] = s_gap; sums[1] = s_cost; sums[2] = s_time; sums[3] = s_dem;
+}
+
+void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st)
+{
+    if (a.pool.n_od == 0) return;
+    pool_update_kernel<<<(a.pool.n_od + 127) / 128, 128, 0, st>>>(a);
+}
+
+} // namespace dtl

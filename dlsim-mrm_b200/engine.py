@@ -1,0 +1,338 @@
+"""ctypes mirror of the engine C ABI (``include/dtalite_b200.h``).
+
+Thin by design: every method is one call into ``lib/libdtalite_b200.so``; there is no Python or CPU
+compute path, and loading fails loudly when the native library is missing.  Method names follow the
+reference functions they replace (``iteration`` = loop body of ``network_assignment``,
+``main_api.cpp:589-728``; ``column_update`` = ``g_update_gradient_cost_and_assigned_flow_in_column_pool``,
+``assignment.h:565``; ``sssp_trees`` = ``NetworkForSP::optimal_label_correcting``, ``routing.h:633``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .problem import ARRAY_SPECS, Problem
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdtalite_b200.so")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Problem(C.Structure):
+    _fields_ = (
+        [(n, C.c_int) for n in ("n_nodes", "n_links", "n_zones", "n_agent_types", "n_periods", "memory_blocks")]
+        + [(n, C.c_void_p) for n in ("link_from", "link_to", "link_tag", "node_zone", "zone_centroid")]
+        + [(n, C.c_void_p) for n in ("fftt", "cap", "alpha", "beta", "vf", "vc", "nlanes", "cap_lane", "qdf",
+                                     "preload", "penalty", "Q_alpha", "Q_beta", "Q_cd", "Q_n", "Q_cp", "Q_s", "t2",
+                                     "L_h", "start_h", "end_h", "plf", "cycle_length", "red_time", "sat_flow",
+                                     "vdf_type", "pce", "occ", "toll", "lr_price", "allowed", "vot")]
+        + [("n_od", C.c_int)]
+        + [(n, C.c_void_p) for n in ("od_o", "od_d", "od_at", "od_tau", "od_vol", "origin_demand")]
+        + [("total_demand_volume", C.c_float)]
+    )
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_columns_per_od", C.c_int), ("rank", C.c_int), ("world_size", C.c_int),
+                ("sssp_delta_factor", C.c_double), ("sssp_block_threads", C.c_int), ("sssp_ctas_per_sm", C.c_int),
+                ("tree_batch_bytes", C.c_size_t), ("column_arena_bytes", C.c_size_t), ("keep_trees", C.c_int)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load the native library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineError(f"native library {p} is missing: run `python -m dlsim_mrm_b200.build` "
+                          "(there is no CPU or Python fallback)")
+    L = C.CDLL(p)
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    L.dtl_last_error.restype = C.c_char_p
+    L.dtl_version.restype = C.c_char_p
+    L.dtl_default_options.argtypes = [vp]
+    L.dtl_create.restype = vp
+    L.dtl_create.argtypes = [vp, vp]
+    L.dtl_destroy.argtypes = [vp]
+    L.dtl_comm_get_unique_id.argtypes = [vp]
+    L.dtl_comm_init.argtypes = [vp, vp]
+    L.dtl_num_tasks.argtypes = [vp]
+    L.dtl_get_tasks.argtypes = [vp] * 4
+    L.dtl_iteration.argtypes = [vp, ci, vp]
+    L.dtl_column_update.argtypes = [vp, ci, vp]
+    L.dtl_finalize.argtypes = [vp, ci, vp]
+    L.dtl_run_assignment.argtypes = [vp, ci, ci, vp, vp]
+    L.dtl_get_link_state.argtypes = [vp, ci] + [vp] * 8
+    L.dtl_get_volume_fixed.argtypes = [vp, ci, vp]
+    L.dtl_get_person_volume_at.argtypes = [vp, ci, ci, vp]
+    L.dtl_get_link_detail.argtypes = [vp, ci] + [vp] * 7
+    L.dtl_get_model_speed.argtypes = [vp, ci, ci, ci, vp]
+    L.dtl_get_gen_cost.argtypes = [vp, ci, ci, vp]
+    L.dtl_num_columns.restype = C.c_longlong
+    L.dtl_num_columns.argtypes = [vp]
+    L.dtl_num_column_links.restype = C.c_longlong
+    L.dtl_num_column_links.argtypes = [vp]
+    L.dtl_get_columns.argtypes = [vp] * 10
+    L.dtl_sssp_trees.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp]
+    L.dtl_vdf.argtypes = [vp, ci] + [vp] * 6
+    L.dtl_scatter.argtypes = [vp, ci]
+    L.dtl_get_tree.argtypes = [vp, ci, vp, vp, vp]
+    L.dtl_get_timing.argtypes = [vp, vp, vp, ci]
+    L.dtl_get_counters.argtypes = [vp, vp, ci]
+    L.dtl_device_bytes.restype = C.c_size_t
+    L.dtl_device_bytes.argtypes = [vp]
+    L.dtl_gmns_read.restype = vp
+    L.dtl_gmns_read.argtypes = [C.c_char_p, ci]
+    L.dtl_gmns_problem.restype = C.POINTER(_Problem)
+    L.dtl_gmns_problem.argtypes = [vp]
+    L.dtl_gmns_free.argtypes = [vp]
+    L.dtl_gmns_last_error.restype = C.c_char_p
+    L.dtl_gmns_ids.argtypes = [vp, vp, vp]
+    L.dtl_gmns_assignment_settings.argtypes = [C.c_char_p, vp]
+    L.dtl_gmns_write_outputs.argtypes = [vp, vp, C.c_char_p]
+    L.network_assignment.restype = cd
+    L.network_assignment.argtypes = [ci] * 7
+    L.dtalite_main.restype = ci
+    if path is None:
+        _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c_problem(p: Problem, keep: dict) -> _Problem:
+    cp = _Problem()
+    for n in ("n_nodes", "n_links", "n_zones", "n_agent_types", "n_periods", "memory_blocks"):
+        setattr(cp, n, int(getattr(p, n)))
+    for name in ARRAY_SPECS:
+        a = np.ascontiguousarray(p.arrays[name], dtype=ARRAY_SPECS[name][0])
+        keep[name] = a
+        setattr(cp, name, _ptr(a))
+    cp.n_od = p.n_od
+    cp.total_demand_volume = float(p.total_demand_volume)
+    return cp
+
+
+def read_gmns(directory: str, memory_blocks: int = 4) -> Problem:
+    """GMNS files -> Problem through the native reader (``dtl_gmns_read``; reference ``g_read_input_data``,
+    ``input.h:2388``, ``g_ReadDemandFileBasedOnDemandFileList``, ``input.h:392``)."""
+    L = load_library()
+    h = L.dtl_gmns_read(os.fsencode(directory), int(memory_blocks))
+    if not h:
+        raise EngineError(L.dtl_gmns_last_error().decode())
+    try:
+        cp = L.dtl_gmns_problem(h).contents
+        N, Lk, Z, A, T = cp.n_nodes, cp.n_links, cp.n_zones, cp.n_agent_types, cp.n_periods
+        q = Problem(N, Lk, Z, A, T, cp.memory_blocks, float(cp.total_demand_volume))
+        n_od = cp.n_od
+        dims = {"N": N, "L": Lk, "Z": Z, "A": A, "TL": T * Lk, "TAL": T * A * Lk, "OD": n_od}
+        for name, (dt, code) in ARRAY_SPECS.items():
+            cnt = dims[code]
+            addr = getattr(cp, name)
+            if cnt == 0 or not addr:
+                q.arrays[name] = np.zeros(0, dtype=dt)
+            else:
+                buf = (C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(addr)
+                q.arrays[name] = np.frombuffer(buf, dtype=dt, count=cnt).copy()
+        node_id = np.zeros(N, np.int32)
+        zone_id = np.zeros(Z, np.int32)
+        L.dtl_gmns_ids(h, _ptr(node_id), _ptr(zone_id))
+        q.node_id, q.zone_id = node_id, zone_id
+        return q.finalize()
+    finally:
+        L.dtl_gmns_free(h)
+
+
+class Engine:
+    """One device-resident assignment problem on one GPU (one rank of a possibly sharded run)."""
+
+    TIMING_CLASSES = ("vdf", "scatter", "sssp", "tie_replay", "backtrace", "column_pool", "all_reduce", "iteration")
+    COUNTERS = ("counted_edges", "relaxations", "pops", "rounds", "tasks", "replayed", "link_refs", "path_nodes")
+
+    def __init__(self, problem: Problem, device: int = -1, rank: int = 0, world_size: int = 1, keep_trees: bool = False,
+                 max_columns_per_od: int = 0, delta_factor: float = 0.0, block_threads: int = 0, ctas_per_sm: int = 0,
+                 tree_batch_bytes: int = 0, column_arena_bytes: int = 0):
+        self.lib = load_library()
+        self.problem = problem
+        self._keep = {}
+        cp = _c_problem(problem, self._keep)
+        opt = _Options()
+        self.lib.dtl_default_options(C.byref(opt))
+        opt.device = device
+        opt.rank, opt.world_size = rank, world_size
+        opt.keep_trees = int(keep_trees)
+        if max_columns_per_od:
+            opt.max_columns_per_od = max_columns_per_od
+        opt.sssp_delta_factor = delta_factor
+        opt.sssp_block_threads = block_threads
+        opt.sssp_ctas_per_sm = ctas_per_sm
+        opt.tree_batch_bytes = tree_batch_bytes
+        opt.column_arena_bytes = column_arena_bytes
+        self.h = self.lib.dtl_create(C.byref(cp), C.byref(opt))
+        if not self.h:
+            raise EngineError(self.lib.dtl_last_error().decode())
+        self.n_tasks = self.lib.dtl_num_tasks(self.h)
+        at = np.zeros(max(self.n_tasks, 1), np.int32); tau = np.zeros_like(at); zone = np.zeros_like(at)
+        self.lib.dtl_get_tasks(self.h, _ptr(at), _ptr(tau), _ptr(zone))
+        self.task_at, self.task_tau, self.task_zone = at[:self.n_tasks], tau[:self.n_tasks], zone[:self.n_tasks]
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dtl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.dtl_last_error().decode())
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load_library()
+        buf = (C.c_ubyte * 128)()
+        if L.dtl_comm_get_unique_id(buf) != 0:
+            raise EngineError(L.dtl_last_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.dtl_comm_init(self.h, buf))
+
+    # -- assignment loop
+    def iteration(self, k: int) -> dict:
+        row = np.zeros(5)
+        self._ck(self.lib.dtl_iteration(self.h, int(k), _ptr(row)))
+        return dict(sysTT=row[0], least=row[1], gap=row[2], avg_tt=row[3], counted_edges=row[4])
+
+    def column_update(self, n: int) -> dict:
+        row = np.zeros(4)
+        self._ck(self.lib.dtl_column_update(self.h, int(n), _ptr(row)))
+        return dict(avg_tt=row[0], total_gap=row[1], rel_gap_pct=row[2], demand=row[3])
+
+    def finalize(self, K: int) -> float:
+        v = C.c_double(0)
+        self._ck(self.lib.dtl_finalize(self.h, int(K), C.byref(v)))
+        return v.value
+
+    def run_assignment(self, K: int, CU: int = 0):
+        it = np.zeros((max(K, 1), 5)); cu = np.zeros((max(CU, 1), 4))
+        self._ck(self.lib.dtl_run_assignment(self.h, int(K), int(CU), _ptr(it), _ptr(cu)))
+        return it[:K], cu[:CU]
+
+    # -- state
+    def link_state(self, tau: int = 0) -> dict:
+        L = self.problem.n_links
+        names = ("tt", "pce_volume", "person_volume", "link_volume", "doc", "voc", "P", "vt2")
+        arrs = [np.zeros(L) for _ in names]
+        self._ck(self.lib.dtl_get_link_state(self.h, tau, *[_ptr(a) for a in arrs]))
+        return dict(zip(names, arrs))
+
+    def volume_fixed(self, tau: int = 0) -> np.ndarray:
+        q = np.zeros(self.problem.n_links, np.int64)
+        self._ck(self.lib.dtl_get_volume_fixed(self.h, tau, _ptr(q)))
+        return q
+
+    def person_volume_at(self, tau: int, at: int) -> np.ndarray:
+        v = np.zeros(self.problem.n_links)
+        self._ck(self.lib.dtl_get_person_volume_at(self.h, tau, at, _ptr(v)))
+        return v
+
+    def link_detail(self, tau: int = 0) -> dict:
+        L = self.problem.n_links
+        names = ("avg_queue_speed", "avg_speed_bpr", "Q_mu", "Q_gamma", "t0", "t3", "severe_congestion_P")
+        arrs = [np.zeros(L) for _ in names]
+        self._ck(self.lib.dtl_get_link_detail(self.h, tau, *[_ptr(a) for a in arrs]))
+        return dict(zip(names, arrs))
+
+    def model_speed(self, tau: int, first_slot: int, n_slots: int) -> np.ndarray:
+        sp = np.zeros((self.problem.n_links, n_slots), np.float32)
+        self._ck(self.lib.dtl_get_model_speed(self.h, tau, first_slot, n_slots, _ptr(sp)))
+        return sp
+
+    def gen_cost(self, at: int, tau: int = 0) -> np.ndarray:
+        c = np.zeros(self.problem.n_links)
+        self._ck(self.lib.dtl_get_gen_cost(self.h, at, tau, _ptr(c)))
+        return c
+
+    def columns(self) -> dict:
+        n = self.lib.dtl_num_columns(self.h)
+        nl = self.lib.dtl_num_column_links(self.h)
+        if n < 0 or nl < 0:
+            raise EngineError(self.lib.dtl_last_error().decode())
+        i32 = lambda m: np.zeros(max(int(m), 1), np.int32)
+        f64 = lambda m: np.zeros(max(int(m), 1), np.float64)
+        od, ns, sq, nlk, nnd, vol, cost, tm, links = i32(n), i32(n), i32(n), i32(n), i32(n), f64(n), f64(n), f64(n), i32(nl)
+        self._ck(self.lib.dtl_get_columns(self.h, *[_ptr(a) for a in (od, ns, sq, nlk, nnd, vol, cost, tm, links)]))
+        return dict(od_index=od[:n], node_sum=ns[:n], seq_no=sq[:n], n_links=nlk[:n], n_nodes=nnd[:n], volume=vol[:n],
+                    cost=cost[:n], time=tm[:n], links=links[:nl])
+
+    # -- kernel-level entry points
+    def sssp_trees(self, at: int, tau: int, zones, cost=None, want_trees: bool = True):
+        zones = np.ascontiguousarray(zones, np.int32)
+        n, N = zones.size, self.problem.n_nodes
+        cost_a = None if cost is None else np.ascontiguousarray(cost, np.float64)
+        lab = np.zeros((n, N)) if want_trees else None
+        pn = np.zeros((n, N), np.int32) if want_trees else None
+        pl = np.zeros((n, N), np.int32) if want_trees else None
+        ties = np.zeros(max(n, 1), np.int32)
+        stats = np.zeros(6)
+        self._ck(self.lib.dtl_sssp_trees(self.h, at, tau, _ptr(cost_a), _ptr(zones), n, _ptr(lab), _ptr(pn), _ptr(pl),
+                                         _ptr(ties), _ptr(stats)))
+        st = dict(ms=stats[0], counted_edges=stats[1], relaxations=stats[2], pops=stats[3], rounds=stats[4],
+                  replayed=stats[5])
+        return lab, pn, pl, ties[:n], st
+
+    def vdf(self, tau: int, volume) -> dict:
+        L = self.problem.n_links
+        v = np.ascontiguousarray(volume, np.float64)
+        names = ("tt", "doc", "voc", "P", "vt2")
+        arrs = [np.zeros(L) for _ in names]
+        self._ck(self.lib.dtl_vdf(self.h, tau, _ptr(v), *[_ptr(a) for a in arrs]))
+        return dict(zip(names, arrs))
+
+    def scatter(self, decay_k: int = -1):
+        self._ck(self.lib.dtl_scatter(self.h, int(decay_k)))
+
+    def tree(self, task: int):
+        N = self.problem.n_nodes
+        lab = np.zeros(N); pn = np.zeros(N, np.int32); pl = np.zeros(N, np.int32)
+        self._ck(self.lib.dtl_get_tree(self.h, int(task), _ptr(lab), _ptr(pn), _ptr(pl)))
+        return lab, pn, pl
+
+    def timing(self, reset: bool = False) -> dict:
+        ms = np.zeros(8); cnt = np.zeros(8, np.int64)
+        self._ck(self.lib.dtl_get_timing(self.h, _ptr(ms), _ptr(cnt), int(reset)))
+        return {"ms": dict(zip(self.TIMING_CLASSES, ms.tolist())), "launches": dict(zip(self.TIMING_CLASSES, cnt.tolist()))}
+
+    def counters(self, reset: bool = False) -> dict:
+        c = np.zeros(8)
+        self._ck(self.lib.dtl_get_counters(self.h, _ptr(c), int(reset)))
+        return dict(zip(self.COUNTERS, c.tolist()))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.dtl_device_bytes(self.h))

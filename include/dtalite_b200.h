@@ -1,0 +1,183 @@
+/* dtalite_b200.h -- C ABI of the B200-native DTALite traffic-assignment hot path.
+ *
+ * Two levels, both plain C (pointers + sizes, no C++/torch types):
+ *
+ *  (A) The reference's own entry point, unchanged:
+ *        double network_assignment(int assignment_mode, int column_generation_iterations,
+ *                                  int column_updating_iterations, int ODME_iterations,
+ *                                  int sensitivity_analysis_iterations, int simulation_iterations,
+ *                                  int number_of_memory_blocks);
+ *      replaces reference src/cpp/config.h:19-28 / main_api.cpp:499.  Reads settings.csv,
+ *      node.csv, link.csv and the demand file(s) from the current directory and writes
+ *      link_performance.csv, route_assignment.csv and final_summary.csv there.
+ *
+ *  (B) An engine API for hosts that keep their own GMNS reader: the network image is passed
+ *      as arrays (dtl_problem) and every stage of the hot loop is one call.  Each entry
+ *      point names the reference function it replaces.
+ *
+ * All calls are synchronous with respect to the host unless stated.  Return value 0 = ok,
+ * non-zero = error (dtl_last_error() has the message).  There is no CPU fallback: when no
+ * CUDA device is usable every compute call fails.
+ */
+#ifndef DTALITE_B200_H
+#define DTALITE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------- (A) drop-in entry point ---------------------------------- */
+double network_assignment(int assignment_mode, int column_generation_iterations, int column_updating_iterations,
+                          int ODME_iterations, int sensitivity_analysis_iterations, int simulation_iterations,
+                          int number_of_memory_blocks);
+/* main() of the reference executable (flash_dta.cpp:140-246): reads settings.csv [assignment]
+ * and calls network_assignment.  Returns the process exit code. */
+int dtalite_main(void);
+
+/* ---------------------------------- (B) engine API ---------------------------------- */
+
+/* Network + demand image.  Same content as the reference's g_node_vector / g_link_vector /
+ * g_zone_vector / column-pool headers after g_read_input_data and connector creation
+ * (main_api.cpp:525-570), as structure-of-arrays.  Per-period arrays are [T][L], per-period-
+ * per-agent-type arrays [T][AT][L], row-major.  All pointers are HOST pointers; they are copied. */
+typedef struct dtl_problem {
+    int n_nodes, n_links, n_zones, n_agent_types, n_periods;
+    int memory_blocks;            /* number_of_memory_blocks after clamping (main_api.cpp:519) */
+    const int* link_from;         /* [L] from_node_seq_no */
+    const int* link_to;           /* [L] to_node_seq_no */
+    const int* link_tag;          /* [L] zone_seq_no_for_outgoing_connector, -1 if none */
+    const int* node_zone;         /* [N] zone seq no for centroid nodes, else -1 */
+    const int* zone_centroid;     /* [Z] centroid node seq no */
+    const double *fftt, *cap, *alpha, *beta, *vf, *vc, *nlanes, *cap_lane, *qdf, *preload, *penalty;
+    const double *Q_alpha, *Q_beta, *Q_cd, *Q_n, *Q_cp, *Q_s, *t2, *L_h, *start_h, *end_h, *plf;
+    const float *cycle_length, *red_time, *sat_flow;
+    const int* vdf_type;          /* 0 = q_vdf, 1 = bpr_vdf (DTA.h:53) */
+    const double *pce, *occ, *toll, *lr_price;
+    const unsigned char* allowed; /* CLink::AllowAgentType (DTA.h:1352) evaluated per (tau, at, link) */
+    const float* vot;             /* [AT] */
+    int n_od;                     /* OD cells with od_volume > 0 sorted by (o, d, at, tau) */
+    const int *od_o, *od_d, *od_at, *od_tau;
+    const double* od_vol;
+    const float* origin_demand;   /* [Z] */
+    float total_demand_volume;
+} dtl_problem;
+
+typedef struct dtl_options {
+    int device;                   /* CUDA device ordinal; -1 = current device */
+    int max_columns_per_od;       /* capacity of each OD cell's column set (>= number of CG iterations) */
+    int rank, world_size;         /* origin zones are sharded  zone % world_size == rank */
+    double sssp_delta_factor;     /* label window of the SSSP kernel in units of the mean link cost; <=0 = default */
+    int sssp_block_threads;       /* 0 = default */
+    int sssp_ctas_per_sm;         /* 0 = default */
+    size_t tree_batch_bytes;      /* memory budget for one batch of shortest-path trees; 0 = default */
+    size_t column_arena_bytes;    /* memory budget for path-link storage of the column pool; 0 = default */
+    int keep_trees;               /* 1 = keep every tree of the last iteration readable (tests) */
+} dtl_options;
+
+typedef struct dtl_engine dtl_engine;
+
+void dtl_default_options(dtl_options* opt);
+dtl_engine* dtl_create(const dtl_problem* p, const dtl_options* opt);
+void dtl_destroy(dtl_engine* e);
+const char* dtl_last_error(void);
+const char* dtl_version(void);
+
+/* Multi-GPU: one process per GPU.  Rank 0 obtains a 128-byte NCCL id, the launcher broadcasts it,
+ * every rank calls dtl_comm_init.  After that the engine all-reduces the fixed-point link-volume
+ * vector once per iteration. */
+int dtl_comm_get_unique_id(unsigned char id128[128]);
+int dtl_comm_init(dtl_engine* e, const unsigned char id128[128]);
+
+/* SSSP tasks (agent type, period, origin zone) owned by this rank, canonical (at, tau, zone) order */
+int dtl_num_tasks(const dtl_engine* e);
+int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone);
+
+/* One column-generation iteration: VDF -> volume scatter (+MSA decay) -> SSSP trees -> column update.
+ * Replaces the loop body main_api.cpp:589-728.
+ * row = { systemTT, least_systemTT, relative_gap, avg_travel_time, counted_edges } */
+int dtl_iteration(dtl_engine* e, int k, double row[5]);
+/* One column-pool gradient-projection iteration; replaces
+ * g_update_gradient_cost_and_assigned_flow_in_column_pool (assignment.h:565).
+ * row = { avg_travel_time, total_gap, relative_gap_percent, total_system_demand } */
+int dtl_column_update(dtl_engine* e, int n, double row[4]);
+/* Final scatter without decay + VDF (main_api.cpp:748-759); returns system travel time in *sys_tt. */
+int dtl_finalize(dtl_engine* e, int K, double* sys_tt);
+/* K iterations + CU column-pool iterations + finalize in one call.
+ * iter_rows [K][5], cu_rows [CU][4] may be NULL. */
+int dtl_run_assignment(dtl_engine* e, int K, int CU, double* iter_rows, double* cu_rows);
+
+/* Link state read-back for one period (arrays of length L, NULL = skip).  pce_volume and
+ * person_volume are the exact fixed-point sums converted to double. */
+int dtl_get_link_state(dtl_engine* e, int tau, double* tt, double* pce_volume, double* person_volume,
+                       double* link_volume, double* doc, double* voc, double* P, double* vt2);
+/* exact fixed-point (Q31.32) PCE volume sums, for bit-identity checks across GPU counts */
+int dtl_get_volume_fixed(dtl_engine* e, int tau, long long* pce_volume_q32);
+/* person volume of one agent type (person_volume_per_period_per_at, assignment.h:142) */
+int dtl_get_person_volume_at(dtl_engine* e, int tau, int at, double* person_volume);
+/* full QVDF outputs of the current link volumes, for link_performance.csv */
+int dtl_get_link_detail(dtl_engine* e, int tau, double* avg_queue_speed, double* avg_speed_bpr, double* Q_mu,
+                        double* Q_gamma, double* t0, double* t3, double* severe_congestion_P);
+/* 5-minute speed profile (CPeriod_VDF::model_speed, VDF.h:277-319) of slots [first_slot, first_slot+n_slots) */
+int dtl_get_model_speed(dtl_engine* e, int tau, int first_slot, int n_slots, float* speed /*[L][n_slots]*/);
+/* generalized link cost of forward star (at, tau) as used by the last SSSP (routing.h:229-231); [L] */
+int dtl_get_gen_cost(dtl_engine* e, int at, int tau, double* cost);
+
+/* column pool read-back, columns in (od index, node_sum ascending) order of this rank's OD cells */
+long long dtl_num_columns(dtl_engine* e);
+long long dtl_num_column_links(dtl_engine* e);
+int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, int* n_links, int* n_nodes,
+                    double* volume, double* cost, double* time, int* links);
+
+/* ---- kernel-level entry points (known-answer tests, benchmarks) ---- */
+
+/* Batched many-source SSSP; replaces NetworkForSP::optimal_label_correcting (routing.h:633) for
+ * n origin zones of forward star (at, tau).  cost: [L] host array of generalized link costs, or
+ * NULL to use the engine's current costs.  Outputs (host, may be NULL): labels [n][N],
+ * pred_node [n][N], pred_link [n][N]; tie_nodes [n] = nodes with >= 2 tight predecessors from
+ * different upstream nodes (such origins are resolved by the serial replay kernel).
+ * stats (may be NULL): { device ms, counted edges, relaxations, queue pops, rounds, replayed origins } */
+int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int* zones, int n, double* labels,
+                   int* pred_node, int* pred_link, int* tie_nodes, double stats[6]);
+/* Elementwise link performance; replaces CPeriod_VDF::calculate_travel_time_based_on_QVDF
+ * (VDF.h:139) over all links of period tau for the given volumes [L]. */
+int dtl_vdf(dtl_engine* e, int tau, const double* volume, double* tt, double* doc, double* voc, double* P,
+            double* vt2);
+/* Path->link volume accumulation of the current column pool; replaces
+ * g_reset_and_update_link_volume_based_on_columns (assignment.h:53).  decay_k < 0 = no MSA decay. */
+int dtl_scatter(dtl_engine* e, int decay_k);
+/* trees of the last dtl_iteration (needs keep_trees): task index in dtl_get_tasks order */
+int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pred_link);
+
+/* device-time accounting (CUDA events on the engine's stream), milliseconds since the last reset:
+ * ms[0]=VDF  ms[1]=scatter  ms[2]=SSSP  ms[3]=tie replay  ms[4]=backtrace/columns  ms[5]=column pool
+ * ms[6]=all-reduce  ms[7]=whole iterations;  counts[i] = kernel launches in each class */
+int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset);
+/* work counters since the last reset: { counted edges (Graph500 convention), relaxations, queue pops,
+ * SSSP rounds, SSSP tasks, replayed origins, column-link references scattered, back-traced path nodes } */
+int dtl_get_counters(dtl_engine* e, double c[8], int reset);
+/* number of HBM bytes the engine holds */
+size_t dtl_device_bytes(const dtl_engine* e);
+
+/* ---- GMNS file contract (host side; no GPU needed) ---- */
+
+/* Reads settings.csv, node.csv, link.csv and the [demand_file_list] files from `dir` exactly as
+ * g_read_input_data / g_ReadDemandFileBasedOnDemandFileList do (input.h:2388, :392) and adds the
+ * virtual connectors (main_api.cpp:534-570).  The returned image is owned by the library. */
+typedef struct dtl_gmns dtl_gmns;
+dtl_gmns* dtl_gmns_read(const char* dir, int number_of_memory_blocks);
+const dtl_problem* dtl_gmns_problem(const dtl_gmns* g);
+void dtl_gmns_free(dtl_gmns* g);
+const char* dtl_gmns_last_error(void);
+/* identifiers for writers / tests: node_id [N], zone_id [Z], link_id strings are not exposed */
+int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id);
+/* settings.csv [assignment] as flash_dta.cpp:171-242 derives them: out = { CG iterations, CU iterations,
+ * ODME iterations, SA iterations, simulation iterations, memory blocks } */
+int dtl_gmns_assignment_settings(const char* dir, int out[6]);
+/* link_performance.csv / route_assignment.csv / final_summary.csv writers (output.h:486-1459) */
+int dtl_gmns_write_outputs(const dtl_gmns* g, dtl_engine* e, const char* dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""Regenerates the golden fixtures under tests/golden/ from the reference itself.  Run in the build
+container (needs /root/reference and oracle/_ref/dtalite_ref, built by oracle/build_ref.sh):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  *_final_summary.txt   the line ranges of the reference's own committed final_summary.csv that pin this
+                        path: two-corridor lines 35-58, 4_101_corridor lines 150-177
+  *_ref.npz             state dumped from the reference engine (oracle/_ref/dtalite_ref trace mode) on
+                        tests/fixtures/<name>: per-iteration rows, link states, the column pool, and
+                        shortest-path trees (full arrays for small cases, SHA-256 digests otherwise)
+"""
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import binding as B  # noqa: E402
+
+REF = os.environ.get("DTL_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def copy_lines(src, first, last, dst):
+    with open(src) as f:
+        lines = f.readlines()
+    with open(dst, "w") as f:
+        f.write(f"# lines {first}-{last} of {os.path.relpath(src, REF)} (reference repository), verbatim\n")
+        f.writelines(lines[first - 1:last])
+
+
+def run_case(name, K, CU, tree_iters, full_tree_zones):
+    src = os.path.join(ROOT, "tests", "fixtures", name)
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in os.listdir(src):
+            shutil.copy(os.path.join(src, f), tmp)
+        env = {"DTL_TRACE_TREES": ",".join(str(k) for k in tree_iters)}
+        B.run_reference(tmp, "trace", K, CU, 4, "dump.bin", env=env, threads=4)
+        d = B.load_dump(os.path.join(tmp, "dump.bin"))
+    N, L, Z, AT, T = (int(x) for x in d["meta"])
+    out = {"meta": d["meta"], "K": np.int32(K), "CU": np.int32(CU)}
+    out["iter_rows"] = np.stack([d[f"iter_row:k={k}"] for k in range(K)])  # k, sysTT, least, gap, avg_tt
+    for key in ("tt", "pce_volume", "person_volume", "vdf_link_volume", "doc", "voc", "P", "vt2"):
+        out[f"final_{key}"] = d[f"{key}:final:tau=0"]
+        if key in ("tt", "pce_volume"):
+            for k in (2, K - 1):
+                out[f"k{k}_{key}_after_vdf"] = d[f"{key}:after_vdf:k={k}:tau=0"]
+            for n in range(CU):
+                out[f"cu{n}_{key}"] = d[f"{key}:cu={n}:tau=0"]
+    out["final_sysTT"] = d["final_sysTT"]
+    for k in tree_iters:
+        for at in range(AT):
+            out[f"gen_cost_k{k}_at{at}"] = d[f"gen_cost:k={k}:at={at}:tau=0"]
+    for key in ("col_o", "col_d", "col_at", "col_tau", "col_node_sum", "col_seq", "col_nlinks", "col_nnodes", "col_volume",
+                "col_cost", "col_time"):
+        out[key] = d[key + ":final"]
+    links = d["col_links:final"]
+    if links.size <= 200000:
+        out["col_links"] = links
+    out["col_links_sha256"] = np.array(sha(links))
+    # per-column digest so a mismatch can be located without shipping every link id
+    off = np.concatenate([[0], np.cumsum(d["col_nlinks:final"])]).astype(np.int64)
+    w = (np.arange(links.size, dtype=np.int64) - np.repeat(off[:-1], d["col_nlinks:final"]) + 1)
+    out["col_link_checksum"] = np.add.reduceat((links.astype(np.int64) + 1) * w, off[:-1]) if links.size else np.zeros(0, np.int64)
+    tree_keys, tree_sha = [], []
+    for key in sorted(k for k in d if k.startswith("label:")):
+        tag = key[len("label:"):]
+        z = int(tag.split("z=")[1])
+        tree_keys.append(tag)
+        tree_sha.append(sha(d["label:" + tag]) + sha(d["pred_link:" + tag]) + sha(d["pred_node:" + tag]))
+        if full_tree_zones is None or z in full_tree_zones:
+            out["tree_label:" + tag] = d["label:" + tag]
+            out["tree_pred_link:" + tag] = d["pred_link:" + tag]
+            out["tree_pred_node:" + tag] = d["pred_node:" + tag]
+    out["tree_keys"] = np.array(tree_keys)
+    out["tree_sha256"] = np.array(tree_sha)
+    # network image digests pin the native GMNS reader without the reference binary
+    p = B.problem_from_dump(d)
+    names = sorted(p.arrays)
+    out["problem_array_names"] = np.array(names)
+    out["problem_array_sha256"] = np.array([sha(p.arrays[n]) for n in names])
+    out["total_demand_volume"] = np.float32(p.total_demand_volume)
+    np.savez_compressed(os.path.join(OUT, f"{name}_ref.npz"), **out)
+    print(name, "->", os.path.getsize(os.path.join(OUT, f"{name}_ref.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    copy_lines(os.path.join(REF, "src/test_case_01_two_corridor/final_summary.csv"), 35, 58,
+               os.path.join(OUT, "two_corridor_final_summary.txt"))
+    copy_lines(os.path.join(REF, "dataset/4_101_corridor/final_summary.csv"), 150, 177,
+               os.path.join(OUT, "corridor_101_final_summary.txt"))
+    run_case("two_corridor", 20, 0, range(20), None)
+    run_case("corridor_101", 20, 5, (0, 2, 19), {7})
