@@ -145,6 +145,7 @@ struct dtl_engine {
     double tasks_done = 0;
 
     ncclComm_t comm = nullptr;
+    bool local_shard = false; // world > 1 without a communicator: the caller reduces the shards (tests)
 
     template <class T>
     int alloc(T** p, size_t n)
@@ -278,7 +279,7 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
 
 int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt)
 {
-    if (e->world <= 1) return 0;
+    if (e->world <= 1 || e->local_shard) return 0;
     if (!e->comm) { set_err("world_size > 1 but dtl_comm_init was not called"); return -1; }
     const int ph = e->phase_begin(6);
     ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, ncclSum, e->comm, e->st);
@@ -649,6 +650,24 @@ int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone)
     return 0;
 }
 
+int dtl_plan_tasks(const dtl_problem* p, int rank, int world_size, int* at, int* tau, int* zone, int capacity)
+{
+    if (!p || world_size < 1 || rank < 0 || rank >= world_size) { set_err("bad arguments"); return -1; }
+    std::vector<int> a, t, z;
+    build_task_list(p, a, t, z);
+    int n = 0;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (z[i] % world_size == rank) {
+            if (n < capacity) {
+                if (at) at[n] = a[i];
+                if (tau) tau[n] = t[i];
+                if (zone) zone[n] = z[i];
+            }
+            ++n;
+        }
+    return n;
+}
+
 int dtl_comm_get_unique_id(unsigned char id128[128])
 {
     if (!g_nccl.load()) return -1;
@@ -663,6 +682,7 @@ int dtl_comm_get_unique_id(unsigned char id128[128])
 int dtl_comm_init(dtl_engine* e, const unsigned char id128[128])
 {
     if (e->world <= 1) return 0;
+    if (!id128) { e->local_shard = true; return 0; } // shard-only mode: no collective, the caller sums the shards
     if (!g_nccl.load()) return -1;
     CK(cudaSetDevice(e->dev));
     ncclUniqueId id;

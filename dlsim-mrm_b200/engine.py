@@ -65,6 +65,7 @@ def load_library(path: str | None = None):
     L.dtl_destroy.argtypes = [vp]
     L.dtl_comm_get_unique_id.argtypes = [vp]
     L.dtl_comm_init.argtypes = [vp, vp]
+    L.dtl_plan_tasks.argtypes = [vp, ci, ci, vp, vp, vp, ci]
     L.dtl_num_tasks.argtypes = [vp]
     L.dtl_get_tasks.argtypes = [vp] * 4
     L.dtl_iteration.argtypes = [vp, ci, vp]
@@ -122,6 +123,19 @@ def _c_problem(p: Problem, keep: dict) -> _Problem:
     cp.n_od = p.n_od
     cp.total_demand_volume = float(p.total_demand_volume)
     return cp
+
+
+def plan_tasks(problem: Problem, rank: int, world_size: int):
+    """Host-only task partition of one rank: arrays (agent type, period, zone)."""
+    L = load_library()
+    keep = {}
+    cp = _c_problem(problem, keep)
+    n = L.dtl_plan_tasks(C.byref(cp), rank, world_size, None, None, None, 0)
+    if n < 0:
+        raise EngineError(L.dtl_last_error().decode())
+    at = np.zeros(max(n, 1), np.int32); tau = np.zeros_like(at); zone = np.zeros_like(at)
+    L.dtl_plan_tasks(C.byref(cp), rank, world_size, _ptr(at), _ptr(tau), _ptr(zone), n)
+    return at[:n], tau[:n], zone[:n]
 
 
 def read_gmns(directory: str, memory_blocks: int = 4) -> Problem:
@@ -218,7 +232,11 @@ class Engine:
             raise EngineError(L.dtl_last_error().decode())
         return bytes(buf)
 
-    def comm_init(self, unique_id: bytes):
+    def comm_init(self, unique_id: bytes | None):
+        """``None`` = shard-only mode (no collective; the caller sums the ranks' fixed-point volumes)."""
+        if unique_id is None:
+            self._ck(self.lib.dtl_comm_init(self.h, None))
+            return
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._ck(self.lib.dtl_comm_init(self.h, buf))
 

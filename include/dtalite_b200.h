@@ -87,7 +87,13 @@ const char* dtl_version(void);
  * every rank calls dtl_comm_init.  After that the engine all-reduces the fixed-point link-volume
  * vector once per iteration. */
 int dtl_comm_get_unique_id(unsigned char id128[128]);
+/* id128 == NULL selects shard-only mode: no collective is issued and the caller sums the ranks' fixed-point
+ * volumes itself (used to check the sharding on one GPU). */
 int dtl_comm_init(dtl_engine* e, const unsigned char id128[128]);
+/* Host-only: the (agent type, period, zone) shortest-path tasks rank `rank` of `world_size` owns, in canonical
+ * order (g_assign_computing_tasks_to_memory_blocks, main_api.cpp:201-275, then zone % world_size == rank).
+ * Returns the number of tasks (may exceed capacity; only `capacity` entries are written). */
+int dtl_plan_tasks(const dtl_problem* p, int rank, int world_size, int* at, int* tau, int* zone, int capacity);
 
 /* SSSP tasks (agent type, period, origin zone) owned by this rank, canonical (at, tau, zone) order */
 int dtl_num_tasks(const dtl_engine* e);

@@ -1,0 +1,287 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same inputs and
+against the golden state dumped from the reference engine.  Bars (BASELINE.json north_star):
+  * shortest-path labels, predecessor trees and path columns bit-exact (ties by the reference's rule),
+  * link volumes, travel times and relative gap within 1e-6 relative.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GOLDEN, ROOT, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # north_star tolerance for volumes / travel times / gap
+
+
+@pytest.fixture(scope="module")
+def D():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import dlsim_mrm_b200 as D
+    return D
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod):
+    """K1 fed the reference's own generalized costs: labels, pred nodes and pred links bit-exact for every origin."""
+    p, g = problems("corridor_101"), golden("corridor_101")
+    o = oracle_mod.Oracle(p)
+    with D.Engine(p) as e:
+        for k, at in ((0, 0), (2, 0), (19, 2)):
+            cost = g[f"gen_cost_k{k}_at{at}"]
+            zones = np.arange(p.n_zones, dtype=np.int32)
+            lab, pn, pl, ties, st = e.sssp_trees(at, 0, zones, cost=cost)
+            fs = o.forward_star(at, 0)
+            e_from = np.repeat(np.arange(p.n_nodes), np.diff(fs[0]))
+            e_tag = p.link_tag[fs[1]]
+            counted = 0
+            for z in zones:
+                rl, rpn, rpl, pops, relax = o.sssp(fs, cost, int(z))
+                assert np.array_equal(lab[z].view(np.int64), rl.view(np.int64)), f"labels differ, k={k} zone {z}"
+                assert np.array_equal(pl[z], rpl), f"pred links differ, k={k} zone {z}"
+                assert np.array_equal(pn[z], rpn), f"pred nodes differ, k={k} zone {z}"
+                counted += int(np.count_nonzero((rl < 1e15)[e_from] & ((e_tag < 0) | (e_tag == z))))
+            assert st["counted_edges"] == counted
+            assert st["relaxations"] >= counted
+            # golden full trees of zone 7 (reference engine itself)
+            tagk = f"k={k}:at={at}:tau=0:z=7"
+            assert np.array_equal(lab[7], g["tree_label:" + tagk]) and np.array_equal(pl[7], g["tree_pred_link:" + tagk])
+            assert np.array_equal(pn[7], g["tree_pred_node:" + tagk])
+
+
+def _tie_grid(n=12):
+    """Uniform n x n grid with unit costs: every interior node has two tight predecessors."""
+    import dlsim_mrm_b200 as D
+    N = n * n
+    links = []
+    for r in range(n):
+        for c in range(n):
+            u = r * n + c
+            if c + 1 < n: links += [(u, u + 1), (u + 1, u)]
+            if r + 1 < n: links += [(u, u + n), (u + n, u)]
+    zones = [0, N - 1, n - 1]
+    cent = [N + i for i in range(len(zones))]
+    lf = [a for a, b in links]; lt = [b for a, b in links]; tag = [-1] * len(links)
+    for zi, node in enumerate(zones):
+        lf += [node, cent[zi]]; lt += [cent[zi], node]; tag += [-1, zi]
+    L, Z = len(lf), len(zones)
+    p = D.Problem(N + Z, L, Z, 1, 1, 4, 6.0)
+    nz = np.full(N + Z, -1, np.int32); nz[cent] = np.arange(Z)
+    p.arrays.update(link_from=np.array(lf, np.int32), link_to=np.array(lt, np.int32), link_tag=np.array(tag, np.int32),
+                    node_zone=nz, zone_centroid=np.array(cent, np.int32),
+                    fftt=np.ones((1, L)), cap=np.full((1, L), 1000.0), vf=np.full((1, L), 60.0), vc=np.full((1, L), 51.0),
+                    nlanes=np.ones((1, L)), cap_lane=np.full((1, L), 1000.0), qdf=np.ones((1, L)), t2=np.full((1, L), 7.5),
+                    L_h=np.ones((1, L)), start_h=np.full((1, L), 7.0), end_h=np.full((1, L), 8.0), vot=np.array([10.0], np.float32),
+                    od_o=np.array([0, 0, 1], np.int32), od_d=np.array([1, 2, 0], np.int32), od_at=np.zeros(3, np.int32),
+                    od_tau=np.zeros(3, np.int32), od_vol=np.array([1.0, 2.0, 3.0]), origin_demand=np.array([3, 3, 0], np.float32))
+    return p.with_defaults().finalize()
+
+
+def test_sssp_ties_follow_the_reference_rule(D, oracle_mod):
+    """Exact FP64 ties: the engine detects them and replays the reference's deque, so the trees still match."""
+    p = _tie_grid()
+    o = oracle_mod.Oracle(p)
+    cost = np.ones(p.n_links)
+    cost[p.link_tag >= 0] = 0.0
+    cost[(p.link_to >= 144)] = 0.0
+    fs = o.forward_star(0, 0)
+    with D.Engine(p) as e:
+        zones = np.arange(p.n_zones, dtype=np.int32)
+        lab, pn, pl, ties, st = e.sssp_trees(0, 0, zones, cost=cost)
+        assert np.all(ties > 0) and st["replayed"] == p.n_zones
+        for z in zones:
+            rl, rpn, rpl, _, _ = o.sssp(fs, cost, int(z))
+            assert np.array_equal(lab[z], rl) and np.array_equal(pl[z], rpl) and np.array_equal(pn[z], rpn)
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def test_vdf_known_answer(D, problems, oracle_mod):
+    p = problems("corridor_101")
+    o = oracle_mod.Oracle(p)
+    rng = np.random.default_rng(7)
+    vol = rng.uniform(0, 1.6, p.n_links) * p.cap[0] * (rng.random(p.n_links) > 0.1)
+    with D.Engine(p) as e:
+        out = e.vdf(0, vol)
+        det = e.link_detail(0)
+        speed = e.model_speed(0, 84, 13)
+    exact = 0
+    for l in range(0, p.n_links, 7):
+        r = o.vdf_link(0, l, float(vol[l]), want_speed=True)
+        for key in ("tt", "doc", "voc", "P", "vt2"):
+            assert abs(out[key][l] - r[key]) <= 1e-12 * max(1.0, abs(r[key])), (key, l, out[key][l], r[key])
+        exact += out["tt"][l] == r["tt"]
+        for key in ("avg_queue_speed", "avg_speed_bpr", "Q_mu", "Q_gamma", "t0", "t3", "severe_congestion_P"):
+            a, b = det[key][l], r[key]
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-9 * max(1.0, abs(b)), (key, l, a, b)
+        assert np.allclose(speed[l], r["model_speed"][84:97], rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert exact >= 0.9 * len(range(0, p.n_links, 7))  # CUDA pow vs glibc pow: <= 2 ulp apart, mostly identical
+
+
+# ------------------------------------------------------------------------------------------------ whole loop
+def _compare_columns(eng_cols, ora_cols):
+    assert np.array_equal(eng_cols["od_index"], ora_cols["od_index"])
+    assert np.array_equal(eng_cols["node_sum"], ora_cols["node_sum"])
+    assert np.array_equal(eng_cols["seq_no"], ora_cols["seq_no"])
+    assert np.array_equal(eng_cols["n_links"], ora_cols["n_links"])
+    assert np.array_equal(eng_cols["n_nodes"], ora_cols["n_nodes"])
+    assert np.array_equal(eng_cols["links"], ora_cols["links"]), "path link sequences must be bit-exact"
+    assert rel_err(eng_cols["volume"], ora_cols["volume"], floor=1e-6) <= TOL
+
+
+@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5)])
+def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod, name, K, CU):
+    p, g = problems(name), golden(name)
+    o = oracle_mod.Oracle(p)
+    o.capture_trees(True)
+    with D.Engine(p, keep_trees=True, max_columns_per_od=K + 4) as e:
+        assert e.n_tasks == o.n_tasks
+        assert np.array_equal(e.task_zone, o.task_zone) and np.array_equal(e.task_at, o.task_at)
+        tree_mismatch = 0
+        for k in range(K):
+            r, ro = e.iteration(k), o.iteration(k)
+            ref = g["iter_rows"][k]
+            for key in ("sysTT", "least", "avg_tt"):
+                assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (k, key, r, ro)
+            assert abs(r["gap"] - ro["gap"]) <= TOL * max(1.0, abs(ro["gap"])), (k, r, ro)
+            assert abs(r["gap"] - ref[3]) <= TOL * max(1.0, abs(ref[3]))
+            assert r["counted_edges"] == ro["counted_edges"]
+            if k in (0, 1, 2, 5, K - 1):
+                lab_o, pn_o, pl_o = o._cap
+                for ti in range(e.n_tasks):
+                    lab, pn, pl = e.tree(ti)
+                    assert rel_err(lab, lab_o[ti]) <= 1e-12
+                    tree_mismatch += int(np.count_nonzero(pl != pl_o[ti]) + np.count_nonzero(pn != pn_o[ti]))
+            st, so = e.link_state(0), o.link_state(0)
+            assert rel_err(st["tt"], so["tt"]) <= TOL
+            assert rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
+        assert tree_mismatch == 0, "predecessor trees must match the reference's"
+        for n in range(CU):
+            r, ro = e.column_update(n), o.column_update(n)
+            for key in ("avg_tt", "total_gap", "rel_gap_pct", "demand"):
+                assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (n, key, r, ro)
+            assert rel_err(e.link_state(0)["tt"], g[f"cu{n}_tt"]) <= TOL
+        sys_tt = e.finalize(K)
+        assert abs(sys_tt - float(g["final_sysTT"][0])) <= TOL * max(1.0, float(g["final_sysTT"][0]))
+        st = e.link_state(0)
+        for key, gk in (("tt", "final_tt"), ("pce_volume", "final_pce_volume"), ("person_volume", "final_person_volume"),
+                        ("link_volume", "final_vdf_link_volume"), ("doc", "final_doc"), ("voc", "final_voc"), ("P", "final_P"),
+                        ("vt2", "final_vt2")):
+            assert rel_err(st[key], g[gk], floor=1e-3) <= TOL, key
+        o.finalize(K)
+        ec, oc = e.columns(), o.columns()
+        _compare_columns(ec, oc)
+        # and against the reference engine's own column pool
+        assert np.array_equal(ec["node_sum"], g["col_node_sum"]) and np.array_equal(ec["n_links"], g["col_nlinks"])
+        assert sha(ec["links"]) == str(g["col_links_sha256"])
+        assert rel_err(ec["volume"], g["col_volume"], floor=1e-6) <= TOL
+        if CU:
+            assert rel_err(ec["cost"], g["col_cost"]) <= TOL and rel_err(ec["time"], g["col_time"]) <= TOL
+        t = e.timing()
+        assert t["launches"]["sssp"] >= K and t["ms"]["sssp"] > 0
+        c = e.counters()
+        assert c["relaxations"] > 0 and c["link_refs"] > 0 and c["path_nodes"] > 0
+
+
+def test_scatter_is_order_independent_and_shards_sum_exactly(D, problems):
+    """Fixed-point integer accumulation: identical bits run to run, and the shards of a 2- or 3-way origin
+    partition add up to exactly the single-GPU vector (what the NCCL all-reduce computes)."""
+    p = problems("corridor_101")
+    def run(world, rank):
+        with D.Engine(p, rank=rank, world_size=world) as e:
+            if world > 1:
+                e.comm_init(None)
+            e.iteration(0)       # builds the first columns of this rank's origins
+            e.scatter(-1)
+            return e.volume_fixed(0), e.n_tasks
+    full, n_full = run(1, 0)
+    again, _ = run(1, 0)
+    assert np.array_equal(full, again)
+    assert full.sum() > 0
+    for world in (2, 3):
+        parts = [run(world, r) for r in range(world)]
+        assert sum(n for _, n in parts) == n_full
+        assert np.array_equal(sum(v for v, _ in parts), full)
+
+
+def test_linearity_of_scatter(D, problems):
+    """Size-independent property: scattering after an MSA decay by k/(k+1) scales every link volume by the same
+    factor (up to the float rounding of each path volume the reference applies, assignment.h:87)."""
+    p = problems("corridor_101")
+    with D.Engine(p) as e:
+        e.iteration(0)
+        e.scatter(1)          # scatter, then decay volumes by 1/2
+        v1 = e.link_state(0)["pce_volume"]
+        e.scatter(-1)
+        v2 = e.link_state(0)["pce_volume"]
+    m = v1 > 1e-3
+    assert m.sum() > 100 and np.allclose(v2[m], 0.5 * v1[m], rtol=1e-5)
+
+
+def test_drop_in_executable_writes_reference_files(D, tmp_path):
+    """network_assignment through the reference-style executable: same files, same summary rows."""
+    exe = os.path.join(ROOT, "dlsim-mrm_b200", "lib", "DTALite_b200")
+    src = os.path.join(FIXTURES, "two_corridor")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    r = subprocess.run([exe], cwd=tmp_path, stdin=subprocess.DEVNULL, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert b"done." in r.stdout
+    summary = open(tmp_path / "final_summary.csv").read().splitlines()
+    gold = [l.strip() for l in open(os.path.join(GOLDEN, "two_corridor_final_summary.txt")) if l[:1].isdigit()]
+    rows = [l for l in summary if l[:1].isdigit()]
+    assert len(rows) == 20
+    for mine, ref in zip(rows, gold):
+        a, b = mine.split(","), ref.split(",")
+        assert a[:4] == b[:4], (mine, ref)                       # iteration, cpu, agents, avg travel time
+        assert abs(float(a[4]) / 100 - float(b[4])) < 5e-6 * max(1, abs(float(b[4])))  # gap printed x100 by the committed source
+    lp = open(tmp_path / "link_performance.csv").read().splitlines()
+    assert lp[0].startswith("link_id,vdf_type,from_node_id,to_node_id,lanes,distance_km") and lp[0].endswith("notes")
+    assert len(lp) == 5
+    cols = lp[0].split(",")
+    first = dict(zip(cols, lp[1].split(",")))
+    assert first["link_id"] == "1" and first["vdf_type"] == "bpr" and first["time_period"] == "0700_0800"
+    ra = open(tmp_path / "route_assignment.csv").read().splitlines()
+    assert ra[0].startswith("first_column,path_no,o_zone_id,d_zone_id,od_pair")
+    assert len(ra) == 3 and ",1->2," in ra[1]
+    vols = sorted(float(dict(zip(ra[0].split(","), l.split(",")))["volume"]) for l in ra[1:])
+    assert abs(sum(vols) - 7000) < 1e-3
+
+
+@pytest.mark.parametrize("workload,K,CU", [("grid2k", 8, 3), ("grid10k", 4, 0)])
+def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, workload, K, CU):
+    """The bench generator at sizes the oracle finishes in seconds: same parity bars as the reference datasets."""
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
+    p = D.read_gmns(str(tmp_path), 8)
+    o = oracle_mod.Oracle(p)
+    o.capture_trees(True)
+    with D.Engine(p, keep_trees=True, max_columns_per_od=K + 4) as e:
+        for k in range(K):
+            r, ro = e.iteration(k), o.iteration(k)
+            for key in ("sysTT", "least"):
+                assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (k, key, r, ro)
+            assert abs(r["gap"] - ro["gap"]) <= TOL * max(1.0, abs(ro["gap"]))
+            assert r["counted_edges"] == ro["counted_edges"]
+            lab_o, pn_o, pl_o = o._cap
+            for ti in range(0, e.n_tasks, 7):
+                lab, pn, pl = e.tree(ti)
+                assert rel_err(lab, lab_o[ti]) <= 1e-12
+                assert np.array_equal(pl, pl_o[ti]) and np.array_equal(pn, pn_o[ti])
+        for n in range(CU):
+            r, ro = e.column_update(n), o.column_update(n)
+            for key in ("avg_tt", "total_gap", "rel_gap_pct"):
+                assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (n, key, r, ro)
+        e.finalize(K); o.finalize(K)
+        st, so = e.link_state(0), o.link_state(0)
+        assert rel_err(st["tt"], so["tt"]) <= TOL and rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
+        _compare_columns(e.columns(), o.columns())
+        assert e.counters()["replayed"] == 0   # jittered lengths: no exact ties
