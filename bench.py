@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- UE-assignment throughput of the B200 DTALite engine on the synthetic regional grid
+(BASELINE.json configs[4]: 100k nodes / 300k links / 2000 zones / 4M trips).
+
+A "step" is one column-generation iteration of the assignment loop (VDF -> volume scatter + MSA decay ->
+all shortest-path trees -> tree back-trace / column update; reference main_api.cpp:589-728) over the whole
+network.  `--gpus N` shards origin zones over N ranks (zone % N), one process per GPU (torchrun); the only
+data-path collective is the all-reduce of the fixed-point link-volume vector.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid100k] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own OpenMP CPU path
+(oracle/_ref/dtalite_ref, the unmodified sources) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ue_assignment_iterations_per_s"
+UNIT = "iter/s"
+BYTES_PER_EDGE = 20.0  # col_to 4 B + cost 8 B + label[to] 8 B per counted edge relaxation
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_dir(name: str) -> str:
+    return os.path.join(tempfile.gettempdir(), f"dtl_bench_{name}_{os.getuid()}")
+
+
+def ensure_workload(name: str) -> str:
+    from dlsim_mrm_b200 import synth
+    d = workload_dir(name)
+    if not os.path.exists(os.path.join(d, ".complete")):
+        tmp = d + f".tmp{os.getpid()}"
+        shutil.rmtree(tmp, ignore_errors=True)
+        synth.write_grid(tmp, **synth.WORKLOADS[name])
+        open(os.path.join(tmp, ".complete"), "w").close()
+        shutil.rmtree(d, ignore_errors=True)
+        os.replace(tmp, d)
+    return d
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_sample(workload: str, steps: int, warmup: int, n_origins: int | None = None):
+    """Run the reference's own CPU path (oracle/_ref/dtalite_ref trace mode, unmodified sources) on a bounded sample of
+    the workload: same network, demand of the first S origin zones only.  Returns per-iteration seconds of the
+    timed steps, the number of trees per iteration, the thread count and the sample description."""
+    from oracle import binding as B
+    if not os.path.exists(B.REF_BIN):
+        raise FileNotFoundError(f"{B.REF_BIN} is missing (built by oracle/build_ref.sh where /root/reference exists)")
+    src = ensure_workload(workload)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    blocks = max(1, min(cores, 100))                     # number_of_memory_blocks = parallel width of the reference
+    S = n_origins or max(96, 2 * blocks)
+    with tempfile.TemporaryDirectory(prefix="dtl_ref_") as tmp:
+        for f in ("node.csv", "link.csv", "settings.csv"):
+            os.symlink(os.path.join(src, f), os.path.join(tmp, f))
+        n_rows = 0
+        with open(os.path.join(src, "demand.csv")) as fi, open(os.path.join(tmp, "demand.csv"), "w") as fo:
+            fo.write(fi.readline())
+            for line in fi:
+                if int(line.split(",", 1)[0]) <= S:
+                    fo.write(line)
+                    n_rows += 1
+        t0 = time.time()
+        _, tm = B.run_reference(tmp, "trace", warmup + steps, 0, blocks, "dump.bin", env={"DTL_TRACE_LIGHT": "1"},
+                                threads=blocks, timeout=3000)
+        wall = time.time() - t0
+    iters = tm["iter_s"][warmup:warmup + steps]
+    trees = tm["n_sssp"] / tm["K"]
+    sample = (f"{workload}: full network, demand of origin zones 1..{S} only ({n_rows} OD rows, {trees:.0f} shortest-path trees "
+              f"per iteration), {warmup}+{steps} iterations, OMP threads = memory blocks = {blocks}; iteration time scaled by "
+              f"(trees in the full workload / trees in the sample)")
+    return dict(iter_s=iters, trees=trees, threads=int(tm["threads"]), blocks=blocks, sample=sample, wall_s=wall, io_s=tm["io_s"],
+                counted_edges_total=tm["counted_edges"], sssp_thread_s=tm["sssp_thread_s"], n_origins=S)
+
+
+def full_trees(workload: str) -> int:
+    from dlsim_mrm_b200 import synth
+    return synth.WORKLOADS[workload]["n_zones"]  # 1 agent type x 1 period: one tree per zone
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    base = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    try:
+        r = reference_sample(args.workload, args.steps, args.warmup)
+    except Exception as ex:  # the oracle always exists in a complete checkout; say why if it does not
+        print(json.dumps({**base, "unavailable": str(ex)[:300]}))
+        return
+    scale = full_trees(args.workload) / r["trees"]
+    sec = statistics.mean(r["iter_s"]) * scale
+    value = 1.0 / sec
+    out = {**base, "value": value, "ms_per_step": sec * 1e3,
+           "config": {"workload": args.workload, "nodes": 100172, "links": 300000, "zones": full_trees(args.workload),
+                      "sample": r["sample"]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": r["sample"]},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "reference_io_s": r["io_s"], "reference_wall_s": r["wall_s"]}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_engine_arm(args, rank, world, local_rank):
+    import torch
+    import dlsim_mrm_b200 as D
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if rank == 0:
+        d = ensure_workload(args.workload)
+    barrier()
+    d = workload_dir(args.workload)
+    if not os.path.exists(os.path.join(d, ".complete")):  # other node-local ranks wait for rank 0's files
+        d = ensure_workload(args.workload)
+    t0 = time.time()
+    p = D.read_gmns(d, 8)
+    read_s = time.time() - t0
+    K, W = args.steps, args.warmup
+
+    def make_engine():
+        e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 4,
+                     delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas)
+        if world > 1:
+            if rank == 0:
+                uid = torch.tensor(list(D.Engine.comm_unique_id()), dtype=torch.uint8, device="cuda")
+            else:
+                uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, 0)
+            e.comm_init(bytes(uid.cpu().tolist()))
+        return e
+
+    # ---- device-resident throughput: inputs already in HBM when the timed region starts ----
+    e = make_engine()
+    for k in range(W):
+        e.iteration(k)
+    e.timing(reset=True); e.counters(reset=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    rows = [e.iteration(W + k) for k in range(K)]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    tm, ctr = e.timing(), e.counters()
+    dev_s = max_over_ranks(tm["ms"]["iteration"] / 1e3)     # CUDA events on the engine's stream, max over ranks
+    wall = max_over_ranks(wall)
+    launches = int(sum(tm["launches"].values()))
+    sssp_ms_launch = tm["ms"]["sssp"] / max(1, tm["launches"]["sssp"])
+    edges_rank = rows[-1]["counted_edges"] / world  # the row holds the all-reduced count; ranks own equal shares of zones
+    launches_per_iter = tm["launches"]["sssp"] / K
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (sssp_ms_launch / 1e3) / 1e9
+    gteps = rows[-1]["counted_edges"] * K / (max_over_ranks(tm["ms"]["sssp"]) / 1e3) / 1e9
+    dev_bytes = e.device_bytes
+    e.close()
+
+    # ---- end to end through the C ABI with host buffers: image upload + K iterations + result read-back ----
+    barrier()
+    t0 = time.perf_counter()
+    e2 = make_engine()
+    for k in range(K):
+        e2.iteration(k)
+    e2.finalize(K)
+    st = e2.link_state(0)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d = sum(a.nbytes for a in p.arrays.values())
+    d2h = sum(a.nbytes for a in st.values()) + K * 16
+    e2.close()
+    barrier()
+
+    out = None
+    if rank == 0:
+        value = K / dev_s
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "nodes": int(p.n_nodes - p.n_zones), "links": int(p.n_links - 2 * p.n_zones),
+                       "zones": int(p.n_zones), "od_rows": int(p.n_od), "trips": float(p.total_demand_volume),
+                       "agent_types": int(p.n_agent_types), "periods": int(p.n_periods),
+                       "parallelism": f"origin zones sharded zone % {world}", "first_timed_iteration": W,
+                       "l2": "inputs larger than L2 (trees 2.4 GB + column pool per iteration vs 126 MB L2)"},
+            "clocks": clocks,
+            "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                    "what": "dtl_create from host arrays + K iterations + finalize + link-state read-back, wall clock"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "dtl::sssp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": edges_rank / launches_per_iter,
+                         "kernel_ms_per_launch": sssp_ms_launch},
+            "sssp_gteps": gteps,
+            "wall_ms_per_step": wall / K * 1e3,
+            "phase_ms_per_step": {k_: v / K for k_, v in tm["ms"].items()},
+            "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},
+            "counted_edges_per_step": rows[-1]["counted_edges"],
+            "relative_gap_last": rows[-1]["gap"],
+            "device_gib": dev_bytes / 2**30, "read_gmns_s": read_s,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = reference_sample(args.workload, args.cpu_steps, 1)
+                scale = full_trees(args.workload) / r["trees"]
+                sec = statistics.mean(r["iter_s"]) * scale
+                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                       "sample": r["sample"],
+                                       "sssp_gteps_per_core": r["counted_edges_total"] / max(1e-9, r["sssp_thread_s"]) / 1e9}
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"[:300]}
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="grid100k")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--delta", type=float, default=0.0)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.warmup < 3 and args.impl == "engine":
+        log("bench.py: note: fewer than 3 warm-up steps")
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_engine_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -273,7 +273,9 @@ int run_trace(int K, int CU, int B, const char* out_path)
     long long counted_edges = 0, n_sssp = 0;
 
     double t_loop0 = now_s();
+    std::vector<double> iter_s;
     for (int k = 0; k < K; ++k) {
+        const double t_iter0 = now_s();
         double total_distance = 0;
         double t0 = now_s();
         double sysTT = update_link_travel_time_and_cost(k, total_distance);              /* main_api.cpp:606 */
@@ -359,6 +361,7 @@ int run_trace(int K, int CU, int B, const char* out_path)
         assignment.summary_file << k << "," << 0.0 << "," << assignment.total_demand_volume << "," << avg_tt << "," << gap * 100 << endl;
         std::vector<double> row = { (double)k, sysTT, least_total, gap, avg_tt };
         dump_f64("iter_row:k=" + std::to_string(k), row);
+        iter_s.push_back(now_s() - t_iter0);
     }
     t_loop = now_s() - t_loop0;
 
@@ -389,9 +392,11 @@ int run_trace(int K, int CU, int B, const char* out_path)
     fclose(g_dump); g_dump = nullptr;
     printf("\nREFTIMING {\"io_s\": %.6f, \"loop_s\": %.6f, \"vdf_s\": %.6f, \"scatter_s\": %.6f, \"sp_region_s\": %.6f, "
            "\"sssp_thread_s\": %.6f, \"backtrace_thread_s\": %.6f, \"cu_s\": %.6f, \"threads\": %d, \"blocks\": %d, "
-           "\"counted_edges\": %lld, \"n_sssp\": %lld, \"K\": %d, \"CU\": %d, \"nodes\": %d, \"links\": %d, \"zones\": %d}\n",
+           "\"counted_edges\": %lld, \"n_sssp\": %lld, \"K\": %d, \"CU\": %d, \"nodes\": %d, \"links\": %d, \"zones\": %d, \"iter_s\": [",
            t_io, t_loop, t_vdf, t_scatter, t_region, s_sssp, s_bt, t_cu, nthreads, nblocks, counted_edges, n_sssp, K, CU,
            N, L, (int)g_zone_vector.size());
+    for (size_t i = 0; i < iter_s.size(); ++i) printf("%s%.6f", i ? ", " : "", iter_s[i]);
+    printf("]}\n");
     fflush(stdout);
     return 0;
 }
