@@ -42,6 +42,29 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, sssp_flags, verbose: bool = False) -> str:
+    """Experiment helper: a copy of the library with extra nvcc flags on kernels_sssp.cu -> lib/variants/<name>.so
+    (selected at run time with DTL_LIB=<path>)."""
+    vdir = os.path.join(LIB_DIR, "variants")
+    odir = os.path.join(vdir, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+    for s in [x for x in sources() if os.path.basename(x) != "main.cpp"]:
+        o = os.path.join(odir, os.path.basename(s) + ".o")
+        extra = list(sssp_flags) if os.path.basename(s) == "kernels_sssp.cu" else []
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose and extra else []) + \
+            ["-x", "cu" if s.endswith(".cu") else "c++", "-c", s, "-o", o]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        if out.returncode != 0:
+            raise RuntimeError(out.stdout.decode())
+        if verbose and extra:
+            sys.stderr.write("\n".join(l for l in out.stdout.decode().splitlines() if "registers" in l or "sssp_kernel" in l) + "\n")
+        objs.append(o)
+    lib = os.path.join(vdir, name + ".so")
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
+    return lib
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile the shared library (and the DTALite_b200 executable) if sources changed."""
     os.makedirs(LIB_DIR, exist_ok=True)

@@ -76,6 +76,8 @@ struct ColumnPool {     // column CSR with fixed slots per OD cell
 
 struct SsspStats { // accumulated on device
     unsigned long long relaxations, pops, rounds, tie_candidates, counted_edges, overflow, tied_origins, replayed;
+    unsigned long long prof[8]; // cycle buckets of thread 0 (only with -DSSSP_PROFILE): init, near, bookkeeping, far, barrier wait
+    unsigned long long stage[8]; // thread 0: entry, label+row, edges, labels, atomics, push
 };
 
 // ------------------------------------------------------------------ kernel launchers

@@ -1072,6 +1072,15 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
         stats[3] = (double)(s1.pops - s0.pops);
         stats[4] = (double)(s1.rounds - s0.rounds);
         stats[5] = (double)(s1.replayed - s0.replayed);
+        if (getenv("DTL_SSSP_PROFILE")) {
+            fprintf(stderr, "sssp cycle buckets (thread 0 of every CTA, summed): init %.3g near %.3g bookkeeping %.3g far %.3g tie %.3g\n",
+                    (double)(s1.prof[0] - s0.prof[0]), (double)(s1.prof[1] - s0.prof[1]), (double)(s1.prof[2] - s0.prof[2]),
+                    (double)(s1.prof[3] - s0.prof[3]), (double)(s1.prof[4] - s0.prof[4]));
+            fprintf(stderr, "  thread-0 stage cycles: entry %.3g label+row %.3g edges %.3g labels %.3g atomics %.3g push %.3g  (pops %.3g)\n",
+                    (double)(s1.stage[0] - s0.stage[0]), (double)(s1.stage[1] - s0.stage[1]), (double)(s1.stage[2] - s0.stage[2]),
+                    (double)(s1.stage[3] - s0.stage[3]), (double)(s1.stage[4] - s0.stage[4]), (double)(s1.stage[5] - s0.stage[5]),
+                    (double)(s1.pops - s0.pops));
+        }
     }
     e->trees_valid = false;
     return 0;

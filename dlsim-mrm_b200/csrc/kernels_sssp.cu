@@ -27,6 +27,9 @@ namespace dtl {
 
 #define INF_BITS 0x430c6bf526340000ULL /* bit pattern of 1.0e15 */
 #define TIE_MARK (-7777)
+#ifndef SSSP_UNR
+#define SSSP_UNR 4 /* edges expanded together per queue entry (memory-level parallelism) */
+#endif
 
 __device__ __forceinline__ double ld_label(const unsigned long long* p)
 {
@@ -87,12 +90,13 @@ __device__ __forceinline__ double block_min(double v, double* s_red)
     return r;
 }
 
-template <int BLOCK>
+template <int BLOCK, int UNR>
 __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 {
     __shared__ int s_task, s_n_next, s_n_far, s_n_far2, s_n_tie, s_overflow;
     __shared__ double s_red[32];
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const int N = a.N;
     QEntry* q_near = a.ws + (size_t)blockIdx.x * a.ws_stride;
     QEntry* q_next = q_near + a.cap_near;
@@ -101,6 +105,17 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
     int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
     const int E = a.row_ptr[N];
     unsigned long long c_relax = 0, c_pops = 0, c_rounds = 0;
+#ifdef SSSP_PROFILE
+    long long pf_t = clock64(), pf_init = 0, pf_near = 0, pf_book = 0, pf_far = 0, pf_tie = 0;
+#define PF(bucket) do { const long long n_ = clock64(); bucket += n_ - pf_t; pf_t = n_; } while (0)
+    long long ps_t = 0, ps[6] = { 0, 0, 0, 0, 0, 0 };
+    // stage clock: the asm consumes `dep`, so it issues only once that value has arrived
+#define PS(k, dep) do { if (tid == 0) { long long n_; unsigned long long d_ = (unsigned long long)(dep); \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "l"(d_) : "memory"); ps[k] += n_ - ps_t; ps_t = n_; } } while (0)
+#else
+#define PF(bucket) do { } while (0)
+#define PS(k, dep) do { } while (0)
+#endif
 
     for (;;) {
         __syncthreads();
@@ -128,52 +143,146 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             st_entry(&q_near[0], 0.0, origin, DTL_NO_PRED);
         }
         __syncthreads();
+        PF(pf_init);
         int n_near = 1;
         double thr = a.delta;
 
         for (;;) {
             while (n_near > 0) {
-                for (int i = tid; i < n_near; i += BLOCK) {
-                    const QEntry q = ld_entry(&q_near[i]);
-                    const double cur = ld_label(&lab[q.node]);
-                    if (cur < q.lab) continue; // a better label was pushed later: that entry expands the node
-                    pred[q.node] = q.link;     // the entry that carries the current label names the tight link
-                    ++c_pops;
-                    const int rb = __ldg(&a.row_ptr[q.node]), re = __ldg(&a.row_ptr[q.node + 1]);
-                    for (int e = rb; e < re; ++e) {
-                        const Edge ed = ld_edge(&a.edges[e]);
-                        int to = ed.to;
-                        if (to < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
-                            to &= 0x7fffffff;
-                            if (__ldg(&a.link_tag[ed.link]) != zone) continue; // routing.h:779-786
+                // Warp-convergent expansion: every lane owns one queue entry, UNR of its edges are relaxed per pass
+                // (edge loads, label loads and atomics of a pass are issued back to back), and the pushes of a pass
+                // are placed with ONE warp scan + one shared-memory atomic per queue instead of per-push atomics.
+                for (int base = 0; base < n_near; base += BLOCK) {
+                    const int i = base + tid;
+                    bool active = i < n_near;
+                    QEntry q;
+                    q.lab = 0.0; q.node = 0; q.link = DTL_NO_PRED;
+                    int rb = 0, re = 0;
+#ifdef SSSP_PROFILE
+                    if (tid == 0) ps_t = clock64();
+#endif
+                    if (active) {
+                        q = ld_entry(&q_near[i]);
+                        PS(0, q.node);
+                        const double cur = ld_label(&lab[q.node]);
+                        rb = __ldg(&a.row_ptr[q.node]);
+                        re = __ldg(&a.row_ptr[q.node + 1]);
+                        PS(1, __double_as_longlong(cur) + rb + re);
+                        if (cur < q.lab) active = false; // a better label was pushed later: that entry expands the node
+                    }
+                    if (active) {
+                        pred[q.node] = q.link;           // the entry that carries the current label names the tight link
+                        ++c_pops;
+                    } else re = rb;
+                    for (int e0 = rb; __any_sync(0xffffffffu, e0 < re); e0 += UNR) {
+                        Edge ed[UNR];
+                        bool ok[UNR];
+                        int to[UNR];
+                        double c[UNR], lw[UNR];
+                        unsigned long long old[UNR];
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            ok[j] = e0 + j < re;
+                            if (ok[j]) ed[j] = ld_edge(&a.edges[e0 + j]);
                         }
-                        ++c_relax;
-                        const double c = q.lab + ed.cost; // routing.h:804
-                        const double lw = ld_label(&lab[to]);
-                        if (c < lw) {                     // routing.h:816
-                            const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
-                            const unsigned long long old = atomicMin(&lab[to], cb);
-                            if (old > cb) {
-                                if (c < thr) {
-                                    const int pos = agg_inc(&s_n_next);
-                                    if (pos < a.cap_near) st_entry(&q_next[pos], c, to, ed.link);
-                                    else s_overflow = 1;
-                                } else {
-                                    const int pos = agg_inc(&s_n_far);
-                                    if (pos < a.cap_far) st_entry(&q_far[pos], c, to, ed.link);
-                                    else s_overflow = 1;
-                                }
-                            } else if (old == cb && to != origin) {
-                                const int pos = agg_inc(&s_n_tie);
-                                if (pos < a.tie_cap) tie_cand[pos] = to;
+                        PS(2, (ok[0] ? ed[0].to : 0) + (ok[UNR - 1] ? ed[UNR - 1].to : 0));
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            to[j] = 0; c[j] = 0.0; lw[j] = 0.0;
+                            if (!ok[j]) continue;
+                            to[j] = ed[j].to;
+                            if (to[j] < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
+                                to[j] &= 0x7fffffff;
+                                if (__ldg(&a.link_tag[ed[j].link]) != zone) ok[j] = false; // routing.h:779-786
                             }
-                        } else if (c == lw && to != origin) {
-                            const int pos = agg_inc(&s_n_tie);
-                            if (pos < a.tie_cap) tie_cand[pos] = to;
                         }
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            if (!ok[j]) continue;
+                            ++c_relax;
+                            c[j] = q.lab + ed[j].cost; // routing.h:804
+                            lw[j] = ld_label(&lab[to[j]]);
+                        }
+                        PS(3, __double_as_longlong(lw[0]) + __double_as_longlong(lw[UNR - 1]));
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            old[j] = 0ULL;
+#if defined(SSSP_EXP_RED)
+                            if (ok[j] && c[j] < lw[j]) { // experiment: fire-and-forget min, push decided by the pre-check
+                                atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
+                                old[j] = ~0ULL;
+                            }
+#elif defined(SSSP_EXP_PLAIN)
+                            if (ok[j] && c[j] < lw[j]) { // experiment: racy plain store
+                                lab[to[j]] = (unsigned long long)__double_as_longlong(c[j]);
+                                old[j] = ~0ULL;
+                            }
+#else
+                            if (ok[j] && c[j] < lw[j])  // routing.h:816
+                                old[j] = atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
+#endif
+                        }
+                        PS(4, old[0] + old[UNR - 1]);
+                        // classify: bit j of near_m / far_m / tie_m
+                        unsigned near_m = 0, far_m = 0, tie_m = 0;
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            if (!ok[j]) continue;
+                            const unsigned long long cb = (unsigned long long)__double_as_longlong(c[j]);
+                            if (c[j] < lw[j]) {
+                                if (old[j] > cb) { if (c[j] < thr) near_m |= 1u << j; else far_m |= 1u << j; }
+                                else if (old[j] == cb && to[j] != origin) tie_m |= 1u << j;
+                            } else if (c[j] == lw[j] && to[j] != origin) tie_m |= 1u << j;
+                        }
+                        // one inclusive scan carries both counts (near in the low half, far in the high half)
+                        const int mine = __popc(near_m) | (__popc(far_m) << 16);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        int base_near = 0, base_far = 0;
+                        if (lane == 31) {
+                            if (total & 0xffff) base_near = atomicAdd(&s_n_next, total & 0xffff);
+                            if (total >> 16) base_far = atomicAdd(&s_n_far, total >> 16);
+                        }
+                        base_near = __shfl_sync(0xffffffffu, base_near, 31);
+                        base_far = __shfl_sync(0xffffffffu, base_far, 31);
+                        int pos_near = base_near + ((incl - mine) & 0xffff);
+                        int pos_far = base_far + ((incl - mine) >> 16);
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            if (near_m & (1u << j)) {
+                                if (pos_near < a.cap_near) st_entry(&q_next[pos_near], c[j], to[j], ed[j].link);
+                                else s_overflow = 1;
+                                ++pos_near;
+                            } else if (far_m & (1u << j)) {
+                                if (pos_far < a.cap_far) st_entry(&q_far[pos_far], c[j], to[j], ed[j].link);
+                                else s_overflow = 1;
+                                ++pos_far;
+                            }
+                        }
+                        if (tie_m) { // exact FP64 ties are rare: slow path
+#pragma unroll
+                            for (int j = 0; j < UNR; ++j)
+                                if (tie_m & (1u << j)) {
+                                    const int pos = atomicAdd(&s_n_tie, 1);
+                                    if (pos < a.tie_cap) tie_cand[pos] = to[j];
+                                }
+                        }
+                        PS(5, 0);
                     }
                 }
+#ifdef SSSP_PROFILE
+                const long long pf_wait0 = clock64();
+#endif
                 __syncthreads();
+#ifdef SSSP_PROFILE
+                pf_tie += clock64() - pf_wait0; // reuse: barrier wait of thread 0 after its own work
+#endif
+                PF(pf_near);
                 n_near = min(s_n_next, a.cap_near);
                 const int n_far_now = s_n_far;
                 __syncthreads();
@@ -195,6 +304,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                     QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
                 }
                 __syncthreads();
+                PF(pf_book);
             }
             // near queue drained: open the next label window from the far pile
             const int n_far = min(s_n_far, a.cap_far);
@@ -227,7 +337,9 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
             ++c_rounds;
             __syncthreads();
+            PF(pf_far);
         }
+        PF(pf_far);
 
         // ---- verify tie candidates against the final labels (reverse star) ----
         __syncthreads();
@@ -263,6 +375,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             }
         }
         __syncthreads();
+        PF(pf_tie);
         if (tid == 0) {
             atomicAdd(&a.stats->tie_candidates, (unsigned long long)n_tie);
             if (s_overflow) atomicAdd(&a.stats->overflow, 1ULL);
@@ -278,16 +391,24 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         atomicAdd(&a.stats->pops, c_pops);
     }
     if (tid == 0) atomicAdd(&a.stats->rounds, c_rounds);
+#ifdef SSSP_PROFILE
+    if (tid == 0) {
+        atomicAdd(&a.stats->prof[0], (unsigned long long)pf_init); atomicAdd(&a.stats->prof[1], (unsigned long long)pf_near);
+        atomicAdd(&a.stats->prof[2], (unsigned long long)pf_book); atomicAdd(&a.stats->prof[3], (unsigned long long)pf_far);
+        atomicAdd(&a.stats->prof[4], (unsigned long long)pf_tie);
+        for (int k = 0; k < 6; ++k) atomicAdd(&a.stats->stage[k], (unsigned long long)ps[k]);
+    }
+#endif
 }
 
 void launch_sssp(const SsspLaunch& a, cudaStream_t st)
 {
     if (a.n_tasks == 0) return;
     switch (a.block) {
-    case 128: sssp_kernel<128><<<a.grid, 128, 0, st>>>(a); break;
-    case 512: sssp_kernel<512><<<a.grid, 512, 0, st>>>(a); break;
-    case 1024: sssp_kernel<1024><<<a.grid, 1024, 0, st>>>(a); break;
-    default: sssp_kernel<256><<<a.grid, 256, 0, st>>>(a); break;
+    case 128: sssp_kernel<128, SSSP_UNR><<<a.grid, 128, 0, st>>>(a); break;
+    case 512: sssp_kernel<512, SSSP_UNR><<<a.grid, 512, 0, st>>>(a); break;
+    case 1024: sssp_kernel<1024, SSSP_UNR><<<a.grid, 1024, 0, st>>>(a); break;
+    default: sssp_kernel<256, SSSP_UNR><<<a.grid, 256, 0, st>>>(a); break;
     }
 }
 
@@ -296,10 +417,10 @@ void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs)
     int n = 0;
     cudaFuncAttributes fa{};
     switch (block) {
-    case 128: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<128>, 128, 0); cudaFuncGetAttributes(&fa, sssp_kernel<128>); break;
-    case 512: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<512>, 512, 0); cudaFuncGetAttributes(&fa, sssp_kernel<512>); break;
-    case 1024: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<1024>, 1024, 0); cudaFuncGetAttributes(&fa, sssp_kernel<1024>); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<256>, 256, 0); cudaFuncGetAttributes(&fa, sssp_kernel<256>); break;
+    case 128: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<128, SSSP_UNR>, 128, 0); cudaFuncGetAttributes(&fa, sssp_kernel<128, SSSP_UNR>); break;
+    case 512: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<512, SSSP_UNR>, 512, 0); cudaFuncGetAttributes(&fa, sssp_kernel<512, SSSP_UNR>); break;
+    case 1024: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<1024, SSSP_UNR>, 1024, 0); cudaFuncGetAttributes(&fa, sssp_kernel<1024, SSSP_UNR>); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<256, SSSP_UNR>, 256, 0); cudaFuncGetAttributes(&fa, sssp_kernel<256, SSSP_UNR>); break;
     }
     if (max_ctas_per_sm) *max_ctas_per_sm = n;
     if (regs) *regs = fa.numRegs;

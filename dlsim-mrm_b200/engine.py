@@ -51,7 +51,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("DTL_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise EngineError(f"native library {p} is missing: run `python -m dlsim_mrm_b200.build` "
                           "(there is no CPU or Python fallback)")
