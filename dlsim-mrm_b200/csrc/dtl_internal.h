@@ -109,16 +109,19 @@ struct SsspLaunch {
     const int* link_tag;
     const int* link_from;
     int n_tasks;             // tasks in this batch
+    int n_run;               // trees to compute in this launch (== n_tasks unless task_list is set)
+    const int* task_list;    // optional: batch-local task indices to (re)compute
     const int* task_origin;  // [n_tasks] origin centroid node
     const int* task_zone;    // [n_tasks] origin zone seq no
     unsigned long long* labels; // [n_tasks][N] FP64 bit patterns
     int* pred_link;          // [n_tasks][N]
-    int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes)
+    int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes); -1 = work queue overflowed
     double delta;
     // per-CTA workspace
     QEntry* ws;              // [grid][ws_stride]
     size_t ws_stride;
     int cap_near, cap_far;
+    int far_trigger;         // far-pile size above which dead entries are dropped between rounds
     int* tie_cand;           // [grid][tie_cap]
     int tie_cap;
     int* task_counter;       // device int, zeroed before launch

@@ -128,6 +128,12 @@ struct dtl_engine {
     QEntry* d_ws = nullptr;
     size_t ws_stride = 0;
     int cap_near = 0, cap_far = 0, tie_cap = 4096;
+    // worst-case queues for the few trees whose frontier outgrows the regular ones (re-run path)
+    QEntry* d_ws_big = nullptr;
+    size_t ws_big_stride = 0;
+    int cap_near_big = 0, cap_far_big = 0, big_grid = 8;
+    int* d_ws_big_tie = nullptr;
+    int* d_rerun_list = nullptr;
     int* d_tie_cand = nullptr;
     int* d_task_counter = nullptr;
     SsspStats* d_stats = nullptr;
@@ -141,8 +147,8 @@ struct dtl_engine {
     std::vector<cudaEvent_t> free_events;
     double ms[8] = { 0 };
     long long launches[8] = { 0 };
-    double ctr_base[8] = { 0 };
-    double tasks_done = 0;
+    double ctr_base[10] = { 0 };
+    double tasks_done = 0, reruns = 0;
 
     ncclComm_t comm = nullptr;
     bool local_shard = false; // world > 1 without a communicator: the caller reduces the shards (tests)
@@ -330,11 +336,12 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     SsspLaunch a{};
     a.N = e->N; a.row_ptr = f.row_ptr; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges;
     a.link_tag = e->d_link_tag; a.link_from = e->d_link_from;
-    a.n_tasks = n_tasks; a.task_origin = d_origin; a.task_zone = d_zone;
+    a.n_tasks = n_tasks; a.n_run = n_tasks; a.task_list = nullptr; a.task_origin = d_origin; a.task_zone = d_zone;
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;
     a.tie_nodes = e->d_tie_nodes;
     a.delta = f.delta;
     a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_near = e->cap_near; a.cap_far = e->cap_far;
+    a.far_trigger = e->cap_far / 2;
     a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
     a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
     return a;
@@ -353,6 +360,32 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
     e->h_tie_nodes.resize(n_tasks);
     CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
+    std::vector<int> rerun;
+    for (int i = 0; i < n_tasks; ++i)
+        if (e->h_tie_nodes[i] < 0) rerun.push_back(i);
+    if (!rerun.empty()) { // frontier outgrew the regular queues: recompute those trees with worst-case capacities
+        if (!e->d_ws_big) {
+            if (e->alloc(&e->d_ws_big, (size_t)e->big_grid * e->ws_big_stride)) return -1;
+            if (e->alloc(&e->d_ws_big_tie, (size_t)e->big_grid * e->tie_cap)) return -1;
+            if (e->alloc(&e->d_rerun_list, std::max(1, e->batch_tasks))) return -1;
+        }
+        CK(cudaMemcpyAsync(e->d_rerun_list, rerun.data(), sizeof(int) * rerun.size(), cudaMemcpyHostToDevice, e->st));
+        SsspLaunch b = a;
+        b.task_list = e->d_rerun_list; b.n_run = (int)rerun.size();
+        b.ws = e->d_ws_big; b.ws_stride = e->ws_big_stride; b.cap_near = e->cap_near_big; b.cap_far = e->cap_far_big;
+        b.tie_cand = e->d_ws_big_tie; b.grid = std::min(e->big_grid, b.n_run);
+        b.far_trigger = e->N + 32; // a compacted pile holds <= N live entries and a round adds <= E: never overflows
+        const int ph2 = e->phase_begin(2);
+        CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
+        launch_sssp(b, e->st);
+        e->phase_end(ph2, 1);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        e->reruns += (double)rerun.size();
+        for (int i : rerun)
+            if (e->h_tie_nodes[i] < 0) { set_err("SSSP work queue overflow with worst-case capacities (internal bound violated)"); return -1; }
+    }
     std::vector<int> replay;
     for (int i = 0; i < n_tasks; ++i)
         if (e->h_tie_nodes[i] > 0) replay.push_back(i);
@@ -389,7 +422,7 @@ int check_flags(dtl_engine* e)
     CK(cudaStreamSynchronize(e->st));
     if (flag & 1) { set_err("column arena exhausted (%lld path links): raise dtl_options.column_arena_bytes", e->pool.arena_cap); return -1; }
     if (flag & 2) { set_err("an OD cell needs more than %d columns: raise dtl_options.max_columns_per_od", e->pool.cap); return -1; }
-    if (s.overflow) { set_err("SSSP work queue overflow (internal capacity bound violated)"); return -1; }
+    (void)s; // queue overflows are handled per batch by re-running those trees with worst-case queues
     return 0;
 }
 
@@ -597,16 +630,23 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_labels, (size_t)e->batch_tasks * N)) return -1;
     if (e->alloc(&e->d_pred, (size_t)e->batch_tasks * N)) return -1;
     if (e->alloc(&e->d_tie_nodes, e->batch_tasks)) return -1;
-    e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 256;
-    if (e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 256;
+    e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 128;
+    if (e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 128;
     int occ = 0, regs = 0;
     sssp_occupancy(e->sssp_block, &occ, &regs);
     if (occ <= 0) { set_err("SSSP kernel cannot be resident on this device (built for sm_100a)"); return -1; }
     int per_sm = o.sssp_ctas_per_sm > 0 ? std::min(o.sssp_ctas_per_sm, occ) : occ;
-    e->cap_near = std::max(N, maxE) + 32;
-    e->cap_far = N + maxE + 32;
+    // worst-case bounds (DESIGN.md "K1 queues"): a round pushes at most E entries, a compacted far pile holds at most
+    // N live entries.  Regular CTAs get much smaller queues; a tree that outgrows them is re-run with the bounds.
+    e->cap_near_big = std::max(N, maxE) + 32;
+    e->cap_far_big = N + maxE + 32;
+    e->ws_big_stride = 2 * (size_t)e->cap_near_big + 2 * (size_t)e->cap_far_big;
+    int qcap = std::max(4096, N / 8);
+    if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) qcap = std::max(32, atoi(env)); // test hook for the re-run path
+    e->cap_near = std::min(e->cap_near_big, qcap);
+    e->cap_far = std::min(e->cap_far_big, 4 * qcap);
     e->ws_stride = 2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far;
-    const size_t ws_budget = std::min<size_t>((size_t)48 << 30, free_b / 3);
+    const size_t ws_budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
     int grid = e->sm_count * per_sm;
     grid = (int)std::min<size_t>(grid, std::max<size_t>(1, ws_budget / (e->ws_stride * sizeof(QEntry))));
     grid = std::min(grid, std::max(1, e->batch_tasks));
@@ -616,7 +656,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
 
     // ---- path-link arena: what is left, bounded by the option ----
     CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t arena_bytes = o.column_arena_bytes ? o.column_arena_bytes : std::min<size_t>((size_t)32 << 30, free_b / 2);
+    size_t arena_bytes = o.column_arena_bytes ? o.column_arena_bytes : std::min<size_t>((size_t)6 << 30, free_b / 4);
     // a column never has more links than nodes: enough for every slot is an upper bound worth respecting on small inputs
     const size_t hard = (slots + 1) * (size_t)(((size_t)N + 3) & ~(size_t)3) * sizeof(int);
     arena_bytes = std::min(arena_bytes, hard);
@@ -732,9 +772,7 @@ int dtl_iteration(dtl_engine* e, int k, double row[5])
     if (do_vdf(e, false, true, nullptr)) return -1;                    // main_api.cpp:606
     if (do_scatter(e, k, false)) return -1;                            // main_api.cpp:618
     const bool want_count = e->counted_edges_cached < 0;
-    unsigned long long before = 0;
     if (want_count) CK(cudaMemsetAsync(&e->d_stats->counted_edges, 0, 8, e->st));
-    (void)before;
     if (trees_and_columns(e, k, want_count)) return -1;                // main_api.cpp:647-699
     launch_sum(e->d_least, e->n_cells, 1, e->d_scalars + 1, e->st);
     CK(cudaGetLastError());
@@ -1137,7 +1175,7 @@ int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset)
     return 0;
 }
 
-int dtl_get_counters(dtl_engine* e, double c[8], int reset)
+int dtl_get_counters(dtl_engine* e, double c[10], int reset)
 {
     CK(cudaSetDevice(e->dev));
     CK(cudaStreamSynchronize(e->st));
@@ -1145,10 +1183,11 @@ int dtl_get_counters(dtl_engine* e, double c[8], int reset)
     unsigned long long ctr[4] = { 0 };
     CK(cudaMemcpy(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost));
-    const double now[8] = { e->counted_edges_cached < 0 ? 0.0 : e->counted_edges_cached, (double)s.relaxations, (double)s.pops,
-                            (double)s.rounds, e->tasks_done, (double)s.replayed, (double)ctr[0], (double)ctr[1] };
+    const double now[10] = { e->counted_edges_cached < 0 ? 0.0 : e->counted_edges_cached, (double)s.relaxations, (double)s.pops,
+                             (double)s.rounds, e->tasks_done, (double)s.replayed, (double)ctr[0], (double)ctr[1], e->reruns,
+                             (double)s.tie_candidates };
     if (c) {
-        for (int i = 0; i < 8; ++i) c[i] = now[i] - e->ctr_base[i];
+        for (int i = 0; i < 10; ++i) c[i] = now[i] - e->ctr_base[i];
         c[0] = now[0]; // counted edges per iteration (static property of the trees), not cumulative
     }
     if (reset) memcpy(e->ctr_base, now, sizeof(now));

@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
     QEntry* q_far = q_next + a.cap_near;
     QEntry* q_far2 = q_far + a.cap_far;
     int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
-    const int E = a.row_ptr[N];
     unsigned long long c_relax = 0, c_pops = 0, c_rounds = 0;
 #ifdef SSSP_PROFILE
     long long pf_t = clock64(), pf_init = 0, pf_near = 0, pf_book = 0, pf_far = 0, pf_tie = 0;
@@ -121,8 +120,8 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         __syncthreads();
         if (tid == 0) s_task = atomicAdd(a.task_counter, 1);
         __syncthreads();
-        const int task = s_task;
-        if (task >= a.n_tasks) break;
+        if (s_task >= a.n_run) break;
+        const int task = a.task_list ? a.task_list[s_task] : s_task;
         const int origin = a.task_origin[task];
         const int zone = a.task_zone[task];
         unsigned long long* lab = a.labels + (size_t)task * N;
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                 if (tid == 0) s_n_next = 0;
                 QEntry* t = q_near; q_near = q_next; q_next = t;
                 ++c_rounds;
-                if (n_far_now > a.cap_far - E) {
+                if (n_far_now > a.far_trigger) {
                     // far pile close to capacity: drop dead entries (at most one live entry per node survives)
                     const int nf = min(n_far_now, a.cap_far);
                     for (int i = tid; i < nf; i += BLOCK) {
@@ -378,7 +377,10 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         PF(pf_tie);
         if (tid == 0) {
             atomicAdd(&a.stats->tie_candidates, (unsigned long long)n_tie);
-            if (s_overflow) atomicAdd(&a.stats->overflow, 1ULL);
+            if (s_overflow) { // a queue was too small: the tree is incomplete, the host re-runs it with worst-case queues
+                atomicAdd(&a.stats->overflow, 1ULL);
+                a.tie_nodes[task] = -1;
+            }
         }
     }
     // flush per-thread counters
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 
 void launch_sssp(const SsspLaunch& a, cudaStream_t st)
 {
-    if (a.n_tasks == 0) return;
+    if (a.n_run == 0) return;
     switch (a.block) {
     case 128: sssp_kernel<128, SSSP_UNR><<<a.grid, 128, 0, st>>>(a); break;
     case 512: sssp_kernel<512, SSSP_UNR><<<a.grid, 512, 0, st>>>(a); break;

@@ -172,7 +172,8 @@ class Engine:
     """One device-resident assignment problem on one GPU (one rank of a possibly sharded run)."""
 
     TIMING_CLASSES = ("vdf", "scatter", "sssp", "tie_replay", "backtrace", "column_pool", "all_reduce", "iteration")
-    COUNTERS = ("counted_edges", "relaxations", "pops", "rounds", "tasks", "replayed", "link_refs", "path_nodes")
+    COUNTERS = ("counted_edges", "relaxations", "pops", "rounds", "tasks", "replayed", "link_refs", "path_nodes", "reruns",
+                "tie_candidates")
 
     def __init__(self, problem: Problem, device: int = -1, rank: int = 0, world_size: int = 1, keep_trees: bool = False,
                  max_columns_per_od: int = 0, delta_factor: float = 0.0, block_threads: int = 0, ctas_per_sm: int = 0,
@@ -347,7 +348,7 @@ class Engine:
         return {"ms": dict(zip(self.TIMING_CLASSES, ms.tolist())), "launches": dict(zip(self.TIMING_CLASSES, cnt.tolist()))}
 
     def counters(self, reset: bool = False) -> dict:
-        c = np.zeros(8)
+        c = np.zeros(10)
         self._ck(self.lib.dtl_get_counters(self.h, _ptr(c), int(reset)))
         return dict(zip(self.COUNTERS, c.tolist()))
 

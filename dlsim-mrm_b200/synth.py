@@ -1,7 +1,7 @@
 """Seeded synthetic regional grid in GMNS files (BASELINE.json config 5).
 
 ``write_grid(dir, rows, cols, n_links, n_zones, ...)`` writes node.csv, link.csv, demand.csv and settings.csv
-that both the reference (oracle/_ref/dtalite_ref) and this engine read.  Defaults give the named size:
+that both the reference executable and this engine read.  Defaults give the named size:
 316 x 317 = 100 172 nodes, 300 000 directed links, 2 000 zones, 4 000 000 trips kept on each origin's 200
 heaviest destinations (400 000 OD rows).  Link lengths are jittered per directed link so that no two paths
 tie exactly in FP64 (exact ties are an artefact of uniform grids).
@@ -166,7 +166,7 @@ def write_grid(directory, K=20, blocks=8, **kw):
 WORKLOADS = {
     # BASELINE.json configs[4]: 100k nodes / 300k links / 2000 zones / 4M trips
     "grid100k": dict(rows=316, cols=317, n_links=300_000, n_zones=2000, total_trips=4_000_000.0, dest_per_origin=200),
-    # same generator, small enough for the CPU oracle in seconds (tests)
+    # same generator, small enough for a CPU run in seconds (tests)
     "grid2k": dict(rows=45, cols=46, n_links=6_200, n_zones=60, total_trips=60_000.0, dest_per_origin=25),
     "grid10k": dict(rows=100, cols=101, n_links=30_000, n_zones=200, total_trips=400_000.0, dest_per_origin=60),
 }

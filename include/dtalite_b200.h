@@ -160,8 +160,9 @@ int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pr
  * ms[6]=all-reduce  ms[7]=whole iterations;  counts[i] = kernel launches in each class */
 int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset);
 /* work counters since the last reset: { counted edges (Graph500 convention), relaxations, queue pops,
- * SSSP rounds, SSSP tasks, replayed origins, column-link references scattered, back-traced path nodes } */
-int dtl_get_counters(dtl_engine* e, double c[8], int reset);
+ * SSSP rounds, SSSP tasks, replayed origins, column-link references scattered, back-traced path nodes,
+ * trees re-run with worst-case queues, tie candidates observed } */
+int dtl_get_counters(dtl_engine* e, double c[10], int reset);
 /* number of HBM bytes the engine holds */
 size_t dtl_device_bytes(const dtl_engine* e);
 

@@ -285,3 +285,19 @@ def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, workload, K, CU)
         assert rel_err(st["tt"], so["tt"]) <= TOL and rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
         _compare_columns(e.columns(), o.columns())
         assert e.counters()["replayed"] == 0   # jittered lengths: no exact ties
+
+
+def test_small_queues_fall_back_to_worst_case_rerun(D, problems, golden, oracle_mod, monkeypatch):
+    """Trees whose frontier outgrows the regular work queues are recomputed with worst-case queues: same bits."""
+    p, g = problems("corridor_101"), golden("corridor_101")
+    o = oracle_mod.Oracle(p)
+    cost = g["gen_cost_k2_at0"]
+    fs = o.forward_star(0, 0)
+    monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "48")
+    with D.Engine(p) as e:
+        zones = np.arange(0, p.n_zones, 9, dtype=np.int32)
+        lab, pn, pl, ties, st = e.sssp_trees(0, 0, zones, cost=cost)
+        assert e.counters()["reruns"] > 0
+        for i, z in enumerate(zones):
+            rl, rpn, rpl, _, _ = o.sssp(fs, cost, int(z))
+            assert np.array_equal(lab[i], rl) and np.array_equal(pl[i], rpl) and np.array_equal(pn[i], rpn)
