@@ -186,12 +186,10 @@ def run_engine_arm(args, rank, world, local_rank):
         if dist:
             dist.barrier()
 
+    from dlsim_mrm_b200 import sharding
+
     def max_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(dist, x, device="cuda")
 
     if rank == 0:
         d = ensure_workload(args.workload)
@@ -207,13 +205,9 @@ def run_engine_arm(args, rank, world, local_rank):
     def make_engine():
         e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 4,
                      delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas)
-        if world > 1:
-            if rank == 0:
-                uid = torch.tensor(list(D.Engine.comm_unique_id()), dtype=torch.uint8, device="cuda")
-            else:
-                uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            dist.broadcast(uid, 0)
-            e.comm_init(bytes(uid.cpu().tolist()))
+        if world > 1:  # rank 0 makes the NCCL id, everybody joins the engine's own communicator
+            uid = sharding.broadcast_bytes(dist, D.Engine.comm_unique_id() if rank == 0 else None, 128, device="cuda")
+            e.comm_init(uid)
         return e
 
     # ---- device-resident throughput: inputs already in HBM when the timed region starts ----
