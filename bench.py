@@ -202,11 +202,14 @@ def run_engine_arm(args, rank, world, local_rank):
     read_s = time.time() - t0
     K, W = args.steps, args.warmup
 
+    uid = None
+    if world > 1:  # rank 0 makes the NCCL id once per process group; engines join (and share) that communicator
+        uid = sharding.broadcast_bytes(dist, D.Engine.comm_unique_id() if rank == 0 else None, 128, device="cuda")
+
     def make_engine():
         e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 4,
                      delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas)
-        if world > 1:  # rank 0 makes the NCCL id, everybody joins the engine's own communicator
-            uid = sharding.broadcast_bytes(dist, D.Engine.comm_unique_id() if rank == 0 else None, 128, device="cuda")
+        if world > 1:
             e.comm_init(uid)
         return e
 
@@ -242,6 +245,8 @@ def run_engine_arm(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     e2 = make_engine()
+    torch.cuda.synchronize()
+    create_s = time.perf_counter() - t0
     for k in range(K):
         e2.iteration(k)
     e2.finalize(K)
@@ -279,7 +284,7 @@ def run_engine_arm(args, rank, world, local_rank):
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},
             "counted_edges_per_step": rows[-1]["counted_edges"],
             "relative_gap_last": rows[-1]["gap"],
-            "device_gib": dev_bytes / 2**30, "read_gmns_s": read_s,
+            "device_gib": dev_bytes / 2**30, "read_gmns_s": read_s, "e2e_create_s": create_s, "e2e_total_s": e2e_s,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -456,7 +456,7 @@ void dtl_destroy(dtl_engine* e)
     if (e->st) cudaStreamSynchronize(e->st);
     e->resolve_timing();
     for (cudaEvent_t ev : e->free_events) cudaEventDestroy(ev);
-    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    // e->comm is shared and lives as long as the process (see dtl_comm_init)
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_scalars) cudaFreeHost(e->h_scalars);
     if (e->st) cudaStreamDestroy(e->st);
@@ -725,10 +725,16 @@ int dtl_comm_init(dtl_engine* e, const unsigned char id128[128])
     if (!id128) { e->local_shard = true; return 0; } // shard-only mode: no collective, the caller sums the shards
     if (!g_nccl.load()) return -1;
     CK(cudaSetDevice(e->dev));
+    // communicators are process-lifetime objects keyed by their id: a second engine of the same run re-uses it
+    static std::map<std::string, ncclComm_t> comms;
+    const std::string key((const char*)id128, 128);
+    auto it = comms.find(key);
+    if (it != comms.end()) { e->comm = it->second; return 0; }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&e->comm, e->world, id, e->rank);
     if (r != ncclSuccess) { set_err("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return -1; }
+    comms[key] = e->comm;
     return 0;
 }
 
