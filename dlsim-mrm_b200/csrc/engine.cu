@@ -640,12 +640,12 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     // N live entries.  Regular CTAs get much smaller queues; a tree that outgrows them is re-run with the bounds.
     e->cap_near_big = std::max(N, maxE) + 32;
     e->cap_far_big = N + maxE + 32;
-    e->ws_big_stride = 2 * (size_t)e->cap_near_big + 2 * (size_t)e->cap_far_big;
+    e->ws_big_stride = (2 * (size_t)e->cap_near_big + 2 * (size_t)e->cap_far_big) * 3 / 2 + 4;
     int qcap = std::max(4096, N / 8);
     if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) qcap = std::max(32, atoi(env)); // test hook for the re-run path
     e->cap_near = std::min(e->cap_near_big, qcap);
     e->cap_far = std::min(e->cap_far_big, 4 * qcap);
-    e->ws_stride = 2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far;
+    e->ws_stride = (2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far) * 3 / 2 + 4; // entries + {row begin, row end} side arrays
     const size_t ws_budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
     int grid = e->sm_count * per_sm;
     grid = (int)std::min<size_t>(grid, std::max<size_t>(1, ws_budget / (e->ws_stride * sizeof(QEntry))));

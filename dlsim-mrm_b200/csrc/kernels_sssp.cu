@@ -30,6 +30,12 @@ namespace dtl {
 #ifndef SSSP_UNR
 #define SSSP_UNR 4 /* edges expanded together per queue entry (memory-level parallelism) */
 #endif
+#ifndef SSSP_ROWINFO
+#define SSSP_ROWINFO 0 /* 1: queue entries carry the node's forward-star row (loaded by the pusher, off the critical path) */
+#endif
+#ifndef SSSP_NOPRE
+#define SSSP_NOPRE 0 /* 1: no label pre-check load, every relaxation is one atomicMin */
+#endif
 
 __device__ __forceinline__ double ld_label(const unsigned long long* p)
 {
@@ -102,6 +108,13 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
     QEntry* q_next = q_near + a.cap_near;
     QEntry* q_far = q_next + a.cap_near;
     QEntry* q_far2 = q_far + a.cap_far;
+#if SSSP_ROWINFO
+    // side arrays {row begin, row end} of every queued node: the expansion need not wait for row_ptr
+    int2* r_near = reinterpret_cast<int2*>(q_far2 + a.cap_far);
+    int2* r_next = r_near + a.cap_near;
+    int2* r_far = r_next + a.cap_near;
+    int2* r_far2 = r_far + a.cap_far;
+#endif
     int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
     unsigned long long c_relax = 0, c_pops = 0, c_rounds = 0;
 #ifdef SSSP_PROFILE
@@ -140,6 +153,9 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         if (tid == 0) {
             lab[origin] = 0ULL; // +0.0
             st_entry(&q_near[0], 0.0, origin, DTL_NO_PRED);
+#if SSSP_ROWINFO
+            r_near[0] = make_int2(a.row_ptr[origin], a.row_ptr[origin + 1]);
+#endif
         }
         __syncthreads();
         PF(pf_init);
@@ -162,10 +178,16 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 #endif
                     if (active) {
                         q = ld_entry(&q_near[i]);
+#if SSSP_ROWINFO
+                        const int2 rr = r_near[i];
+                        rb = rr.x; re = rr.y;
+#endif
                         PS(0, q.node);
                         const double cur = ld_label(&lab[q.node]);
+#if !SSSP_ROWINFO
                         rb = __ldg(&a.row_ptr[q.node]);
                         re = __ldg(&a.row_ptr[q.node + 1]);
+#endif
                         PS(1, __double_as_longlong(cur) + rb + re);
                         if (cur < q.lab) active = false; // a better label was pushed later: that entry expands the node
                     }
@@ -200,7 +222,11 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                             if (!ok[j]) continue;
                             ++c_relax;
                             c[j] = q.lab + ed[j].cost; // routing.h:804
+#if !SSSP_NOPRE
                             lw[j] = ld_label(&lab[to[j]]);
+#else
+                            lw[j] = DTL_MAX_LABEL_COST * 2; // no pre-check: the atomic below decides
+#endif
                         }
                         PS(3, __double_as_longlong(lw[0]) + __double_as_longlong(lw[UNR - 1]));
 #pragma unroll
@@ -221,6 +247,14 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                                 old[j] = atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
 #endif
                         }
+#if SSSP_ROWINFO
+                        int2 prow[UNR];
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            prow[j] = make_int2(0, 0);
+                            if (ok[j] && c[j] < lw[j]) { prow[j].x = __ldg(&a.row_ptr[to[j]]); prow[j].y = __ldg(&a.row_ptr[to[j] + 1]); }
+                        }
+#endif
                         PS(4, old[0] + old[UNR - 1]);
                         // classify: bit j of near_m / far_m / tie_m
                         unsigned near_m = 0, far_m = 0, tie_m = 0;
@@ -232,6 +266,9 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                                 if (old[j] > cb) { if (c[j] < thr) near_m |= 1u << j; else far_m |= 1u << j; }
                                 else if (old[j] == cb && to[j] != origin) tie_m |= 1u << j;
                             } else if (c[j] == lw[j] && to[j] != origin) tie_m |= 1u << j;
+#if SSSP_ROWINFO && SSSP_NOPRE
+                            if (!((near_m | far_m) & (1u << j))) prow[j] = make_int2(0, 0);
+#endif
                         }
                         // one inclusive scan carries both counts (near in the low half, far in the high half)
                         const int mine = __popc(near_m) | (__popc(far_m) << 16);
@@ -254,12 +291,20 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 #pragma unroll
                         for (int j = 0; j < UNR; ++j) {
                             if (near_m & (1u << j)) {
-                                if (pos_near < a.cap_near) st_entry(&q_next[pos_near], c[j], to[j], ed[j].link);
-                                else s_overflow = 1;
+                                if (pos_near < a.cap_near) {
+                                    st_entry(&q_next[pos_near], c[j], to[j], ed[j].link);
+#if SSSP_ROWINFO
+                                    r_next[pos_near] = prow[j];
+#endif
+                                } else s_overflow = 1;
                                 ++pos_near;
                             } else if (far_m & (1u << j)) {
-                                if (pos_far < a.cap_far) st_entry(&q_far[pos_far], c[j], to[j], ed[j].link);
-                                else s_overflow = 1;
+                                if (pos_far < a.cap_far) {
+                                    st_entry(&q_far[pos_far], c[j], to[j], ed[j].link);
+#if SSSP_ROWINFO
+                                    r_far[pos_far] = prow[j];
+#endif
+                                } else s_overflow = 1;
                                 ++pos_far;
                             }
                         }
@@ -287,6 +332,9 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                 __syncthreads();
                 if (tid == 0) s_n_next = 0;
                 QEntry* t = q_near; q_near = q_next; q_next = t;
+#if SSSP_ROWINFO
+                { int2* tr = r_near; r_near = r_next; r_next = tr; }
+#endif
                 ++c_rounds;
                 if (n_far_now > a.far_trigger) {
                     // far pile close to capacity: drop dead entries (at most one live entry per node survives)
@@ -296,11 +344,17 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                         if (ld_label(&lab[q.node]) == q.lab) {
                             const int pos = agg_inc(&s_n_far2);
                             st_entry(&q_far2[pos], q.lab, q.node, q.link);
+#if SSSP_ROWINFO
+                            r_far2[pos] = r_far[i];
+#endif
                         }
                     }
                     __syncthreads();
                     if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; }
                     QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
+#if SSSP_ROWINFO
+                    { int2* tr = r_far; r_far = r_far2; r_far2 = tr; }
+#endif
                 }
                 __syncthreads();
                 PF(pf_book);
@@ -321,11 +375,18 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                 if (ld_label(&lab[q.node]) == q.lab) {
                     if (q.lab < thr) {
                         const int pos = agg_inc(&s_n_next);
-                        if (pos < a.cap_near) st_entry(&q_near[pos], q.lab, q.node, q.link);
-                        else s_overflow = 1;
+                        if (pos < a.cap_near) {
+                            st_entry(&q_near[pos], q.lab, q.node, q.link);
+#if SSSP_ROWINFO
+                            r_near[pos] = r_far[i];
+#endif
+                        } else s_overflow = 1;
                     } else {
                         const int pos = agg_inc(&s_n_far2);
                         st_entry(&q_far2[pos], q.lab, q.node, q.link);
+#if SSSP_ROWINFO
+                        r_far2[pos] = r_far[i];
+#endif
                     }
                 }
             }
@@ -334,6 +395,9 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             __syncthreads();
             if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; s_n_next = 0; }
             QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
+#if SSSP_ROWINFO
+            { int2* tr = r_far; r_far = r_far2; r_far2 = tr; }
+#endif
             ++c_rounds;
             __syncthreads();
             PF(pf_far);

@@ -1,0 +1,118 @@
+"""Authors the GMNS fixtures under tests/fixtures/ from the reference's datasets (run in the build container):
+
+    python tests/fixtures/make_fixtures.py
+
+  two_corridor   src/test_case_01_two_corridor, inputs verbatim
+  corridor_101   dataset/4_101_corridor, inputs verbatim minus measurement.csv / supply_side_scenario.csv
+                 (those switch on ODME and scenario analysis, outside the accelerated path)
+  corridor_3     dataset/3_corridor_Network/.../network (BASELINE.json configs[1]): node.csv / link.csv verbatim;
+                 input_demand.csv with its header renamed to the column-format names; AUTHORED settings.csv
+                 (column demand for two agent types, one 4-hour period, BPR) -- the shipped settings name path /
+                 activity demand and a subarea, which the committed reference source cannot run
+  asu_qvdf       dataset/2_ASU/network (BASELINE.json configs[2]): link.csv verbatim; node.csv with AUTHORED zone ids
+                 on every 27th node (the dataset ships without zones); AUTHORED demand and settings with
+                 vdf_type=qvdf on every link type, so the queue VDF branch is exercised
+"""
+import csv
+import os
+import shutil
+
+REF = os.environ.get("DTL_REFERENCE_DIR", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def copy(src_dir, dst, names):
+    os.makedirs(dst, exist_ok=True)
+    for n in names:
+        shutil.copy(os.path.join(REF, src_dir, n), os.path.join(dst, n))
+
+
+def corridor_3():
+    src = "dataset/3_corridor_Network/3-corridor_Network_BaceCase/network"
+    dst = os.path.join(HERE, "corridor_3")
+    copy(src, dst, ["node.csv", "link.csv"])
+    with open(os.path.join(REF, src, "input_demand.csv")) as f:
+        rows = list(csv.reader(f))
+    with open(os.path.join(dst, "demand.csv"), "w") as f:
+        f.write("o_zone_id,d_zone_id,volume\n")
+        for r in rows[1:]:
+            if r and r[0]:
+                f.write(",".join(r[:3]) + "\n")
+    open(os.path.join(dst, "settings.csv"), "w").write(
+        "[assignment],,assignment_mode,column_generation_iterations,column_updating_iterations,number_of_memory_blocks\n"
+        ",,dta,20,20,4\n"
+        ",,,,,\n"
+        "[agent_type],agent_type,name,,vot,flow_type,pce,person_occupancy\n"
+        ",sov,passenger,,10,0,1,1\n"
+        ",hov,HOV2,,15,0,1,2\n"
+        ",,,,,,,\n"
+        "[link_type],link_type,link_type_name,,agent_type_blocklist,type_code,traffic_flow_code\n"
+        ",1,motorway,,,f,0\n,3,primary,,,a,0\n,4,residential,,,a,0\n,5,secondary,,,a,0\n,6,tertiary,,,a,0\n,11,unclassified,,,a,0\n"
+        ",,,,,,\n"
+        "[demand_period],demand_period_id,demand_period,,time_period\n"
+        ",1,AM,,0600_1000\n"
+        ",,,,\n"
+        "[demand_file_list],file_sequence_no,file_name,,format_type,demand_period,agent_type,scale_factor\n"
+        ",1,demand.csv,,column,AM,sov,6.4\n"
+        ",2,demand.csv,,column,AM,hov,1.6\n"
+        ",,,,,,,\n"
+        "[output_file_configuration],,path_output,major_path_volume_threshold\n"
+        ",,1,0.1\n")
+
+
+def asu_qvdf():
+    src = "dataset/2_ASU/network"
+    dst = os.path.join(HERE, "asu_qvdf")
+    copy(src, dst, ["link.csv"])
+    with open(os.path.join(REF, src, "node.csv")) as f:
+        rows = list(csv.reader(f))
+    hdr = rows[0]
+    zi = hdr.index("zone_id")
+    zones = []
+    out = [hdr]
+    for i, r in enumerate(rows[1:]):
+        if not r or not r[hdr.index("node_id")]:
+            continue
+        r = list(r)
+        if i % 27 == 5:
+            zones.append(len(zones) + 1)
+            r[zi] = str(zones[-1])
+        out.append(r)
+    with open(os.path.join(dst, "node.csv"), "w", newline="") as f:
+        csv.writer(f, lineterminator="\n").writerows(out)
+    with open(os.path.join(dst, "demand.csv"), "w") as f:
+        f.write("o_zone_id,d_zone_id,volume\n")
+        for o in zones:
+            for d in zones:
+                if o != d:
+                    f.write(f"{o},{d},{40 + 37 * ((o * 7 + d * 3) % 11)}.5\n")
+    with open(os.path.join(REF, src, "link.csv")) as f:
+        lrows = list(csv.reader(f))
+    lti = lrows[0].index("link_type")
+    types = sorted({r[lti] for r in lrows[1:] if len(r) > lti and r[lti]}, key=int)
+    lt = "".join(f",{t},type{t},,,a,0,qvdf\n" for t in types)
+    open(os.path.join(dst, "settings.csv"), "w").write(
+        "[assignment],,assignment_mode,column_generation_iterations,column_updating_iterations,number_of_memory_blocks\n"
+        ",,dta,20,0,4\n"
+        ",,,,,\n"
+        "[agent_type],agent_type,name,,vot,flow_type,pce,person_occupancy\n"
+        ",auto,passenger,,10,0,1,1\n"
+        ",,,,,,,\n"
+        "[link_type],link_type,link_type_name,,agent_type_blocklist,type_code,traffic_flow_code,vdf_type\n" + lt +
+        ",,,,,,,\n"
+        "[demand_period],demand_period_id,demand_period,,time_period\n"
+        ",1,AM,,0700_0800\n"
+        ",,,,\n"
+        "[demand_file_list],file_sequence_no,file_name,,format_type,demand_period,agent_type\n"
+        ",1,demand.csv,,column,AM,auto\n"
+        ",,,,,,\n"
+        "[output_file_configuration],,path_output,major_path_volume_threshold\n"
+        ",,1,0.1\n")
+
+
+if __name__ == "__main__":
+    copy("src/test_case_01_two_corridor", os.path.join(HERE, "two_corridor"), ["node.csv", "link.csv", "demand.csv", "settings.csv"])
+    copy("dataset/4_101_corridor", os.path.join(HERE, "corridor_101"), ["node.csv", "link.csv", "demand.csv", "settings.csv"])
+    corridor_3()
+    asu_qvdf()
+    print("fixtures written under", HERE)

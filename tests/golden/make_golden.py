@@ -100,3 +100,5 @@ if __name__ == "__main__":
                os.path.join(OUT, "corridor_101_final_summary.txt"))
     run_case("two_corridor", 20, 0, range(20), None)
     run_case("corridor_101", 20, 5, (0, 2, 19), {7})
+    run_case("corridor_3", 20, 20, range(20), None)       # authored fixture, BASELINE.json configs[1]
+    run_case("asu_qvdf", 20, 3, (0, 2, 19), None)         # authored fixture, queue VDF, BASELINE.json configs[2]

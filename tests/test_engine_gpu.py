@@ -137,7 +137,7 @@ def _compare_columns(eng_cols, ora_cols):
     assert rel_err(eng_cols["volume"], ora_cols["volume"], floor=1e-6) <= TOL
 
 
-@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5)])
+@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5), ("corridor_3", 20, 20), ("asu_qvdf", 20, 3)])
 def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod, name, K, CU):
     p, g = problems(name), golden(name)
     o = oracle_mod.Oracle(p)

@@ -56,7 +56,7 @@ def test_oracle_reproduces_reference_golden_rows(problems, oracle_mod, name, K, 
         assert _fmt6(r["rel_gap_pct"]) == gap
 
 
-@pytest.mark.parametrize("name", ["two_corridor", "corridor_101"])
+@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "asu_qvdf"])
 def test_oracle_matches_reference_engine_state(problems, golden, oracle_mod, name):
     p, g = problems(name), golden(name)
     K, CU = int(g["K"]), int(g["CU"])
