@@ -21,6 +21,8 @@
 // the reference deque (push-back for new nodes, push-front for re-entered ones).
 //
 // Roofline: HBM/L2 bound, 20 B per counted edge.  Compiled with -fmad=false.
+#include <cstdlib>
+
 #include "dtl_internal.h"
 
 namespace dtl {
@@ -32,6 +34,9 @@ namespace dtl {
 #endif
 #ifndef SSSP_ROWINFO
 #define SSSP_ROWINFO 0 /* 1: queue entries carry the node's forward-star row (loaded by the pusher, off the critical path) */
+#endif
+#ifndef SSSP_EDGEPAR
+#define SSSP_EDGEPAR 0 /* 1: edge-parallel expansion (one edge per thread) instead of one queue entry per lane */
 #endif
 #ifndef SSSP_NOPRE
 #define SSSP_NOPRE 0 /* 1: no label pre-check load, every relaxation is one atomicMin */
@@ -101,6 +106,10 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 {
     __shared__ int s_task, s_n_next, s_n_far, s_n_far2, s_n_tie, s_overflow;
     __shared__ double s_red[32];
+#if SSSP_EDGEPAR
+    __shared__ double s_lab[BLOCK];
+    __shared__ int s_rb[BLOCK], s_off[BLOCK + 1], s_wsum[BLOCK / 32];
+#endif
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int N = a.N;
@@ -164,6 +173,102 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 
         for (;;) {
             while (n_near > 0) {
+#if SSSP_EDGEPAR
+                // Edge-parallel expansion: phase A validates a chunk of BLOCK queue entries (one per thread) and scans their
+                // degrees; phase B gives every thread ONE edge of the chunk, so all lanes relax and pushes are ballots.
+                for (int base = 0; base < n_near; base += BLOCK) {
+                    const int i = base + tid;
+                    int deg = 0;
+                    if (i < n_near) {
+                        const QEntry q = ld_entry(&q_near[i]);
+                        const double cur = ld_label(&lab[q.node]);
+                        if (!(cur < q.lab)) { // else: a better label was pushed later, that entry expands the node
+                            const int rb = __ldg(&a.row_ptr[q.node]), re = __ldg(&a.row_ptr[q.node + 1]);
+                            pred[q.node] = q.link; // the entry that carries the current label names the tight link
+                            ++c_pops;
+                            deg = re - rb;
+                            s_lab[tid] = q.lab;
+                            s_rb[tid] = rb;
+                        }
+                    }
+                    int incl = deg;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (lane == 31) s_wsum[tid >> 5] = incl;
+                    __syncthreads();
+                    int wbase = 0;
+#pragma unroll
+                    for (int w = 0; w < BLOCK / 32; ++w)
+                        if (w < (tid >> 5)) wbase += s_wsum[w];
+                    s_off[tid] = wbase + incl - deg;
+                    if (tid == BLOCK - 1) s_off[BLOCK] = wbase + incl;
+                    __syncthreads();
+                    const int total = s_off[BLOCK];
+                    for (int eb = 0; eb < total; eb += BLOCK) {
+                        const int e = eb + tid;
+                        bool ok = e < total;
+                        int lo = 0;
+                        if (ok) { // owner entry: last j with s_off[j] <= e
+                            int hi = BLOCK;
+#pragma unroll
+                            for (int step = 0; step < 10; ++step) {
+                                const int mid = (lo + hi) >> 1;
+                                if (hi - lo > 1) { if (s_off[mid] <= e) lo = mid; else hi = mid; }
+                            }
+                        }
+                        Edge ed;
+                        ed.cost = 0.0; ed.to = 0; ed.link = 0;
+                        double qlab = 0.0;
+                        if (ok) {
+                            ed = ld_edge(&a.edges[s_rb[lo] + (e - s_off[lo])]);
+                            qlab = s_lab[lo];
+                        }
+                        int to = ed.to;
+                        if (ok && to < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
+                            to &= 0x7fffffff;
+                            if (__ldg(&a.link_tag[ed.link]) != zone) ok = false; // routing.h:779-786
+                        }
+                        bool is_near = false, is_far = false, is_tie = false;
+                        const double c = qlab + ed.cost; // routing.h:804
+                        if (ok) {
+                            ++c_relax;
+                            const double lw = ld_label(&lab[to]);
+                            if (c < lw) {             // routing.h:816
+                                const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+                                const unsigned long long old = atomicMin(&lab[to], cb);
+                                if (old > cb) { is_near = c < thr; is_far = !is_near; }
+                                else if (old == cb && to != origin) is_tie = true;
+                            } else if (c == lw && to != origin) is_tie = true;
+                        }
+                        const unsigned nm = __ballot_sync(0xffffffffu, is_near), fm = __ballot_sync(0xffffffffu, is_far);
+                        int bn = 0, bf = 0;
+                        if (lane == 0) {
+                            if (nm) bn = atomicAdd(&s_n_next, __popc(nm));
+                            if (fm) bf = atomicAdd(&s_n_far, __popc(fm));
+                        }
+                        bn = __shfl_sync(0xffffffffu, bn, 0);
+                        bf = __shfl_sync(0xffffffffu, bf, 0);
+                        const unsigned lt = (1u << lane) - 1;
+                        if (is_near) {
+                            const int pos = bn + __popc(nm & lt);
+                            if (pos < a.cap_near) st_entry(&q_next[pos], c, to, ed.link);
+                            else s_overflow = 1;
+                        } else if (is_far) {
+                            const int pos = bf + __popc(fm & lt);
+                            if (pos < a.cap_far) st_entry(&q_far[pos], c, to, ed.link);
+                            else s_overflow = 1;
+                        }
+                        if (is_tie) { // exact FP64 ties are rare: slow path
+                            const int pos = atomicAdd(&s_n_tie, 1);
+                            if (pos < a.tie_cap) tie_cand[pos] = to;
+                        }
+                    }
+                    __syncthreads(); // the chunk's shared arrays are reused
+                }
+#else
                 // Warp-convergent expansion: every lane owns one queue entry, UNR of its edges are relaxed per pass
                 // (edge loads, label loads and atomics of a pass are issued back to back), and the pushes of a pass
                 // are placed with ONE warp scan + one shared-memory atomic per queue instead of per-push atomics.
@@ -319,6 +424,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
                         PS(5, 0);
                     }
                 }
+#endif
 #ifdef SSSP_PROFILE
                 const long long pf_wait0 = clock64();
 #endif
@@ -470,6 +576,15 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
 void launch_sssp(const SsspLaunch& a, cudaStream_t st)
 {
     if (a.n_run == 0) return;
+    static bool carveout_set = false;
+    if (!carveout_set) { // the kernel needs < 5 KB of shared memory: give the rest of the 228 KB to L1 (edges, row pointers)
+        carveout_set = true;
+        const int pct = getenv("DTL_SSSP_CARVEOUT") ? atoi(getenv("DTL_SSSP_CARVEOUT")) : 0;
+        cudaFuncSetAttribute(sssp_kernel<128, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(sssp_kernel<256, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(sssp_kernel<512, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(sssp_kernel<1024, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     switch (a.block) {
     case 128: sssp_kernel<128, SSSP_UNR><<<a.grid, 128, 0, st>>>(a); break;
     case 512: sssp_kernel<512, SSSP_UNR><<<a.grid, 512, 0, st>>>(a); break;
