@@ -36,6 +36,7 @@ struct ForwardStar {
     int n_edges = 0;
     int* row_ptr = nullptr;   // [N+1]
     Edge* edges = nullptr;    // [E] forward-star order == reference scan order
+    int2* rows = nullptr;     // [N] {row_ptr[i], row_ptr[i+1]}: one 8-byte load per node
     int* in_ptr = nullptr;    // [N+1] reverse star (tie verification only)
     int2* in_edges = nullptr; // [E] {from node, forward edge index}
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
@@ -76,8 +77,8 @@ struct ColumnPool {     // column CSR with fixed slots per OD cell
 
 struct SsspStats { // accumulated on device
     unsigned long long relaxations, pops, rounds, tie_candidates, counted_edges, overflow, tied_origins, replayed;
-    unsigned long long prof[8]; // cycle buckets of thread 0 (only with -DSSSP_PROFILE): init, near, bookkeeping, far, barrier wait
-    unsigned long long stage[8]; // thread 0: entry, label+row, edges, labels, atomics, push
+    unsigned long long prof[8]; // [0] near-queue entries spilled to the far pile (shared-memory queue full)
+    unsigned long long stage[8]; // -DSSSP_PROFILE: thread 0's cycles per expansion stage
 };
 
 // ------------------------------------------------------------------ kernel launchers
@@ -103,6 +104,7 @@ int vdf_blocks(int n);
 struct SsspLaunch {
     int N;
     const int* row_ptr;
+    const int2* rows;        // [N] {row begin, row end}
     const Edge* edges;
     const int* in_ptr;
     const int2* in_edges;
@@ -117,10 +119,11 @@ struct SsspLaunch {
     int* pred_link;          // [n_tasks][N]
     int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes); -1 = work queue overflowed
     double delta;
-    // per-CTA workspace
+    // per-CTA workspace: two far piles of cap_far entries in global memory; the near queues live in shared memory
     QEntry* ws;              // [grid][ws_stride]
     size_t ws_stride;
-    int cap_near, cap_far;
+    int cap_smem;            // entries per shared-memory near queue (two buffers, 28 B per entry)
+    int cap_far;
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
     int* tie_cand;           // [grid][tie_cap]
     int tie_cap;
@@ -133,7 +136,7 @@ void launch_sssp(const SsspLaunch& a, cudaStream_t st);
 void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
                         cudaStream_t st);
 void launch_count_edges(const SsspLaunch& a, cudaStream_t st);
-void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);
+void sssp_occupancy(int block, int cap_smem, int* max_ctas_per_sm, int* regs);
 
 struct ColumnLaunch {
     int N, L, T, AT;

@@ -5,15 +5,22 @@
 // that all 148 SMs stay busy whatever the per-origin frontier sizes are.  Per origin the CTA runs a
 // near/far (delta-window) label-correcting search:
 //   * labels are FP64 bit patterns in HBM/L2 (one 8-byte word per node and origin); a relaxation is
-//     one 16-byte edge load, one 8-byte label load and -- only when it improves -- one 64-bit
-//     atomicMin (non-negative doubles order like unsigned integers), so any interleaving converges to
-//     the same Bellman fixed point the reference's serial deque reaches: min over paths of the
-//     left-to-right FP64 sum.  Labels are therefore bit-exact whatever the schedule.
-//   * the frontier is a queue of (node, label-at-push, link) entries compacted with warp-aggregated
-//     shared-memory counters; an entry is live iff its label still equals the node's label, so each
-//     label value of a node is expanded exactly once and the entry's link IS the tight predecessor.
-//   * entries beyond the current label window go to a far pile that is re-bucketed when the near
-//     queue drains (window = min live far label + delta).
+//     one 64-bit atomicMin (non-negative doubles order like unsigned integers), so any interleaving
+//     converges to the same Bellman fixed point the reference's serial deque reaches: min over paths of
+//     the left-to-right FP64 sum.  Labels are therefore bit-exact whatever the schedule.
+//   * the frontier (near queue of the current and of the next round) lives in SHARED MEMORY: entries
+//     {label-at-push, node, link, forward-star row, parent node}.  An entry is live iff its label still
+//     equals the node's label, so each label value of a node is expanded exactly once and the live
+//     entry's link IS the tight predecessor link.
+//   * the kernel is latency bound (a chain of dependent L2/HBM round trips per round), so the chain is
+//     kept at TWO trips: (1) the liveness load of label[node] is issued together with the node's edge
+//     loads (the row comes with the entry, fetched by the pusher in the shadow of its atomic);
+//     (2) the atomicMin of every out-edge, issued together with the row fetch of the head node.
+//   * the relaxation back to the node the entry came from is skipped when c > label-at-push: it can
+//     never improve (c > label-at-push >= the parent's label when it pushed >= its label now).
+//   * entries beyond the current label window go to a far pile in global memory that is re-bucketed
+//     when the near queue drains (window = min live far label + delta); a near queue that outgrows its
+//     shared-memory capacity spills to the same pile.
 // Predecessors: the reference's predecessor is the unique tight in-edge unless two different upstream
 // nodes tie exactly in FP64; every such tie is observed in-flight as an equality c == label[w]
 //  and recorded as a candidate, verified against the final labels over the reverse
@@ -29,18 +36,16 @@ namespace dtl {
 
 #define INF_BITS 0x430c6bf526340000ULL /* bit pattern of 1.0e15 */
 #define TIE_MARK (-7777)
-#ifndef SSSP_UNR
-#define SSSP_UNR 4 /* edges expanded together per queue entry (memory-level parallelism) */
+#ifndef SSSP_G
+#define SSSP_G 4 /* lanes per queue entry: every lane relaxes one out-edge of the entry's node per pass (power of two <= 32) */
 #endif
-#ifndef SSSP_ROWINFO
-#define SSSP_ROWINFO 0 /* 1: queue entries carry the node's forward-star row (loaded by the pusher, off the critical path) */
+#ifndef SSSP_PREFETCH
+#define SSSP_PREFETCH 1 /* the pusher prefetches the pushed node's forward-star row into L1 for the round that expands it */
 #endif
-#ifndef SSSP_EDGEPAR
-#define SSSP_EDGEPAR 0 /* 1: edge-parallel expansion (one edge per thread) instead of one queue entry per lane */
+#ifndef SSSP_MINB
+#define SSSP_MINB 4 /* register cap: resident CTAs per SM wanted at 256 threads (scaled with the block size) */
 #endif
-#ifndef SSSP_NOPRE
-#define SSSP_NOPRE 0 /* 1: no label pre-check load, every relaxation is one atomicMin */
-#endif
+#define SSSP_MIN_CTAS(BLOCK) ((SSSP_MINB * 256 / (BLOCK)) > 0 ? (SSSP_MINB * 256 / (BLOCK)) : 1)
 
 __device__ __forceinline__ double ld_label(const unsigned long long* p)
 {
@@ -64,11 +69,15 @@ __device__ __forceinline__ QEntry ld_entry(const QEntry* p)
     q.link = v.w;
     return q;
 }
-__device__ __forceinline__ void st_entry(QEntry* p, double lab, int node, int link)
+__device__ __forceinline__ int4 pack_entry(double lab, int node, int link)
 {
     int4 v;
     v.x = __double2loint(lab); v.y = __double2hiint(lab); v.z = node; v.w = link;
-    *reinterpret_cast<int4*>(p) = v;
+    return v;
+}
+__device__ __forceinline__ void st_entry(QEntry* p, double lab, int node, int link)
+{
+    *reinterpret_cast<int4*>(p) = pack_entry(lab, node, link);
 }
 
 // warp-aggregated slot allocation on a shared-memory counter (works under divergence)
@@ -101,41 +110,67 @@ __device__ __forceinline__ double block_min(double v, double* s_red)
     return r;
 }
 
-template <int BLOCK, int UNR>
-__global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
+// routing.h:677-689 for one tree: label = 1e15, predecessor = -9999 (16-byte stores where the alignment allows)
+template <int BLOCK>
+__device__ __forceinline__ void init_tree(unsigned long long* lab, int* pred, int N)
 {
-    __shared__ int s_task, s_n_next, s_n_far, s_n_far2, s_n_tie, s_overflow;
+    const int tid = threadIdx.x;
+    {
+        const int head = (int)(((uintptr_t)lab >> 3) & 1); // elements before the first 16-byte boundary
+        const int nv = (N - head) >> 1;
+        ulonglong2* v = reinterpret_cast<ulonglong2*>(lab + head);
+        const ulonglong2 x = make_ulonglong2(INF_BITS, INF_BITS);
+        for (int i = tid; i < nv; i += BLOCK) v[i] = x;
+        if (tid == 0) {
+            if (head) lab[0] = INF_BITS;
+            for (int i = head + 2 * nv; i < N; ++i) lab[i] = INF_BITS;
+        }
+    }
+    {
+        const int head = min(N, (int)((4 - (((uintptr_t)pred >> 2) & 3)) & 3));
+        const int nv = (N - head) >> 2;
+        int4* v = reinterpret_cast<int4*>(pred + head);
+        const int4 x = make_int4(DTL_NO_PRED, DTL_NO_PRED, DTL_NO_PRED, DTL_NO_PRED);
+        for (int i = tid; i < nv; i += BLOCK) v[i] = x;
+        if (tid == 0) {
+            for (int i = 0; i < head; ++i) pred[i] = DTL_NO_PRED;
+            for (int i = head + 4 * nv; i < N; ++i) pred[i] = DTL_NO_PRED;
+        }
+    }
+}
+
+template <int BLOCK, int G>
+__global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspLaunch a)
+{
+    extern __shared__ int4 s_dyn[];
+    __shared__ int s_task, s_cnt[3], s_n_far, s_n_far2, s_n_tie, s_overflow, s_spill;
     __shared__ double s_red[32];
-#if SSSP_EDGEPAR
-    __shared__ double s_lab[BLOCK];
-    __shared__ int s_rb[BLOCK], s_off[BLOCK + 1], s_wsum[BLOCK / 32];
-#endif
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int k = tid & (G - 1); // edge slot of this lane inside its group of G lanes (one group per queue entry)
     const int N = a.N;
-    QEntry* q_near = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    QEntry* q_next = q_near + a.cap_near;
-    QEntry* q_far = q_next + a.cap_near;
+    const int CAP = a.cap_smem;
+    // shared-memory near queues: two buffers (this round / next round) of CAP entries, structure of arrays
+    int4* const s_q = s_dyn;                                   // {label lo, label hi, node, link}
+    int2* const s_r = reinterpret_cast<int2*>(s_q + 2 * CAP);  // {row begin, row end} of the node's forward star
+    int* const s_p = reinterpret_cast<int*>(s_r + 2 * CAP);    // the node the entry was pushed from
+    QEntry* q_far = a.ws + (size_t)blockIdx.x * a.ws_stride;
     QEntry* q_far2 = q_far + a.cap_far;
-#if SSSP_ROWINFO
-    // side arrays {row begin, row end} of every queued node: the expansion need not wait for row_ptr
-    int2* r_near = reinterpret_cast<int2*>(q_far2 + a.cap_far);
-    int2* r_next = r_near + a.cap_near;
-    int2* r_far = r_next + a.cap_near;
-    int2* r_far2 = r_far + a.cap_far;
-#endif
     int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
-    unsigned long long c_relax = 0, c_pops = 0, c_rounds = 0;
+    unsigned c_relax = 0, c_pops = 0, c_rounds = 0;
+    if (tid == 0) s_spill = 0;
 #ifdef SSSP_PROFILE
-    long long pf_t = clock64(), pf_init = 0, pf_near = 0, pf_book = 0, pf_far = 0, pf_tie = 0;
-#define PF(bucket) do { const long long n_ = clock64(); bucket += n_ - pf_t; pf_t = n_; } while (0)
-    long long ps_t = 0, ps[6] = { 0, 0, 0, 0, 0, 0 };
-    // stage clock: the asm consumes `dep`, so it issues only once that value has arrived
-#define PS(k, dep) do { if (tid == 0) { long long n_; unsigned long long d_ = (unsigned long long)(dep); \
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "l"(d_) : "memory"); ps[k] += n_ - ps_t; ps_t = n_; } } while (0)
+    // thread 0's cycles per phase: [1] init [2] expansion [3] round barrier [4] re-bucketing [5] tie check; [6] re-bucketings [7] entries read
+    long long pf_t = clock64(), pf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#define PF(k_) do { const long long n_ = clock64(); pf[k_] += n_ - pf_t; pf_t = n_; } while (0)
+    // stage clocks of thread 0 inside the expansion; the asm consumes `dep`, so it issues only once that value has arrived:
+    // [0] entry read [1] edges [2] filter/add [3] atomics + rows [4] push [5] next edges issued; [6] passes
+    long long ps_t = 0, ps[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#define PS(k_, dep) do { if (tid == 0) { long long n_; unsigned long long d_ = (unsigned long long)(dep); \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "l"(d_) : "memory"); ps[k_] += n_ - ps_t; ps_t = n_; } } while (0)
 #else
-#define PF(bucket) do { } while (0)
-#define PS(k, dep) do { } while (0)
+#define PF(k_) do { } while (0)
+#define PS(k_, dep) do { } while (0)
 #endif
 
     for (;;) {
@@ -149,321 +184,173 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         unsigned long long* lab = a.labels + (size_t)task * N;
         int* pred = a.pred_link + (size_t)task * N;
 
-        for (int i = tid; i < N; i += BLOCK) { // routing.h:677-689
-            lab[i] = INF_BITS;
-            pred[i] = DTL_NO_PRED;
-        }
+        init_tree<BLOCK>(lab, pred, N);
+        const int2 orow = make_int2(__ldg(&a.row_ptr[origin]), __ldg(&a.row_ptr[origin + 1])); // a.rows hides connector-only rows
         if (tid == 0) {
-            s_n_next = 0; s_n_far = 0; s_n_far2 = 0; s_n_tie = 0; s_overflow = 0;
+            s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
+            s_n_far = 0; s_n_far2 = 0; s_n_tie = 0; s_overflow = 0;
             a.tie_nodes[task] = 0;
         }
         __syncthreads();
-        if (a.row_ptr[origin + 1] - a.row_ptr[origin] == 0) continue; // routing.h:692: origin has no out-link
+        if (orow.y - orow.x == 0) continue; // routing.h:692: origin has no out-link
         if (tid == 0) {
             lab[origin] = 0ULL; // +0.0
-            st_entry(&q_near[0], 0.0, origin, DTL_NO_PRED);
-#if SSSP_ROWINFO
-            r_near[0] = make_int2(a.row_ptr[origin], a.row_ptr[origin + 1]);
-#endif
+            s_q[0] = pack_entry(0.0, origin, DTL_NO_PRED);
+            s_r[0] = orow;
+            s_p[0] = -1;
         }
         __syncthreads();
-        PF(pf_init);
+        PF(1);
         int n_near = 1;
+        int buf = 0; // near-queue buffer read this round
+        int ci = 0;  // s_cnt[ci] counted this round's entries, pushes count into s_cnt[ci+1], s_cnt[ci+2] is cleared
         double thr = a.delta;
 
         for (;;) {
             while (n_near > 0) {
-#if SSSP_EDGEPAR
-                // Edge-parallel expansion: phase A validates a chunk of BLOCK queue entries (one per thread) and scans their
-                // degrees; phase B gives every thread ONE edge of the chunk, so all lanes relax and pushes are ballots.
-                for (int base = 0; base < n_near; base += BLOCK) {
-                    const int i = base + tid;
-                    int deg = 0;
+                const int ci1 = ci == 2 ? 0 : ci + 1;
+                const int ci2 = ci1 == 2 ? 0 : ci1 + 1;
+                const int in0 = buf * CAP, out0 = (buf ^ 1) * CAP; // first slot of the queue read / written this round
+                // Expansion: a group of G lanes owns one queue entry, every lane one of its edges (a second pass only for nodes
+                // with more than G out-edges).  The chain of a pass is: entry from shared memory -> edge (L1: prefetched by the
+                // pusher) -> atomicMin round trip -> ballot-placed push.  The liveness of the entry is NOT waited for: relaxing
+                // with a superseded label is harmless (it is a real path cost), only the predecessor store needs it.
+                for (int base = 0; base < n_near; base += BLOCK / G) {
+                    if (base + (tid & ~31) / G >= n_near) continue; // no entry for this warp
+                    const int i = base + tid / G;
+                    double qlab = 0.0;
+                    int node = 0, qlink = DTL_NO_PRED, parent = -1, e0 = 0, re = 0;
+#ifdef SSSP_PROFILE
+                    if (tid == 0) ps_t = clock64();
+#endif
                     if (i < n_near) {
-                        const QEntry q = ld_entry(&q_near[i]);
-                        const double cur = ld_label(&lab[q.node]);
-                        if (!(cur < q.lab)) { // else: a better label was pushed later, that entry expands the node
-                            const int rb = __ldg(&a.row_ptr[q.node]), re = __ldg(&a.row_ptr[q.node + 1]);
-                            pred[q.node] = q.link; // the entry that carries the current label names the tight link
-                            ++c_pops;
-                            deg = re - rb;
-                            s_lab[tid] = q.lab;
-                            s_rb[tid] = rb;
-                        }
+                        const int4 qv = s_q[in0 + i];
+                        const int2 rr = s_r[in0 + i];
+                        parent = s_p[in0 + i];
+                        qlab = __hiloint2double(qv.y, qv.x); node = qv.z; qlink = qv.w;
+                        e0 = rr.x + k; re = rr.y;
                     }
-                    int incl = deg;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += v;
-                    }
-                    if (lane == 31) s_wsum[tid >> 5] = incl;
-                    __syncthreads();
-                    int wbase = 0;
-#pragma unroll
-                    for (int w = 0; w < BLOCK / 32; ++w)
-                        if (w < (tid >> 5)) wbase += s_wsum[w];
-                    s_off[tid] = wbase + incl - deg;
-                    if (tid == BLOCK - 1) s_off[BLOCK] = wbase + incl;
-                    __syncthreads();
-                    const int total = s_off[BLOCK];
-                    for (int eb = 0; eb < total; eb += BLOCK) {
-                        const int e = eb + tid;
-                        bool ok = e < total;
-                        int lo = 0;
-                        if (ok) { // owner entry: last j with s_off[j] <= e
-                            int hi = BLOCK;
-#pragma unroll
-                            for (int step = 0; step < 10; ++step) {
-                                const int mid = (lo + hi) >> 1;
-                                if (hi - lo > 1) { if (s_off[mid] <= e) lo = mid; else hi = mid; }
-                            }
-                        }
-                        Edge ed;
-                        ed.cost = 0.0; ed.to = 0; ed.link = 0;
-                        double qlab = 0.0;
-                        if (ok) {
-                            ed = ld_edge(&a.edges[s_rb[lo] + (e - s_off[lo])]);
-                            qlab = s_lab[lo];
-                        }
+                    PS(0, node + e0 + parent);
+                    unsigned long long cur = 0ULL;
+                    const bool head = k == 0 && i < n_near;
+                    if (head) cur = __ldcg(&lab[node]); // consumed after the atomics have returned
+                    Edge ed;
+                    ed.cost = 0.0; ed.to = 0; ed.link = 0;
+                    if (e0 < re) ed = ld_edge(&a.edges[e0]);
+                    PS(1, ed.to);
+                    bool first = true;
+                    while (__any_sync(0xffffffffu, e0 < re)) {
+                        bool ok = e0 < re;
                         int to = ed.to;
                         if (ok && to < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
                             to &= 0x7fffffff;
                             if (__ldg(&a.link_tag[ed.link]) != zone) ok = false; // routing.h:779-786
                         }
-                        bool is_near = false, is_far = false, is_tie = false;
                         const double c = qlab + ed.cost; // routing.h:804
-                        if (ok) {
+                        if (to == parent && c > qlab) ok = false; // back to where the entry came from: cannot improve
+                        const bool near_c = c < thr;
+                        PS(2, ok + near_c + to);
+                        // the one long trip: the atomic, and in its shadow the forward-star row of a head that may enter the near queue
+                        const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+                        unsigned long long old = 0ULL;
+                        int2 prow = make_int2(0, 0);
+                        if (ok) { // routing.h:816
                             ++c_relax;
-                            const double lw = ld_label(&lab[to]);
-                            if (c < lw) {             // routing.h:816
-                                const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
-                                const unsigned long long old = atomicMin(&lab[to], cb);
-                                if (old > cb) { is_near = c < thr; is_far = !is_near; }
-                                else if (old == cb && to != origin) is_tie = true;
-                            } else if (c == lw && to != origin) is_tie = true;
+                            old = atomicMin(&lab[to], cb);
+                            if (near_c) prow = __ldg(&a.rows[to]);
                         }
+                        const bool imp = ok && old > cb;
+                        const bool is_near = imp && near_c, is_far = imp && !near_c;
+                        PS(3, imp + prow.x);
                         const unsigned nm = __ballot_sync(0xffffffffu, is_near), fm = __ballot_sync(0xffffffffu, is_far);
-                        int bn = 0, bf = 0;
-                        if (lane == 0) {
-                            if (nm) bn = atomicAdd(&s_n_next, __popc(nm));
-                            if (fm) bf = atomicAdd(&s_n_far, __popc(fm));
+                        if (nm | fm) {
+                            int bn = 0, bf = 0;
+                            if (lane == 0) {
+                                if (nm) bn = atomicAdd(&s_cnt[ci1], __popc(nm));
+                                if (fm) bf = atomicAdd(&s_n_far, __popc(fm));
+                            }
+                            bn = __shfl_sync(0xffffffffu, bn, 0);
+                            bf = __shfl_sync(0xffffffffu, bf, 0);
+                            const unsigned lt = (1u << lane) - 1;
+                            if (is_near) {
+                                const int pos = bn + __popc(nm & lt);
+                                if (pos < CAP) {
+                                    s_q[out0 + pos] = pack_entry(c, to, ed.link);
+                                    s_r[out0 + pos] = prow;
+                                    s_p[out0 + pos] = node;
+#if SSSP_PREFETCH
+                                    if (prow.y > prow.x) {
+                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + prow.x));
+                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + prow.y - 1));
+                                    }
+#endif
+                                } else { // shared-memory queue full: the entry waits in the far pile for the next re-bucketing
+                                    const int pf_ = atomicAdd(&s_n_far, 1);
+                                    if (pf_ < a.cap_far) st_entry(&q_far[pf_], c, to, ed.link);
+                                    else s_overflow = 1;
+                                    atomicAdd(&s_spill, 1);
+                                }
+                            } else if (is_far) {
+                                const int pos = bf + __popc(fm & lt);
+                                if (pos < a.cap_far) st_entry(&q_far[pos], c, to, ed.link);
+                                else s_overflow = 1;
+                            }
                         }
-                        bn = __shfl_sync(0xffffffffu, bn, 0);
-                        bf = __shfl_sync(0xffffffffu, bf, 0);
-                        const unsigned lt = (1u << lane) - 1;
-                        if (is_near) {
-                            const int pos = bn + __popc(nm & lt);
-                            if (pos < a.cap_near) st_entry(&q_next[pos], c, to, ed.link);
-                            else s_overflow = 1;
-                        } else if (is_far) {
-                            const int pos = bf + __popc(fm & lt);
-                            if (pos < a.cap_far) st_entry(&q_far[pos], c, to, ed.link);
-                            else s_overflow = 1;
-                        }
-                        if (is_tie) { // exact FP64 ties are rare: slow path
+                        if (ok && old == cb && to != origin) { // exact FP64 ties are rare: slow path
                             const int pos = atomicAdd(&s_n_tie, 1);
                             if (pos < a.tie_cap) tie_cand[pos] = to;
                         }
-                    }
-                    __syncthreads(); // the chunk's shared arrays are reused
-                }
-#else
-                // Warp-convergent expansion: every lane owns one queue entry, UNR of its edges are relaxed per pass
-                // (edge loads, label loads and atomics of a pass are issued back to back), and the pushes of a pass
-                // are placed with ONE warp scan + one shared-memory atomic per queue instead of per-push atomics.
-                for (int base = 0; base < n_near; base += BLOCK) {
-                    const int i = base + tid;
-                    bool active = i < n_near;
-                    QEntry q;
-                    q.lab = 0.0; q.node = 0; q.link = DTL_NO_PRED;
-                    int rb = 0, re = 0;
+                        if (first) {
+                            first = false;
+                            // the entry that carries the current label names the tight link (a superseded entry leaves it to its successor)
+                            if (head && !(cur < (unsigned long long)__double_as_longlong(qlab))) {
+                                pred[node] = qlink;
+                                ++c_pops;
+                            }
+                        }
+                        PS(4, 0);
+                        e0 += G;
+                        if (e0 < re) ed = ld_edge(&a.edges[e0]);
+                        PS(5, ed.to);
 #ifdef SSSP_PROFILE
-                    if (tid == 0) ps_t = clock64();
+                        ps[6] += 1;
 #endif
-                    if (active) {
-                        q = ld_entry(&q_near[i]);
-#if SSSP_ROWINFO
-                        const int2 rr = r_near[i];
-                        rb = rr.x; re = rr.y;
-#endif
-                        PS(0, q.node);
-                        const double cur = ld_label(&lab[q.node]);
-#if !SSSP_ROWINFO
-                        rb = __ldg(&a.row_ptr[q.node]);
-                        re = __ldg(&a.row_ptr[q.node + 1]);
-#endif
-                        PS(1, __double_as_longlong(cur) + rb + re);
-                        if (cur < q.lab) active = false; // a better label was pushed later: that entry expands the node
                     }
-                    if (active) {
-                        pred[q.node] = q.link;           // the entry that carries the current label names the tight link
+                    if (first && head && !(cur < (unsigned long long)__double_as_longlong(qlab))) { // entry without usable out-edges
+                        pred[node] = qlink;
                         ++c_pops;
-                    } else re = rb;
-                    for (int e0 = rb; __any_sync(0xffffffffu, e0 < re); e0 += UNR) {
-                        Edge ed[UNR];
-                        bool ok[UNR];
-                        int to[UNR];
-                        double c[UNR], lw[UNR];
-                        unsigned long long old[UNR];
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            ok[j] = e0 + j < re;
-                            if (ok[j]) ed[j] = ld_edge(&a.edges[e0 + j]);
-                        }
-                        PS(2, (ok[0] ? ed[0].to : 0) + (ok[UNR - 1] ? ed[UNR - 1].to : 0));
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            to[j] = 0; c[j] = 0.0; lw[j] = 0.0;
-                            if (!ok[j]) continue;
-                            to[j] = ed[j].to;
-                            if (to[j] < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
-                                to[j] &= 0x7fffffff;
-                                if (__ldg(&a.link_tag[ed[j].link]) != zone) ok[j] = false; // routing.h:779-786
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            if (!ok[j]) continue;
-                            ++c_relax;
-                            c[j] = q.lab + ed[j].cost; // routing.h:804
-#if !SSSP_NOPRE
-                            lw[j] = ld_label(&lab[to[j]]);
-#else
-                            lw[j] = DTL_MAX_LABEL_COST * 2; // no pre-check: the atomic below decides
-#endif
-                        }
-                        PS(3, __double_as_longlong(lw[0]) + __double_as_longlong(lw[UNR - 1]));
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            old[j] = 0ULL;
-#if defined(SSSP_EXP_RED)
-                            if (ok[j] && c[j] < lw[j]) { // experiment: fire-and-forget min, push decided by the pre-check
-                                atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
-                                old[j] = ~0ULL;
-                            }
-#elif defined(SSSP_EXP_PLAIN)
-                            if (ok[j] && c[j] < lw[j]) { // experiment: racy plain store
-                                lab[to[j]] = (unsigned long long)__double_as_longlong(c[j]);
-                                old[j] = ~0ULL;
-                            }
-#else
-                            if (ok[j] && c[j] < lw[j])  // routing.h:816
-                                old[j] = atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
-#endif
-                        }
-#if SSSP_ROWINFO
-                        int2 prow[UNR];
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            prow[j] = make_int2(0, 0);
-                            if (ok[j] && c[j] < lw[j]) { prow[j].x = __ldg(&a.row_ptr[to[j]]); prow[j].y = __ldg(&a.row_ptr[to[j] + 1]); }
-                        }
-#endif
-                        PS(4, old[0] + old[UNR - 1]);
-                        // classify: bit j of near_m / far_m / tie_m
-                        unsigned near_m = 0, far_m = 0, tie_m = 0;
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            if (!ok[j]) continue;
-                            const unsigned long long cb = (unsigned long long)__double_as_longlong(c[j]);
-                            if (c[j] < lw[j]) {
-                                if (old[j] > cb) { if (c[j] < thr) near_m |= 1u << j; else far_m |= 1u << j; }
-                                else if (old[j] == cb && to[j] != origin) tie_m |= 1u << j;
-                            } else if (c[j] == lw[j] && to[j] != origin) tie_m |= 1u << j;
-#if SSSP_ROWINFO && SSSP_NOPRE
-                            if (!((near_m | far_m) & (1u << j))) prow[j] = make_int2(0, 0);
-#endif
-                        }
-                        // one inclusive scan carries both counts (near in the low half, far in the high half)
-                        const int mine = __popc(near_m) | (__popc(far_m) << 16);
-                        int incl = mine;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        const int total = __shfl_sync(0xffffffffu, incl, 31);
-                        int base_near = 0, base_far = 0;
-                        if (lane == 31) {
-                            if (total & 0xffff) base_near = atomicAdd(&s_n_next, total & 0xffff);
-                            if (total >> 16) base_far = atomicAdd(&s_n_far, total >> 16);
-                        }
-                        base_near = __shfl_sync(0xffffffffu, base_near, 31);
-                        base_far = __shfl_sync(0xffffffffu, base_far, 31);
-                        int pos_near = base_near + ((incl - mine) & 0xffff);
-                        int pos_far = base_far + ((incl - mine) >> 16);
-#pragma unroll
-                        for (int j = 0; j < UNR; ++j) {
-                            if (near_m & (1u << j)) {
-                                if (pos_near < a.cap_near) {
-                                    st_entry(&q_next[pos_near], c[j], to[j], ed[j].link);
-#if SSSP_ROWINFO
-                                    r_next[pos_near] = prow[j];
-#endif
-                                } else s_overflow = 1;
-                                ++pos_near;
-                            } else if (far_m & (1u << j)) {
-                                if (pos_far < a.cap_far) {
-                                    st_entry(&q_far[pos_far], c[j], to[j], ed[j].link);
-#if SSSP_ROWINFO
-                                    r_far[pos_far] = prow[j];
-#endif
-                                } else s_overflow = 1;
-                                ++pos_far;
-                            }
-                        }
-                        if (tie_m) { // exact FP64 ties are rare: slow path
-#pragma unroll
-                            for (int j = 0; j < UNR; ++j)
-                                if (tie_m & (1u << j)) {
-                                    const int pos = atomicAdd(&s_n_tie, 1);
-                                    if (pos < a.tie_cap) tie_cand[pos] = to[j];
-                                }
-                        }
-                        PS(5, 0);
                     }
                 }
-#endif
 #ifdef SSSP_PROFILE
-                const long long pf_wait0 = clock64();
+                pf[7] += n_near;
 #endif
-                __syncthreads();
-#ifdef SSSP_PROFILE
-                pf_tie += clock64() - pf_wait0; // reuse: barrier wait of thread 0 after its own work
-#endif
-                PF(pf_near);
-                n_near = min(s_n_next, a.cap_near);
-                const int n_far_now = s_n_far;
-                __syncthreads();
-                if (tid == 0) s_n_next = 0;
-                QEntry* t = q_near; q_near = q_next; q_next = t;
-#if SSSP_ROWINFO
-                { int2* tr = r_near; r_near = r_next; r_next = tr; }
-#endif
+                PF(2);
+                if (tid == 0) s_cnt[ci2] = 0; // last read before the previous barrier, pushed into from the round after next
+                // the one barrier of a round; thread 0's view of the far pile may miss this round's pushes of slower warps
+                // (accounted for in the worst-case capacity), but every thread gets the same decision
+                const int compact = __syncthreads_or(tid == 0 && s_n_far > a.far_trigger);
+                PF(3);
+                ci = ci1;
+                buf ^= 1;
+                n_near = min(s_cnt[ci], CAP);
                 ++c_rounds;
-                if (n_far_now > a.far_trigger) {
+                if (compact) {
                     // far pile close to capacity: drop dead entries (at most one live entry per node survives)
-                    const int nf = min(n_far_now, a.cap_far);
+                    __syncthreads(); // every thread has read its n_near; nobody pushes any more
+                    const int nf = min(s_n_far, a.cap_far);
+                    __syncthreads();
                     for (int i = tid; i < nf; i += BLOCK) {
                         const QEntry q = ld_entry(&q_far[i]);
                         if (ld_label(&lab[q.node]) == q.lab) {
                             const int pos = agg_inc(&s_n_far2);
                             st_entry(&q_far2[pos], q.lab, q.node, q.link);
-#if SSSP_ROWINFO
-                            r_far2[pos] = r_far[i];
-#endif
                         }
                     }
                     __syncthreads();
                     if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; }
                     QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
-#if SSSP_ROWINFO
-                    { int2* tr = r_far; r_far = r_far2; r_far2 = tr; }
-#endif
+                    __syncthreads();
                 }
-                __syncthreads();
-                PF(pf_book);
             }
             // near queue drained: open the next label window from the far pile
             const int n_far = min(s_n_far, a.cap_far);
@@ -479,36 +366,38 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             for (int i = tid; i < n_far; i += BLOCK) {
                 const QEntry q = ld_entry(&q_far[i]);
                 if (ld_label(&lab[q.node]) == q.lab) {
-                    if (q.lab < thr) {
-                        const int pos = agg_inc(&s_n_next);
-                        if (pos < a.cap_near) {
-                            st_entry(&q_near[pos], q.lab, q.node, q.link);
-#if SSSP_ROWINFO
-                            r_near[pos] = r_far[i];
+                    int pos = CAP;
+                    if (q.lab < thr) pos = agg_inc(&s_cnt[ci]);
+                    if (pos < CAP) {
+                        const int2 row = __ldg(&a.rows[q.node]);
+                        s_q[buf * CAP + pos] = pack_entry(q.lab, q.node, q.link);
+                        s_r[buf * CAP + pos] = row;
+                        s_p[buf * CAP + pos] = q.link >= 0 ? __ldg(&a.link_from[q.link]) : -1;
+#if SSSP_PREFETCH
+                        if (row.y > row.x) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + row.x));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + row.y - 1));
+                        }
 #endif
-                        } else s_overflow = 1;
-                    } else {
-                        const int pos = agg_inc(&s_n_far2);
-                        st_entry(&q_far2[pos], q.lab, q.node, q.link);
-#if SSSP_ROWINFO
-                        r_far2[pos] = r_far[i];
-#endif
+                    } else { // beyond the window, or the shared-memory queue is full: stays in the pile
+                        const int pf_ = agg_inc(&s_n_far2);
+                        st_entry(&q_far2[pf_], q.lab, q.node, q.link);
                     }
                 }
             }
             __syncthreads();
-            n_near = min(s_n_next, a.cap_near);
+            n_near = min(s_cnt[ci], CAP);
             __syncthreads();
-            if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; s_n_next = 0; }
+            if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; }
             QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
-#if SSSP_ROWINFO
-            { int2* tr = r_far; r_far = r_far2; r_far2 = tr; }
-#endif
             ++c_rounds;
             __syncthreads();
-            PF(pf_far);
+#ifdef SSSP_PROFILE
+            pf[6] += 1;
+#endif
+            PF(4);
         }
-        PF(pf_far);
+        PF(4);
 
         // ---- verify tie candidates against the final labels (reverse star) ----
         __syncthreads();
@@ -544,10 +433,10 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
             }
         }
         __syncthreads();
-        PF(pf_tie);
+        PF(5);
         if (tid == 0) {
             atomicAdd(&a.stats->tie_candidates, (unsigned long long)n_tie);
-            if (s_overflow) { // a queue was too small: the tree is incomplete, the host re-runs it with worst-case queues
+            if (s_overflow) { // the far pile was too small: the tree is incomplete, the host re-runs it with worst-case capacity
                 atomicAdd(&a.stats->overflow, 1ULL);
                 a.tie_nodes[task] = -1;
             }
@@ -559,49 +448,50 @@ __global__ void __launch_bounds__(BLOCK) sssp_kernel(SsspLaunch a)
         c_pops += __shfl_xor_sync(0xffffffffu, c_pops, o);
     }
     if ((tid & 31) == 0) {
-        atomicAdd(&a.stats->relaxations, c_relax);
-        atomicAdd(&a.stats->pops, c_pops);
+        atomicAdd(&a.stats->relaxations, (unsigned long long)c_relax);
+        atomicAdd(&a.stats->pops, (unsigned long long)c_pops);
     }
-    if (tid == 0) atomicAdd(&a.stats->rounds, c_rounds);
-#ifdef SSSP_PROFILE
+    __syncthreads();
     if (tid == 0) {
-        atomicAdd(&a.stats->prof[0], (unsigned long long)pf_init); atomicAdd(&a.stats->prof[1], (unsigned long long)pf_near);
-        atomicAdd(&a.stats->prof[2], (unsigned long long)pf_book); atomicAdd(&a.stats->prof[3], (unsigned long long)pf_far);
-        atomicAdd(&a.stats->prof[4], (unsigned long long)pf_tie);
-        for (int k = 0; k < 6; ++k) atomicAdd(&a.stats->stage[k], (unsigned long long)ps[k]);
-    }
+        atomicAdd(&a.stats->rounds, (unsigned long long)c_rounds);
+        if (s_spill) atomicAdd(&a.stats->prof[0], (unsigned long long)s_spill);
+#ifdef SSSP_PROFILE
+        for (int j = 1; j < 8; ++j) atomicAdd(&a.stats->prof[j], (unsigned long long)pf[j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(&a.stats->stage[j], (unsigned long long)ps[j]);
 #endif
+    }
+}
+
+static size_t sssp_smem_bytes(int cap_smem) { return (size_t)2 * cap_smem * (sizeof(int4) + sizeof(int2) + sizeof(int)); }
+
+template <int BLOCK>
+static cudaError_t sssp_prepare(size_t smem)
+{
+    return cudaFuncSetAttribute(sssp_kernel<BLOCK, SSSP_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 void launch_sssp(const SsspLaunch& a, cudaStream_t st)
 {
     if (a.n_run == 0) return;
-    static bool carveout_set = false;
-    if (!carveout_set) { // the kernel needs < 5 KB of shared memory: give the rest of the 228 KB to L1 (edges, row pointers)
-        carveout_set = true;
-        const int pct = getenv("DTL_SSSP_CARVEOUT") ? atoi(getenv("DTL_SSSP_CARVEOUT")) : 0;
-        cudaFuncSetAttribute(sssp_kernel<128, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(sssp_kernel<256, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(sssp_kernel<512, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(sssp_kernel<1024, SSSP_UNR>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
+    const size_t smem = sssp_smem_bytes(a.cap_smem);
     switch (a.block) {
-    case 128: sssp_kernel<128, SSSP_UNR><<<a.grid, 128, 0, st>>>(a); break;
-    case 512: sssp_kernel<512, SSSP_UNR><<<a.grid, 512, 0, st>>>(a); break;
-    case 1024: sssp_kernel<1024, SSSP_UNR><<<a.grid, 1024, 0, st>>>(a); break;
-    default: sssp_kernel<256, SSSP_UNR><<<a.grid, 256, 0, st>>>(a); break;
+    case 128: sssp_prepare<128>(smem); sssp_kernel<128, SSSP_G><<<a.grid, 128, smem, st>>>(a); break;
+    case 512: sssp_prepare<512>(smem); sssp_kernel<512, SSSP_G><<<a.grid, 512, smem, st>>>(a); break;
+    case 1024: sssp_prepare<1024>(smem); sssp_kernel<1024, SSSP_G><<<a.grid, 1024, smem, st>>>(a); break;
+    default: sssp_prepare<256>(smem); sssp_kernel<256, SSSP_G><<<a.grid, 256, smem, st>>>(a); break;
     }
 }
 
-void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs)
+void sssp_occupancy(int block, int cap_smem, int* max_ctas_per_sm, int* regs)
 {
     int n = 0;
     cudaFuncAttributes fa{};
+    const size_t smem = sssp_smem_bytes(cap_smem);
     switch (block) {
-    case 128: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<128, SSSP_UNR>, 128, 0); cudaFuncGetAttributes(&fa, sssp_kernel<128, SSSP_UNR>); break;
-    case 512: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<512, SSSP_UNR>, 512, 0); cudaFuncGetAttributes(&fa, sssp_kernel<512, SSSP_UNR>); break;
-    case 1024: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<1024, SSSP_UNR>, 1024, 0); cudaFuncGetAttributes(&fa, sssp_kernel<1024, SSSP_UNR>); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<256, SSSP_UNR>, 256, 0); cudaFuncGetAttributes(&fa, sssp_kernel<256, SSSP_UNR>); break;
+    case 128: sssp_prepare<128>(smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<128, SSSP_G>, 128, smem); cudaFuncGetAttributes(&fa, sssp_kernel<128, SSSP_G>); break;
+    case 512: sssp_prepare<512>(smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<512, SSSP_G>, 512, smem); cudaFuncGetAttributes(&fa, sssp_kernel<512, SSSP_G>); break;
+    case 1024: sssp_prepare<1024>(smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<1024, SSSP_G>, 1024, smem); cudaFuncGetAttributes(&fa, sssp_kernel<1024, SSSP_G>); break;
+    default: sssp_prepare<256>(smem); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sssp_kernel<256, SSSP_G>, 256, smem); cudaFuncGetAttributes(&fa, sssp_kernel<256, SSSP_G>); break;
     }
     if (max_ctas_per_sm) *max_ctas_per_sm = n;
     if (regs) *regs = fa.numRegs;
