@@ -119,10 +119,11 @@ struct SsspLaunch {
     int* pred_link;          // [n_tasks][N]
     int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes); -1 = work queue overflowed
     double delta;
-    // per-CTA workspace: two far piles of cap_far entries in global memory; the near queues live in shared memory
+    // per-CTA workspace: two far piles of cap_far entries in global memory; the round queues live in shared memory
     QEntry* ws;              // [grid][ws_stride]
     size_t ws_stride;
-    int cap_smem;            // entries per shared-memory near queue (two buffers, 28 B per entry)
+    int cap_items;           // edge items per shared-memory round queue (two buffers, 32 B per item)
+    int cap_heads;           // head entries per shared-memory round queue (two buffers, 16 B per head)
     int cap_far;
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
     int* tie_cand;           // [grid][tie_cap]
@@ -136,7 +137,7 @@ void launch_sssp(const SsspLaunch& a, cudaStream_t st);
 void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
                         cudaStream_t st);
 void launch_count_edges(const SsspLaunch& a, cudaStream_t st);
-void sssp_occupancy(int block, int cap_smem, int* max_ctas_per_sm, int* regs);
+void sssp_occupancy(int block, int cap_items, int cap_heads, int* max_ctas_per_sm, int* regs);
 
 struct ColumnLaunch {
     int N, L, T, AT;

@@ -127,7 +127,7 @@ struct dtl_engine {
     int sssp_block = 256, sssp_grid = 0;
     QEntry* d_ws = nullptr;
     size_t ws_stride = 0;
-    int cap_smem = 0, cap_far = 0, tie_cap = 4096;
+    int cap_items = 0, cap_heads = 0, cap_far = 0, tie_cap = 4096;
     // worst-case queues for the few trees whose frontier outgrows the regular ones (re-run path)
     QEntry* d_ws_big = nullptr;
     size_t ws_big_stride = 0;
@@ -349,7 +349,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;
     a.tie_nodes = e->d_tie_nodes;
     a.delta = f.delta;
-    a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_smem = e->cap_smem; a.cap_far = e->cap_far;
+    a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_items = e->cap_items; a.cap_heads = e->cap_heads; a.cap_far = e->cap_far;
     a.far_trigger = e->cap_far / 2;
     a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
     a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
@@ -641,11 +641,14 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_tie_nodes, e->batch_tasks)) return -1;
     e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 256;
     if (e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 256;
-    // near queues live in shared memory (28 B per entry, two buffers); entries that do not fit spill to the far pile
-    e->cap_smem = e->sssp_block >= 512 ? 1024 : 512;
-    if (const char* env = getenv("DTL_SSSP_SMEM_CAP")) e->cap_smem = std::max(32, std::min(4000, atoi(env)));
+    // round queues live in shared memory (32 B per edge item, 16 B per head, two buffers); pushes that do not fit spill
+    // to the far pile
+    e->cap_items = e->sssp_block >= 512 ? 1536 : 768;
+    if (const char* env = getenv("DTL_SSSP_ICAP")) e->cap_items = std::max(64, std::min(3000, atoi(env)));
+    e->cap_heads = std::max(32, e->cap_items / 3);
+    if (const char* env = getenv("DTL_SSSP_HCAP")) e->cap_heads = std::max(32, std::min(3000, atoi(env)));
     int occ = 0, regs = 0;
-    sssp_occupancy(e->sssp_block, e->cap_smem, &occ, &regs);
+    sssp_occupancy(e->sssp_block, e->cap_items, e->cap_heads, &occ, &regs);
     if (occ <= 0) { set_err("SSSP kernel cannot be resident on this device (built for sm_100a)"); return -1; }
     int per_sm = o.sssp_ctas_per_sm > 0 ? std::min(o.sssp_ctas_per_sm, occ) : occ;
     // worst-case bound of the far pile (DESIGN.md "K1 queues"): a compacted pile holds at most N live entries, a round
@@ -1138,7 +1141,7 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
                                 "entries read %.3g rounds %.3g\n", d[1], d[2], d[3], d[4], d[5], d[6], d[7], (double)(s1.rounds - s0.rounds));
             for (int k = 0; k < 8; ++k) d[k] = (double)(s1.stage[k] - s0.stage[k]);
             if (d[1] > 0)
-                fprintf(stderr, "sssp thread-0 stage cycles: entry %.3g label+edges %.3g filter %.3g atomics+rows %.3g push %.3g next edges %.3g | "
+                fprintf(stderr, "sssp thread-0 stage cycles: item %.3g (unused) %.3g filter %.3g atomic+row %.3g push %.3g heads+wait %.3g | "
                                 "passes %.3g\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6]);
         }
     }
