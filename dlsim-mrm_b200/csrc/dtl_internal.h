@@ -77,8 +77,8 @@ struct ColumnPool {     // column CSR with fixed slots per OD cell
 
 struct SsspStats { // accumulated on device
     unsigned long long relaxations, pops, rounds, tie_candidates, counted_edges, overflow, tied_origins, replayed;
-    unsigned long long prof[8]; // [0] near-queue entries spilled to the far pile (shared-memory queue full)
-    unsigned long long stage[8]; // -DSSSP_PROFILE: thread 0's cycles per expansion stage
+    unsigned long long prof[8]; // unused
+    unsigned long long stage[8]; // unused
 };
 
 // ------------------------------------------------------------------ kernel launchers
@@ -119,12 +119,10 @@ struct SsspLaunch {
     int* pred_link;          // [n_tasks][N]
     int* tie_nodes;          // [n_tasks] out: verified tie nodes (>= 2 tight upstream nodes); -1 = work queue overflowed
     double delta;
-    // per-CTA workspace: two far piles of cap_far entries in global memory; the round queues live in shared memory
+    // per-CTA workspace: two near queues of cap_near entries and two far piles of cap_far entries
     QEntry* ws;              // [grid][ws_stride]
     size_t ws_stride;
-    int cap_items;           // edge items per shared-memory round queue (two buffers, 32 B per item)
-    int cap_heads;           // head entries per shared-memory round queue (two buffers, 16 B per head)
-    int cap_far;
+    int cap_near, cap_far;
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
     int* tie_cand;           // [grid][tie_cap]
     int tie_cap;
@@ -137,7 +135,7 @@ void launch_sssp(const SsspLaunch& a, cudaStream_t st);
 void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
                         cudaStream_t st);
 void launch_count_edges(const SsspLaunch& a, cudaStream_t st);
-void sssp_occupancy(int block, int cap_items, int cap_heads, int* max_ctas_per_sm, int* regs);
+void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);
 
 struct ColumnLaunch {
     int N, L, T, AT;

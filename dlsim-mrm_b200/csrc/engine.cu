@@ -127,11 +127,11 @@ struct dtl_engine {
     int sssp_block = 256, sssp_grid = 0;
     QEntry* d_ws = nullptr;
     size_t ws_stride = 0;
-    int cap_items = 0, cap_heads = 0, cap_far = 0, tie_cap = 4096;
+    int cap_near = 0, cap_far = 0, tie_cap = 4096;
     // worst-case queues for the few trees whose frontier outgrows the regular ones (re-run path)
     QEntry* d_ws_big = nullptr;
     size_t ws_big_stride = 0;
-    int cap_far_big = 0, big_grid = 8;
+    int cap_near_big = 0, cap_far_big = 0, big_grid = 8;
     int* d_ws_big_tie = nullptr;
     int* d_rerun_list = nullptr;
     int* d_tie_cand = nullptr;
@@ -349,7 +349,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;
     a.tie_nodes = e->d_tie_nodes;
     a.delta = f.delta;
-    a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_items = e->cap_items; a.cap_heads = e->cap_heads; a.cap_far = e->cap_far;
+    a.ws = e->d_ws; a.ws_stride = e->ws_stride; a.cap_near = e->cap_near; a.cap_far = e->cap_far;
     a.far_trigger = e->cap_far / 2;
     a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
     a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
@@ -381,7 +381,7 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
         CK(cudaMemcpyAsync(e->d_rerun_list, rerun.data(), sizeof(int) * rerun.size(), cudaMemcpyHostToDevice, e->st));
         SsspLaunch b = a;
         b.task_list = e->d_rerun_list; b.n_run = (int)rerun.size();
-        b.ws = e->d_ws_big; b.ws_stride = e->ws_big_stride; b.cap_far = e->cap_far_big;
+        b.ws = e->d_ws_big; b.ws_stride = e->ws_big_stride; b.cap_near = e->cap_near_big; b.cap_far = e->cap_far_big;
         b.tie_cand = e->d_ws_big_tie; b.grid = std::min(e->big_grid, b.n_run);
         b.far_trigger = e->N + 32; // a compacted pile holds <= N live entries, a round adds <= E, the trigger may lag one round: never overflows
         const int ph2 = e->phase_begin(2);
@@ -639,27 +639,23 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_labels, (size_t)e->batch_tasks * N)) return -1;
     if (e->alloc(&e->d_pred, (size_t)e->batch_tasks * N)) return -1;
     if (e->alloc(&e->d_tie_nodes, e->batch_tasks)) return -1;
-    e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 256;
-    if (e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 256;
-    // round queues live in shared memory (32 B per edge item, 16 B per head, two buffers); pushes that do not fit spill
-    // to the far pile
-    e->cap_items = e->sssp_block >= 512 ? 1536 : 768;
-    if (const char* env = getenv("DTL_SSSP_ICAP")) e->cap_items = std::max(64, std::min(3000, atoi(env)));
-    e->cap_heads = std::max(32, e->cap_items / 3);
-    if (const char* env = getenv("DTL_SSSP_HCAP")) e->cap_heads = std::max(32, std::min(3000, atoi(env)));
+    e->sssp_block = o.sssp_block_threads ? o.sssp_block_threads : 128;
+    if (e->sssp_block != 64 && e->sssp_block != 128 && e->sssp_block != 256 && e->sssp_block != 512 && e->sssp_block != 1024) e->sssp_block = 128;
     int occ = 0, regs = 0;
-    sssp_occupancy(e->sssp_block, e->cap_items, e->cap_heads, &occ, &regs);
+    sssp_occupancy(e->sssp_block, &occ, &regs);
     if (occ <= 0) { set_err("SSSP kernel cannot be resident on this device (built for sm_100a)"); return -1; }
     int per_sm = o.sssp_ctas_per_sm > 0 ? std::min(o.sssp_ctas_per_sm, occ) : occ;
-    // worst-case bound of the far pile (DESIGN.md "K1 queues"): a compacted pile holds at most N live entries, a round
-    // pushes at most E entries, and the compaction trigger may lag one round.  Regular CTAs get a much smaller pile; a
-    // tree that outgrows it is re-run with the bound.
+    // worst-case bounds (DESIGN.md "K1 queues"): a round pushes at most E entries, a compacted far pile holds at most
+    // N live entries, and the compaction trigger may lag one round.  Regular CTAs get much smaller queues; a tree that
+    // outgrows them is re-run with the bounds.
+    e->cap_near_big = std::max(N, maxE) + 32;
     e->cap_far_big = N + 2 * maxE + 64;
-    e->ws_big_stride = 2 * (size_t)e->cap_far_big + 4;
-    int qcap = std::max(16384, N / 2);
+    e->ws_big_stride = 2 * (size_t)e->cap_near_big + 2 * (size_t)e->cap_far_big + 4;
+    int qcap = std::max(4096, N / 8);
     if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) qcap = std::max(32, atoi(env)); // test hook for the re-run path
-    e->cap_far = std::min(e->cap_far_big, qcap);
-    e->ws_stride = 2 * (size_t)e->cap_far + 4;
+    e->cap_near = std::min(e->cap_near_big, qcap);
+    e->cap_far = std::min(e->cap_far_big, 4 * qcap);
+    e->ws_stride = 2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far + 4;
     const size_t ws_budget = std::min<size_t>((size_t)16 << 30, free_b / 4);
     int grid = e->sm_count * per_sm;
     grid = (int)std::min<size_t>(grid, std::max<size_t>(1, ws_budget / (e->ws_stride * sizeof(QEntry))));
@@ -1130,20 +1126,6 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
         stats[3] = (double)(s1.pops - s0.pops);
         stats[4] = (double)(s1.rounds - s0.rounds);
         stats[5] = (double)(s1.replayed - s0.replayed);
-        if (getenv("DTL_SSSP_PROFILE"))
-        {
-            fprintf(stderr, "sssp: near-queue entries spilled to the far pile %.3g, queue re-runs %.3g\n",
-                    (double)(s1.prof[0] - s0.prof[0]), (double)(s1.overflow - s0.overflow));
-            double d[8];
-            for (int k = 0; k < 8; ++k) d[k] = (double)(s1.prof[k] - s0.prof[k]);
-            if (d[2] > 0) // only a -DSSSP_PROFILE build fills these
-                fprintf(stderr, "sssp thread-0 cycles: init %.3g expansion %.3g barrier %.3g re-bucket %.3g tie %.3g | re-bucketings %.3g "
-                                "entries read %.3g rounds %.3g\n", d[1], d[2], d[3], d[4], d[5], d[6], d[7], (double)(s1.rounds - s0.rounds));
-            for (int k = 0; k < 8; ++k) d[k] = (double)(s1.stage[k] - s0.stage[k]);
-            if (d[1] > 0)
-                fprintf(stderr, "sssp thread-0 stage cycles: item %.3g (unused) %.3g filter %.3g atomic+row %.3g push %.3g heads+wait %.3g | "
-                                "passes %.3g\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6]);
-        }
     }
     e->trees_valid = false;
     return 0;
