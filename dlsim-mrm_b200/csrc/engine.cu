@@ -339,6 +339,26 @@ int do_scatter(dtl_engine* e, int decay_k, bool person)
     return 0;
 }
 
+// K1 has two kernels (DESIGN.md "K1"): with many trees per SM the global-queue kernel's throughput wins; with few trees per
+// SM (an origin shard on one of several GPUs) a launch lasts as long as one tree, and the shared-memory-queue kernel's
+// short rounds with a big CTA per tree win.  DTL_SSSP_KERNEL=gq|smq forces one (tests).
+void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
+{
+    const char* force = getenv("DTL_SSSP_KERNEL");
+    const int per_sm = (a.n_run + e->sm_count - 1) / std::max(1, e->sm_count);
+    bool smq = per_sm <= 4 && !e->opt.sssp_block_threads; // an explicit block size asks for the global-queue kernel
+    if (force && !strcmp(force, "gq")) smq = false;
+    if (force && !strcmp(force, "smq")) smq = true;
+    a.smq = smq ? 1 : 0;
+    if (!smq) return;
+    a.block = per_sm <= 1 ? 1024 : per_sm <= 2 ? 512 : 256;
+    if (const char* env = getenv("DTL_SSSP_SMQ_BLOCK")) a.block = atoi(env) == 256 ? 256 : atoi(env) == 512 ? 512 : 1024;
+    a.cap_smem = 2 * a.block;
+    if (const char* env = getenv("DTL_SSSP_SMQ_DELTA")) a.delta *= atof(env); // experiment hook: wider label window in latency mode
+    if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) a.cap_smem = std::min(a.cap_smem, std::max(32, atoi(env))); // test hook
+    a.grid = std::min(std::min(e->sssp_grid, e->sm_count * (1024 / a.block)), std::max(1, a.n_run));
+}
+
 SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone,
                             int tree_off)
 {
@@ -353,6 +373,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     a.far_trigger = e->cap_far / 2;
     a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
     a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
+    choose_sssp_variant(e, a);
     return a;
 }
 
@@ -363,7 +384,8 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
     SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
     const int ph = e->phase_begin(2);
     CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
-    launch_sssp(a, e->st);
+    if (a.smq) launch_sssp_smq(a, e->st);
+    else launch_sssp(a, e->st);
     e->phase_end(ph, 1);
     CK(cudaGetLastError());
     e->h_tie_nodes.resize(n_tasks);
@@ -386,7 +408,8 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
         b.far_trigger = e->N + 32; // a compacted pile holds <= N live entries, a round adds <= E, the trigger may lag one round: never overflows
         const int ph2 = e->phase_begin(2);
         CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
-        launch_sssp(b, e->st);
+        if (b.smq) launch_sssp_smq(b, e->st);
+        else launch_sssp(b, e->st);
         e->phase_end(ph2, 1);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
@@ -652,7 +675,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     e->cap_far_big = N + 2 * maxE + 64;
     e->ws_big_stride = 2 * (size_t)e->cap_near_big + 2 * (size_t)e->cap_far_big + 4;
     int qcap = std::max(4096, N / 8);
-    if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) qcap = std::max(32, atoi(env)); // test hook for the re-run path
+    if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) qcap = std::max(4, atoi(env)); // test hook for the re-run path
     e->cap_near = std::min(e->cap_near_big, qcap);
     e->cap_far = std::min(e->cap_far_big, 4 * qcap);
     e->ws_stride = 2 * (size_t)e->cap_near + 2 * (size_t)e->cap_far + 4;

@@ -31,8 +31,13 @@ def sha(a):
 
 
 # ------------------------------------------------------------------------------------------------ K1
-def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod):
+KERNELS = ["gq", "smq"]  # global-memory queues (many trees per SM) / shared-memory queues (few trees per SM)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod, monkeypatch, kernel):
     """K1 fed the reference's own generalized costs: labels, pred nodes and pred links bit-exact for every origin."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
     p, g = problems("corridor_101"), golden("corridor_101")
     o = oracle_mod.Oracle(p)
     with D.Engine(p) as e:
@@ -86,8 +91,10 @@ def _tie_grid(n=12):
     return p.with_defaults().finalize()
 
 
-def test_sssp_ties_follow_the_reference_rule(D, oracle_mod):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sssp_ties_follow_the_reference_rule(D, oracle_mod, monkeypatch, kernel):
     """Exact FP64 ties: the engine detects them and replays the reference's deque, so the trees still match."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
     p = _tie_grid()
     o = oracle_mod.Oracle(p)
     cost = np.ones(p.n_links)
@@ -256,9 +263,11 @@ def test_drop_in_executable_writes_reference_files(D, tmp_path):
     assert abs(sum(vols) - 7000) < 1e-3
 
 
-@pytest.mark.parametrize("workload,K,CU", [("grid2k", 8, 3), ("grid10k", 4, 0)])
-def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, workload, K, CU):
+@pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"), ("grid10k", 4, 0, "gq"),
+                                                  ("grid10k", 4, 0, "smq")])
+def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, monkeypatch, workload, K, CU, kernel):
     """The bench generator at sizes the oracle finishes in seconds: same parity bars as the reference datasets."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
     from dlsim_mrm_b200 import synth
     synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
     p = D.read_gmns(str(tmp_path), 8)
@@ -287,13 +296,16 @@ def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, workload, K, CU)
         assert e.counters()["replayed"] == 0   # jittered lengths: no exact ties
 
 
-def test_small_queues_fall_back_to_worst_case_rerun(D, problems, golden, oracle_mod, monkeypatch):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_small_queues_fall_back_to_worst_case_rerun(D, problems, golden, oracle_mod, monkeypatch, kernel):
     """Trees whose frontier outgrows the regular work queues are recomputed with worst-case queues: same bits."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
     p, g = problems("corridor_101"), golden("corridor_101")
     o = oracle_mod.Oracle(p)
     cost = g["gen_cost_k2_at0"]
     fs = o.forward_star(0, 0)
-    monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "48")
+    # the shared-memory-queue kernel spills and compacts, so only a far pile of a few entries makes it give up
+    monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "48" if kernel == "gq" else "4")
     with D.Engine(p) as e:
         zones = np.arange(0, p.n_zones, 9, dtype=np.int32)
         lab, pn, pl, ties, st = e.sssp_trees(0, 0, zones, cost=cost)
