@@ -56,6 +56,17 @@ def ensure_workload(name: str) -> str:
     return d
 
 
+def k1_traffic(n_gpus: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same command
+    (profiles/k1_traffic.json, written by scripts/ncu_traffic.py); None when no capture of this GPU count is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(str(n_gpus), {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -275,7 +286,7 @@ def run_engine_arm(args, rank, world, local_rank):
                     "what": "dtl_create from host arrays + K iterations + finalize + link-state read-back, wall clock"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "dtl::sssp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": k1_traffic(world), "peak_source": peak_src,
                          "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": edges_rank / launches_per_iter,
                          "kernel_ms_per_launch": sssp_ms_launch},
             "sssp_gteps": gteps,
