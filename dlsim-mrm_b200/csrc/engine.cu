@@ -346,17 +346,25 @@ void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
 {
     const char* force = getenv("DTL_SSSP_KERNEL");
     const int per_sm = (a.n_run + e->sm_count - 1) / std::max(1, e->sm_count);
-    bool smq = per_sm <= 4 && !e->opt.sssp_block_threads; // an explicit block size asks for the global-queue kernel
-    if (force && !strcmp(force, "gq")) smq = false;
-    if (force && !strcmp(force, "smq")) smq = true;
-    a.smq = smq ? 1 : 0;
-    if (!smq) return;
+    int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 2 : 0; // an explicit block size asks for the global-queue kernel
+    if (force && !strcmp(force, "gq")) v = 0;
+    if (force && !strcmp(force, "smq")) v = 1;
+    if (force && !strcmp(force, "async")) v = 2;
+    a.smq = v;
+    if (!v) return;
     a.block = per_sm <= 1 ? 1024 : per_sm <= 2 ? 512 : 256;
     if (const char* env = getenv("DTL_SSSP_SMQ_BLOCK")) a.block = atoi(env) == 256 ? 256 : atoi(env) == 512 ? 512 : 1024;
-    a.cap_smem = 2 * a.block;
-    if (const char* env = getenv("DTL_SSSP_SMQ_DELTA")) a.delta *= atof(env); // experiment hook: wider label window in latency mode
+    a.cap_smem = (v == 2 ? 4 : 2) * a.block; // async: one array per label window; smq: two round buffers
     if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) a.cap_smem = std::min(a.cap_smem, std::max(32, atoi(env))); // test hook
+    if (const char* env = getenv("DTL_SSSP_SMQ_DELTA")) a.delta *= atof(env); // experiment hook: wider label window in latency mode
     a.grid = std::min(std::min(e->sssp_grid, e->sm_count * (1024 / a.block)), std::max(1, a.n_run));
+}
+
+static void launch_sssp_variant(const SsspLaunch& a, cudaStream_t st)
+{
+    if (a.smq == 2) launch_sssp_async(a, st);
+    else if (a.smq == 1) launch_sssp_smq(a, st);
+    else launch_sssp(a, st);
 }
 
 SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone,
@@ -384,8 +392,7 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
     SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
     const int ph = e->phase_begin(2);
     CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
-    if (a.smq) launch_sssp_smq(a, e->st);
-    else launch_sssp(a, e->st);
+    launch_sssp_variant(a, e->st);
     e->phase_end(ph, 1);
     CK(cudaGetLastError());
     e->h_tie_nodes.resize(n_tasks);
@@ -405,11 +412,11 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
         b.task_list = e->d_rerun_list; b.n_run = (int)rerun.size();
         b.ws = e->d_ws_big; b.ws_stride = e->ws_big_stride; b.cap_near = e->cap_near_big; b.cap_far = e->cap_far_big;
         b.tie_cand = e->d_ws_big_tie; b.grid = std::min(e->big_grid, b.n_run);
+        b.smq = 0; b.block = e->sssp_block; // the worst-case bounds are the global-queue kernel's
         b.far_trigger = e->N + 32; // a compacted pile holds <= N live entries, a round adds <= E, the trigger may lag one round: never overflows
         const int ph2 = e->phase_begin(2);
         CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
-        if (b.smq) launch_sssp_smq(b, e->st);
-        else launch_sssp(b, e->st);
+        launch_sssp_variant(b, e->st);
         e->phase_end(ph2, 1);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
