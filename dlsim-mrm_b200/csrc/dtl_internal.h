@@ -124,7 +124,7 @@ struct SsspLaunch {
     size_t ws_stride;
     int cap_near, cap_far;
     int cap_smem;            // shared-memory-queue variant: entries per near queue (two buffers, 28 B per entry)
-    int smq;                 // 0: global-queue kernel; few trees per SM: 1 = shared-memory round queues, 2 = asynchronous windows
+    int smq;                 // 1: launch the shared-memory-queue variant (few trees per SM)
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
     int* tie_cand;           // [grid][tie_cap]
     int tie_cap;
@@ -134,7 +134,6 @@ struct SsspLaunch {
 };
 void launch_sssp(const SsspLaunch& a, cudaStream_t st);     // global-memory queues: many trees per SM
 void launch_sssp_smq(const SsspLaunch& a, cudaStream_t st); // shared-memory queues: few trees per SM
-void launch_sssp_async(const SsspLaunch& a, cudaStream_t st); // shared-memory queue without rounds: few trees per SM
 // exact serial emulation of the reference deque for origins whose tree has tied predecessors
 void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
                         cudaStream_t st);

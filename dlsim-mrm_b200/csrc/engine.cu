@@ -346,15 +346,14 @@ void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
 {
     const char* force = getenv("DTL_SSSP_KERNEL");
     const int per_sm = (a.n_run + e->sm_count - 1) / std::max(1, e->sm_count);
-    int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 2 : 0; // an explicit block size asks for the global-queue kernel
+    int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 1 : 0; // an explicit block size asks for the global-queue kernel
     if (force && !strcmp(force, "gq")) v = 0;
     if (force && !strcmp(force, "smq")) v = 1;
-    if (force && !strcmp(force, "async")) v = 2;
     a.smq = v;
     if (!v) return;
     a.block = per_sm <= 1 ? 1024 : per_sm <= 2 ? 512 : 256;
     if (const char* env = getenv("DTL_SSSP_SMQ_BLOCK")) a.block = atoi(env) == 256 ? 256 : atoi(env) == 512 ? 512 : 1024;
-    a.cap_smem = (v == 2 ? 4 : 2) * a.block; // async: one array per label window; smq: two round buffers
+    a.cap_smem = 2 * a.block;
     if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) a.cap_smem = std::min(a.cap_smem, std::max(32, atoi(env))); // test hook
     if (const char* env = getenv("DTL_SSSP_SMQ_DELTA")) a.delta *= atof(env); // experiment hook: wider label window in latency mode
     a.grid = std::min(std::min(e->sssp_grid, e->sm_count * (1024 / a.block)), std::max(1, a.n_run));
@@ -362,8 +361,7 @@ void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
 
 static void launch_sssp_variant(const SsspLaunch& a, cudaStream_t st)
 {
-    if (a.smq == 2) launch_sssp_async(a, st);
-    else if (a.smq == 1) launch_sssp_smq(a, st);
+    if (a.smq == 1) launch_sssp_smq(a, st);
     else launch_sssp(a, st);
 }
 

@@ -31,7 +31,7 @@ def sha(a):
 
 
 # ------------------------------------------------------------------------------------------------ K1
-KERNELS = ["gq", "smq", "async"]  # global-memory queues (many trees per SM) / shared-memory queues, with rounds or asynchronous (few trees per SM)
+KERNELS = ["gq", "smq"]  # global-memory queues (many trees per SM) / shared-memory queues (few trees per SM)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -263,8 +263,8 @@ def test_drop_in_executable_writes_reference_files(D, tmp_path):
     assert abs(sum(vols) - 7000) < 1e-3
 
 
-@pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"), ("grid2k", 8, 3, "async"),
-                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq"), ("grid10k", 4, 0, "async")])
+@pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"),
+                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq")])
 def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, monkeypatch, workload, K, CU, kernel):
     """The bench generator at sizes the oracle finishes in seconds: same parity bars as the reference datasets."""
     monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
