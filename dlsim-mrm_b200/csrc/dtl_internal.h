@@ -37,6 +37,8 @@ struct ForwardStar {
     int* row_ptr = nullptr;   // [N+1]
     Edge* edges = nullptr;    // [E] forward-star order == reference scan order
     int2* rows = nullptr;     // [N] {row_ptr[i], row_ptr[i+1]}: one 8-byte load per node
+    int4* link_info = nullptr; // [L] {from node, row begin of the to-node, row end of the to-node, 0}: what the expansion of an
+                              // entry reached over link l needs, in one 16-byte load
     int* in_ptr = nullptr;    // [N+1] reverse star (tie verification only)
     int2* in_edges = nullptr; // [E] {from node, forward edge index}
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
@@ -105,6 +107,7 @@ struct SsspLaunch {
     int N;
     const int* row_ptr;
     const int2* rows;        // [N] {row begin, row end}
+    const int4* link_info;   // [L] {from node, row begin of the to-node, row end of the to-node, 0}
     const Edge* edges;
     const int* in_ptr;
     const int2* in_edges;

@@ -285,6 +285,12 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
     }
     if (e->upload(&f.row_ptr, row.data(), row.size())) return -1;
     if (e->upload(&f.rows, rows.data(), rows.size())) return -1;
+    std::vector<int4> link_info(std::max(L, 1));
+    for (int l = 0; l < L; ++l) {
+        const int2 r = rows[p->link_to[l]];
+        link_info[l] = make_int4(p->link_from[l], r.x, r.y, 0);
+    }
+    if (e->upload(&f.link_info, link_info.data(), link_info.size())) return -1;
     if (e->upload(&f.edges, edges.data(), edges.size())) return -1;
     if (e->upload(&f.in_ptr, in_ptr.data(), in_ptr.size())) return -1;
     if (e->upload(&f.in_edges, in_edges.data(), in_edges.size())) return -1;
@@ -369,7 +375,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
                             int tree_off)
 {
     SsspLaunch a{};
-    a.N = e->N; a.row_ptr = f.row_ptr; a.rows = f.rows; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges;
+    a.N = e->N; a.row_ptr = f.row_ptr; a.rows = f.rows; a.link_info = f.link_info; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges;
     a.link_tag = e->d_link_tag; a.link_from = e->d_link_from;
     a.n_tasks = n_tasks; a.n_run = n_tasks; a.task_list = nullptr; a.task_origin = d_origin; a.task_zone = d_zone;
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;

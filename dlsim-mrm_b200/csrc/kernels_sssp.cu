@@ -47,7 +47,7 @@ namespace dtl {
 template <int BLOCK, int UNR>
 __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspLaunch a)
 {
-    __shared__ int s_task, s_cnt[3], s_n_far, s_n_far2, s_n_tie, s_overflow;
+    __shared__ int s_task, s_cnt[3], s_n_far, s_n_far2, s_n_tie, s_overflow, s_rounds;
     __shared__ double s_red[32];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
     QEntry* q_next = q_near + a.cap_near;
     QEntry* q_far = q_next + a.cap_near;
     QEntry* q_far2 = q_far + a.cap_far;
-    int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
-    unsigned c_relax = 0, c_pops = 0, c_rounds = 0;
+    unsigned c_relax = 0, c_pops = 0;
+    if (threadIdx.x == 0) s_rounds = 0;
 
     for (;;) {
         __syncthreads();
@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
                     if (active) {
                         q = ld_entry(&q_near[i]);
                         const double cur = ld_label(&lab[q.node]);
-                        int2 rr = __ldg(&a.rows[q.node]);
-                        if (q.link >= 0) parent = __ldg(&a.link_from[q.link]);
-                        else rr = orow; // the origin's own entry
-                        rb = rr.x; re = rr.y;
+                        if (q.link >= 0) { // the link the entry came over names the parent and the row of this node in one load
+                            const int4 li = __ldg(&a.link_info[q.link]);
+                            parent = li.x; rb = li.y; re = li.z;
+                        } else { rb = __ldg(&a.row_ptr[q.node]); re = __ldg(&a.row_ptr[q.node + 1]); } // the origin's own entry
                         if (cur < q.lab) active = false; // a better label was pushed later: that entry expands the node
                     }
                     if (active) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
                             for (int j = 0; j < UNR; ++j)
                                 if (tie_m & (1u << j)) {
                                     const int pos = atomicAdd(&s_n_tie, 1);
-                                    if (pos < a.tie_cap) tie_cand[pos] = to[j];
+                                    if (pos < a.tie_cap) a.tie_cand[(size_t)blockIdx.x * a.tie_cap + pos] = to[j];
                                 }
                         }
                     }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
                 ci = ci1;
                 n_near = min(s_cnt[ci], a.cap_near);
                 QEntry* t = q_near; q_near = q_next; q_next = t;
-                ++c_rounds;
+                if (tid == 0) ++s_rounds;
                 if (compact) {
                     // far pile close to capacity: drop dead entries (at most one live entry per node survives)
                     __syncthreads(); // every thread has read its n_near; nobody pushes any more
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
             __syncthreads();
             if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; }
             QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
-            ++c_rounds;
+            if (tid == 0) ++s_rounds;
             __syncthreads();
         }
 
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
             const bool all_nodes = n_tie > a.tie_cap;
             const int n_check = all_nodes ? N : n_tie;
             for (int i = tid; i < n_check; i += BLOCK) {
-                const int w = all_nodes ? i : tie_cand[i];
+                const int w = all_nodes ? i : a.tie_cand[(size_t)blockIdx.x * a.tie_cap + i];
                 if (w == origin) continue;
                 const double lw = ld_label(&lab[w]);
                 if (!(lw < DTL_MAX_LABEL_COST)) continue;
@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(BLOCK, SSSP_MIN_CTAS(BLOCK)) sssp_kernel(SsspL
         atomicAdd(&a.stats->relaxations, (unsigned long long)c_relax);
         atomicAdd(&a.stats->pops, (unsigned long long)c_pops);
     }
-    if (tid == 0) atomicAdd(&a.stats->rounds, (unsigned long long)c_rounds);
+    __syncthreads();
+    if (tid == 0) atomicAdd(&a.stats->rounds, (unsigned long long)s_rounds);
 }
 
 void launch_sssp(const SsspLaunch& a, cudaStream_t st)
