@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "dtalite_ref")
+REF_BIN_TP4 = os.path.join(HERE, "_ref", "dtalite_ref_tp4")  # same sources with MAX_TIMEPERIODS = 4 (multi-period fixtures)
 
 _DT = {0: np.int32, 1: np.float64, 2: np.float32, 3: np.int64}
 
@@ -243,18 +244,19 @@ class Oracle:
 
 
 def run_reference(workdir: str, mode: str, K: int, CU: int, B: int, out: str | None = None, env: dict | None = None,
-                  timeout: float = 3600, threads: int | None = None):
+                  timeout: float = 3600, threads: int | None = None, multi_period: bool = False):
     """Run oracle/_ref/dtalite_ref in ``workdir`` (stdin closed: the reference blocks on getchar()
     when it stops on an error, utils.cpp:41-46).  Returns (stdout_text, timing_dict_or_None)."""
     import json
-    if not os.path.exists(REF_BIN):
-        raise FileNotFoundError(REF_BIN)
+    ref_bin = REF_BIN_TP4 if multi_period else REF_BIN
+    if not os.path.exists(ref_bin):
+        raise FileNotFoundError(ref_bin)
     e = dict(os.environ)
     if threads:
         e["OMP_NUM_THREADS"] = str(threads)
     if env:
         e.update(env)
-    cmd = [REF_BIN, mode, str(K), str(CU), str(B)] + ([out] if out else [])
+    cmd = [ref_bin, mode, str(K), str(CU), str(B)] + ([out] if out else [])
     r = subprocess.run(cmd, cwd=workdir, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        env=e, timeout=timeout)
     text = r.stdout.decode(errors="replace")

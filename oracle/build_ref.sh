@@ -41,3 +41,16 @@ g++ $CXXFLAGS -c "$HERE/ref_harness.cpp" -o "$STAGE/ref_harness.o" &
 wait
 g++ -fopenmp -o "$OUT/dtalite_ref" "$STAGE/ref_harness.o" "$STAGE/utils.o" "$STAGE/simulation.o" "$STAGE/DTA_geometry.o"
 echo "built $OUT/dtalite_ref"
+
+# Second binary for multi-period fixtures: the committed source caps the number of demand periods with a compile-time
+# constant (DTA.h:15, MAX_TIMEPERIODS = 2, and settings with 2 periods already stop); the commented-out line next to it
+# (DTA.h:17) is the larger setting.  Constant-only change in the staging copy, no arithmetic touched.
+sed -i -E '15s/MAX_TIMEPERIODS = 2;/MAX_TIMEPERIODS = 4;/' "$STAGE/DTA.h"
+grep -q 'MAX_TIMEPERIODS = 4;' "$STAGE/DTA.h" || { echo "build_ref.sh: MAX_TIMEPERIODS patch did not apply" >&2; exit 1; }
+g++ $CXXFLAGS -c "$STAGE/utils.cpp" -o "$STAGE/utils.o" &
+g++ $CXXFLAGS -c "$STAGE/simulation.cpp" -o "$STAGE/simulation.o" &
+g++ $CXXFLAGS -c "$STAGE/DTA_geometry.cpp" -o "$STAGE/DTA_geometry.o" &
+g++ $CXXFLAGS -c "$HERE/ref_harness.cpp" -o "$STAGE/ref_harness.o" &
+wait
+g++ -fopenmp -o "$OUT/dtalite_ref_tp4" "$STAGE/ref_harness.o" "$STAGE/utils.o" "$STAGE/simulation.o" "$STAGE/DTA_geometry.o"
+echo "built $OUT/dtalite_ref_tp4"

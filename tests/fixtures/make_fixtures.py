@@ -9,6 +9,9 @@
                  input_demand.csv with its header renamed to the column-format names; AUTHORED settings.csv
                  (column demand for two agent types, one 4-hour period, BPR) -- the shipped settings name path /
                  activity demand and a subarea, which the committed reference source cannot run
+  corridor_3_2p  the same network with TWO demand periods (AM, PM: the reference's MAX_TIMEPERIODS) and an AUTHORED
+                 allowed_uses = "sov" on every 7th link, so per-period arrays and the per-agent-type forward-star
+                 filter (routing.h:275-297) are exercised
   asu_qvdf       dataset/2_ASU/network (BASELINE.json configs[2]): link.csv verbatim; node.csv with AUTHORED zone ids
                  on every 27th node (the dataset ships without zones); AUTHORED demand and settings with
                  vdf_type=qvdf on every link type, so the queue VDF branch is exercised
@@ -58,6 +61,28 @@ def corridor_3():
         ",,,,,,,\n"
         "[output_file_configuration],,path_output,major_path_volume_threshold\n"
         ",,1,0.1\n")
+
+
+def corridor_3_2p():
+    src = os.path.join(HERE, "corridor_3")
+    dst = os.path.join(HERE, "corridor_3_2p")
+    os.makedirs(dst, exist_ok=True)
+    for n in ("node.csv", "demand.csv"):
+        shutil.copy(os.path.join(src, n), os.path.join(dst, n))
+    with open(os.path.join(src, "link.csv")) as f:
+        rows = list(csv.reader(f))
+    au, li = rows[0].index("allowed_uses"), rows[0].index("link_id")
+    for r in rows[1:]:
+        if r and r[li] and int(r[li]) % 7 == 3:
+            r[au] = "sov"
+    with open(os.path.join(dst, "link.csv"), "w", newline="") as f:
+        csv.writer(f, lineterminator="\n").writerows(rows)
+    s = open(os.path.join(src, "settings.csv")).read()
+    s = s.replace(",,dta,20,20,4\n", ",,dta,12,6,4\n")
+    s = s.replace(",1,AM,,0600_1000\n", ",1,AM,,0600_1000\n,2,PM,,1500_1900\n")
+    s = s.replace(",2,demand.csv,,column,AM,hov,1.6\n", ",2,demand.csv,,column,AM,hov,1.6\n,3,demand.csv,,column,PM,sov,5.0\n"
+                  ",4,demand.csv,,column,PM,hov,2.5\n")
+    open(os.path.join(dst, "settings.csv"), "w").write(s)
 
 
 def asu_qvdf():
@@ -114,5 +139,6 @@ if __name__ == "__main__":
     copy("src/test_case_01_two_corridor", os.path.join(HERE, "two_corridor"), ["node.csv", "link.csv", "demand.csv", "settings.csv"])
     copy("dataset/4_101_corridor", os.path.join(HERE, "corridor_101"), ["node.csv", "link.csv", "demand.csv", "settings.csv"])
     corridor_3()
+    corridor_3_2p()
     asu_qvdf()
     print("fixtures written under", HERE)

@@ -38,13 +38,13 @@ def copy_lines(src, first, last, dst):
         f.writelines(lines[first - 1:last])
 
 
-def run_case(name, K, CU, tree_iters, full_tree_zones):
+def run_case(name, K, CU, tree_iters, full_tree_zones, multi_period=False):
     src = os.path.join(ROOT, "tests", "fixtures", name)
     with tempfile.TemporaryDirectory() as tmp:
         for f in os.listdir(src):
             shutil.copy(os.path.join(src, f), tmp)
         env = {"DTL_TRACE_TREES": ",".join(str(k) for k in tree_iters)}
-        B.run_reference(tmp, "trace", K, CU, 4, "dump.bin", env=env, threads=4)
+        B.run_reference(tmp, "trace", K, CU, 4, "dump.bin", env=env, threads=4, multi_period=multi_period)
         d = B.load_dump(os.path.join(tmp, "dump.bin"))
     N, L, Z, AT, T = (int(x) for x in d["meta"])
     out = {"meta": d["meta"], "K": np.int32(K), "CU": np.int32(CU)}
@@ -56,10 +56,20 @@ def run_case(name, K, CU, tree_iters, full_tree_zones):
                 out[f"k{k}_{key}_after_vdf"] = d[f"{key}:after_vdf:k={k}:tau=0"]
             for n in range(CU):
                 out[f"cu{n}_{key}"] = d[f"{key}:cu={n}:tau=0"]
+    for tau in range(1, T):  # further demand periods: same keys with a ":tau=t" suffix
+        for key in ("tt", "pce_volume", "person_volume", "vdf_link_volume", "doc", "voc", "P", "vt2"):
+            out[f"final_{key}:tau={tau}"] = d[f"{key}:final:tau={tau}"]
+            if key in ("tt", "pce_volume"):
+                for k in (2, K - 1):
+                    out[f"k{k}_{key}_after_vdf:tau={tau}"] = d[f"{key}:after_vdf:k={k}:tau={tau}"]
+                for n in range(CU):
+                    out[f"cu{n}_{key}:tau={tau}"] = d[f"{key}:cu={n}:tau={tau}"]
     out["final_sysTT"] = d["final_sysTT"]
     for k in tree_iters:
         for at in range(AT):
             out[f"gen_cost_k{k}_at{at}"] = d[f"gen_cost:k={k}:at={at}:tau=0"]
+            for tau in range(1, T):
+                out[f"gen_cost_k{k}_at{at}_tau{tau}"] = d[f"gen_cost:k={k}:at={at}:tau={tau}"]
     for key in ("col_o", "col_d", "col_at", "col_tau", "col_node_sum", "col_seq", "col_nlinks", "col_nnodes", "col_volume",
                 "col_cost", "col_time"):
         out[key] = d[key + ":final"]
@@ -102,3 +112,5 @@ if __name__ == "__main__":
     run_case("corridor_101", 20, 5, (0, 2, 19), {7})
     run_case("corridor_3", 20, 20, range(20), None)       # authored fixture, BASELINE.json configs[1]
     run_case("asu_qvdf", 20, 3, (0, 2, 19), None)         # authored fixture, queue VDF, BASELINE.json configs[2]
+    # two demand periods + allowed_uses filter; needs the MAX_TIMEPERIODS = 4 build of the reference (oracle/build_ref.sh)
+    run_case("corridor_3_2p", 12, 6, range(12), None, multi_period=True)

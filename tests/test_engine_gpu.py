@@ -144,7 +144,13 @@ def _compare_columns(eng_cols, ora_cols):
     assert rel_err(eng_cols["volume"], ora_cols["volume"], floor=1e-6) <= TOL
 
 
-@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5), ("corridor_3", 20, 20), ("asu_qvdf", 20, 3)])
+def _sfx(tau):
+    """golden keys of demand periods after the first carry a ":tau=t" suffix"""
+    return "" if tau == 0 else f":tau={tau}"
+
+
+@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5), ("corridor_3", 20, 20),
+                                       ("corridor_3_2p", 12, 6), ("asu_qvdf", 20, 3)])
 def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod, name, K, CU):
     p, g = problems(name), golden(name)
     o = oracle_mod.Oracle(p)
@@ -152,6 +158,7 @@ def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod
     with D.Engine(p, keep_trees=True, max_columns_per_od=K + 4) as e:
         assert e.n_tasks == o.n_tasks
         assert np.array_equal(e.task_zone, o.task_zone) and np.array_equal(e.task_at, o.task_at)
+        assert np.array_equal(e.task_tau, o.task_tau)
         tree_mismatch = 0
         for k in range(K):
             r, ro = e.iteration(k), o.iteration(k)
@@ -167,22 +174,25 @@ def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod
                     lab, pn, pl = e.tree(ti)
                     assert rel_err(lab, lab_o[ti]) <= 1e-12
                     tree_mismatch += int(np.count_nonzero(pl != pl_o[ti]) + np.count_nonzero(pn != pn_o[ti]))
-            st, so = e.link_state(0), o.link_state(0)
-            assert rel_err(st["tt"], so["tt"]) <= TOL
-            assert rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
+            for tau in range(p.n_periods):
+                st, so = e.link_state(tau), o.link_state(tau)
+                assert rel_err(st["tt"], so["tt"]) <= TOL
+                assert rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
         assert tree_mismatch == 0, "predecessor trees must match the reference's"
         for n in range(CU):
             r, ro = e.column_update(n), o.column_update(n)
             for key in ("avg_tt", "total_gap", "rel_gap_pct", "demand"):
                 assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (n, key, r, ro)
-            assert rel_err(e.link_state(0)["tt"], g[f"cu{n}_tt"]) <= TOL
+            for tau in range(p.n_periods):
+                assert rel_err(e.link_state(tau)["tt"], g[f"cu{n}_tt" + _sfx(tau)]) <= TOL
         sys_tt = e.finalize(K)
         assert abs(sys_tt - float(g["final_sysTT"][0])) <= TOL * max(1.0, float(g["final_sysTT"][0]))
-        st = e.link_state(0)
-        for key, gk in (("tt", "final_tt"), ("pce_volume", "final_pce_volume"), ("person_volume", "final_person_volume"),
-                        ("link_volume", "final_vdf_link_volume"), ("doc", "final_doc"), ("voc", "final_voc"), ("P", "final_P"),
-                        ("vt2", "final_vt2")):
-            assert rel_err(st[key], g[gk], floor=1e-3) <= TOL, key
+        for tau in range(p.n_periods):
+            st = e.link_state(tau)
+            for key, gk in (("tt", "final_tt"), ("pce_volume", "final_pce_volume"), ("person_volume", "final_person_volume"),
+                            ("link_volume", "final_vdf_link_volume"), ("doc", "final_doc"), ("voc", "final_voc"),
+                            ("P", "final_P"), ("vt2", "final_vt2")):
+                assert rel_err(st[key], g[gk + _sfx(tau)], floor=1e-3) <= TOL, (key, tau)
         o.finalize(K)
         ec, oc = e.columns(), o.columns()
         _compare_columns(ec, oc)

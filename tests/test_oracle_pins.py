@@ -56,7 +56,12 @@ def test_oracle_reproduces_reference_golden_rows(problems, oracle_mod, name, K, 
         assert _fmt6(r["rel_gap_pct"]) == gap
 
 
-@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "asu_qvdf"])
+def _sfx(tau):
+    """golden keys of demand periods after the first carry a ":tau=t" suffix"""
+    return "" if tau == 0 else f":tau={tau}"
+
+
+@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "corridor_3_2p", "asu_qvdf"])
 def test_oracle_matches_reference_engine_state(problems, golden, oracle_mod, name):
     p, g = problems(name), golden(name)
     K, CU = int(g["K"]), int(g["CU"])
@@ -72,8 +77,8 @@ def test_oracle_matches_reference_engine_state(problems, golden, oracle_mod, nam
         ref = g["iter_rows"][k]
         assert r["sysTT"] == ref[1] and r["least"] == ref[2] and r["gap"] == ref[3] and r["avg_tt"] == ref[4]
         if f"k{k}_tt_after_vdf" in g:
-            st = o.link_state(0)
-            assert np.array_equal(st["tt"], g[f"k{k}_tt_after_vdf"])
+            for tau in range(p.n_periods):
+                assert np.array_equal(o.link_state(tau)["tt"], g[f"k{k}_tt_after_vdf" + _sfx(tau)])
         lab, pn, pl = o._cap
         for ti in range(o.n_tasks):
             tag = f"k={k}:at={o.task_at[ti]}:tau={o.task_tau[ti]}:z={o.task_zone[ti]}"
@@ -83,18 +88,21 @@ def test_oracle_matches_reference_engine_state(problems, golden, oracle_mod, nam
     assert checked == len(tree_keys)
     for n in range(CU):
         o.column_update(n)
-        st = o.link_state(0)
-        assert np.array_equal(st["tt"], g[f"cu{n}_tt"])
-        assert np.array_equal(st["pce_volume"], g[f"cu{n}_pce_volume"])
+        for tau in range(p.n_periods):
+            st = o.link_state(tau)
+            assert np.array_equal(st["tt"], g[f"cu{n}_tt" + _sfx(tau)])
+            assert np.array_equal(st["pce_volume"], g[f"cu{n}_pce_volume" + _sfx(tau)])
     assert o.finalize(K) == float(g["final_sysTT"][0])
-    st = o.link_state(0)
-    for key in ("tt", "pce_volume", "person_volume", "doc", "voc", "P", "vt2"):
-        assert np.array_equal(st[key], g[f"final_{key}"]), key
-    assert np.array_equal(st["link_volume"], g["final_vdf_link_volume"])
+    for tau in range(p.n_periods):
+        st = o.link_state(tau)
+        for key in ("tt", "pce_volume", "person_volume", "doc", "voc", "P", "vt2"):
+            assert np.array_equal(st[key], g[f"final_{key}" + _sfx(tau)]), (key, tau)
+        assert np.array_equal(st["link_volume"], g["final_vdf_link_volume" + _sfx(tau)])
     c = o.columns()
     od = c["od_index"]
     assert np.array_equal(p.od_o[od], g["col_o"]) and np.array_equal(p.od_d[od], g["col_d"])
     assert np.array_equal(p.od_at[od], g["col_at"]) and np.array_equal(c["node_sum"], g["col_node_sum"])
+    assert np.array_equal(p.od_tau[od], g["col_tau"])
     assert np.array_equal(c["seq_no"], g["col_seq"]) and np.array_equal(c["n_links"], g["col_nlinks"])
     assert np.array_equal(c["n_nodes"], g["col_nnodes"])
     assert np.array_equal(c["volume"], g["col_volume"])
