@@ -12,6 +12,11 @@
   corridor_3_2p  the same network with TWO demand periods (AM, PM: the reference's MAX_TIMEPERIODS) and an AUTHORED
                  allowed_uses = "sov" on every 7th link, so per-period arrays and the per-agent-type forward-star
                  filter (routing.h:275-297) are exercised
+  edge_cases     AUTHORED from scratch: a 4 x 4 grid with two agent types plus the corner cases of the path -- a zone on an
+                 island no other zone can reach (unreachable destinations, label 1e15 / predecessor -9999), a zone whose
+                 only way out is closed to one agent type (that agent type's tree stops at the first node), a zone without
+                 any demand, parallel links between one node pair, demand rows that the reader must skip (o == d, unknown
+                 zone, zero volume) and a volume below the 1e-6 back-trace threshold
   asu_qvdf       dataset/2_ASU/network (BASELINE.json configs[2]): link.csv verbatim; node.csv with AUTHORED zone ids
                  on every 27th node (the dataset ships without zones); AUTHORED demand and settings with
                  vdf_type=qvdf on every link type, so the queue VDF branch is exercised
@@ -85,6 +90,64 @@ def corridor_3_2p():
     open(os.path.join(dst, "settings.csv"), "w").write(s)
 
 
+def edge_cases():
+    dst = os.path.join(HERE, "edge_cases")
+    os.makedirs(dst, exist_ok=True)
+    n = 4
+    nid = lambda r, c: r * n + c + 1
+    zone_of = {nid(0, 0): 1, nid(0, 3): 2, nid(3, 0): 3, nid(3, 3): 4, 17: 5, nid(1, 1): 6}
+    with open(os.path.join(dst, "node.csv"), "w") as f:
+        f.write("node_id,name,x_coord,y_coord,node_type,ctrl_type,zone_id,geometry\n")
+        for r in range(n):
+            for c in range(n):
+                i = nid(r, c)
+                f.write(f"{i},,{c * 0.01:.4f},{r * 0.01:.4f},,,{zone_of.get(i, '')},\n")
+        f.write(f"17,,0.1000,0.1000,,,{zone_of[17]},\n18,,0.1100,0.1000,,,,\n")  # the island: nodes 17 <-> 18 only
+    links = []
+    for r in range(n):
+        for c in range(n):
+            if c + 1 < n:
+                links += [(nid(r, c), nid(r, c + 1)), (nid(r, c + 1), nid(r, c))]
+            if r + 1 < n:
+                links += [(nid(r, c), nid(r + 1, c)), (nid(r + 1, c), nid(r, c))]
+    links += [(17, 18), (18, 17), (nid(1, 2), nid(2, 2))]  # the last one duplicates an existing node pair (parallel link)
+    with open(os.path.join(dst, "link.csv"), "w") as f:
+        f.write("link_id,name,from_node_id,to_node_id,facility_type,link_type,dir_flag,length,lanes,free_speed,capacity,allowed_uses\n")
+        for k, (a, b) in enumerate(links, 1):
+            length = 800 + 37 * ((a * 13 + b * 7) % 23)                    # no two paths tie exactly
+            uses = "truck" if a == nid(3, 3) else ""                       # zone 4 can be left by trucks only
+            speed = (25, 35, 45)[k % 3]
+            f.write(f"{k},,{a},{b},,{1 + k % 2},1,{length},{1 + k % 3},{speed},{900 + 200 * (k % 4)},{uses}\n")
+    with open(os.path.join(dst, "demand.csv"), "w") as f:
+        f.write("o_zone_id,d_zone_id,volume\n")
+        f.write("1,2,900\n1,3,450.5\n1,4,300\n2,1,800\n2,3,120\n3,4,610\n4,1,275\n4,2,33\n"
+                "1,5,50\n5,1,40\n"          # to / from the island: never reachable
+                "2,2,77\n"                    # o == d: skipped by the reader
+                "9,1,10\n1,9,10\n"           # unknown zones: skipped
+                "3,1,0\n"                     # zero volume
+                "3,2,0.0000005\n")            # below the 1e-6 threshold of the back-trace
+    open(os.path.join(dst, "settings.csv"), "w").write(
+        "[assignment],,assignment_mode,column_generation_iterations,column_updating_iterations,number_of_memory_blocks\n"
+        ",,dta,10,4,4\n"
+        ",,,,,\n"
+        "[agent_type],agent_type,name,,vot,flow_type,pce,person_occupancy\n"
+        ",auto,passenger,,10,0,1,1\n"
+        ",truck,truck,,25,0,2.5,1\n"
+        ",,,,,,,\n"
+        "[link_type],link_type,link_type_name,,agent_type_blocklist,type_code,traffic_flow_code\n"
+        ",1,major,,,a,0\n,2,minor,,,a,0\n"
+        ",,,,,,\n"
+        "[demand_period],demand_period_id,demand_period,,time_period\n"
+        ",1,AM,,0700_0900\n"
+        ",,,,\n"
+        "[demand_file_list],file_sequence_no,file_name,,format_type,demand_period,agent_type,scale_factor\n"
+        ",1,demand.csv,,column,AM,auto,6\n"
+        ",2,demand.csv,,column,AM,truck,1.2\n"
+        ",,,,,,,\n"
+        "[output_file_configuration],,path_output,major_path_volume_threshold\n"
+        ",,1,0.1\n")
+
+
 def asu_qvdf():
     src = "dataset/2_ASU/network"
     dst = os.path.join(HERE, "asu_qvdf")
@@ -140,5 +203,6 @@ if __name__ == "__main__":
     copy("dataset/4_101_corridor", os.path.join(HERE, "corridor_101"), ["node.csv", "link.csv", "demand.csv", "settings.csv"])
     corridor_3()
     corridor_3_2p()
+    edge_cases()
     asu_qvdf()
     print("fixtures written under", HERE)

@@ -114,3 +114,4 @@ if __name__ == "__main__":
     run_case("asu_qvdf", 20, 3, (0, 2, 19), None)         # authored fixture, queue VDF, BASELINE.json configs[2]
     # two demand periods + allowed_uses filter; needs the MAX_TIMEPERIODS = 4 build of the reference (oracle/build_ref.sh)
     run_case("corridor_3_2p", 12, 6, range(12), None, multi_period=True)
+    run_case("edge_cases", 10, 4, range(10), None)        # authored corner cases: unreachable zones, closed links, skipped demand rows
