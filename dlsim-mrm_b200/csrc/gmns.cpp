@@ -825,21 +825,29 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                 float sum = 0;
                 int cnt = 0;
                 for (int q = 0; q < 3; ++q) {
-                    const int slot = t / 5 + q - first_slot;
-                    float v = speed[tau][(size_t)i * n_slots + slot];
-                    // slots outside the demand period keep the reader's initial value: the free speed (input.h:3490-3496)
-                    const int abs_slot = t / 5 + q;
-                    const int s0 = (int)(g.start_h[k] * 60) / 5, s1 = (int)(g.end_h[k] * 60) / 5;
-                    if (abs_slot < s0 || abs_slot > s1) v = (float)g.free_speed[i];
+                    // model_speed[] is ONE array per link (DTA.h:1179): every demand period's VDF call writes the slots of its
+                    // own time window (VDF.h:313), later periods last, and every row of the link prints the merged profile;
+                    // slots outside all windows keep the reader's initial value, the free speed (input.h:3490-3496)
+                    const int slot = t / 5 + q - first_slot, abs_slot = t / 5 + q;
+                    float v = (float)g.free_speed[i];
+                    for (int t2 = 0; t2 < T; ++t2) {
+                        const size_t k2 = (size_t)t2 * L + i;
+                        const int s0 = (int)(g.start_h[k2] * 60) / 5, s1 = (int)(g.end_h[k2] * 60) / 5;
+                        if (abs_slot >= s0 && abs_slot <= s1) v = speed[t2][(size_t)i * n_slots + slot];
+                    }
                     if (v >= 1) { sum += v; ++cnt; }
                 }
                 fprintf(f, "%.3f,", sum / std::max(1, cnt));
             }
             fprintf(f, "%s,", "");
-            fprintf(f, "%.3f,%.3f,%.3f,", 0.0, 0.0, 0.0);
-            fprintf(f, "%.3f,%.3f,%.3f,", 0.0, 0.0, 0.0);
-            fprintf(f, "%.3f,%.3f,%.3f,", 0.0, 0.0, 0.0);
-            fprintf(f, "%.3f,%.3f,%.3f,", 0.0, 0.0, 0.0);
+            // base case / after the sensitivity-analysis stage (g_record_corridor_performance_summary, output.h:60-98).  Without
+            // a supply-side scenario that stage only recomputes volumes and times from the final columns (main_api.cpp:772-1072),
+            // which is the state dtl_finalize leaves: both records are the final state and the differences are zero.
+            const double vb = vehicle_volume, sb = spd, db = doc[tau][i], pb = P[tau][i];
+            fprintf(f, "%.3f,%.3f,%.3f,", vb, vb, vb - vb);
+            fprintf(f, "%.3f,%.3f,%.3f,", sb, sb, sb - sb);
+            fprintf(f, "%.3f,%.3f,%.3f,", db, db, db - db);
+            fprintf(f, "%.3f,%.3f,%.3f,", pb, pb, pb - pb);
             fprintf(f, "period-based\n");
         }
     }

@@ -103,7 +103,23 @@ def run_case(name, K, CU, tree_iters, full_tree_zones, multi_period=False):
     print(name, "->", os.path.getsize(os.path.join(OUT, f"{name}_ref.npz")) // 1024, "KiB")
 
 
+def reference_output_files(name, K, CU, multi_period=False):
+    """link_performance.csv / route_assignment.csv as the reference's own network_assignment() writes them
+    (harness mode "golden": the unmodified entry point, main_api.cpp:499) -> tests/golden/outputs/."""
+    src = os.path.join(ROOT, "tests", "fixtures", name)
+    os.makedirs(os.path.join(OUT, "outputs"), exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in os.listdir(src):
+            shutil.copy(os.path.join(src, f), tmp)
+        B.run_reference(tmp, "golden", K, CU, 4, None, threads=4, multi_period=multi_period)
+        for f in ("link_performance", "route_assignment"):
+            shutil.copy(os.path.join(tmp, f + ".csv"), os.path.join(OUT, "outputs", f"{name}_{f}.csv"))
+
+
 if __name__ == "__main__":
+    for name_, K_, CU_, mp_ in (("two_corridor", 20, 0, False), ("corridor_3", 20, 20, False), ("edge_cases", 10, 4, False),
+                                ("corridor_3_2p", 12, 6, True)):
+        reference_output_files(name_, K_, CU_, mp_)
     copy_lines(os.path.join(REF, "src/test_case_01_two_corridor/final_summary.csv"), 35, 58,
                os.path.join(OUT, "two_corridor_final_summary.txt"))
     copy_lines(os.path.join(REF, "dataset/4_101_corridor/final_summary.csv"), 150, 177,
