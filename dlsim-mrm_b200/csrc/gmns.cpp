@@ -13,7 +13,9 @@
 // analysis, simulation) stop with an explicit message and a non-zero exit status; nothing blocks on stdin
 // (the reference's g_program_stop() does, utils.cpp:41-46).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +24,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dtalite_b200.h"
@@ -738,12 +741,36 @@ int dtl_gmns_assignment_settings(const char* dir_c, int out[6])
     return 0;
 }
 
+// printf into a growing string (the writers format rows in parallel and write them in order)
+static void appendf(std::string& out, const char* fmt, ...)
+{
+    char b[512];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    if (n < 0) return;
+    if ((size_t)n < sizeof b) { out.append(b, (size_t)n); return; }
+    std::vector<char> big((size_t)n + 1);
+    va_start(ap, fmt);
+    vsnprintf(big.data(), big.size(), fmt, ap);
+    va_end(ap);
+    out.append(big.data(), (size_t)n);
+}
+
 // -------------------------------------------------------------------------------------------------
 int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
 {
     if (!gp || !e) return -1;
     const dtl_gmns& g = *gp;
     const std::string dir = dir_c && *dir_c ? dir_c : ".";
+    const bool trace = getenv("DTL_IO_TRACE") != nullptr;
+    auto t_phase = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (trace) fprintf(stderr, "write_outputs: %s %.3f s\n", what, std::chrono::duration<double>(now - t_phase).count());
+        t_phase = now;
+    };
     const int L = g.prob.n_links, T = g.prob.n_periods, AT = g.prob.n_agent_types, Z = g.prob.n_zones;
     std::vector<std::vector<double>> tt(T), pce(T), person(T), lv(T), doc(T), voc(T), P(T), vt2(T), qs(T), sbpr(T), qmu(T), qg(T), t0(T),
         t3(T), sev(T);
@@ -767,6 +794,7 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         speed[tau].assign((size_t)L * n_slots, 0.0f);
         if (dtl_get_model_speed(e, tau, first_slot, n_slots, speed[tau].data())) return -1;
     }
+    phase("link state read-back");
     // ---- link_performance.csv, output.h:533-779 ----
     FILE* f = fopen((dir + "/link_performance.csv").c_str(), "w");
     if (!f) { g_io_err = "File link_performance.csv cannot be opened."; return -1; }
@@ -781,11 +809,11 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
     fprintf(f, "scenario_code,volume_before,volume_after,volume_diff,speed_before,speed_after,speed_diff,DoC_before,DoC_after,Doc_diff,"
                "P_before,P_after,P_diff,");
     fprintf(f, "notes\n");
-    for (int i = 0; i < L; ++i) {
-        if (g.link_type[i] == -1) continue; // virtual connectors
+    auto format_link = [&](int i, std::string& out) {
+        if (g.link_type[i] == -1) return; // virtual connectors
         float total_vehicle_volume = 0;
         for (int tau = 0; tau < T; ++tau) total_vehicle_volume += pce[tau][i] + g.preload[(size_t)tau * L + i];
-        if (total_vehicle_volume < 0.001) continue;
+        if (total_vehicle_volume < 0.001) return;
         for (int tau = 0; tau < T; ++tau) {
             if (g.periods[tau].n_files == 0) continue;
             const size_t k = (size_t)tau * L + i;
@@ -805,22 +833,22 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
             const float PDT_vf = person_volume * (avg_tt - g.fftt[k]) / 60.0;
             const float PDT_vc = std::max(0.0, person_volume * (avg_tt - g.fftt[k] * g.free_speed[i] / std::max(0.001f, (float)g.cutoff_speed[i])) / 60.0);
             const double lane_based_D = std::max(0.0, lv[tau][i]) * g.qdf[k] / std::max(0.000001, g.nlanes[k]);
-            fprintf(f, "%s,%s,%d,%d,%f,%f,%f,%f,%d,%d,", g.link_id[i].c_str(), g.link_vdf_type[i] == 1 ? "bpr" : "qvdf",
+            appendf(out, "%s,%s,%d,%d,%f,%f,%f,%f,%d,%d,", g.link_id[i].c_str(), g.link_vdf_type[i] == 1 ? "bpr" : "qvdf",
                     g.node_id[g.link_from[i]], g.node_id[g.link_to[i]], g.nlanes[k], g.dist_km[i], g.dist_mile[i], g.fftt_min[i],
                     g.meso_link_id[i], 0);
-            fprintf(f, "%s,%s,%d,%d,%d,%d,%d,%s,%s,%s,", g.tmc_code[i].c_str(), g.tmc_corridor_name[i].c_str(), g.tmc_corridor_id[i], 0,
+            appendf(out, "%s,%s,%d,%d,%d,%d,%d,%s,%s,%s,", g.tmc_code[i].c_str(), g.tmc_corridor_name[i].c_str(), g.tmc_corridor_id[i], 0,
                     g.tmc_road_sequence[i], -1, g.link_type[i], g.link_type_code[i].c_str(), g.vdf_code[i].c_str(),
                     g.periods[tau].time_period.c_str());
-            fprintf(f, "%.3f,%.3f,%.3f,", vehicle_volume, g.ref_volume[i], ref_diff);
-            fprintf(f, ",,,,");
-            fprintf(f, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", preload, person_volume, avg_tt, spd, speed_ratio, voc[tau][i],
+            appendf(out, "%.3f,%.3f,%.3f,", vehicle_volume, g.ref_volume[i], ref_diff);
+            appendf(out, ",,,,");
+            appendf(out, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", preload, person_volume, avg_tt, spd, speed_ratio, voc[tau][i],
                     doc[tau][i], g.cap_lane[k], 0.0, 0.0);
-            fprintf(f, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", 0.0 / std::max(1.0f, vehicle_volume), g.qdf[k], g.nlanes[k],
+            appendf(out, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", 0.0 / std::max(1.0f, vehicle_volume), g.qdf[k], g.nlanes[k],
                     lane_based_D, g.Q_cd[k], g.Q_n[k], P[tau][i], sev[tau][i], g.vf[k], g.vc[k]);
-            fprintf(f, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", g.Q_cp[k], g.Q_s[k], qs[tau][i], vt2[tau][i], VMT, VHT, PMT, PHT,
+            appendf(out, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", g.Q_cp[k], g.Q_s[k], qs[tau][i], vt2[tau][i], VMT, VHT, PMT, PHT,
                     PDT_vf, PDT_vc);
-            fprintf(f, "\"%s\",", g.geometry[i].c_str());
-            for (int at = 0; at < AT; ++at) fprintf(f, "%.3f,", person_at[tau][at][i]);
+            appendf(out, "\"%s\",", g.geometry[i].c_str());
+            for (int at = 0; at < AT; ++at) appendf(out, "%.3f,", person_at[tau][at][i]);
             for (int t = 6 * 60; t < 20 * 60; t += 15) { // CLink::get_model_15_min_speed, DTA.h:1194-1214
                 float sum = 0;
                 int cnt = 0;
@@ -837,21 +865,42 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                     }
                     if (v >= 1) { sum += v; ++cnt; }
                 }
-                fprintf(f, "%.3f,", sum / std::max(1, cnt));
+                appendf(out, "%.3f,", sum / std::max(1, cnt));
             }
-            fprintf(f, "%s,", "");
+            appendf(out, "%s,", "");
             // base case / after the sensitivity-analysis stage (g_record_corridor_performance_summary, output.h:60-98).  Without
             // a supply-side scenario that stage only recomputes volumes and times from the final columns (main_api.cpp:772-1072),
             // which is the state dtl_finalize leaves: both records are the final state and the differences are zero.
             const double vb = vehicle_volume, sb = spd, db = doc[tau][i], pb = P[tau][i];
-            fprintf(f, "%.3f,%.3f,%.3f,", vb, vb, vb - vb);
-            fprintf(f, "%.3f,%.3f,%.3f,", sb, sb, sb - sb);
-            fprintf(f, "%.3f,%.3f,%.3f,", db, db, db - db);
-            fprintf(f, "%.3f,%.3f,%.3f,", pb, pb, pb - pb);
-            fprintf(f, "period-based\n");
+            appendf(out, "%.3f,%.3f,%.3f,", vb, vb, vb - vb);
+            appendf(out, "%.3f,%.3f,%.3f,", sb, sb, sb - sb);
+            appendf(out, "%.3f,%.3f,%.3f,", db, db, db - db);
+            appendf(out, "%.3f,%.3f,%.3f,", pb, pb, pb - pb);
+            appendf(out, "period-based\n");
+        }
+    };
+    {
+        const size_t chunk = 1024;
+        const int n_threads = (int)std::max<size_t>(1, std::min<size_t>({ (size_t)32, (size_t)std::max(1u, std::thread::hardware_concurrency()),
+                                                                           ((size_t)L + chunk - 1) / chunk }));
+        std::vector<std::string> bufs(n_threads);
+        for (size_t base = 0; base < (size_t)L; base += chunk * n_threads) {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_threads; ++t) {
+                const size_t r0 = base + chunk * t, r1 = std::min((size_t)L, r0 + chunk);
+                bufs[t].clear();
+                if (r0 >= r1) continue;
+                pool.emplace_back([&, t, r0, r1] {
+                    for (size_t r = r0; r < r1; ++r) format_link((int)r, bufs[t]);
+                });
+            }
+            for (auto& th : pool) th.join();
+            for (int t = 0; t < n_threads; ++t)
+                if (!bufs[t].empty()) fwrite(bufs[t].data(), 1, bufs[t].size(), f);
         }
     }
     fclose(f);
+    phase("link_performance.csv");
     // ---- route_assignment.csv, output.h:814-1456 ----
     f = fopen((dir + "/route_assignment.csv").c_str(), "w");
     if (!f) { g_io_err = "File route_assignment.csv cannot be opened."; return -1; }
@@ -885,9 +934,34 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         if (g.od_tau[ia] != g.od_tau[ib]) return g.od_tau[ia] < g.od_tau[ib];
         return g.od_at[ia] < g.od_at[ib];
     });
-    int count = 1;
     (void)Z;
-    for (long long oc : order) {
+    phase("column read-back and ordering");
+    // Rows are formatted in parallel and written in order: the file is ~2.5 KB per column (node, link and coordinate
+    // sequences), gigabytes on a regional network, and one fprintf stream made it the longest phase of the whole run.
+    // Per-node / per-link text is formatted once; the row prefix keeps the reference's printf format (output.h:1248-1445).
+    std::vector<long long> kept; // columns that are written, in output order: more than two physical nodes (output.h:1239)
+    kept.reserve(order.size());
+    for (long long oc : order)
+        if (n_nodes[oc] - 2 > 2) kept.push_back(oc);
+    const int N = g.prob.n_nodes;
+    std::vector<std::string> node_seq(N), node_xy(N), link_seq(L);
+    {
+        char b[160];
+        for (int n = 0; n < N; ++n) {
+            snprintf(b, sizeof b, "%d;", g.node_id[n]);
+            node_seq[n] = b;
+            snprintf(b, sizeof b, "%f %f", g.node_x[n], g.node_y[n]);
+            node_xy[n] = b;
+        }
+        for (int l = 0; l < L; ++l) link_seq[l] = g.link_id[l] + ";";
+    }
+    std::string sa_cols;
+    {
+        char b[64];
+        for (int it = 0; it <= g.sa_iterations; ++it) { snprintf(b, sizeof b, "%f,", -1.0); sa_cols += b; }
+        for (int it = 0; it <= g.sa_iterations; ++it) { snprintf(b, sizeof b, "%f,", 0.0); sa_cols += b; }
+    }
+    auto format_row = [&](long long oc, int count, std::string& out) {
         const int cell = od_index[oc];
         const int o = g.od_o[cell], d = g.od_d[cell], at = g.od_at[cell], tau = g.od_tau[cell];
         const int* pl = links.data() + first_link[oc];
@@ -904,32 +978,52 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                 if (g.link_type[l] != 1000) path_tt_no_access += ltt;
             }
         }
-        if (m_nodes - 2 <= 2) continue; // output.h:1239: at most two physical nodes
         const double vol = std::max(0.001, volume[oc]);
-        fprintf(f, ",%d,%d,%d,%d,%d,%d->%d,%d,%d,%s,%s,%d,%s,%s,%.4f,%d,%d,%d,%d,%d,%.1f,%d,%.1f,%.4f,%.4f,%.4f,%.4f,%.4f,", count,
-                g.zone_id[o], g.zone_id[d], o, d, g.zone_id[o], g.zone_id[d], seq[oc], seq[oc] + 1, "", "", 0, g.agents[at].name.c_str(),
-                g.periods[tau].name.c_str(), vol, 0, 0, 0, 0, 0, path_toll, m_nodes - 2, (double)path_tt, path_tt, path_tt_no_access, dist,
-                dist_km, dist_ml);
+        char b[1024];
+        const int nb = snprintf(b, sizeof b, ",%d,%d,%d,%d,%d,%d->%d,%d,%d,%s,%s,%d,%s,%s,%.4f,%d,%d,%d,%d,%d,%.1f,%d,%.1f,%.4f,%.4f,%.4f,%.4f,%.4f,",
+                                count, g.zone_id[o], g.zone_id[d], o, d, g.zone_id[o], g.zone_id[d], seq[oc], seq[oc] + 1, "", "", 0,
+                                g.agents[at].name.c_str(), g.periods[tau].name.c_str(), vol, 0, 0, 0, 0, 0, path_toll, m_nodes - 2,
+                                (double)path_tt, path_tt, path_tt_no_access, dist, dist_km, dist_ml);
+        out.append(b, std::min<size_t>(nb > 0 ? nb : 0, sizeof b - 1));
         // nodes: origin centroid, then the head of every link; the virtual first/last connector is stripped
-        for (int q = 0; q + 1 < m_links; ++q) fprintf(f, "%d;", g.node_id[g.link_to[pl[q]]]);
-        fprintf(f, ",");
-        for (int q = 1; q + 1 < m_links; ++q) fprintf(f, "%s;", g.link_id[pl[q]].c_str());
-        fprintf(f, ",");
-        for (int it = 0; it <= g.sa_iterations; ++it) fprintf(f, "%f,", -1.0);
-        for (int it = 0; it <= g.sa_iterations; ++it) fprintf(f, "%f,", 0.0);
+        for (int q = 0; q + 1 < m_links; ++q) out += node_seq[g.link_to[pl[q]]];
+        out += ',';
+        for (int q = 1; q + 1 < m_links; ++q) out += link_seq[pl[q]];
+        out += ',';
+        out += sa_cols;
         if (volume[oc] >= 5 || count < 3000) {
-            fprintf(f, "\"LINESTRING (");
+            out += "\"LINESTRING (";
             for (int q = 0; q + 1 < m_links; ++q) {
-                const int n = g.link_to[pl[q]];
-                fprintf(f, "%f %f", g.node_x[n], g.node_y[n]);
-                if (q + 2 < m_links) fprintf(f, ", ");
+                out += node_xy[g.link_to[pl[q]]];
+                if (q + 2 < m_links) out += ", ";
             }
-            fprintf(f, ")\"");
+            out += ")\"";
         }
-        if (volume[oc] >= 5) fprintf(f, ",,,,");
-        fprintf(f, "\n");
-        ++count;
+        if (volume[oc] >= 5) out += ",,,,";
+        out += '\n';
+    };
+    const size_t n_rows = kept.size();
+    const size_t chunk = 2048;
+    const int n_threads = (int)std::max<size_t>(1, std::min<size_t>({ (size_t)32, (size_t)std::max(1u, std::thread::hardware_concurrency()),
+                                                                       (n_rows + chunk - 1) / chunk }));
+    std::vector<std::string> bufs(n_threads);
+    bool write_failed = false;
+    for (size_t base = 0; base < n_rows && !write_failed; base += chunk * n_threads) {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; ++t) {
+            const size_t r0 = base + chunk * t, r1 = std::min(n_rows, r0 + chunk);
+            bufs[t].clear();
+            if (r0 >= r1) continue;
+            pool.emplace_back([&, t, r0, r1] {
+                for (size_t r = r0; r < r1; ++r) format_row(kept[r], (int)r + 1, bufs[t]);
+            });
+        }
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < n_threads; ++t)
+            if (!bufs[t].empty() && fwrite(bufs[t].data(), 1, bufs[t].size(), f) != bufs[t].size()) write_failed = true;
     }
+    if (write_failed) { fclose(f); g_io_err = "File route_assignment.csv cannot be written."; return -1; }
+    phase("route_assignment.csv rows");
     fclose(f);
     return 0;
 }
@@ -947,15 +1041,22 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     };
     if (ODME_iterations > 0) fail("ODME is outside the accelerated path (ODME_iterations must be 0)");
     if (simulation_iterations > 0) fail("the mesoscopic simulator is outside the accelerated path (simulation_iterations must be 0)");
+    using clk = std::chrono::steady_clock;
+    const auto t_start = clk::now();
+    auto since = [](clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); };
     dtl_gmns* g = dtl_gmns_read(".", number_of_memory_blocks);
     if (!g) fail(g_io_err);
+    const double s_read = since(t_start);
     if (sensitivity_analysis_iterations > 0) fail("supply-side scenario analysis is outside the accelerated path (sensitivity_analysis_iterations must be 0)");
     g->sa_iterations = std::max(0, sensitivity_analysis_iterations);
     dtl_options opt;
     dtl_default_options(&opt);
     opt.max_columns_per_od = std::max(4, column_generation_iterations + 4);
+    const auto t_create = clk::now();
     dtl_engine* e = dtl_create(dtl_gmns_problem(g), &opt);
     if (!e) fail(dtl_last_error());
+    const double s_create = since(t_create);
+    const auto t_loop = clk::now();
     std::ofstream summary("final_summary.csv");
     printf("DTALite (B200): %d nodes, %d links, %d zones, %d agent types, %d OD cells, %d shortest-path trees per iteration\n",
            g->prob.n_nodes, g->prob.n_links, g->prob.n_zones, g->prob.n_agent_types, g->prob.n_od, dtl_num_tasks(e));
@@ -980,8 +1081,13 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     }
     double sys = 0;
     if (dtl_finalize(e, column_generation_iterations, &sys)) fail(dtl_last_error()); // main_api.cpp:748-759
+    const double s_loop = since(t_loop);
+    const auto t_write = clk::now();
     if (dtl_gmns_write_outputs(g, e, ".")) fail(g_io_err.empty() ? dtl_last_error() : g_io_err);
+    const double s_write = since(t_write);
     summary.close();
+    printf("wall clock: read input files %.3f s, device image %.3f s, %d + %d assignment iterations %.3f s, write output files %.3f s\n",
+           s_read, s_create, column_generation_iterations, column_updating_iterations, s_loop, s_write);
     dtl_destroy(e);
     dtl_gmns_free(g);
     printf("done.\n");
