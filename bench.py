@@ -67,6 +67,19 @@ def k1_traffic(n_gpus: int):
         return None
 
 
+def other_kernels(tm, ctr, K, p, peak):
+    """K2a / K3 / K4 of a step: algorithmic GB/s (SURVEY.md 8d: 12 B per back-traced path node; 12 B per column-link reference;
+    160 B per (link, period)) over the event-timed phase, and the fraction of the measured HBM peak."""
+    out = {}
+    for name, phase, nbytes in (("K2a backtrace", "backtrace", 12.0 * ctr["path_nodes"]), ("K3 scatter", "scatter", 12.0 * ctr["link_refs"]),
+                                ("K4 vdf", "vdf", 160.0 * float(p.n_links) * float(p.n_periods) * K)):
+        ms = tm["ms"].get(phase, 0.0)
+        if ms > 0:
+            gbs = nbytes / (ms / 1e3) / 1e9
+            out[name] = {"ms_per_step": ms / K, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
+    return out
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -290,6 +303,8 @@ def run_engine_arm(args, rank, world, local_rank):
                          "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": edges_rank / launches_per_iter,
                          "kernel_ms_per_launch": sssp_ms_launch},
             "sssp_gteps": gteps,
+            # the other kernels of a step against the same HBM peak (algorithmic bytes of SURVEY.md 8d; this rank's share)
+            "other_kernels": other_kernels(tm, ctr, K, p, peak),
             "wall_ms_per_step": wall / K * 1e3,
             "phase_ms_per_step": {k_: v / K for k_, v in tm["ms"].items()},
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},

@@ -13,3 +13,8 @@ ncu --set full --import-source on --clock-control none -k regex:'sssp_kernel|bac
 ncu -i gpurun_out/ncu_full_${tag}.ncu-rep --page raw --csv > gpurun_out/ncu_full_${tag}_raw.csv 2>/dev/null
 ncu -i gpurun_out/ncu_full_${tag}.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/ncu_full_${tag}_src.csv 2>/dev/null
 tail -3 gpurun_out/ncu_full_${tag}.log
+# DRAM traffic of the dominant kernel at the bench configuration (2 000 trees in one launch): roofline.traffic
+ncu --set full --clock-control none -k regex:sssp_kernel -s 4 -c 1 -f -o gpurun_out/ncu_k1_bench_${tag} \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_k1_bench_${tag}.log 2>&1
+ncu -i gpurun_out/ncu_k1_bench_${tag}.ncu-rep --page raw --csv > gpurun_out/ncu_k1_bench_${tag}_raw.csv 2>/dev/null
+tail -2 gpurun_out/ncu_k1_bench_${tag}.log
