@@ -169,6 +169,7 @@ struct ScatterLaunch {
     ColumnPool pool;
     const int *od_at, *od_tau;
     const double *pce, *occ; // [T*AT*L]
+    const double *pce_uni, *occ_uni; // [T*AT] the value when every link of (tau, at) carries the same one, NaN otherwise
     unsigned long long* pce_fix;
     unsigned long long* person_fix; // may be null (skipped inside the CG loop)
     int decay_k;                    // <0: none
@@ -187,6 +188,7 @@ struct PoolUpdateLaunch {
     const float* vot;
     int n;                 // column-pool iteration index
     double* od_sums;       // [n_od][4]: gap, cost, time, demand contributions
+    double2* link_cost;    // [T*AT*L] workspace: {travel time, generalized first-order cost} per (tau, at, link)
 };
 void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st);
 

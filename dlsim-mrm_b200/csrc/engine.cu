@@ -106,6 +106,8 @@ struct dtl_engine {
     VdfParams vp{};
     LinkState ls{};
     double *d_pce = nullptr, *d_occ = nullptr, *d_toll = nullptr, *d_lr = nullptr;
+    double *d_pce_uni = nullptr, *d_occ_uni = nullptr; // [T*AT]
+    double2* d_link_cost = nullptr;                    // [T*AT*L] K2b workspace
     float* d_vot = nullptr;
     double *d_block_sums = nullptr, *d_scalars = nullptr, *d_volume_tmp = nullptr;
     double* h_scalars = nullptr; // pinned [16]
@@ -335,6 +337,7 @@ int do_scatter(dtl_engine* e, int decay_k, bool person)
     ScatterLaunch a{};
     a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
     a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.pce = e->d_pce; a.occ = e->d_occ;
+    a.pce_uni = e->d_pce_uni; a.occ_uni = e->d_occ_uni;
     a.pce_fix = e->ls.pce_fix; a.person_fix = person ? e->ls.person_fix : nullptr;
     a.decay_k = decay_k; a.link_refs = e->d_counters + 0;
     launch_scatter(a, e->st);
@@ -606,6 +609,20 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
 #undef UPV
     if (e->upload(&e->d_pce, p->pce, TAL)) return -1;
     if (e->upload(&e->d_occ, p->occ, TAL)) return -1;
+    { // per (tau, at): the PCE / occupancy when all links share it (K3 then skips the gather), NaN otherwise
+        std::vector<double> pu((size_t)T * AT), ou((size_t)T * AT);
+        for (int ta = 0; ta < T * AT; ++ta) {
+            const double* a0 = p->pce + (size_t)ta * L;
+            const double* o0 = p->occ + (size_t)ta * L;
+            bool ps = true, os = true;
+            for (int l = 1; l < L && (ps || os); ++l) { ps = ps && a0[l] == a0[0]; os = os && o0[l] == o0[0]; }
+            pu[ta] = ps && L > 0 ? a0[0] : std::nan("");
+            ou[ta] = os && L > 0 ? o0[0] : std::nan("");
+        }
+        if (e->upload(&e->d_pce_uni, pu.data(), pu.size())) return -1;
+        if (e->upload(&e->d_occ_uni, ou.data(), ou.size())) return -1;
+        if (e->alloc(&e->d_link_cost, TAL)) return -1;
+    }
     if (e->upload(&e->d_toll, p->toll, TAL)) return -1;
     if (e->upload(&e->d_lr, p->lr_price, TAL)) return -1;
     if (e->upload(&e->d_vot, p->vot, AT)) return -1;
@@ -865,6 +882,7 @@ int dtl_column_update(dtl_engine* e, int n, double row[4])
     a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
     a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.od_vol = e->d_od_vol;
     a.tt = e->ls.tt; a.penalty = e->vp.penalty; a.toll = e->d_toll; a.vot = e->d_vot; a.n = n; a.od_sums = e->d_od_sums;
+    a.link_cost = e->d_link_cost;
     const int ph5 = e->phase_begin(5);
     launch_pool_update(a, e->st);
     for (int j = 0; j < 4; ++j) launch_sum(e->d_od_sums + j, e->n_cells, 4, e->d_scalars + 4 + j, e->st);

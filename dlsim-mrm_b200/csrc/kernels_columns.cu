@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
     const int at = a.od_at[cell], tau = a.od_tau[cell];
     const double* pce = a.pce + ((size_t)tau * a.AT + at) * a.L;
     const double* occ = a.occ + ((size_t)tau * a.AT + at) * a.L;
+    // one PCE / occupancy for every link of this (period, agent type) is the common case: no gather then (same product)
+    const double pce_u = a.pce_uni[tau * a.AT + at], occ_u = PERSON ? a.occ_uni[tau * a.AT + at] : 0.0;
+    const bool pce_same = pce_u == pce_u, occ_same = occ_u == occ_u;
     unsigned long long* acc = a.pce_fix + (size_t)tau * a.L;
     unsigned long long* per = PERSON ? a.person_fix + (size_t)tau * (1 + a.AT) * a.L : nullptr;
     unsigned long long* per_at = PERSON ? per + (size_t)(1 + at) * a.L : nullptr;
@@ -122,10 +125,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
         if (f != 0.0f) {
             for (int q = lane; q < n; q += 32) {
                 const int l = __ldg(&links[q]);
-                const double x = f * __ldg(&pce[l]);                 // assignment.h:140
+                const double x = f * (pce_same ? pce_u : __ldg(&pce[l])); // assignment.h:140
                 atomicAdd(&acc[l], (unsigned long long)__double2ll_rn(x * DTL_FIX_SCALE));
                 if (PERSON) {
-                    const unsigned long long y = (unsigned long long)__double2ll_rn(f * __ldg(&occ[l]) * DTL_FIX_SCALE);
+                    const unsigned long long y =
+                        (unsigned long long)__double2ll_rn(f * (occ_same ? occ_u : __ldg(&occ[l])) * DTL_FIX_SCALE);
                     atomicAdd(&per[l], y);                           // assignment.h:141
                     atomicAdd(&per_at[l], y);                        // assignment.h:142
                 }
@@ -147,9 +151,49 @@ void launch_scatter(const ScatterLaunch& a, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b: one thread per OD cell.  Path costs are left-to-right FP64 sums in path order exactly like the
-// reference (DTA.h:1154-1164, assignment.h:723-736), so the arg-min ("first strict minimum in ascending
-// node_sum order", assignment.h:757) and the flow shifts reproduce the reference's decisions.
+// K2b, three launches.  (1) per (period, agent type, link): {travel time, first-order gradient cost} with the reference's
+// expression  tt + penalty + toll / VOT * 60  (DTA.h:1157) evaluated ONCE per link instead of once per column link, in one
+// 16-byte record so that a column link costs one gather.  (2) one thread per column slot: path cost / time as
+// left-to-right FP64 sums in path order exactly like the reference (DTA.h:1154-1164, assignment.h:723-736).  (3) one thread
+// per OD cell: arg-min ("first strict minimum in ascending node_sum order", assignment.h:757) and the flow shifts.
+__global__ void __launch_bounds__(256) pool_link_cost_kernel(PoolUpdateLaunch a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)a.T * a.AT * a.L;
+    if (i >= n) return;
+    const int l = (int)(i % a.L);
+    const int ta = (int)(i / a.L); // tau * AT + at
+    const int tau = ta / a.AT, at = ta - tau * a.AT;
+    const double t = a.tt[(size_t)tau * a.L + l];
+    a.link_cost[i] = make_double2(t, t + a.penalty[(size_t)tau * a.L + l] + a.toll[i] / a.vot[at] * 60); // DTA.h:1157
+}
+
+__global__ void __launch_bounds__(128) pool_column_cost_kernel(PoolUpdateLaunch a)
+{
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const ColumnPool& P = a.pool;
+    if (slot >= (size_t)P.n_od * P.cap) return;
+    const int cell = (int)(slot / P.cap);
+    if ((int)(slot - (size_t)cell * P.cap) >= P.count[cell]) return;
+    const double2* lc = a.link_cost + ((size_t)a.od_tau[cell] * a.AT + a.od_at[cell]) * a.L;
+    const int n = P.n_links[slot];
+    const int4* links = reinterpret_cast<const int4*>(P.arena + P.offset[slot]);
+    double path_cost = 0, path_time = 0;
+    for (int q = 0; q < n; q += 4) {
+        const int4 v = __ldg(&links[q >> 2]);
+        const int ls[4] = { v.x, v.y, v.z, v.w };
+        double2 c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) // the four gathers of a 16-byte group of link ids are issued together
+            c[r] = q + r < n ? __ldg(&lc[ls[r]]) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (q + r < n) { path_time += c[r].x; path_cost += c[r].y; }
+    }
+    P.cost[slot] = path_cost;
+    P.time[slot] = path_time;
+}
+
 __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,34 +203,8 @@ __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
     double* sums = a.od_sums + (size_t)cell * 4;
     double s_gap = 0, s_cost = 0, s_time = 0, s_dem = 0;
     if (cnt > 0) {
-        const int at = a.od_at[cell], tau = a.od_tau[cell];
-        const double* tt = a.tt + (size_t)tau * a.L;
-        const double* pen = a.penalty + (size_t)tau * a.L;
-        const double* toll = a.toll + ((size_t)tau * a.AT + at) * a.L;
-        const float vot = a.vot[at];
         const size_t base = (size_t)cell * P.cap;
         const double od_volume = a.od_vol[cell];
-        // pass 1: path cost / time of every column
-        for (int j = 0; j < cnt; ++j) {
-            const int n = P.n_links[base + j];
-            const int4* links = reinterpret_cast<const int4*>(P.arena + P.offset[base + j]);
-            double path_cost = 0, path_time = 0;
-            for (int q = 0; q < n; q += 4) {
-                const int4 v = __ldg(&links[q >> 2]);
-                const int ls[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (q + r < n) {
-                        const int l = ls[r];
-                        const double t = __ldg(&tt[l]);
-                        path_time += t;
-                        path_cost += t + __ldg(&pen[l]) + __ldg(&toll[l]) / vot * 60; // DTA.h:1157
-                    }
-                }
-            }
-            P.cost[base + j] = path_cost;
-            P.time[base + j] = path_time;
-        }
         // pass 2: arg-min in ascending node_sum order with strict '<' (std::map order, assignment.h:686-767)
         double least_cost = 999999;
         int least = -1, least_key = 0;
@@ -241,6 +259,9 @@ __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
 void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st)
 {
     if (a.pool.n_od == 0) return;
+    const size_t n_lc = (size_t)a.T * a.AT * a.L, n_slots = (size_t)a.pool.n_od * a.pool.cap;
+    pool_link_cost_kernel<<<(unsigned)((n_lc + 255) / 256), 256, 0, st>>>(a);
+    pool_column_cost_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(a);
     pool_update_kernel<<<(a.pool.n_od + 127) / 128, 128, 0, st>>>(a);
 }
 
