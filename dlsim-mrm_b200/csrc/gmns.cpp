@@ -13,6 +13,7 @@
 // analysis, simulation) stop with an explicit message and a non-zero exit status; nothing blocks on stdin
 // (the reference's g_program_stop() does, utils.cpp:41-46).
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -107,23 +108,83 @@ public:
     {
         const std::string* s = raw(name, required);
         if (!s) return false;
-        std::istringstream ss(*s);
         T v;
-        ss >> v;
-        if (ss.fail()) return false;
+        if (!parse(s->c_str(), v)) return false;
         if (required && nonnegative && v < 0) v = 0;
         value = v;
         return true;
     }
+    // Field names are string literals at the call sites: the literal's address caches the column index, so a row of
+    // thirty fields costs thirty pointer look-ups instead of thirty std::string constructions and map searches.
+    template <class T>
+    bool get(const char* name, T& value, bool required = true, bool nonnegative = true)
+    {
+        const std::string* s = raw_cached(name, required);
+        if (!s) return false;
+        T v;
+        if (!parse(s->c_str(), v)) return false;
+        if (required && nonnegative && v < 0) v = 0;
+        value = v;
+        return true;
+    }
+    bool get(const char* name, std::string& value, bool required = true)
+    {
+        const std::string* s = raw_cached(name, required);
+        if (!s) return false;
+        value = *s;
+        return true;
+    }
+    bool has(const char* name) const { return index_.count(name) != 0; }
 
 private:
     std::ifstream in_;
     std::map<std::string, int> index_;
     std::vector<std::string> values_;
+    std::vector<std::pair<const char*, int>> cache_; // literal address -> column index (-1: no such column); reset with the header
+
+    // the stream extraction the reference's parser performs (operator>> of an istringstream), without the stream:
+    // leading white space skipped, the longest valid prefix converted, failure when nothing converts
+    static bool parse(const char* s, double& v) { char* e; v = strtod(s, &e); return e != s; }
+    static bool parse(const char* s, float& v) { char* e; v = strtof(s, &e); return e != s; }
+    static bool parse(const char* s, long& v)
+    {
+        char* e;
+        errno = 0;
+        v = strtol(s, &e, 10);
+        return e != s && errno != ERANGE;
+    }
+    static bool parse(const char* s, int& v)
+    {
+        char* e;
+        const long long x = strtoll(s, &e, 10);
+        if (e == s) return false;
+        if (x > 2147483647LL || x < -2147483648LL) return false; // operator>> sets failbit on overflow
+        v = (int)x;
+        return true;
+    }
+    const std::string* raw_cached(const char* name, bool required)
+    {
+        int col = -2;
+        for (const auto& c : cache_)
+            if (c.first == name) { col = c.second; break; }
+        if (col == -2) {
+            auto it = index_.find(name);
+            col = it == index_.end() ? -1 : it->second;
+            cache_.emplace_back(name, col);
+        }
+        if (col < 0) {
+            if (required) stop(std::string("Field ") + name + " in file " + file + " does not exist. Please check the file.");
+            return nullptr;
+        }
+        if (values_.empty() || col >= (int)values_.size()) return nullptr;
+        const std::string& s = values_[col];
+        return s.empty() ? nullptr : &s;
+    }
 
     void set_header(const std::string& line)
     {
         index_.clear();
+        cache_.clear();
         if (line.empty()) return;
         std::vector<std::string> names = split(line);
         for (size_t i = 0; i < names.size(); ++i) {
@@ -398,6 +459,17 @@ void read_network(dtl_gmns& g)
     // ---- link.csv, input.h:3207-3678 ----
     {
         Csv p;
+        // per-period / per-agent-type field names, built once: their c_str() addresses key the reader's column cache
+        std::vector<std::string> n_pce(AT), n_fftt(T), n_cap(T), n_alpha(T), n_beta(T), n_uses(T), n_preload(T), n_penalty(T),
+            n_toll((size_t)T * AT);
+        for (int at = 0; at < AT; ++at) n_pce[at] = "VDF_pce" + g.agents[at].name;
+        for (int tau = 0; tau < T; ++tau) {
+            const std::string pid = std::to_string(g.periods[tau].id);
+            n_fftt[tau] = "VDF_fftt" + pid; n_cap[tau] = "VDF_cap" + pid; n_alpha[tau] = "VDF_alpha" + pid; n_beta[tau] = "VDF_beta" + pid;
+            n_uses[tau] = "VDF_allowed_uses" + pid; n_preload[tau] = "VDF_preload" + pid; n_penalty[tau] = "VDF_penalty" + pid;
+            for (int at = 0; at < AT; ++at) n_toll[(size_t)tau * AT + at] = "VDF_toll" + g.agents[at].name + pid;
+        }
+        const std::string n_ref = "VDF_ref_link_volume" + std::to_string(g.periods[0].id);
         p.open(g.dir + "/link.csv");
         int type_warnings = 0;
         while (p.read_record()) {
@@ -448,7 +520,7 @@ void read_network(dtl_gmns& g)
             const double dist = length_m / 1609.0;
             std::vector<PerPeriod> per(T);
             std::vector<double> pce_at(AT, -1.0);
-            for (int at = 0; at < AT; ++at) p.get("VDF_pce" + g.agents[at].name, pce_at[at], false, true);
+            for (int at = 0; at < AT; ++at) p.get(n_pce[at].c_str(), pce_at[at], false, true);
             for (int tau = 0; tau < T; ++tau) {
                 PerPeriod v = default_period(tau);
                 const Period& d = g.periods[tau];
@@ -464,18 +536,17 @@ void read_network(dtl_gmns& g)
                 v.start_h = d.start_slot * 5 / 60.0;
                 v.end_h = d.end_slot * 5 / 60.0;
                 v.L = d.hours; v.t2 = d.t2; v.plf = 1;
-                const std::string pid = std::to_string(d.id);
                 double fftt_in = -1;
-                p.get("VDF_fftt" + pid, fftt_in, false, false);
+                p.get(n_fftt[tau].c_str(), fftt_in, false, false);
                 const bool req = fftt_in >= 0;
                 if (req) v.fftt = fftt_in;
-                p.get("VDF_cap" + pid, v.cap, req, false);
-                p.get("VDF_alpha" + pid, v.alpha, req, false);
-                p.get("VDF_beta" + pid, v.beta, req, false);
-                if (!p.get("VDF_allowed_uses" + pid, v.allowed_uses, false)) p.get("allowed_uses", v.allowed_uses, false);
-                p.get("VDF_preload" + pid, v.preload, false, false);
-                for (int at = 0; at < AT; ++at) p.get("VDF_toll" + g.agents[at].name + pid, v.toll[at], false, false);
-                p.get("VDF_penalty" + pid, v.penalty, false, false);
+                p.get(n_cap[tau].c_str(), v.cap, req, false);
+                p.get(n_alpha[tau].c_str(), v.alpha, req, false);
+                p.get(n_beta[tau].c_str(), v.beta, req, false);
+                if (!p.get(n_uses[tau].c_str(), v.allowed_uses, false)) p.get("allowed_uses", v.allowed_uses, false);
+                p.get(n_preload[tau].c_str(), v.preload, false, false);
+                for (int at = 0; at < AT; ++at) p.get(n_toll[(size_t)tau * AT + at].c_str(), v.toll[at], false, false);
+                p.get(n_penalty[tau].c_str(), v.penalty, false, false);
                 if (cell_type >= 2) v.penalty += 1.0 / 60.0;
                 p.get("cycle_length", v.cycle, false, false);
                 if (v.cycle >= 1) {
@@ -491,7 +562,7 @@ void read_network(dtl_gmns& g)
                 per[tau] = v;
             }
             double ref_vol = -1;
-            p.get("VDF_ref_link_volume" + std::to_string(g.periods[0].id), ref_vol, false, false);
+            p.get(n_ref.c_str(), ref_vol, false, false);
             p.get("tmc", tmc, false);
             int tmc_cid = -1, tmc_seq = -1;
             if (!tmc.empty()) { tmc_cid = 1; tmc_seq = 1; p.get("tmc_corridor_id", tmc_cid, false); p.get("tmc_road_sequence", tmc_seq, false); }
@@ -668,12 +739,23 @@ dtl_gmns* dtl_gmns_read(const char* dir, int number_of_memory_blocks)
 {
     dtl_gmns* g = new dtl_gmns();
     g->dir = dir && *dir ? dir : ".";
+    const bool trace = getenv("DTL_IO_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (trace) fprintf(stderr, "gmns_read: %s %.3f s\n", what, std::chrono::duration<double>(now - t0).count());
+        t0 = now;
+    };
     try {
         read_settings(*g);
+        phase("settings.csv");
         read_network(*g);
+        phase("node.csv + link.csv + connectors");
         read_demand(*g);
+        phase("demand files");
         read_output_configuration(*g);
         bind_problem(*g, number_of_memory_blocks);
+        phase("problem image");
     } catch (const StopError& e) {
         g_io_err = e.what();
         delete g;
