@@ -231,8 +231,10 @@ def run_engine_arm(args, rank, world, local_rank):
         uid = sharding.broadcast_bytes(dist, D.Engine.comm_unique_id() if rank == 0 else None, 128, device="cuda")
 
     def make_engine():
+        # the dense-OD variant stores ~200 path links per column for 4 M OD cells: give the path-link arena what it needs
+        arena = (40 << 30) // max(1, world) if args.workload.endswith("_dense") else 0
         e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 4,
-                     delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas)
+                     delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas, column_arena_bytes=arena)
         if world > 1:
             e.comm_init(uid)
         return e

@@ -166,6 +166,9 @@ def write_grid(directory, K=20, blocks=8, **kw):
 WORKLOADS = {
     # BASELINE.json configs[4]: 100k nodes / 300k links / 2000 zones / 4M trips
     "grid100k": dict(rows=316, cols=317, n_links=300_000, n_zones=2000, total_trips=4_000_000.0, dest_per_origin=200),
+    # the dense-OD variant of SURVEY.md 8d: every zone pair carries demand (3 998 000 OD rows); GPU only -- the reference's
+    # column pool would need ~40 GB of host memory
+    "grid100k_dense": dict(rows=316, cols=317, n_links=300_000, n_zones=2000, total_trips=4_000_000.0, dest_per_origin=1999),
     # same generator, small enough for a CPU run in seconds (tests)
     "grid2k": dict(rows=45, cols=46, n_links=6_200, n_zones=60, total_trips=60_000.0, dest_per_origin=25),
     "grid10k": dict(rows=100, cols=101, n_links=30_000, n_zones=200, total_trips=400_000.0, dest_per_origin=60),
