@@ -44,18 +44,19 @@ def main():
         print()
     if len(sys.argv) > 2:
         rows = list(csv.reader(open(sys.argv[2])))
-        fn = ""
-        lines = []
+        per_fn, fn = {}, ""
         for r in rows:
             if r and r[0] == "Function Name":
                 fn = r[1]
             elif r and r[0].strip().isdigit() and len(r) > 7 and r[4].isdigit():
-                lines.append((int(r[4]), r[0], r[7], r[1]))
-        tot = sum(x[0] for x in lines) or 1
-        print(f"## hottest source lines of `{fn}` (warp stall samples, all)\n")
-        print("| line | samples | share | instructions executed | source |\n|---|---|---|---|---|")
-        for s, ln, ie, src in sorted(lines, reverse=True)[:25]:
-            print(f"| {ln} | {s} | {100.0 * s / tot:.1f}% | {ie} | `{src.strip()[:100]}` |")
+                per_fn.setdefault(fn, []).append((int(r[4]), r[0], r[7], r[1]))
+        for fn, lines in per_fn.items():
+            tot = sum(x[0] for x in lines) or 1
+            print(f"## hottest source lines of `{fn}` (warp stall samples, all)\n")
+            print("| line | samples | share | instructions executed | source |\n|---|---|---|---|---|")
+            for s_, ln, ie, src in sorted(lines, reverse=True)[:12]:
+                print(f"| {ln} | {s_} | {100.0 * s_ / tot:.1f}% | {ie} | `{src.strip()[:100]}` |")
+            print()
 
 
 if __name__ == "__main__":
