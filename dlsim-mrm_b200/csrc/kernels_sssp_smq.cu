@@ -3,8 +3,8 @@
 // where the time of a launch is the latency of one tree, not the throughput of the SM.
 //   * the near queues of the current and of the next round live in shared memory: entries {label-at-push, node, link,
 //     forward-star row, parent node};
-//   * G lanes own one queue entry and relax one out-edge each (a second pass only for nodes with more than G out-edges),
-//     so a round of a big CTA is a single pass with every warp busy;
+//   * G lanes own one queue entry and relax U out-edges each per pass (G = U = 2: a second pass only for nodes with more
+//     than four out-edges), so a round of a big CTA is a single pass with every warp busy;
 //   * the dependent chain of a round is two round trips: edge load -> atomicMin.  The row comes with the entry (fetched by
 //     the pusher in the shadow of its atomic), the liveness of the entry is not waited for (relaxing with a superseded
 //     label is harmless: it is a real path cost), only the predecessor store needs it;
@@ -17,14 +17,17 @@
 namespace dtl {
 
 #ifndef SMQ_G
-#define SMQ_G 4 /* lanes per queue entry (power of two <= 32) */
+#define SMQ_G 2 /* lanes per queue entry (power of two <= 32) */
+#endif
+#ifndef SMQ_U
+#define SMQ_U 2 /* edges per lane and pass: G * U out-edges of a node are relaxed in one pass */
 #endif
 #ifndef SMQ_PREFETCH
 #define SMQ_PREFETCH 0 /* 1: the pusher prefetches the pushed node's edge row into L1 (no measurable effect on B200) */
 #endif
 #define SMQ_MIN_CTAS(BLOCK) (1024 / (BLOCK)) /* 64 registers per thread: 1024 threads per SM */
 
-template <int BLOCK, int G>
+template <int BLOCK, int G, int U>
 __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(SsspLaunch a)
 {
     extern __shared__ int4 s_dyn[];
@@ -82,8 +85,8 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                 const int ci1 = ci == 2 ? 0 : ci + 1;
                 const int ci2 = ci1 == 2 ? 0 : ci1 + 1;
                 const int in0 = buf * CAP, out0 = (buf ^ 1) * CAP; // first slot of the queue read / written this round
-                // Expansion: a group of G lanes owns one queue entry, every lane one of its edges (a second pass only for nodes
-                // with more than G out-edges).  The chain of a pass is: entry from shared memory -> edge (L1: prefetched by the
+                // Expansion: a group of G lanes owns one queue entry, every lane U of its edges (a second pass only for nodes
+                // with more than G * U out-edges).  The chain of a pass is: entry from shared memory -> edge (L1: prefetched by the
                 // pusher) -> atomicMin round trip -> ballot-placed push.  The liveness of the entry is NOT waited for: relaxing
                 // with a superseded label is harmless (it is a real path cost), only the predecessor store needs it.
                 for (int base = 0; base < n_near; base += BLOCK / G) {
@@ -96,73 +99,105 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                         const int2 rr = s_r[in0 + i];
                         parent = s_p[in0 + i];
                         qlab = __hiloint2double(qv.y, qv.x); node = qv.z; qlink = qv.w;
-                        e0 = rr.x + k; re = rr.y;
+                        e0 = rr.x + k * U; re = rr.y;
                     }
                     unsigned long long cur = 0ULL;
                     const bool head = k == 0 && i < n_near;
                     if (head) cur = __ldcg(&lab[node]); // consumed after the atomics have returned
-                    Edge ed;
-                    ed.cost = 0.0; ed.to = 0; ed.link = 0;
-                    if (e0 < re) ed = ld_edge(&a.edges[e0]);
+                    Edge ed[U];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        ed[j].cost = 0.0; ed[j].to = 0; ed[j].link = 0;
+                        if (e0 + j < re) ed[j] = ld_edge(&a.edges[e0 + j]);
+                    }
                     bool first = true;
                     while (__any_sync(0xffffffffu, e0 < re)) {
-                        bool ok = e0 < re;
-                        int to = ed.to;
-                        if (ok && to < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
-                            to &= 0x7fffffff;
-                            if (__ldg(&a.link_tag[ed.link]) != zone) ok = false; // routing.h:779-786
+                        unsigned ok_m = 0, near_c = 0; // bit j: edge j is relaxed / its head falls into the near window
+                        double c[U];
+                        int to[U];
+#pragma unroll
+                        for (int j = 0; j < U; ++j) {
+                            to[j] = ed[j].to;
+                            c[j] = qlab + ed[j].cost; // routing.h:804
+                            bool ok = e0 + j < re;
+                            if (ok && to[j] < 0) { // outgoing connector of a zone: only the origin zone may leave its centroid
+                                to[j] &= 0x7fffffff;
+                                if (__ldg(&a.link_tag[ed[j].link]) != zone) ok = false; // routing.h:779-786
+                            }
+                            if (to[j] == parent && c[j] > qlab) ok = false; // back to where the entry came from: cannot improve
+                            if (ok) {
+                                ok_m |= 1u << j;
+                                if (c[j] < thr) near_c |= 1u << j;
+                            }
                         }
-                        const double c = qlab + ed.cost; // routing.h:804
-                        if (to == parent && c > qlab) ok = false; // back to where the entry came from: cannot improve
-                        const bool near_c = c < thr;
-                        // the one long trip: the atomic, and in its shadow the forward-star row of a head that may enter the near queue
-                        const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
-                        unsigned long long old = 0ULL;
-                        int2 prow = make_int2(0, 0);
-                        if (ok) { // routing.h:816
-                            ++c_relax;
-                            old = atomicMin(&lab[to], cb);
-                            if (near_c) prow = __ldg(&a.rows[to]);
+                        c_relax += __popc(ok_m);
+                        // the one long trip: the atomics, and in their shadow the forward-star rows of the heads that may enter the near queue
+                        unsigned long long old[U];
+                        int2 prow[U];
+#pragma unroll
+                        for (int j = 0; j < U; ++j) {
+                            old[j] = 0ULL;
+                            prow[j] = make_int2(0, 0);
+                            if (ok_m & (1u << j)) { // routing.h:816
+                                old[j] = atomicMin(&lab[to[j]], (unsigned long long)__double_as_longlong(c[j]));
+                                if (near_c & (1u << j)) prow[j] = __ldg(&a.rows[to[j]]);
+                            }
                         }
-                        const bool imp = ok && old > cb;
-                        const bool is_near = imp && near_c, is_far = imp && !near_c;
-                        const unsigned nm = __ballot_sync(0xffffffffu, is_near), fm = __ballot_sync(0xffffffffu, is_far);
-                        if (nm | fm) {
+                        unsigned near_m = 0, far_m = 0, tie_m = 0;
+#pragma unroll
+                        for (int j = 0; j < U; ++j) {
+                            if (!(ok_m & (1u << j))) continue;
+                            const unsigned long long cb = (unsigned long long)__double_as_longlong(c[j]);
+                            if (old[j] > cb) { if (near_c & (1u << j)) near_m |= 1u << j; else far_m |= 1u << j; }
+                            else if (old[j] == cb && to[j] != origin) tie_m |= 1u << j;
+                        }
+                        // one inclusive scan carries both counts (near in the low half, far in the high half)
+                        const int mine = __popc(near_m) | (__popc(far_m) << 16);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (total) {
                             int bn = 0, bf = 0;
-                            if (lane == 0) {
-                                if (nm) bn = atomicAdd(&s_cnt[ci1], __popc(nm));
-                                if (fm) bf = atomicAdd(&s_n_far, __popc(fm));
+                            if (lane == 31) {
+                                if (total & 0xffff) bn = atomicAdd(&s_cnt[ci1], total & 0xffff);
+                                if (total >> 16) bf = atomicAdd(&s_n_far, total >> 16);
                             }
-                            bn = __shfl_sync(0xffffffffu, bn, 0);
-                            bf = __shfl_sync(0xffffffffu, bf, 0);
-                            const unsigned lt = (1u << lane) - 1;
-                            if (is_near) {
-                                const int pos = bn + __popc(nm & lt);
-                                if (pos < CAP) {
-                                    s_q[out0 + pos] = pack_entry(c, to, ed.link);
-                                    s_r[out0 + pos] = prow;
-                                    s_p[out0 + pos] = node;
-#if SMQ_PREFETCH
-                                    if (prow.y > prow.x) {
-                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + prow.x));
-                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.edges + prow.y - 1));
+                            bn = __shfl_sync(0xffffffffu, bn, 31);
+                            bf = __shfl_sync(0xffffffffu, bf, 31);
+                            int pos_near = bn + ((incl - mine) & 0xffff);
+                            int pos_far = bf + ((incl - mine) >> 16);
+#pragma unroll
+                            for (int j = 0; j < U; ++j) {
+                                if (near_m & (1u << j)) {
+                                    if (pos_near < CAP) {
+                                        s_q[out0 + pos_near] = pack_entry(c[j], to[j], ed[j].link);
+                                        s_r[out0 + pos_near] = prow[j];
+                                        s_p[out0 + pos_near] = node;
+                                    } else { // shared-memory queue full: the entry waits in the far pile for the next re-bucketing
+                                        const int pf_ = atomicAdd(&s_n_far, 1);
+                                        if (pf_ < a.cap_far) st_entry(&q_far[pf_], c[j], to[j], ed[j].link);
+                                        else s_overflow = 1;
+                                        atomicAdd(&s_spill, 1);
                                     }
-#endif
-                                } else { // shared-memory queue full: the entry waits in the far pile for the next re-bucketing
-                                    const int pf_ = atomicAdd(&s_n_far, 1);
-                                    if (pf_ < a.cap_far) st_entry(&q_far[pf_], c, to, ed.link);
+                                    ++pos_near;
+                                } else if (far_m & (1u << j)) {
+                                    if (pos_far < a.cap_far) st_entry(&q_far[pos_far], c[j], to[j], ed[j].link);
                                     else s_overflow = 1;
-                                    atomicAdd(&s_spill, 1);
+                                    ++pos_far;
                                 }
-                            } else if (is_far) {
-                                const int pos = bf + __popc(fm & lt);
-                                if (pos < a.cap_far) st_entry(&q_far[pos], c, to, ed.link);
-                                else s_overflow = 1;
                             }
                         }
-                        if (ok && old == cb && to != origin) { // exact FP64 ties are rare: slow path
-                            const int pos = atomicAdd(&s_n_tie, 1);
-                            if (pos < a.tie_cap) tie_cand[pos] = to;
+                        if (tie_m) { // exact FP64 ties are rare: slow path
+#pragma unroll
+                            for (int j = 0; j < U; ++j)
+                                if (tie_m & (1u << j)) {
+                                    const int pos = atomicAdd(&s_n_tie, 1);
+                                    if (pos < a.tie_cap) tie_cand[pos] = to[j];
+                                }
                         }
                         if (first) {
                             first = false;
@@ -172,8 +207,10 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                                 ++c_pops;
                             }
                         }
-                        e0 += G;
-                        if (e0 < re) ed = ld_edge(&a.edges[e0]);
+                        e0 += G * U;
+#pragma unroll
+                        for (int j = 0; j < U; ++j)
+                            if (e0 + j < re) ed[j] = ld_edge(&a.edges[e0 + j]);
                     }
                     if (first && head && !(cur < (unsigned long long)__double_as_longlong(qlab))) { // entry without usable out-edges
                         pred[node] = qlink;
@@ -312,8 +349,8 @@ template <int BLOCK>
 static void smq_launch(const SsspLaunch& a, cudaStream_t st)
 {
     const size_t smem = smq_smem_bytes(a.cap_smem);
-    cudaFuncSetAttribute(sssp_smq_kernel<BLOCK, SMQ_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sssp_smq_kernel<BLOCK, SMQ_G><<<a.grid, BLOCK, smem, st>>>(a);
+    cudaFuncSetAttribute(sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U><<<a.grid, BLOCK, smem, st>>>(a);
 }
 
 void launch_sssp_smq(const SsspLaunch& a, cudaStream_t st)
