@@ -1178,6 +1178,12 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
         stats[3] = (double)(s1.pops - s0.pops);
         stats[4] = (double)(s1.rounds - s0.rounds);
         stats[5] = (double)(s1.replayed - s0.replayed);
+        if (getenv("DTL_SSSP_PROFILE")) { // filled by a -DSSSP_PROFILE build of the shared-memory-queue kernel
+            double d[8];
+            for (int k = 0; k < 8; ++k) d[k] = (double)(s1.prof[k] - s0.prof[k]);
+            fprintf(stderr, "sssp: spilled %.3g | thread-0 cycles: init %.3g expansion %.3g barrier %.3g re-bucket %.3g | passes %.3g entries %.3g "
+                            "rounds %.3g\n", d[0], d[1], d[2], d[3], d[4], d[6], d[7], (double)(s1.rounds - s0.rounds));
+        }
     }
     e->trees_valid = false;
     return 0;

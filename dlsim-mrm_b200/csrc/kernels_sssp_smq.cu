@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
     int* tie_cand = a.tie_cand + (size_t)blockIdx.x * a.tie_cap;
     unsigned c_relax = 0, c_pops = 0, c_rounds = 0;
     if (tid == 0) s_spill = 0;
+#ifdef SSSP_PROFILE
+    // thread 0's cycles: [1] init [2] expansion [3] round barrier [4] re-bucketing [5] tie check; [6] passes of warp 0 [7] entries read
+    long long pf_t = clock64(), pf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#define PF(k_) do { const long long n_ = clock64(); pf[k_] += n_ - pf_t; pf_t = n_; } while (0)
+#else
+#define PF(k_) do { } while (0)
+#endif
 
     for (;;) {
         __syncthreads();
@@ -75,6 +82,7 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
             s_p[0] = -1;
         }
         __syncthreads();
+        PF(1);
         int n_near = 1;
         int buf = 0; // near-queue buffer read this round
         int ci = 0;  // s_cnt[ci] counted this round's entries, pushes count into s_cnt[ci+1], s_cnt[ci+2] is cleared
@@ -112,6 +120,9 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                     }
                     bool first = true;
                     while (__any_sync(0xffffffffu, e0 < re)) {
+#ifdef SSSP_PROFILE
+                        pf[6] += 1;
+#endif
                         unsigned ok_m = 0, near_c = 0; // bit j: edge j is relaxed / its head falls into the near window
                         double c[U];
                         int to[U];
@@ -217,10 +228,15 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                         ++c_pops;
                     }
                 }
+#ifdef SSSP_PROFILE
+                pf[7] += n_near;
+#endif
+                PF(2);
                 if (tid == 0) s_cnt[ci2] = 0; // last read before the previous barrier, pushed into from the round after next
                 // the one barrier of a round; thread 0's view of the far pile may miss this round's pushes of slower warps
                 // (accounted for in the worst-case capacity), but every thread gets the same decision
                 const int compact = __syncthreads_or(tid == 0 && s_n_far > a.far_trigger);
+                PF(3);
                 ci = ci1;
                 buf ^= 1;
                 n_near = min(s_cnt[ci], CAP);
@@ -283,7 +299,9 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
             QEntry* t2 = q_far; q_far = q_far2; q_far2 = t2;
             ++c_rounds;
             __syncthreads();
+            PF(4);
         }
+        PF(4);
 
         // ---- verify tie candidates against the final labels (reverse star) ----
         __syncthreads();
@@ -340,6 +358,9 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
     if (tid == 0) {
         atomicAdd(&a.stats->rounds, (unsigned long long)c_rounds);
         if (s_spill) atomicAdd(&a.stats->prof[0], (unsigned long long)s_spill); // entries that did not fit the shared-memory queue
+#ifdef SSSP_PROFILE
+        for (int j = 1; j < 8; ++j) atomicAdd(&a.stats->prof[j], (unsigned long long)pf[j]);
+#endif
     }
 }
 
