@@ -114,6 +114,13 @@ def reference_output_files(name, K, CU, multi_period=False):
         B.run_reference(tmp, "golden", K, CU, 4, None, threads=4, multi_period=multi_period)
         for f in ("link_performance", "route_assignment"):
             shutil.copy(os.path.join(tmp, f + ".csv"), os.path.join(OUT, "outputs", f"{name}_{f}.csv"))
+        # final_summary.csv: the rows this path produces (iteration rows main_api.cpp:724-727, column-pool rows assignment.h:909-911)
+        with open(os.path.join(tmp, "final_summary.csv")) as f, open(os.path.join(OUT, "outputs", f"{name}_final_summary_rows.txt"), "w") as o:
+            seen = False
+            for line in f:
+                seen = seen or line.startswith("Iteration, CPU Running Time")
+                if seen and (line[:1].isdigit() and line.count(",") == 4 or line.startswith("column updating: iteration")):
+                    o.write(line)
 
 
 if __name__ == "__main__":

@@ -76,3 +76,25 @@ def test_output_files_match_the_reference(native, tmp_path, name, K, CU):
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     for f in ("link_performance", "route_assignment"):
         _compare_csv(tmp_path / f"{f}.csv", os.path.join(GOLDEN, "outputs", f"{name}_{f}.csv"))
+    # final_summary.csv: iteration rows (iteration, CPU time, agents, average travel time, gap %) and column-pool rows
+    import re
+    def pick(path, after_header):
+        rows, seen = [], not after_header
+        for l in open(path):
+            seen = seen or l.startswith("Iteration, CPU Running Time")
+            if seen and (l[:1].isdigit() and l.count(",") == 4 or l.startswith("column updating: iteration")):
+                rows.append(l.strip())
+        return rows
+    mine, ref = pick(tmp_path / "final_summary.csv", True), pick(os.path.join(GOLDEN, "outputs", f"{name}_final_summary_rows.txt"), False)
+    assert len(mine) == len(ref) == K + CU, (len(mine), len(ref))
+    num = re.compile(r"-?\d+\.?\d*(?:[eE][-+]?\d+)?")
+    for a_, b_ in zip(mine, ref):
+        if a_[:1].isdigit():
+            x, y = a_.split(","), b_.split(",")
+            assert x[0] == y[0] and x[2] == y[2], (a_, b_)              # iteration, number of agents; CPU time is not compared
+            for u, v in zip(x[3:5], y[3:5]):                             # 6 significant digits are printed
+                assert abs(float(u) - float(v)) <= 2e-5 * max(1e-3, abs(float(v))), (a_, b_)
+        else:
+            assert num.sub("#", a_) == num.sub("#", b_), (a_, b_)       # same text around the numbers
+            for u, v in zip(num.findall(a_), num.findall(b_)):
+                assert abs(float(u) - float(v)) <= 2e-5 * max(1e-3, abs(float(v))), (a_, b_)
