@@ -44,6 +44,9 @@ struct ForwardStar {
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
     double delta = 1.0;       // current label window of the near/far SSSP
     std::vector<int> h_row_ptr;
+    std::vector<int> h_to;      // [E] head node of every forward-star edge (host copy for the origin-bundle planner)
+    std::vector<float> h_cost0; // [E] free-flow travel time of every edge
+    mutable std::vector<float> h_embed; // [2N] landmark-distance coordinates of every node (filled on first use)
 };
 
 struct VdfParams { // [T*L] each, reference CPeriod_VDF (VDF.h:369-466)
@@ -141,6 +144,23 @@ void launch_sssp_smq(const SsspLaunch& a, cudaStream_t st); // shared-memory que
 void launch_sssp_replay(const SsspLaunch& a, const int* replay_tasks, int n_replay, int* status_ws, int* next_ws,
                         cudaStream_t st);
 void launch_count_edges(const SsspLaunch& a, cudaStream_t st);
+
+// origin-bundle variant (kernels_sssp_bundle.cu): B neighbouring origins share one search over node-major label rows
+struct BundleLaunch {
+    SsspLaunch s;            // network, tasks, output trees, delta, stats (queues of `s` are not used)
+    int B;                   // origins per bundle: 4, 8 or 16
+    int lpt;                 // origins per thread: 2 or 4
+    int n_bundles;
+    const int* bundle_tasks; // [n_bundles][B] batch-local task index, -1 = empty slot
+    unsigned long long* bl;  // [n_bundles][N][B] labels, node-major
+    int2* far;               // [grid][2][cap_far] far piles {node, float key}
+    int cap_far;
+    int cap_near;            // shared-memory near queue: entries per buffer
+    int* bundle_counter;     // device int, zeroed before launch
+    int grid, block;
+};
+void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);
+size_t bundle_smem_bytes(int N, int cap_near); // dynamic shared memory of one CTA: two queue bits per node + two near queues
 void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);
 
 struct ColumnLaunch {

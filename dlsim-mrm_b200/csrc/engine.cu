@@ -13,6 +13,8 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <queue>
+#include <tuple>
 
 #include "dtl_internal.h"
 
@@ -142,6 +144,17 @@ struct dtl_engine {
     unsigned long long* d_counters = nullptr; // [0] link refs, [1] path nodes
     int *d_replay_tasks = nullptr, *d_replay_status = nullptr, *d_replay_next = nullptr;
     int replay_cap = 0;
+    // origin-bundle kernel (kernels_sssp_bundle.cu): node-major label rows, per-CTA state words and far piles, bundle plans
+    std::vector<int> h_task_origin;
+    unsigned long long* d_bl = nullptr;
+    size_t bl_cap = 0;          // elements
+    int2* d_bfar = nullptr;
+    int bundle_grid = 0, bundle_cap_far = 0;
+    int* d_bundle_counter = nullptr;
+    struct BundlePlan { int B = 0, n_bundles = 0; int* d_tasks = nullptr; };
+    std::map<std::tuple<int, int, int, int>, BundlePlan> bundle_plans; // (forward star, first task, tasks, B)
+    int* d_bundle_tmp = nullptr;
+    size_t bundle_tmp_cap = 0;
     double counted_edges_cached = -1;
 
     // timing
@@ -275,6 +288,12 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
         for (int ei = row[u]; ei < row[u + 1]; ++ei) in_edges[icur[edges[ei].to & 0x7fffffff]++] = make_int2(u, ei);
     f.n_edges = E;
     f.h_row_ptr = row;
+    f.h_to.resize(E);
+    f.h_cost0.resize(E);
+    for (int ei = 0; ei < E; ++ei) {
+        f.h_to[ei] = edges[ei].to & 0x7fffffff;
+        f.h_cost0[ei] = (float)p->fftt[(size_t)tau * L + edges[ei].link];
+    }
     const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
     f.delta = factor * (cost_n ? cost_sum / (double)cost_n : 1.0);
     std::vector<int2> rows(std::max(N, 1));
@@ -348,6 +367,169 @@ int do_scatter(dtl_engine* e, int decay_k, bool person)
     return 0;
 }
 
+
+// ---- origin bundles (kernels_sssp_bundle.cu) ------------------------------------------------------------------------
+// The bundle kernel shares one search between B origins; it pays off when the origins of a bundle are close to each other
+// in travel time.  Origins are grouped by a k-d split of a two-dimensional landmark embedding of the network: free-flow
+// distances from two far-apart landmark nodes (host Dijkstra, once per forward star).
+static void host_dijkstra(const ForwardStar& f, int N, int src, std::vector<float>& dist)
+{
+    dist.assign(N, INFINITY);
+    typedef std::pair<float, int> QE;
+    std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+    dist[src] = 0.f;
+    pq.push(QE(0.f, src));
+    while (!pq.empty()) {
+        const QE t = pq.top();
+        pq.pop();
+        if (t.first > dist[t.second]) continue;
+        for (int ei = f.h_row_ptr[t.second]; ei < f.h_row_ptr[t.second + 1]; ++ei) {
+            const float c = t.first + std::max(0.f, f.h_cost0[ei]);
+            if (c < dist[f.h_to[ei]]) { dist[f.h_to[ei]] = c; pq.push(QE(c, f.h_to[ei])); }
+        }
+    }
+}
+
+static int farthest(const std::vector<float>& d)
+{
+    int best = -1;
+    for (int i = 0; i < (int)d.size(); ++i)
+        if (std::isfinite(d[i]) && (best < 0 || d[i] > d[best])) best = i;
+    return best;
+}
+
+static void ensure_embedding(const ForwardStar& f, int N)
+{
+    if (!f.h_embed.empty()) return;
+    f.h_embed.assign((size_t)2 * N, 0.f);
+    int s0 = -1;
+    for (int i = 0; i < N && s0 < 0; ++i)
+        if (f.h_row_ptr[i + 1] > f.h_row_ptr[i]) s0 = i;
+    if (s0 < 0) return;
+    std::vector<float> d0, dA, dC, dD;
+    host_dijkstra(f, N, s0, d0);
+    const int A = farthest(d0);
+    host_dijkstra(f, N, A, dA);
+    const int C = farthest(dA);
+    host_dijkstra(f, N, C, dC);
+    int D = -1; // far from both A and C: the third corner
+    float best = -1.f;
+    for (int i = 0; i < N; ++i)
+        if (std::isfinite(dA[i]) && std::isfinite(dC[i]) && std::min(dA[i], dC[i]) > best) { best = std::min(dA[i], dC[i]); D = i; }
+    if (D < 0) D = C;
+    host_dijkstra(f, N, D, dD);
+    float big = 1.f;
+    for (int i = 0; i < N; ++i) {
+        if (std::isfinite(dA[i])) big = std::max(big, dA[i]);
+        if (std::isfinite(dD[i])) big = std::max(big, dD[i]);
+    }
+    for (int i = 0; i < N; ++i) {
+        f.h_embed[2 * i] = std::isfinite(dA[i]) ? dA[i] : 2.f * big;
+        f.h_embed[2 * i + 1] = std::isfinite(dD[i]) ? dD[i] : 2.f * big;
+    }
+}
+
+static void kd_split(std::vector<int>& idx, int lo, int hi, int B, const float* embed, const int* origin, std::vector<int>& out)
+{
+    const int n = hi - lo;
+    if (n <= B) {
+        for (int i = 0; i < B; ++i) out.push_back(i < n ? idx[lo + i] : -1);
+        return;
+    }
+    const int nb = (n + B - 1) / B;
+    const int left = (nb / 2) * B;
+    float mn[2] = { INFINITY, INFINITY }, mx[2] = { -INFINITY, -INFINITY };
+    for (int i = lo; i < hi; ++i)
+        for (int d = 0; d < 2; ++d) {
+            const float x = embed[2 * origin[idx[i]] + d];
+            mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x);
+        }
+    const int dim = (mx[1] - mn[1]) > (mx[0] - mn[0]) ? 1 : 0;
+    std::nth_element(idx.begin() + lo, idx.begin() + lo + left, idx.begin() + hi, [&](int x, int y) {
+        const float cx = embed[2 * origin[x] + dim], cy = embed[2 * origin[y] + dim];
+        return cx < cy || (cx == cy && x < y);
+    });
+    kd_split(idx, lo, lo + left, B, embed, origin, out);
+    kd_split(idx, lo + left, hi, B, embed, origin, out);
+}
+
+// bundles of the batch [0, n_tasks): returns a device array [n_bundles][B] of batch-local task indices
+static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* h_origin, int plan_key, int B,
+                        const int** d_tasks, int* n_bundles)
+{
+    const int fsi = (int)(&f - e->fs.data());
+    const auto key = std::make_tuple(fsi, plan_key, n_tasks, B);
+    if (plan_key >= 0) {
+        auto it = e->bundle_plans.find(key);
+        if (it != e->bundle_plans.end()) { *d_tasks = it->second.d_tasks; *n_bundles = it->second.n_bundles; return 0; }
+    }
+    ensure_embedding(f, e->N);
+    std::vector<int> idx(n_tasks), out;
+    std::iota(idx.begin(), idx.end(), 0);
+    if (getenv("DTL_BUNDLE_NO_CLUSTER")) { // experiment hook: bundles of consecutive tasks
+        for (int i = 0; i < (n_tasks + B - 1) / B * B; ++i) out.push_back(i < n_tasks ? i : -1);
+    } else {
+        kd_split(idx, 0, n_tasks, B, f.h_embed.data(), h_origin, out);
+    }
+    const int nb = (int)out.size() / B;
+    int* d = nullptr;
+    if (plan_key >= 0) {
+        if (e->alloc(&d, out.size())) return -1;
+        dtl_engine::BundlePlan pl;
+        pl.B = B; pl.n_bundles = nb; pl.d_tasks = d;
+        e->bundle_plans[key] = pl;
+    } else {
+        if (e->bundle_tmp_cap < out.size()) {
+            if (e->alloc(&e->d_bundle_tmp, out.size() * 2)) return -1;
+            e->bundle_tmp_cap = out.size() * 2;
+        }
+        d = e->d_bundle_tmp;
+    }
+    CK(cudaMemcpyAsync(d, out.data(), sizeof(int) * out.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaStreamSynchronize(e->st)); // `out` is pageable and local
+    *d_tasks = d; *n_bundles = nb;
+    return 0;
+}
+
+static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLaunch& a, const int* h_origin, int plan_key, BundleLaunch& b)
+{
+    const int n = a.n_tasks;
+    int B = 16;
+    if (n < 16 * e->sm_count / 2) B = 8;
+    if (n < 8 * e->sm_count / 2) B = 4;
+    if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
+    b.s = a;
+    b.B = B;
+    b.lpt = B >= 8 ? 4 : 2;
+    if (const char* env = getenv("DTL_BUNDLE_LPT")) b.lpt = atoi(env) == 2 || B < 8 ? 2 : 4;
+    if (plan_bundles(e, f, n, h_origin, plan_key, B, &b.bundle_tasks, &b.n_bundles)) return -1;
+    b.block = 1024;
+    if (const char* env = getenv("DTL_BUNDLE_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024;
+    // shared memory of a CTA: two queue bits per node, the rest for the two near queues (12 bytes per entry)
+    const int ctas_per_sm = b.block <= 512 && b.lpt <= 2 ? 2 : 1;
+    const size_t smem_cta = (size_t)220 * 1024 / ctas_per_sm;
+    const size_t fixed = bundle_smem_bytes(e->N, 0);
+    b.cap_near = fixed + 24 * 64 <= smem_cta ? (int)std::min<size_t>(8192, (smem_cta - fixed) / 24) : 0;
+    if (b.cap_near == 0) { set_err("origin-bundle kernel: %d nodes do not fit the shared-memory queue bits", e->N); return -1; }
+    if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) b.cap_near = std::min(b.cap_near, std::max(8, atoi(env))); // test hook for the re-run path
+    const int max_grid = e->sm_count * ctas_per_sm;
+    if (!e->d_bfar) {
+        e->bundle_grid = e->sm_count * 2;
+        e->bundle_cap_far = 2 * e->N + 1024;
+        if (e->alloc(&e->d_bfar, (size_t)e->bundle_grid * 2 * e->bundle_cap_far)) return -1;
+        if (e->alloc(&e->d_bundle_counter, 1)) return -1;
+    }
+    const size_t need = (size_t)b.n_bundles * B * e->N;
+    if (e->bl_cap < need) {
+        if (e->alloc(&e->d_bl, need)) return -1; // the previous, smaller buffer stays allocated until dtl_destroy
+        e->bl_cap = need;
+    }
+    b.bl = e->d_bl; b.far = e->d_bfar; b.cap_far = e->bundle_cap_far;
+    b.bundle_counter = e->d_bundle_counter;
+    b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
+    return 0;
+}
+
 // K1 has two kernels (DESIGN.md "K1"): with many trees per SM the global-queue kernel's throughput wins; with few trees per
 // SM (an origin shard on one of several GPUs) a launch lasts as long as one tree, and the shared-memory-queue kernel's
 // short rounds with a big CTA per tree win.  DTL_SSSP_KERNEL=gq|smq forces one (tests).
@@ -358,8 +540,10 @@ void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
     int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 1 : 0; // an explicit block size asks for the global-queue kernel
     if (force && !strcmp(force, "gq")) v = 0;
     if (force && !strcmp(force, "smq")) v = 1;
+    if (force && !strcmp(force, "bundle")) v = 2;
+    if (v == 2 && bundle_smem_bytes(e->N, 64) > (size_t)110 * 1024) v = 0; // the per-node queue bits must fit in shared memory
     a.smq = v;
-    if (!v) return;
+    if (v != 1) return;
     a.block = per_sm <= 1 ? 1024 : per_sm <= 2 ? 512 : 256;
     if (const char* env = getenv("DTL_SSSP_SMQ_BLOCK")) a.block = atoi(env) == 256 ? 256 : atoi(env) == 512 ? 512 : 1024;
     a.cap_smem = 2 * a.block;
@@ -394,13 +578,22 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
 
 // run the SSSP kernel for one batch (trees land in d_labels/d_pred), replay tied origins
 int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, bool count_edges,
-                   int tree_off = 0)
+                   int tree_off, const int* h_origin, int plan_key)
 {
     SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
-    const int ph = e->phase_begin(2);
-    CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
-    launch_sssp_variant(a, e->st);
-    e->phase_end(ph, 1);
+    if (a.smq == 2) { // origin bundles: one search per B neighbouring origins, then labels -> trees
+        BundleLaunch b{};
+        if (make_bundle_launch(e, f, a, h_origin, plan_key, b)) return -1;
+        const int ph = e->phase_begin(2);
+        CK(cudaMemsetAsync(e->d_bundle_counter, 0, sizeof(int), e->st));
+        launch_sssp_bundle(b, e->st);
+        e->phase_end(ph, 2);
+    } else {
+        const int ph = e->phase_begin(2);
+        CK(cudaMemsetAsync(e->d_task_counter, 0, sizeof(int), e->st));
+        launch_sssp_variant(a, e->st);
+        e->phase_end(ph, 1);
+    }
     CK(cudaGetLastError());
     e->h_tie_nodes.resize(n_tasks);
     CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
@@ -565,6 +758,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         origin[i] = p->zone_centroid[e->task_zone[i]];
         skip[i] = n_out[origin[i]] == 0; // routing.h:428
     }
+    e->h_task_origin = origin;
     if (e->upload(&e->d_task_origin, origin.data(), n_tasks)) return -1;
     if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
     if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
@@ -811,7 +1005,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         while (t1 < n_tasks && t1 - t0 < e->batch_tasks && fs_index(e, e->task_at[t1], e->task_tau[t1]) == fsi) ++t1;
         const int nb = t1 - t0;
         const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
-        if (run_sssp_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, want_count, tree_off)) return -1;
+        if (run_sssp_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, want_count, tree_off, e->h_task_origin.data() + t0, t0)) return -1;
         ColumnLaunch c{};
         c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
         c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
@@ -1145,7 +1339,7 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
         cudaMemcpy(d_zone, zones + b0, sizeof(int) * nb, cudaMemcpyHostToDevice);
         cudaEvent_t ea = e->get_event(), eb = e->get_event();
         cudaEventRecord(ea, e->st);
-        rc = run_sssp_batch(e, f, nb, d_origin, d_zone, true);
+        rc = run_sssp_batch(e, f, nb, d_origin, d_zone, true, 0, origin.data() + b0, -1);
         cudaEventRecord(eb, e->st);
         if (rc) break;
         if (cudaStreamSynchronize(e->st) != cudaSuccess) { set_err("SSSP batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; break; }
@@ -1182,7 +1376,8 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
             double d[8];
             for (int k = 0; k < 8; ++k) d[k] = (double)(s1.prof[k] - s0.prof[k]);
             fprintf(stderr, "sssp: spilled %.3g | thread-0 cycles: init %.3g expansion %.3g barrier %.3g re-bucket %.3g | passes %.3g entries %.3g "
-                            "rounds %.3g\n", d[0], d[1], d[2], d[3], d[4], d[6], d[7], (double)(s1.rounds - s0.rounds));
+                            "rounds %.3g | bundle kernel, inside a pass: until the label row arrived %.3g, until the atomics returned %.3g\n",
+                    d[0], d[1], d[2], d[3], d[4], d[6], d[7], (double)(s1.rounds - s0.rounds), (double)(s1.stage[0] - s0.stage[0]), d[5]);
         }
     }
     e->trees_valid = false;

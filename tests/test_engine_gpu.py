@@ -31,7 +31,8 @@ def sha(a):
 
 
 # ------------------------------------------------------------------------------------------------ K1
-KERNELS = ["gq", "smq"]  # global-memory queues (many trees per SM) / shared-memory queues (few trees per SM)
+# global-memory queues (many trees per SM) / shared-memory queues (few trees per SM) / origin bundles (B origins per search)
+KERNELS = ["gq", "smq", "bundle"]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -61,6 +62,29 @@ def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod, monkeyp
             tagk = f"k={k}:at={at}:tau=0:z=7"
             assert np.array_equal(lab[7], g["tree_label:" + tagk]) and np.array_equal(pl[7], g["tree_pred_link:" + tagk])
             assert np.array_equal(pn[7], g["tree_pred_node:" + tagk])
+
+
+@pytest.mark.parametrize("B,block,cluster", [(4, 1024, 1), (8, 512, 1), (16, 1024, 1), (16, 512, 0), (8, 1024, 0)])
+def test_sssp_bundle_sizes(D, problems, golden, oracle_mod, monkeypatch, B, block, cluster):
+    """Origin-bundle kernel at every bundle size / CTA size, with and without spatial clustering of the origins."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", "bundle")
+    monkeypatch.setenv("DTL_BUNDLE_B", str(B))
+    monkeypatch.setenv("DTL_BUNDLE_BLOCK", str(block))
+    if not cluster:
+        monkeypatch.setenv("DTL_BUNDLE_NO_CLUSTER", "1")
+    p, g = problems("corridor_101"), golden("corridor_101")
+    o = oracle_mod.Oracle(p)
+    with D.Engine(p) as e:
+        for k, at in ((2, 0), (19, 2)):
+            cost = g[f"gen_cost_k{k}_at{at}"]
+            zones = np.arange(p.n_zones, dtype=np.int32)[::-1].copy()   # 99 origins: the last bundle is ragged
+            lab, pn, pl, ties, st = e.sssp_trees(at, 0, zones, cost=cost)
+            fs = o.forward_star(at, 0)
+            for i, z in enumerate(zones):
+                rl, rpn, rpl, pops, relax = o.sssp(fs, cost, int(z))
+                assert np.array_equal(lab[i].view(np.int64), rl.view(np.int64)), f"labels differ, k={k} zone {z}"
+                assert np.array_equal(pl[i], rpl) and np.array_equal(pn[i], rpn), f"predecessors differ, k={k} zone {z}"
+            assert st["replayed"] == 0 and e.counters()["reruns"] == 0
 
 
 def _tie_grid(n=12):
@@ -273,8 +297,8 @@ def test_drop_in_executable_writes_reference_files(D, tmp_path):
     assert abs(sum(vols) - 7000) < 1e-3
 
 
-@pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"),
-                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq")])
+@pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"), ("grid2k", 8, 3, "bundle"),
+                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq"), ("grid10k", 4, 0, "bundle")])
 def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, monkeypatch, workload, K, CU, kernel):
     """The bench generator at sizes the oracle finishes in seconds: same parity bars as the reference datasets."""
     monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
