@@ -45,7 +45,6 @@ struct ForwardStar {
     double delta = 1.0;       // current label window of the near/far SSSP
     std::vector<int> h_row_ptr;
     std::vector<int> h_to;      // [E] head node of every forward-star edge (host copy for the origin-bundle planner)
-    std::vector<float> h_cost0; // [E] free-flow travel time of every edge
     mutable std::vector<float> h_embed; // [2N] landmark-distance coordinates of every node (filled on first use)
 };
 

@@ -155,6 +155,7 @@ struct dtl_engine {
     std::map<std::tuple<int, int, int, int>, BundlePlan> bundle_plans; // (forward star, first task, tasks, B)
     int* d_bundle_tmp = nullptr;
     size_t bundle_tmp_cap = 0;
+    int last_sssp_variant = -1;
     double counted_edges_cached = -1;
 
     // timing
@@ -289,11 +290,7 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
     f.n_edges = E;
     f.h_row_ptr = row;
     f.h_to.resize(E);
-    f.h_cost0.resize(E);
-    for (int ei = 0; ei < E; ++ei) {
-        f.h_to[ei] = edges[ei].to & 0x7fffffff;
-        f.h_cost0[ei] = (float)p->fftt[(size_t)tau * L + edges[ei].link];
-    }
+    for (int ei = 0; ei < E; ++ei) f.h_to[ei] = edges[ei].to & 0x7fffffff;
     const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
     f.delta = factor * (cost_n ? cost_sum / (double)cost_n : 1.0);
     std::vector<int2> rows(std::max(N, 1));
@@ -370,23 +367,19 @@ int do_scatter(dtl_engine* e, int decay_k, bool person)
 
 // ---- origin bundles (kernels_sssp_bundle.cu) ------------------------------------------------------------------------
 // The bundle kernel shares one search between B origins; it pays off when the origins of a bundle are close to each other
-// in travel time.  Origins are grouped by a k-d split of a two-dimensional landmark embedding of the network: free-flow
-// distances from two far-apart landmark nodes (host Dijkstra, once per forward star).
-static void host_dijkstra(const ForwardStar& f, int N, int src, std::vector<float>& dist)
+// in the network.  Origins are grouped by a k-d split of a two-dimensional landmark embedding: hop distances from two
+// far-apart landmark nodes (host breadth-first searches, once per forward star, a few milliseconds for 100 000 nodes).
+static void host_bfs(const ForwardStar& f, int N, int src, std::vector<float>& dist)
 {
     dist.assign(N, INFINITY);
-    typedef std::pair<float, int> QE;
-    std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+    std::vector<int> q;
+    q.reserve(N);
     dist[src] = 0.f;
-    pq.push(QE(0.f, src));
-    while (!pq.empty()) {
-        const QE t = pq.top();
-        pq.pop();
-        if (t.first > dist[t.second]) continue;
-        for (int ei = f.h_row_ptr[t.second]; ei < f.h_row_ptr[t.second + 1]; ++ei) {
-            const float c = t.first + std::max(0.f, f.h_cost0[ei]);
-            if (c < dist[f.h_to[ei]]) { dist[f.h_to[ei]] = c; pq.push(QE(c, f.h_to[ei])); }
-        }
+    q.push_back(src);
+    for (size_t h = 0; h < q.size(); ++h) {
+        const int u = q[h];
+        for (int ei = f.h_row_ptr[u]; ei < f.h_row_ptr[u + 1]; ++ei)
+            if (dist[f.h_to[ei]] == INFINITY) { dist[f.h_to[ei]] = dist[u] + 1.f; q.push_back(f.h_to[ei]); }
     }
 }
 
@@ -407,17 +400,17 @@ static void ensure_embedding(const ForwardStar& f, int N)
         if (f.h_row_ptr[i + 1] > f.h_row_ptr[i]) s0 = i;
     if (s0 < 0) return;
     std::vector<float> d0, dA, dC, dD;
-    host_dijkstra(f, N, s0, d0);
+    host_bfs(f, N, s0, d0);
     const int A = farthest(d0);
-    host_dijkstra(f, N, A, dA);
+    host_bfs(f, N, A, dA);
     const int C = farthest(dA);
-    host_dijkstra(f, N, C, dC);
+    host_bfs(f, N, C, dC);
     int D = -1; // far from both A and C: the third corner
     float best = -1.f;
     for (int i = 0; i < N; ++i)
         if (std::isfinite(dA[i]) && std::isfinite(dC[i]) && std::min(dA[i], dC[i]) > best) { best = std::min(dA[i], dC[i]); D = i; }
     if (D < 0) D = C;
-    host_dijkstra(f, N, D, dD);
+    host_bfs(f, N, D, dD);
     float big = 1.f;
     for (int i = 0; i < N; ++i) {
         if (std::isfinite(dA[i])) big = std::max(big, dA[i]);
@@ -500,8 +493,8 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
     b.s = a;
     b.B = B;
-    b.lpt = B >= 8 ? 4 : 2;
-    if (const char* env = getenv("DTL_BUNDLE_LPT")) b.lpt = atoi(env) == 2 || B < 8 ? 2 : 4;
+    b.lpt = 2; // origins per thread; 4 measured slower (fewer warps to hide the round trips)
+    if (const char* env = getenv("DTL_BUNDLE_LPT")) b.lpt = atoi(env) == 4 && B >= 8 ? 4 : 2;
     if (plan_bundles(e, f, n, h_origin, plan_key, B, &b.bundle_tasks, &b.n_bundles)) return -1;
     b.block = 1024;
     if (const char* env = getenv("DTL_BUNDLE_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024;
@@ -530,14 +523,23 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     return 0;
 }
 
-// K1 has two kernels (DESIGN.md "K1"): with many trees per SM the global-queue kernel's throughput wins; with few trees per
-// SM (an origin shard on one of several GPUs) a launch lasts as long as one tree, and the shared-memory-queue kernel's
-// short rounds with a big CTA per tree win.  DTL_SSSP_KERNEL=gq|smq forces one (tests).
+// K1 has three kernels (DESIGN.md "K1").  Per launch:
+//   * origin bundles (kernels_sssp_bundle.cu) when the launch fills the GPU with bundles of 16 origins: a wave of bundles (one
+//     per SM) lasts about as long as 8.8 x #SM trees of the global-queue kernel, whatever the number of bundles in it, and
+//     the label -> tree pass costs ~15 % of a global-queue tree per tree (calibrated on the config-5 grid);
+//   * global-memory queues (kernels_sssp.cu) with many trees per SM otherwise: throughput of the SM;
+//   * shared-memory queues (kernels_sssp_smq.cu) with few trees per SM (an origin shard on one of several GPUs): a launch
+//     lasts as long as one tree, and short rounds with a big CTA per tree win.
+// DTL_SSSP_KERNEL=gq|smq|bundle forces one (tests, experiments).
 void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
 {
     const char* force = getenv("DTL_SSSP_KERNEL");
     const int per_sm = (a.n_run + e->sm_count - 1) / std::max(1, e->sm_count);
     int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 1 : 0; // an explicit block size asks for the global-queue kernel
+    if (!e->opt.sssp_block_threads && !a.task_list) {
+        const int waves = ((a.n_run + 15) / 16 + e->sm_count - 1) / std::max(1, e->sm_count);
+        if (0.85 * a.n_run > 8.8 * e->sm_count * waves) v = 2;
+    }
     if (force && !strcmp(force, "gq")) v = 0;
     if (force && !strcmp(force, "smq")) v = 1;
     if (force && !strcmp(force, "bundle")) v = 2;
@@ -581,6 +583,7 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
                    int tree_off, const int* h_origin, int plan_key)
 {
     SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
+    e->last_sssp_variant = a.smq;
     if (a.smq == 2) { // origin bundles: one search per B neighbouring origins, then labels -> trees
         BundleLaunch b{};
         if (make_bundle_launch(e, f, a, h_origin, plan_key, b)) return -1;
@@ -935,6 +938,7 @@ dtl_engine* dtl_create(const dtl_problem* p, const dtl_options* opt)
 }
 
 size_t dtl_device_bytes(const dtl_engine* e) { return e ? e->dev_bytes : 0; }
+int dtl_sssp_kernel_used(const dtl_engine* e) { return e ? e->last_sssp_variant : -1; }
 int dtl_num_tasks(const dtl_engine* e) { return (int)e->task_at.size(); }
 int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone)
 {

@@ -26,7 +26,9 @@
 
 namespace dtl {
 
+#ifndef BND_U
 #define BND_U 4 /* out-edges of a node relaxed per pass */
+#endif
 #define BND_DEAD_KEY 0xffffffffu
 #ifndef BND_PRECHECK
 #define BND_PRECHECK 0 /* 1: load the head's label row first and issue atomics only for origins that improve (one more round trip, far fewer atomics) */
@@ -416,65 +418,87 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 512 && LPT <= 2 ? 2 : 1) sssp_
     }
 }
 
-// Final labels of a bundle -> per-tree labels[task][N] and predecessor links.  One group of B lanes per node: the rows of
-// the node and of its upstream nodes are coalesced loads; a tile of TN nodes is transposed through shared memory so that
-// every tree receives TN consecutive labels / predecessors.
+// Final labels of a bundle -> per-tree labels[task][N] and predecessor links.  One block per tile of TN nodes and bundle:
+//   1. the reverse-star records of the tile (upstream node, cost, link, zone-tag flag) are staged in shared memory by all
+//      threads at once (two dependent round trips for the whole tile instead of three per node);
+//   2. one group of B lanes per node: the label rows of the node and of its upstream nodes are coalesced loads, issued
+//      together; the tight in-edge is the predecessor (two tight upstream nodes = a tie, left to the serial replay);
+//   3. the tile is transposed through shared memory so that every tree receives TN consecutive labels / predecessors.
+#define FIN_CAP 384 /* reverse-star records staged per tile (a tile with more falls back to global loads for the rest) */
 template <int B, int TN>
 __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
 {
     __shared__ unsigned long long s_lab[B][TN + 1];
     __shared__ int s_pred[B][TN + 1];
     __shared__ int s_task[B];
+    __shared__ int s_ptr[TN + 1];
+    __shared__ double s_cost[FIN_CAP];
+    __shared__ int s_from[FIN_CAP], s_link[FIN_CAP], s_eidx[FIN_CAP]; // s_link: bit 31 = zone-tagged connector
     const int tid = threadIdx.x;
     const int g = tid & (B - 1);
     const int N = a.s.N;
     const int bundle = blockIdx.y;
     const int v0 = blockIdx.x * TN;
+    const int nt = min(TN, N - v0);
     int task = __ldg(&a.bundle_tasks[bundle * B + g]);
     if (task >= 0 && a.s.tie_nodes[task] < 0) task = -1; // the search of this bundle overflowed: the host re-runs its trees
     if (tid < B) s_task[tid] = task;
     const int origin = task >= 0 ? __ldg(&a.s.task_origin[task]) : -1;
     const int zone = task >= 0 ? __ldg(&a.s.task_zone[task]) : -1;
     const unsigned long long* const bl = a.bl + (size_t)bundle * N * B;
+    if (tid <= nt) s_ptr[tid] = __ldg(&a.s.in_ptr[v0 + tid]);
+    __syncthreads();
+    const int p0 = s_ptr[0];
+    const int n_stage = min(s_ptr[nt] - p0, FIN_CAP);
+    for (int i = tid; i < n_stage; i += 256) {
+        const int2 ie = __ldg(&a.s.in_edges[p0 + i]);
+        const Edge ed = ld_edge(&a.s.edges[ie.y]);
+        s_from[i] = ie.x; s_eidx[i] = ie.y; s_cost[i] = ed.cost;
+        s_link[i] = ed.link | (ed.to < 0 ? 0x80000000 : 0);
+    }
+    __syncthreads();
     unsigned n_ties = 0;
-    for (int j = tid / B; j < TN; j += 256 / B) {
+    for (int j = tid / B; j < nt; j += 256 / B) {
         const int v = v0 + j;
-        if (v >= N) break;
         const unsigned long long lvb = __ldg(&bl[(size_t)v * B + g]);
         int pred = DTL_NO_PRED;
         const bool need = task >= 0 && lvb < INF_BITS && v != origin;
         const double lv = __longlong_as_double((long long)lvb);
-        int first_u = -1, best_e = 0x7fffffff;
+        int first_u = -1, best_e = 0x7fffffff, best_link = DTL_NO_PRED;
         bool multi = false;
-        const int j1 = __ldg(&a.s.in_ptr[v + 1]);
-        for (int jj = __ldg(&a.s.in_ptr[v]); jj < j1; jj += 4) { // four upstream rows in flight per lane
-            int2 ie[4];
-            Edge ed[4];
+        const int j1 = s_ptr[j + 1] - p0;
+        for (int jj = s_ptr[j] - p0; jj < j1; jj += 4) { // four upstream rows in flight per lane
+            int from[4], link[4], eidx[4];
+            double cost[4];
             unsigned long long lub[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ie[q] = jj + q < j1 ? __ldg(&a.s.in_edges[jj + q]) : make_int2(-1, 0);
-#pragma unroll
             for (int q = 0; q < 4; ++q) {
+                from[q] = -1; link[q] = 0; eidx[q] = 0; cost[q] = 0.0;
                 lub[q] = INF_BITS;
-                ed[q].cost = 0.0; ed[q].to = 0; ed[q].link = 0;
-                if (ie[q].x >= 0) {
-                    ed[q] = ld_edge(&a.s.edges[ie[q].y]);
-                    lub[q] = __ldg(&bl[(size_t)ie[q].x * B + g]);
+                if (jj + q < j1) {
+                    if (jj + q < FIN_CAP) {
+                        from[q] = s_from[jj + q]; link[q] = s_link[jj + q]; eidx[q] = s_eidx[jj + q]; cost[q] = s_cost[jj + q];
+                    } else { // tile with more reverse-star records than the staging area
+                        const int2 ie = __ldg(&a.s.in_edges[p0 + jj + q]);
+                        const Edge ed = ld_edge(&a.s.edges[ie.y]);
+                        from[q] = ie.x; eidx[q] = ie.y; cost[q] = ed.cost; link[q] = ed.link | (ed.to < 0 ? 0x80000000 : 0);
+                    }
+                    lub[q] = __ldg(&bl[(size_t)from[q] * B + g]);
                 }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!need || !(lub[q] < INF_BITS)) continue;
-                if (ed[q].to < 0 && __ldg(&a.s.link_tag[ed[q].link]) != zone) continue;
-                if (__longlong_as_double((long long)lub[q]) + ed[q].cost == lv) {
-                    if (first_u < 0) first_u = ie[q].x;
-                    if (ie[q].x != first_u) multi = true;
-                    else if (ie[q].y < best_e) best_e = ie[q].y; // parallel links from one upstream node: first in scan order
+                if (link[q] < 0 && __ldg(&a.s.link_tag[link[q] & 0x7fffffff]) != zone) continue; // routing.h:779-786
+                if (__longlong_as_double((long long)lub[q]) + cost[q] == lv) {
+                    if (first_u < 0) first_u = from[q];
+                    if (from[q] != first_u) multi = true;
+                    else if (eidx[q] < best_e) { best_e = eidx[q]; best_link = link[q] & 0x7fffffff; } // parallel links: first in scan order
                 }
             }
         }
         if (multi) { pred = TIE_MARK; ++n_ties; }
-        else if (first_u >= 0) pred = __ldg(&a.s.edges[best_e].link);
+        else if (first_u >= 0) pred = best_link;
         s_lab[g][j] = lvb;
         s_pred[g][j] = pred;
     }
@@ -483,7 +507,7 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
     for (int idx = tid; idx < B * TN; idx += 256) {
         const int b = idx / TN, j = idx - b * TN;
         const int t = s_task[b];
-        if (t >= 0 && v0 + j < N) {
+        if (t >= 0 && j < nt) {
             a.s.labels[(size_t)t * N + v0 + j] = s_lab[b][j];
             a.s.pred_link[(size_t)t * N + v0 + j] = s_pred[b][j];
         }

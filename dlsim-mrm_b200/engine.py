@@ -352,6 +352,15 @@ class Engine:
         self._ck(self.lib.dtl_get_counters(self.h, _ptr(c), int(reset)))
         return dict(zip(self.COUNTERS, c.tolist()))
 
+    K1_KERNELS = {0: "dtl::sssp_kernel", 1: "dtl::sssp_smq_kernel", 2: "dtl::sssp_bundle_kernel + dtl::bundle_finish_kernel"}
+
+    @property
+    def sssp_kernel(self) -> str:
+        """Name of the K1 kernel(s) the last shortest-path launch used."""
+        self.lib.dtl_sssp_kernel_used.restype = C.c_int
+        self.lib.dtl_sssp_kernel_used.argtypes = [C.c_void_p]
+        return self.K1_KERNELS.get(int(self.lib.dtl_sssp_kernel_used(self.h)), "none")
+
     @property
     def device_bytes(self) -> int:
         return int(self.lib.dtl_device_bytes(self.h))
