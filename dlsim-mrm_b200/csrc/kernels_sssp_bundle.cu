@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
     __shared__ int s_task[B];
     __shared__ int s_ptr[TN + 1];
     __shared__ double s_cost[FIN_CAP];
-    __shared__ int s_from[FIN_CAP], s_link[FIN_CAP], s_eidx[FIN_CAP]; // s_link: bit 31 = zone-tagged connector
+    __shared__ int2 s_fl[FIN_CAP]; // {upstream node, link | bit 31 = zone-tagged connector}, in reverse-star (= forward scan) order
     const int tid = threadIdx.x;
     const int g = tid & (B - 1);
     const int N = a.s.N;
@@ -453,8 +453,8 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
     for (int i = tid; i < n_stage; i += 256) {
         const int2 ie = __ldg(&a.s.in_edges[p0 + i]);
         const Edge ed = ld_edge(&a.s.edges[ie.y]);
-        s_from[i] = ie.x; s_eidx[i] = ie.y; s_cost[i] = ed.cost;
-        s_link[i] = ed.link | (ed.to < 0 ? 0x80000000 : 0);
+        s_cost[i] = ed.cost;
+        s_fl[i] = make_int2(ie.x, ed.link | (ed.to < 0 ? 0x80000000 : 0));
     }
     __syncthreads();
     unsigned n_ties = 0;
@@ -464,36 +464,37 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
         int pred = DTL_NO_PRED;
         const bool need = task >= 0 && lvb < INF_BITS && v != origin;
         const double lv = __longlong_as_double((long long)lvb);
-        int first_u = -1, best_e = 0x7fffffff, best_link = DTL_NO_PRED;
+        int first_u = -1, best_link = DTL_NO_PRED;
         bool multi = false;
         const int j1 = s_ptr[j + 1] - p0;
         for (int jj = s_ptr[j] - p0; jj < j1; jj += 4) { // four upstream rows in flight per lane
-            int from[4], link[4], eidx[4];
+            int2 fl[4];
             double cost[4];
             unsigned long long lub[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                from[q] = -1; link[q] = 0; eidx[q] = 0; cost[q] = 0.0;
+                fl[q] = make_int2(-1, 0); cost[q] = 0.0;
                 lub[q] = INF_BITS;
                 if (jj + q < j1) {
                     if (jj + q < FIN_CAP) {
-                        from[q] = s_from[jj + q]; link[q] = s_link[jj + q]; eidx[q] = s_eidx[jj + q]; cost[q] = s_cost[jj + q];
+                        fl[q] = s_fl[jj + q]; cost[q] = s_cost[jj + q];
                     } else { // tile with more reverse-star records than the staging area
                         const int2 ie = __ldg(&a.s.in_edges[p0 + jj + q]);
                         const Edge ed = ld_edge(&a.s.edges[ie.y]);
-                        from[q] = ie.x; eidx[q] = ie.y; cost[q] = ed.cost; link[q] = ed.link | (ed.to < 0 ? 0x80000000 : 0);
+                        fl[q] = make_int2(ie.x, ed.link | (ed.to < 0 ? 0x80000000 : 0)); cost[q] = ed.cost;
                     }
-                    lub[q] = __ldg(&bl[(size_t)from[q] * B + g]);
+                    lub[q] = __ldg(&bl[(size_t)fl[q].x * B + g]);
                 }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!need || !(lub[q] < INF_BITS)) continue;
-                if (link[q] < 0 && __ldg(&a.s.link_tag[link[q] & 0x7fffffff]) != zone) continue; // routing.h:779-786
+                if (fl[q].y < 0 && __ldg(&a.s.link_tag[fl[q].y & 0x7fffffff]) != zone) continue; // routing.h:779-786
                 if (__longlong_as_double((long long)lub[q]) + cost[q] == lv) {
-                    if (first_u < 0) first_u = from[q];
-                    if (from[q] != first_u) multi = true;
-                    else if (eidx[q] < best_e) { best_e = eidx[q]; best_link = link[q] & 0x7fffffff; } // parallel links: first in scan order
+                    // the reverse star lists a node's in-edges in forward scan order: of parallel links from one upstream node the
+                    // first one met is the one a serial scan keeps
+                    if (first_u < 0) { first_u = fl[q].x; best_link = fl[q].y & 0x7fffffff; }
+                    else if (fl[q].x != first_u) multi = true;
                 }
             }
         }

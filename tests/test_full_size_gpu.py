@@ -39,6 +39,7 @@ def test_trees_carry_a_bellman_certificate_and_columns_conserve_demand(D, grid):
         for k in range(K):
             r = e.iteration(k)
         assert e.n_tasks == p.n_zones
+        assert "bundle" in e.sssp_kernel              # 2 000 trees per launch: the origin-bundle kernel is the one under test here
         cost = e.gen_cost(0, 0)                      # generalized costs the last trees were computed with
         lf, lt, tag = p.link_from, p.link_to, p.link_tag
         counted = 0.0
