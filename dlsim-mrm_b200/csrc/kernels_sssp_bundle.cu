@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 512 && LPT <= 2 ? 2 : 1) sssp_
 // Final labels of a bundle -> per-tree labels[task][N] and predecessor links.  One block per tile of TN nodes and bundle:
 //   1. the reverse-star records of the tile (upstream node, cost, link, zone-tag flag) are staged in shared memory by all
 //      threads at once (two dependent round trips for the whole tile instead of three per node);
-//   2. one group of B lanes per node: the label rows of the node and of its upstream nodes are coalesced loads, issued
-//      together; the tight in-edge is the predecessor (two tight upstream nodes = a tie, left to the serial replay);
+//   2. one group of B/2 threads per node (two origins per thread): the label rows of the node and of its upstream nodes are
+//      coalesced 16-byte loads, issued together; the tight in-edge is the predecessor (two tight upstream nodes = a tie, left to the serial replay);
 //   3. the tile is transposed through shared memory so that every tree receives TN consecutive labels / predecessors.
 #define FIN_CAP 384 /* reverse-star records staged per tile (a tile with more falls back to global loads for the rest) */
 template <int B, int TN>
@@ -434,18 +434,23 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
     __shared__ int s_ptr[TN + 1];
     __shared__ double s_cost[FIN_CAP];
     __shared__ int2 s_fl[FIN_CAP]; // {upstream node, link | bit 31 = zone-tagged connector}, in reverse-star (= forward scan) order
+    constexpr int G = B / 2; // threads per node: thread g holds origins 2g and 2g+1 (16-byte loads)
     const int tid = threadIdx.x;
-    const int g = tid & (B - 1);
+    const int g = tid & (G - 1);
     const int N = a.s.N;
     const int bundle = blockIdx.y;
     const int v0 = blockIdx.x * TN;
     const int nt = min(TN, N - v0);
-    int task = __ldg(&a.bundle_tasks[bundle * B + g]);
-    if (task >= 0 && a.s.tie_nodes[task] < 0) task = -1; // the search of this bundle overflowed: the host re-runs its trees
-    if (tid < B) s_task[tid] = task;
-    const int origin = task >= 0 ? __ldg(&a.s.task_origin[task]) : -1;
-    const int zone = task >= 0 ? __ldg(&a.s.task_zone[task]) : -1;
-    const unsigned long long* const bl = a.bl + (size_t)bundle * N * B;
+    int task[2], origin[2], zone[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        task[t] = __ldg(&a.bundle_tasks[bundle * B + 2 * g + t]);
+        if (task[t] >= 0 && a.s.tie_nodes[task[t]] < 0) task[t] = -1; // the search of this bundle overflowed: the host re-runs its trees
+        origin[t] = task[t] >= 0 ? __ldg(&a.s.task_origin[task[t]]) : -1;
+        zone[t] = task[t] >= 0 ? __ldg(&a.s.task_zone[task[t]]) : -1;
+    }
+    if (tid < G) { s_task[2 * tid] = task[0]; s_task[2 * tid + 1] = task[1]; }
+    const ulonglong2* const bl2 = reinterpret_cast<const ulonglong2*>(a.bl + (size_t)bundle * N * B) + g;
     if (tid <= nt) s_ptr[tid] = __ldg(&a.s.in_ptr[v0 + tid]);
     __syncthreads();
     const int p0 = s_ptr[0];
@@ -457,24 +462,24 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
         s_fl[i] = make_int2(ie.x, ed.link | (ed.to < 0 ? 0x80000000 : 0));
     }
     __syncthreads();
-    unsigned n_ties = 0;
-    for (int j = tid / B; j < nt; j += 256 / B) {
+    unsigned n_ties0 = 0, n_ties1 = 0;
+    for (int j = tid / G; j < nt; j += 256 / G) {
         const int v = v0 + j;
-        const unsigned long long lvb = __ldg(&bl[(size_t)v * B + g]);
-        int pred = DTL_NO_PRED;
-        const bool need = task >= 0 && lvb < INF_BITS && v != origin;
-        const double lv = __longlong_as_double((long long)lvb);
-        int first_u = -1, best_link = DTL_NO_PRED;
-        bool multi = false;
+        const ulonglong2 lvb = __ldg(bl2 + (size_t)v * G);
+        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0];
+        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1];
+        const double lv0 = __longlong_as_double((long long)lvb.x), lv1 = __longlong_as_double((long long)lvb.y);
+        int first0 = -1, first1 = -1, link0 = DTL_NO_PRED, link1 = DTL_NO_PRED;
+        bool multi0 = false, multi1 = false;
         const int j1 = s_ptr[j + 1] - p0;
-        for (int jj = s_ptr[j] - p0; jj < j1; jj += 4) { // four upstream rows in flight per lane
+        for (int jj = s_ptr[j] - p0; jj < j1; jj += 4) { // four upstream rows in flight per thread
             int2 fl[4];
             double cost[4];
-            unsigned long long lub[4];
+            ulonglong2 lub[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 fl[q] = make_int2(-1, 0); cost[q] = 0.0;
-                lub[q] = INF_BITS;
+                lub[q] = make_ulonglong2(INF_BITS, INF_BITS);
                 if (jj + q < j1) {
                     if (jj + q < FIN_CAP) {
                         fl[q] = s_fl[jj + q]; cost[q] = s_cost[jj + q];
@@ -483,27 +488,37 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
                         const Edge ed = ld_edge(&a.s.edges[ie.y]);
                         fl[q] = make_int2(ie.x, ed.link | (ed.to < 0 ? 0x80000000 : 0)); cost[q] = ed.cost;
                     }
-                    lub[q] = __ldg(&bl[(size_t)fl[q].x * B + g]);
+                    lub[q] = __ldg(bl2 + (size_t)fl[q].x * G);
                 }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (!need || !(lub[q] < INF_BITS)) continue;
-                if (fl[q].y < 0 && __ldg(&a.s.link_tag[fl[q].y & 0x7fffffff]) != zone) continue; // routing.h:779-786
-                if (__longlong_as_double((long long)lub[q]) + cost[q] == lv) {
-                    // the reverse star lists a node's in-edges in forward scan order: of parallel links from one upstream node the
-                    // first one met is the one a serial scan keeps
-                    if (first_u < 0) { first_u = fl[q].x; best_link = fl[q].y & 0x7fffffff; }
-                    else if (fl[q].x != first_u) multi = true;
+                if (fl[q].x < 0) continue;
+                bool ok0 = need0 && lub[q].x < INF_BITS, ok1 = need1 && lub[q].y < INF_BITS;
+                if (fl[q].y < 0) { // routing.h:779-786
+                    const int tag = __ldg(&a.s.link_tag[fl[q].y & 0x7fffffff]);
+                    ok0 = ok0 && tag == zone[0];
+                    ok1 = ok1 && tag == zone[1];
+                }
+                // the reverse star lists a node's in-edges in forward scan order: of parallel links from one upstream node the
+                // first one met is the one a serial scan keeps
+                if (ok0 && __longlong_as_double((long long)lub[q].x) + cost[q] == lv0) {
+                    if (first0 < 0) { first0 = fl[q].x; link0 = fl[q].y & 0x7fffffff; }
+                    else if (fl[q].x != first0) multi0 = true;
+                }
+                if (ok1 && __longlong_as_double((long long)lub[q].y) + cost[q] == lv1) {
+                    if (first1 < 0) { first1 = fl[q].x; link1 = fl[q].y & 0x7fffffff; }
+                    else if (fl[q].x != first1) multi1 = true;
                 }
             }
         }
-        if (multi) { pred = TIE_MARK; ++n_ties; }
-        else if (first_u >= 0) pred = best_link;
-        s_lab[g][j] = lvb;
-        s_pred[g][j] = pred;
+        if (multi0) { link0 = TIE_MARK; ++n_ties0; }
+        if (multi1) { link1 = TIE_MARK; ++n_ties1; }
+        s_lab[2 * g][j] = lvb.x; s_lab[2 * g + 1][j] = lvb.y;
+        s_pred[2 * g][j] = link0; s_pred[2 * g + 1][j] = link1;
     }
-    if (n_ties) atomicAdd(&a.s.tie_nodes[task], (int)n_ties);
+    if (n_ties0) atomicAdd(&a.s.tie_nodes[task[0]], (int)n_ties0);
+    if (n_ties1) atomicAdd(&a.s.tie_nodes[task[1]], (int)n_ties1);
     __syncthreads();
     for (int idx = tid; idx < B * TN; idx += 256) {
         const int b = idx / TN, j = idx - b * TN;
