@@ -939,6 +939,21 @@ dtl_engine* dtl_create(const dtl_problem* p, const dtl_options* opt)
 
 size_t dtl_device_bytes(const dtl_engine* e) { return e ? e->dev_bytes : 0; }
 int dtl_sssp_kernel_used(const dtl_engine* e) { return e ? e->last_sssp_variant : -1; }
+int dtl_plan_bundles(const int* row_ptr, const int* head, int n_nodes, const int* origins, int n, int B, int* out, int capacity)
+{
+    if (!row_ptr || !head || !origins || n_nodes <= 0 || n < 0 || (B != 4 && B != 8 && B != 16)) { set_err("bad arguments"); return -1; }
+    for (int i = 0; i < n; ++i)
+        if (origins[i] < 0 || origins[i] >= n_nodes) { set_err("origin %d out of range", origins[i]); return -1; }
+    ForwardStar f;
+    f.h_row_ptr.assign(row_ptr, row_ptr + n_nodes + 1);
+    f.h_to.assign(head, head + row_ptr[n_nodes]);
+    ensure_embedding(f, n_nodes);
+    std::vector<int> idx(n), res;
+    std::iota(idx.begin(), idx.end(), 0);
+    kd_split(idx, 0, n, B, f.h_embed.data(), origins, res);
+    for (size_t i = 0; i < res.size() && (int)i < capacity; ++i) out[i] = res[i];
+    return (int)res.size() / B;
+}
 int dtl_num_tasks(const dtl_engine* e) { return (int)e->task_at.size(); }
 int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone)
 {
