@@ -443,19 +443,31 @@ void read_network(dtl_gmns& g)
         float cycle, red, sat;
         int vdf_type;
         std::string allowed_uses;
-        std::vector<double> pce, occ, toll, lr;
+        std::vector<double> at4; // [4][AT]: pce, occ, toll, lr of every agent type in one block
+        int AT = 0;
+        double* pce() { return at4.data(); }
+        double* occ() { return at4.data() + AT; }
+        double* toll() { return at4.data() + 2 * AT; }
+        double* lr() { return at4.data() + 3 * AT; }
+        const double* pce() const { return at4.data(); }
+        const double* occ() const { return at4.data() + AT; }
+        const double* toll() const { return at4.data() + 2 * AT; }
+        const double* lr() const { return at4.data() + 3 * AT; }
     };
     std::vector<std::vector<PerPeriod>> lp;
-    auto default_period = [&](int tau) { // CPeriod_VDF(), VDF.h:57-74
-        (void)tau;
+    auto make_default_period = [&]() { // CPeriod_VDF(), VDF.h:57-74
         PerPeriod v{};
         v.fftt = 1; v.cap = 1; v.alpha = 0.39999993; v.beta = 4; v.vf = 60; v.vc = 45; v.nlanes = 1; v.cap_lane = 0; v.qdf = -1;
         v.preload = 0; v.penalty = 0; v.Q_alpha = 0.272876961; v.Q_beta = 4; v.Q_cd = 0.954946463; v.Q_n = 1.141574427;
         v.Q_cp = 0.400089684; v.Q_s = 4; v.t2 = 1; v.L = 1; v.start_h = 0; v.end_h = 0; v.plf = 1;
         v.cycle = -1; v.red = 0; v.sat = 1800; v.vdf_type = 0;
-        v.pce.assign(AT, 1.0); v.occ.assign(AT, 1.0); v.toll.assign(AT, 0.0); v.lr.assign(AT, 0.0);
+        v.AT = AT;
+        v.at4.assign((size_t)4 * AT, 0.0);
+        for (int at = 0; at < AT; ++at) { v.pce()[at] = 1.0; v.occ()[at] = 1.0; }
         return v;
     };
+    const PerPeriod period_proto = make_default_period();
+    auto default_period = [&](int) -> const PerPeriod& { return period_proto; };
     // ---- link.csv, input.h:3207-3678 ----
     {
         Csv p;
@@ -498,7 +510,7 @@ void read_network(dtl_gmns& g)
                     ++type_warnings;
                 }
             } else link_type = link_type_in;
-            const LinkType lt = link_types[link_type];
+            const LinkType& lt = link_types[link_type];
             int tag = -1;
             if (lt.type_code == "c" && g.node_zone_org[from] >= 1) {
                 auto zi = zone_seq.find(g.node_zone_org[from]);
@@ -525,8 +537,8 @@ void read_network(dtl_gmns& g)
                 PerPeriod v = default_period(tau);
                 const Period& d = g.periods[tau];
                 for (int at = 0; at < AT; ++at) {
-                    v.pce[at] = pce_at[at] > 0 ? pce_at[at] : g.agents[at].pce;
-                    v.occ[at] = g.agents[at].occ;
+                    v.pce()[at] = pce_at[at] > 0 ? pce_at[at] : g.agents[at].pce;
+                    v.occ()[at] = g.agents[at].occ;
                 }
                 v.vdf_type = lt.vdf_type;
                 v.cap_lane = lane_cap; v.nlanes = lanes;
@@ -545,7 +557,7 @@ void read_network(dtl_gmns& g)
                 p.get(n_beta[tau].c_str(), v.beta, req, false);
                 if (!p.get(n_uses[tau].c_str(), v.allowed_uses, false)) p.get("allowed_uses", v.allowed_uses, false);
                 p.get(n_preload[tau].c_str(), v.preload, false, false);
-                for (int at = 0; at < AT; ++at) p.get(n_toll[(size_t)tau * AT + at].c_str(), v.toll[at], false, false);
+                for (int at = 0; at < AT; ++at) p.get(n_toll[(size_t)tau * AT + at].c_str(), v.toll()[at], false, false);
                 p.get(n_penalty[tau].c_str(), v.penalty, false, false);
                 if (cell_type >= 2) v.penalty += 1.0 / 60.0;
                 p.get("cycle_length", v.cycle, false, false);
@@ -559,7 +571,7 @@ void read_network(dtl_gmns& g)
                     p.get("red_time", v.red, false);
                     if (sat_in > 1000) v.sat = sat_in;
                 }
-                per[tau] = v;
+                per[tau] = std::move(v);
             }
             double ref_vol = -1;
             p.get(n_ref.c_str(), ref_vol, false, false);
@@ -573,7 +585,7 @@ void read_network(dtl_gmns& g)
             g.meso_link_id.push_back(meso >= 0 ? meso : -1);
             g.free_speed.push_back(free_speed); g.cutoff_speed.push_back((float)cutoff); g.dist_km.push_back(length_m / 1000.0);
             g.dist_mile.push_back(dist); g.fftt_min.push_back(length_m / 1609.0 / free_speed * 60); g.ref_volume.push_back(ref_vol);
-            lp.push_back(per);
+            lp.push_back(std::move(per));
         }
     }
     // ---- link_qvdf.csv defaults, input.h:2153-2300 (no per-link overrides supported) ----
@@ -592,7 +604,7 @@ void read_network(dtl_gmns& g)
             for (int tau = 0; tau < T; ++tau) {
                 PerPeriod v = default_period(tau);
                 v.cap_lane = 99999; v.fftt = 0.0001; v.alpha = 0; v.beta = 0;
-                per[tau] = v;
+                per[tau] = std::move(v);
             }
             g.link_from.push_back(dir == 0 ? i : centroid);
             g.link_to.push_back(dir == 0 ? centroid : i);
@@ -602,7 +614,7 @@ void read_network(dtl_gmns& g)
             g.link_type.push_back(-1); g.link_vdf_type.push_back(0); g.meso_link_id.push_back(-1);
             g.free_speed.push_back(100); g.cutoff_speed.push_back(100); g.dist_km.push_back(0); g.dist_mile.push_back(0);
             g.fftt_min.push_back(0.1); g.ref_volume.push_back(-1);
-            lp.push_back(per);
+            lp.push_back(std::move(per));
         }
     }
     // ---- transpose into the [T][L] / [T][AT][L] image ----
@@ -626,7 +638,7 @@ void read_network(dtl_gmns& g)
             if (tau == 0) g.link_allowed_uses[l] = v.allowed_uses;
             for (int at = 0; at < AT; ++at) {
                 const size_t a = ((size_t)tau * AT + at) * L + l;
-                g.pce[a] = v.pce[at]; g.occ[a] = v.occ[at]; g.toll[a] = v.toll[at]; g.lr_price[a] = v.lr[at];
+                g.pce[a] = v.pce()[at]; g.occ[a] = v.occ()[at]; g.toll[a] = v.toll()[at]; g.lr_price[a] = v.lr()[at];
                 // CLink::AllowAgentType, DTA.h:1352-1367: empty or "all" admits everyone, else substring match
                 g.allowed[a] = v.allowed_uses.empty() || v.allowed_uses == "all" || v.allowed_uses.find(g.agents[at].name) != std::string::npos;
             }
