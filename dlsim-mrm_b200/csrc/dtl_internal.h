@@ -149,6 +149,8 @@ struct BundleLaunch {
     SsspLaunch s;            // network, tasks, output trees, delta, stats (queues of `s` are not used)
     int B;                   // origins per bundle: 4, 8 or 16
     int lpt;                 // origins per thread: 2 or 4
+    int async;               // 1: search without round barriers (kernels_sssp_bundle_async.cu; cap_near = ring size, a power of two)
+    int near_limit;          // async: entries queued or in flight above which the bundle gives up (<= ring size; test hook)
     int n_bundles;
     const int* bundle_tasks; // [n_bundles][B] batch-local task index, -1 = empty slot
     unsigned long long* bl;  // [n_bundles][N][B] labels, node-major
@@ -159,6 +161,8 @@ struct BundleLaunch {
     int grid, block;
 };
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);
+void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st);
+size_t bundle_async_smem_bytes(int N, int ring);
 size_t bundle_smem_bytes(int N, int cap_near); // dynamic shared memory of one CTA: two queue bits per node + two near queues
 void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);
 

@@ -505,6 +505,21 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     b.cap_near = fixed + 24 * 64 <= smem_cta ? (int)std::min<size_t>(8192, (smem_cta - fixed) / 24) : 0;
     if (b.cap_near == 0) { set_err("origin-bundle kernel: %d nodes do not fit the shared-memory queue bits", e->N); return -1; }
     if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) b.cap_near = std::min(b.cap_near, std::max(8, atoi(env))); // test hook for the re-run path
+    // B >= 8: the search without round barriers inside a label window (ring-buffer near queue, kernels_sssp_bundle_async.cu) is
+    // 20 % faster than the round-synchronous one at the bench configuration; DTL_BUNDLE_ASYNC=0 selects the latter
+    b.async = 0;
+    const char* async_env = getenv("DTL_BUNDLE_ASYNC");
+    if (B >= 8 && !(async_env && atoi(async_env) == 0) && !getenv("DTL_BUNDLE_BLOCK") && !getenv("DTL_BUNDLE_LPT")) {
+        b.async = 1;
+        b.block = 1024; b.lpt = 2;
+        int ring = 1;
+        while ((size_t)2 * ring * 12 + fixed <= (size_t)226 * 1024 && 2 * ring <= 16384) ring *= 2;
+        if (ring < 1024) { set_err("origin-bundle kernel: %d nodes leave no room for the shared-memory ring", e->N); return -1; }
+        b.cap_near = ring; // far more slots than the 128 tickets the groups of a CTA can hold: a ticket never meets the slot of an older lap
+        b.near_limit = ring;
+        if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) b.near_limit = std::min(ring, std::max(8, atoi(env))); // test hook for the re-run path
+        if (!(e->opt.sssp_delta_factor > 0)) b.s.delta *= 1.5; // windows of 12 mean link costs: fewer block-wide re-bucketing steps
+    }
     const int max_grid = e->sm_count * ctas_per_sm;
     if (!e->d_bfar) {
         e->bundle_grid = e->sm_count * 2;

@@ -22,51 +22,9 @@
 //   * Predecessors are not tracked in flight: bundle_finish_kernel derives them from the final labels (the reference's
 //     predecessor link is the unique tight in-edge; two tight upstream nodes = an order-dependent tie, marked for the
 //     serial replay exactly like in the other kernels) while it transposes the labels into the per-tree layout.
-#include "sssp_common.cuh"
+#include "sssp_bundle_common.cuh"
 
 namespace dtl {
-
-#ifndef BND_U
-#define BND_U 4 /* out-edges of a node relaxed per pass */
-#endif
-#define BND_DEAD_KEY 0xffffffffu
-#ifndef BND_PRECHECK
-#define BND_PRECHECK 0 /* 1: load the head's label row first and issue atomics only for origins that improve (one more round trip, far fewer atomics) */
-#endif
-
-// per-node queue bits in shared memory, two per node: bit 0 = the node has an entry in the near queue of this or the next
-// round, bit 1 = it has an entry in the far pile
-#define ST_WORD(n) ((n) >> 4)
-#define ST_SHIFT(n) (((n) & 15) << 1)
-
-// scheduling key of a label: the high word of the FP64 bit pattern (non-negative doubles order like unsigned integers;
-// 20 mantissa bits are plenty for deciding which label window a node belongs to -- the key never touches a label)
-__device__ __forceinline__ unsigned key_of(unsigned long long bits) { return (unsigned)(bits >> 32); }
-
-template <int BLOCK>
-__device__ __forceinline__ unsigned block_min_u32(unsigned v, unsigned* s_red)
-{
-    v = __reduce_min_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned w = threadIdx.x < BLOCK / 32 ? s_red[threadIdx.x] : 0xffffffffu;
-        w = __reduce_min_sync(0xffffffffu, w);
-        if (threadIdx.x == 0) s_red[0] = w;
-    }
-    __syncthreads();
-    const unsigned r = s_red[0];
-    __syncthreads();
-    return r;
-}
-
-template <int G>
-__device__ __forceinline__ unsigned group_min_u32(unsigned v)
-{
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // B origins per bundle, LPT per thread: a group of G = B/LPT threads owns one queue entry (a node), thread g holds the labels
 // of origins g*LPT .. g*LPT+LPT-1 (16-byte loads).  The instruction stream of a pass (queue pop, edge records, tag checks, row
@@ -542,6 +500,11 @@ static void bundle_launch(const BundleLaunch& a, cudaStream_t st)
     const size_t smem = bundle_smem_bytes(a.s.N, a.cap_near);
     cudaFuncSetAttribute(sssp_bundle_kernel<BLOCK, B, LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sssp_bundle_kernel<BLOCK, B, LPT><<<a.grid, BLOCK, smem, st>>>(a);
+}
+
+template <int B>
+static void finish_launch(const BundleLaunch& a, cudaStream_t st)
+{
     constexpr int TN = 64;
     const dim3 grid((a.s.N + TN - 1) / TN, a.n_bundles);
     bundle_finish_kernel<B, TN><<<grid, 256, 0, st>>>(a);
@@ -558,10 +521,17 @@ static void bundle_launch_block(const BundleLaunch& a, cudaStream_t st)
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st)
 {
     if (a.n_bundles == 0) return;
+    if (a.async) launch_sssp_bundle_async_search(a, st); // experiment: no round barriers inside a label window
+    else
     switch (a.B) {
     case 4: bundle_launch_block<4, 2>(a, st); break;
     case 8: a.lpt >= 4 ? bundle_launch_block<8, 4>(a, st) : bundle_launch_block<8, 2>(a, st); break;
     default: a.lpt >= 4 ? bundle_launch_block<16, 4>(a, st) : bundle_launch_block<16, 2>(a, st); break;
+    }
+    switch (a.B) {
+    case 4: finish_launch<4>(a, st); break;
+    case 8: finish_launch<8>(a, st); break;
+    default: finish_launch<16>(a, st); break;
     }
 }
 

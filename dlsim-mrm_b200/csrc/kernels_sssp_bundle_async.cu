@@ -1,0 +1,346 @@
+// K1, origin-bundle search WITHOUT round barriers inside a label window (experiment: DTL_BUNDLE_ASYNC=1).
+// Same labels, same node-major layout, same queue bits and far pile as sssp_bundle_kernel (kernels_sssp_bundle.cu); what
+// changes is the near queue: a ring buffer in shared memory that the groups of a CTA consume while other groups still
+// produce into it.  A round-synchronous pass has every warp in the same phase (an issue burst, then everybody waits for
+// the same round trips, then a barrier); here the phases of different warps overlap.
+//   * producers reserve a slot with one atomicAdd on the tail, write the row, fence, then publish node+1 into the slot;
+//   * every group owns one ticket (atomicAdd on the head) and polls its slot; the ticket is kept until its entry shows up;
+//   * s_pending counts entries that are queued or being expanded; when it reaches zero the window is drained, all warps
+//     leave the loop, and the CTA re-buckets the far pile exactly like the round-synchronous kernel;
+//   * the ring has far more slots (>= 1 024) than the CTA has ticket holders (128 groups), so a ticket can never meet the
+//     slot of an older lap; a ring that wraps onto an unconsumed slot, or a far pile that overflows, aborts the bundle (its trees are recomputed
+//     by the global-queue kernel, like any other overflow).
+// Correctness does not depend on the order of expansions (see kernels_sssp_bundle.cu): the protocol "clear the node's queue
+// bits, then read its label row" / "atomicMin, then set the bit and push" is unchanged.
+#include "sssp_bundle_common.cuh"
+
+namespace dtl {
+
+#ifndef BND_ASYNC_SLEEP
+#define BND_ASYNC_SLEEP 40 /* ns an idle warp sleeps between two polls of its ring slots */
+#endif
+
+template <int BLOCK, int B>
+__global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunch a)
+{
+    constexpr int LPT = 2;
+    constexpr int G = B / LPT;
+    constexpr int PR = (BND_U + G - 1) / G;
+    extern __shared__ int s_dyn[];
+    __shared__ int s_bundle, s_head, s_tail, s_pending, s_n_far, s_n_far2, s_overflow;
+    __shared__ unsigned s_red[32];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int g = tid & (G - 1);
+    const int gfirst = lane & ~(G - 1);
+    const unsigned gmask = ((1u << G) - 1u) << gfirst;
+    const int N = a.s.N;
+    const int RING = a.cap_near; // power of two
+    const int RMASK = RING - 1;
+    const int CAPF = a.cap_far;
+    const int n_words = (N + 15) >> 4;
+    unsigned* const s_state = reinterpret_cast<unsigned*>(s_dyn);            // [n_words]
+    int2* const s_r = reinterpret_cast<int2*>(s_dyn + ((n_words + 1) & ~1)); // [RING] forward-star row of the entry's node
+    volatile int* const s_q = reinterpret_cast<int*>(s_r + RING);            // [RING] node + 1, 0 = empty slot
+    int2* q_far = a.far + (size_t)blockIdx.x * 2 * CAPF;
+    int2* q_far2 = q_far + CAPF;
+    unsigned long long c_relax = 0;
+    unsigned c_pops = 0, c_rounds = 0;
+
+    // publish one entry into the ring (any thread)
+    auto push_near = [&](int node, int2 row) {
+        const int queued = atomicAdd(&s_pending, 1);
+        const int slot = atomicAdd(&s_tail, 1) & RMASK;
+        if (s_q[slot] != 0 || queued >= a.near_limit) { // the ring wrapped onto an unconsumed entry (or the test hook's limit)
+            s_overflow = 1;
+            atomicSub(&s_pending, 1);
+            return;
+        }
+        s_r[slot] = row;
+        __threadfence_block();
+        s_q[slot] = node + 1;
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_bundle = atomicAdd(a.bundle_counter, 1);
+        __syncthreads();
+        const int bundle = s_bundle;
+        if (bundle >= a.n_bundles) break;
+        int zone[LPT];
+        unsigned has_task = 0;
+#pragma unroll
+        for (int t = 0; t < LPT; ++t) {
+            const int task = __ldg(&a.bundle_tasks[bundle * B + g * LPT + t]);
+            zone[t] = task >= 0 ? __ldg(&a.s.task_zone[task]) : -1;
+            has_task |= (unsigned)(task >= 0) << t;
+        }
+        unsigned long long* const bl = a.bl + (size_t)bundle * N * B;
+        unsigned long long* const blg = bl + g * LPT;
+
+        {
+            ulonglong2* v = reinterpret_cast<ulonglong2*>(bl);
+            const size_t nv = (size_t)N * B / 2;
+            const ulonglong2 x = make_ulonglong2(INF_BITS, INF_BITS);
+            for (size_t i = tid; i < nv; i += BLOCK) v[i] = x;
+        }
+        for (int i = tid; i < n_words; i += BLOCK) s_state[i] = 0u;
+        for (int i = tid; i < RING; i += BLOCK) s_q[i] = 0;
+        if (tid == 0) { s_head = 0; s_tail = 0; s_pending = 0; s_n_far = 0; s_n_far2 = 0; s_overflow = 0; }
+        __syncthreads();
+        if (tid < B) { // seed: every origin relaxes its own (unhidden) row once with label 0; the heads wait in the far pile
+            const int task = __ldg(&a.bundle_tasks[bundle * B + tid]);
+            if (task >= 0) {
+                const int origin = __ldg(&a.s.task_origin[task]);
+                const int oz = __ldg(&a.s.task_zone[task]);
+                bl[(size_t)origin * B + tid] = 0ULL;
+                a.s.tie_nodes[task] = 0;
+                const int r1 = __ldg(&a.s.row_ptr[origin + 1]);
+                for (int e = __ldg(&a.s.row_ptr[origin]); e < r1; ++e) {
+                    const Edge ed = ld_edge(&a.s.edges[e]);
+                    int to = ed.to;
+                    if (to < 0) {
+                        to &= 0x7fffffff;
+                        if (__ldg(&a.s.link_tag[ed.link]) != oz) continue;
+                    }
+                    if (to == origin) continue;
+                    const double c = 0.0 + ed.cost;
+                    const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+                    const unsigned long long old = atomicMin(&bl[(size_t)to * B + tid], cb);
+                    ++c_relax;
+                    if (old > cb) {
+                        const unsigned o = atomicOr(&s_state[ST_WORD(to)], 2u << ST_SHIFT(to));
+                        if (!((o >> ST_SHIFT(to)) & 3u)) {
+                            const int pos = atomicAdd(&s_n_far, 1);
+                            if (pos < CAPF) q_far[pos] = make_int2(to, (int)key_of(cb));
+                            else s_overflow = 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        unsigned thr = 0u;
+        bool failed = false;
+
+        for (;;) {
+            // ---- open the next label window from the far pile (block-wide, like the round-synchronous kernel) ----
+            const int n_far = min(s_n_far, CAPF);
+            if (n_far == 0) break;
+            unsigned mm = BND_DEAD_KEY;
+            for (int i = tid; i < n_far; i += BLOCK) {
+                const int2 q = q_far[i];
+                if ((s_state[ST_WORD(q.x)] >> ST_SHIFT(q.x)) & 2u) mm = min(mm, (unsigned)q.y);
+            }
+            mm = block_min_u32<BLOCK>(mm, s_red);
+            if (mm == BND_DEAD_KEY) break;
+            thr = key_of((unsigned long long)__double_as_longlong(__hiloint2double((int)mm, 0) + a.s.delta));
+            if (thr <= mm) thr = mm + 1;
+            if (tid == 0) { s_head = 0; s_tail = 0; } // the ring is empty here: every published entry was consumed
+            __syncthreads();
+            for (int base = 0; base < n_far; base += BLOCK / G) {
+                if (base + (tid & ~31) / G >= n_far) continue;
+                const int i = base + tid / G;
+                const bool have = i < n_far;
+                const int v = have ? q_far[i].x : 0;
+                const int w = ST_WORD(v), sh = ST_SHIFT(v);
+                unsigned o = 0;
+                if (have && g == 0) o = atomicAnd(&s_state[w], ~(2u << sh)) >> sh;
+                o = __shfl_sync(0xffffffffu, o, gfirst);
+                const bool live = (o & 2u) != 0;
+                unsigned k = BND_DEAD_KEY;
+                if (live) {
+                    const ulonglong2 lab = __ldcg(reinterpret_cast<const ulonglong2*>(blg + (size_t)v * B));
+                    k = min(key_of(lab.x), key_of(lab.y));
+                }
+                const unsigned key = group_min_u32<G>(k);
+                if (live && g == 0) {
+                    if (key < thr) {
+                        const unsigned o2 = atomicOr(&s_state[w], 1u << sh);
+                        if (!((o2 >> sh) & 1u)) push_near(v, __ldg(&a.s.rows[v]));
+                    } else {
+                        atomicOr(&s_state[w], 2u << sh);
+                        const int pos = atomicAdd(&s_n_far2, 1);
+                        q_far2[pos] = make_int2(v, (int)key);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { s_n_far = s_n_far2; s_n_far2 = 0; }
+            int2* t2 = q_far; q_far = q_far2; q_far2 = t2;
+            ++c_rounds;
+            __syncthreads();
+            if (s_overflow) { failed = true; break; }
+
+            // ---- drain the window: every group consumes ring entries until nothing is queued or in flight ----
+            int ticket = -1; // this group's claim on a ring position (leader's register, broadcast when needed)
+            for (;;) {
+                if (g == 0 && ticket < 0) ticket = atomicAdd(&s_head, 1);
+                int node1 = 0;
+                bool reserved = false; // a producer holds this group's slot and is about to publish into it
+                if (g == 0) {
+                    node1 = s_q[ticket & RMASK];
+                    reserved = node1 == 0 && ticket < *reinterpret_cast<volatile int*>(&s_tail);
+                }
+                const unsigned ready = __ballot_sync(0xffffffffu, node1 != 0);
+                const unsigned soon = __ballot_sync(0xffffffffu, reserved);
+                if (ready == 0u || soon != 0u) {
+                    // nothing for this warp yet: leave when the window is drained or the bundle is aborted, otherwise poll again.
+                    // With some entries ready and others about to be published the warp polls once more, so that one pass of
+                    // the instruction stream below serves all of them.
+                    const int pend = *reinterpret_cast<volatile int*>(&s_pending);
+                    const int ovf = *reinterpret_cast<volatile int*>(&s_overflow);
+                    if (ovf || (ready == 0u && pend == 0)) break;
+                    if (soon == 0u) __nanosleep(BND_ASYNC_SLEEP);
+                    continue;
+                }
+                const bool have = __shfl_sync(0xffffffffu, node1, gfirst) != 0;
+                int u = 0;
+                int2 row = make_int2(0, 0);
+                unsigned was = 0;
+                if (have && g == 0) {
+                    u = node1 - 1;
+                    const volatile int* rr = reinterpret_cast<const volatile int*>(&s_r[ticket & RMASK]);
+                    row.x = rr[0]; row.y = rr[1];
+                    __threadfence_block();
+                    s_q[ticket & RMASK] = 0; // the slot is free again
+                    ticket = -1;
+                    was = atomicAnd(&s_state[ST_WORD(u)], ~(3u << ST_SHIFT(u))) >> ST_SHIFT(u);
+                }
+                u = __shfl_sync(0xffffffffu, u, gfirst);
+                row.x = __shfl_sync(0xffffffffu, row.x, gfirst);
+                row.y = __shfl_sync(0xffffffffu, row.y, gfirst);
+                int e0 = row.x;
+                const int re = row.y;
+                double cost[BND_U];
+                int to[BND_U];
+#pragma unroll
+                for (int j = 0; j < BND_U; ++j) {
+                    cost[j] = 0.0; to[j] = 0;
+                    if (e0 + j < re) {
+                        const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[e0 + j]));
+                        cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
+                    }
+                }
+                was = __shfl_sync(0xffffffffu, was, gfirst) & 3u;
+                double lu[LPT];
+                unsigned act = 0;
+                {
+                    ulonglong2 lab = make_ulonglong2(INF_BITS, INF_BITS);
+                    if (was) lab = __ldcg(reinterpret_cast<const ulonglong2*>(blg + (size_t)u * B));
+                    lu[0] = __longlong_as_double((long long)lab.x);
+                    lu[1] = __longlong_as_double((long long)lab.y);
+                    act = ((unsigned)(lab.x < INF_BITS) | (unsigned)(lab.y < INF_BITS) << 1) & has_task;
+                }
+                if (have) {
+                    if (g == 0) ++c_pops;
+                    c_relax += (unsigned)__popc(act) * (unsigned)(re - e0);
+                }
+                while (__any_sync(0xffffffffu, e0 < re)) {
+                    unsigned long long old[BND_U][LPT];
+                    int2 prow[PR];
+                    unsigned okm = 0;
+#pragma unroll
+                    for (int j = 0; j < BND_U; ++j) {
+                        const bool valid = e0 + j < re;
+                        unsigned ok = valid ? act : 0u;
+                        if (to[j] < 0) { // routing.h:779-786
+                            to[j] &= 0x7fffffff;
+                            const int tag = __ldg(&a.s.link_tag[__ldg(&a.s.edges[e0 + j].link)]);
+#pragma unroll
+                            for (int t = 0; t < LPT; ++t)
+                                if (tag != zone[t]) ok &= ~(1u << t);
+                        }
+                        unsigned long long* const p = blg + (size_t)to[j] * B;
+#pragma unroll
+                        for (int t = 0; t < LPT; ++t) {
+                            old[j][t] = 0ULL;
+                            if ((ok >> t) & 1u) old[j][t] = atomicMin(p + t, (unsigned long long)__double_as_longlong(lu[t] + cost[j])); // routing.h:804,816
+                        }
+                        okm |= ok << (j * LPT);
+                        if (valid && g == (j % G)) prow[j / G] = __ldg(&a.s.rows[to[j]]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < BND_U; ++j) {
+                        bool imp = false;
+                        unsigned k = BND_DEAD_KEY;
+#pragma unroll
+                        for (int t = 0; t < LPT; ++t) {
+                            const unsigned long long cb = (unsigned long long)__double_as_longlong(lu[t] + cost[j]);
+                            if ((okm >> (j * LPT + t)) & 1u) {
+                                imp = imp || old[j][t] > cb;
+                                k = min(k, min(key_of(old[j][t]), key_of(cb)));
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, imp);
+                        if (bal == 0u) continue;
+                        const unsigned key = group_min_u32<G>(k);
+                        if ((bal & gmask) && g == (j % G)) {
+                            const int w = ST_WORD(to[j]), sh = ST_SHIFT(to[j]);
+                            if (key < thr) {
+                                const unsigned o = atomicOr(&s_state[w], 1u << sh);
+                                if (!((o >> sh) & 1u)) push_near(to[j], prow[j / G]);
+                            } else {
+                                const unsigned o = atomicOr(&s_state[w], 2u << sh);
+                                if (!((o >> sh) & 3u)) {
+                                    const int pos = atomicAdd(&s_n_far, 1);
+                                    if (pos < CAPF) q_far[pos] = make_int2(to[j], (int)key);
+                                    else s_overflow = 1;
+                                }
+                            }
+                        }
+                    }
+                    e0 += BND_U;
+#pragma unroll
+                    for (int j = 0; j < BND_U; ++j)
+                        if (e0 + j < re) {
+                            const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[e0 + j]));
+                            cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
+                        }
+                }
+                __syncwarp();
+                if (have && g == 0) atomicSub(&s_pending, 1); // after every push of this expansion
+            }
+            __syncthreads();
+            if (s_overflow) { failed = true; break; }
+        }
+        if (failed) {
+            __syncthreads();
+            if (tid < B) {
+                const int task = __ldg(&a.bundle_tasks[bundle * B + tid]);
+                if (task >= 0) a.s.tie_nodes[task] = -1;
+            }
+            if (tid == 0) atomicAdd(&a.s.stats->overflow, 1ULL);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c_relax += __shfl_xor_sync(0xffffffffu, c_relax, o);
+        c_pops += __shfl_xor_sync(0xffffffffu, c_pops, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.s.stats->relaxations, c_relax);
+        atomicAdd(&a.s.stats->pops, (unsigned long long)c_pops);
+    }
+    if (tid == 0) atomicAdd(&a.s.stats->rounds, (unsigned long long)c_rounds);
+}
+
+size_t bundle_async_smem_bytes(int N, int ring)
+{
+    const size_t words = (((size_t)(N + 15) >> 4) + 1) & ~(size_t)1;
+    return words * sizeof(unsigned) + (size_t)ring * (sizeof(int2) + sizeof(int));
+}
+
+void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st)
+{
+    if (a.n_bundles == 0) return;
+    const size_t smem = bundle_async_smem_bytes(a.s.N, a.cap_near);
+    if (a.B == 8) {
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sssp_bundle_async_kernel<1024, 8><<<a.grid, 1024, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sssp_bundle_async_kernel<1024, 16><<<a.grid, 1024, smem, st>>>(a);
+    }
+}
+
+} // namespace dtl

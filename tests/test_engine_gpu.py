@@ -66,8 +66,9 @@ def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod, monkeyp
 
 @pytest.mark.parametrize("B,block,cluster", [(4, 1024, 1), (8, 512, 1), (16, 1024, 1), (16, 512, 0), (8, 1024, 0)])
 def test_sssp_bundle_sizes(D, problems, golden, oracle_mod, monkeypatch, B, block, cluster):
-    """Origin-bundle kernel at every bundle size / CTA size, with and without spatial clustering of the origins."""
+    """Round-synchronous origin-bundle kernel at every bundle size / CTA size, with and without spatial clustering of the origins."""
     monkeypatch.setenv("DTL_SSSP_KERNEL", "bundle")
+    monkeypatch.setenv("DTL_BUNDLE_ASYNC", "0")
     monkeypatch.setenv("DTL_BUNDLE_B", str(B))
     monkeypatch.setenv("DTL_BUNDLE_BLOCK", str(block))
     if not cluster:
@@ -78,6 +79,28 @@ def test_sssp_bundle_sizes(D, problems, golden, oracle_mod, monkeypatch, B, bloc
         for k, at in ((2, 0), (19, 2)):
             cost = g[f"gen_cost_k{k}_at{at}"]
             zones = np.arange(p.n_zones, dtype=np.int32)[::-1].copy()   # 99 origins: the last bundle is ragged
+            lab, pn, pl, ties, st = e.sssp_trees(at, 0, zones, cost=cost)
+            fs = o.forward_star(at, 0)
+            for i, z in enumerate(zones):
+                rl, rpn, rpl, pops, relax = o.sssp(fs, cost, int(z))
+                assert np.array_equal(lab[i].view(np.int64), rl.view(np.int64)), f"labels differ, k={k} zone {z}"
+                assert np.array_equal(pl[i], rpl) and np.array_equal(pn[i], rpn), f"predecessors differ, k={k} zone {z}"
+            assert st["replayed"] == 0 and e.counters()["reruns"] == 0
+
+
+@pytest.mark.parametrize("B", [16, 8])
+def test_sssp_bundle_async_window(D, problems, golden, oracle_mod, monkeypatch, B):
+    """Origin-bundle search without round barriers inside a label window (ring-buffer near queue; the default for bundles of
+    8 and 16 origins): same bits."""
+    monkeypatch.setenv("DTL_SSSP_KERNEL", "bundle")
+    monkeypatch.delenv("DTL_BUNDLE_ASYNC", raising=False)
+    monkeypatch.setenv("DTL_BUNDLE_B", str(B))
+    p, g = problems("corridor_101"), golden("corridor_101")
+    o = oracle_mod.Oracle(p)
+    with D.Engine(p) as e:
+        for k, at in ((2, 0), (19, 2)):
+            cost = g[f"gen_cost_k{k}_at{at}"]
+            zones = np.arange(p.n_zones, dtype=np.int32)
             lab, pn, pl, ties, st = e.sssp_trees(at, 0, zones, cost=cost)
             fs = o.forward_star(at, 0)
             for i, z in enumerate(zones):
