@@ -605,6 +605,7 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
         const int ph = e->phase_begin(2);
         CK(cudaMemsetAsync(e->d_bundle_counter, 0, sizeof(int), e->st));
         launch_sssp_bundle(b, e->st);
+        if (b.async) e->last_sssp_variant = 3;
         e->phase_end(ph, 2);
     } else {
         const int ph = e->phase_begin(2);

@@ -352,7 +352,8 @@ class Engine:
         self._ck(self.lib.dtl_get_counters(self.h, _ptr(c), int(reset)))
         return dict(zip(self.COUNTERS, c.tolist()))
 
-    K1_KERNELS = {0: "dtl::sssp_kernel", 1: "dtl::sssp_smq_kernel", 2: "dtl::sssp_bundle_kernel + dtl::bundle_finish_kernel"}
+    K1_KERNELS = {0: "dtl::sssp_kernel", 1: "dtl::sssp_smq_kernel", 2: "dtl::sssp_bundle_kernel + dtl::bundle_finish_kernel",
+                  3: "dtl::sssp_bundle_async_kernel + dtl::bundle_finish_kernel"}
 
     @property
     def sssp_kernel(self) -> str:

@@ -171,7 +171,8 @@ int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset);
  * trees re-run with worst-case queues, tie candidates observed } */
 int dtl_get_counters(dtl_engine* e, double c[10], int reset);
 /* which K1 kernel the last shortest-path launch used: 0 = global-memory queues, 1 = shared-memory queues,
- * 2 = origin bundles (search + label->tree pass, two launches); -1 before the first launch */
+ * 2 = origin bundles, round-synchronous search (search + label->tree pass, two launches), 3 = origin bundles, search
+ * without round barriers (the default for bundles); -1 before the first launch */
 int dtl_sssp_kernel_used(const dtl_engine* e);
 /* number of HBM bytes the engine holds */
 size_t dtl_device_bytes(const dtl_engine* e);
