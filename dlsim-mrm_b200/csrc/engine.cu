@@ -1413,6 +1413,9 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
             fprintf(stderr, "sssp: spilled %.3g | thread-0 cycles: init %.3g expansion %.3g barrier %.3g re-bucket %.3g | passes %.3g entries %.3g "
                             "rounds %.3g | bundle kernel, inside a pass: until the label row arrived %.3g, until the atomics returned %.3g\n",
                     d[0], d[1], d[2], d[3], d[4], d[6], d[7], (double)(s1.rounds - s0.rounds), (double)(s1.stage[0] - s0.stage[0]), d[5]);
+            if (s1.stage[3] > s0.stage[3])
+                fprintf(stderr, "sssp: asynchronous bundle search, cycles per bundle: max (since engine creation) %.4g, mean %.4g over %.0f bundles\n",
+                        (double)s1.stage[1], (double)(s1.stage[2] - s0.stage[2]) / (double)(s1.stage[3] - s0.stage[3]), (double)(s1.stage[3] - s0.stage[3]));
         }
     }
     e->trees_valid = false;

@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
         __syncthreads();
         const int bundle = s_bundle;
         if (bundle >= a.n_bundles) break;
+#ifdef SSSP_PROFILE
+        const long long pf_start = clock64(); // per-bundle search time: stage[1] = max, stage[2] = sum, stage[3] = bundles
+#endif
         int zone[LPT];
         unsigned has_task = 0;
 #pragma unroll
@@ -304,6 +307,14 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
             __syncthreads();
             if (s_overflow) { failed = true; break; }
         }
+#ifdef SSSP_PROFILE
+        if (tid == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - pf_start);
+            atomicMax(&a.s.stats->stage[1], dt);
+            atomicAdd(&a.s.stats->stage[2], dt);
+            atomicAdd(&a.s.stats->stage[3], 1ULL);
+        }
+#endif
         if (failed) {
             __syncthreads();
             if (tid < B) {

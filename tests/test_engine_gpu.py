@@ -31,14 +31,22 @@ def sha(a):
 
 
 # ------------------------------------------------------------------------------------------------ K1
-# global-memory queues (many trees per SM) / shared-memory queues (few trees per SM) / origin bundles (B origins per search)
-KERNELS = ["gq", "smq", "bundle"]
+# global-memory queues (many trees per SM) / shared-memory queues (few trees per SM) / origin bundles (B origins per search;
+# "bundle": bundle size by tree count = round-synchronous bundles of 4 at these sizes, "bundle16": bundles of 16 = the search
+# without round barriers that the bench configuration runs)
+KERNELS = ["gq", "smq", "bundle", "bundle16"]
+
+
+def _force_kernel(monkeypatch, kernel):
+    monkeypatch.setenv("DTL_SSSP_KERNEL", "bundle" if kernel.startswith("bundle") else kernel)
+    if kernel == "bundle16":
+        monkeypatch.setenv("DTL_BUNDLE_B", "16")
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_sssp_known_answer_corridor_101(D, problems, golden, oracle_mod, monkeypatch, kernel):
     """K1 fed the reference's own generalized costs: labels, pred nodes and pred links bit-exact for every origin."""
-    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
+    _force_kernel(monkeypatch, kernel)
     p, g = problems("corridor_101"), golden("corridor_101")
     o = oracle_mod.Oracle(p)
     with D.Engine(p) as e:
@@ -141,7 +149,7 @@ def _tie_grid(n=12):
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_sssp_ties_follow_the_reference_rule(D, oracle_mod, monkeypatch, kernel):
     """Exact FP64 ties: the engine detects them and replays the reference's deque, so the trees still match."""
-    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
+    _force_kernel(monkeypatch, kernel)
     p = _tie_grid()
     o = oracle_mod.Oracle(p)
     cost = np.ones(p.n_links)
@@ -321,10 +329,11 @@ def test_drop_in_executable_writes_reference_files(D, tmp_path):
 
 
 @pytest.mark.parametrize("workload,K,CU,kernel", [("grid2k", 8, 3, "gq"), ("grid2k", 8, 3, "smq"), ("grid2k", 8, 3, "bundle"),
-                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq"), ("grid10k", 4, 0, "bundle")])
+                                                  ("grid10k", 4, 0, "gq"), ("grid10k", 4, 0, "smq"), ("grid10k", 4, 0, "bundle"),
+                                                  ("grid10k", 4, 0, "bundle16")])
 def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, monkeypatch, workload, K, CU, kernel):
     """The bench generator at sizes the oracle finishes in seconds: same parity bars as the reference datasets."""
-    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
+    _force_kernel(monkeypatch, kernel)
     from dlsim_mrm_b200 import synth
     synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
     p = D.read_gmns(str(tmp_path), 8)
@@ -356,7 +365,7 @@ def test_synthetic_grid_matches_oracle(D, oracle_mod, tmp_path, monkeypatch, wor
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_small_queues_fall_back_to_worst_case_rerun(D, problems, golden, oracle_mod, monkeypatch, kernel):
     """Trees whose frontier outgrows the regular work queues are recomputed with worst-case queues: same bits."""
-    monkeypatch.setenv("DTL_SSSP_KERNEL", kernel)
+    _force_kernel(monkeypatch, kernel)
     p, g = problems("corridor_101"), golden("corridor_101")
     o = oracle_mod.Oracle(p)
     cost = g["gen_cost_k2_at0"]
