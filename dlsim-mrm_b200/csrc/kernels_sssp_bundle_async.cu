@@ -7,6 +7,7 @@
 //   * every group owns one ticket (atomicAdd on the head) and polls its slot; the ticket is kept until its entry shows up;
 //   * s_pending counts entries that are queued or being expanded; when it reaches zero the window is drained, all warps
 //     leave the loop, and the CTA re-buckets the far pile exactly like the round-synchronous kernel;
+//   * an idle warp that has polled for about a second without the window draining gives the bundle up (watchdog);
 //   * the ring has far more slots (>= 1 024) than the CTA has ticket holders (128 groups), so a ticket can never meet the
 //     slot of an older lap; a ring that wraps onto an unconsumed slot, or a far pile that overflows, aborts the bundle (its trees are recomputed
 //     by the global-queue kernel, like any other overflow).
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
 
             // ---- drain the window: every group consumes ring entries until nothing is queued or in flight ----
             int ticket = -1; // this group's claim on a ring position (leader's register, broadcast when needed)
+            unsigned idle_polls = 0;
             for (;;) {
                 if (g == 0 && ticket < 0) ticket = atomicAdd(&s_head, 1);
                 int node1 = 0;
@@ -195,8 +197,12 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     const int ovf = *reinterpret_cast<volatile int*>(&s_overflow);
                     if (ovf || (ready == 0u && pend == 0)) break;
                     if (soon == 0u) __nanosleep(BND_ASYNC_SLEEP);
+                    // watchdog: a window drains in micro- to milliseconds; a warp that has polled for about a second gives the
+                    // bundle up (its trees are recomputed by the global-queue kernel) instead of spinning on a lost wake-up
+                    if (++idle_polls > (1u << 24)) s_overflow = 1;
                     continue;
                 }
+                idle_polls = 0;
                 const bool have = __shfl_sync(0xffffffffu, node1, gfirst) != 0;
                 int u = 0;
                 int2 row = make_int2(0, 0);
