@@ -529,6 +529,7 @@ void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st)
     default: a.lpt >= 4 ? bundle_launch_block<16, 4>(a, st) : bundle_launch_block<16, 2>(a, st); break;
     }
     switch (a.B) {
+    case 2: finish_launch<2>(a, st); break;
     case 4: finish_launch<4>(a, st); break;
     case 8: finish_launch<8>(a, st); break;
     default: finish_launch<16>(a, st); break;

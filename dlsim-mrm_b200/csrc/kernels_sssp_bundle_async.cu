@@ -5,7 +5,7 @@
 // the same round trips, then a barrier); here the phases of different warps overlap.
 //   * producers reserve a slot with one atomicAdd on the tail, write the row, fence, then publish node+1 into the slot;
 //   * every group owns one ticket (atomicAdd on the head) and polls its slot; the ticket is kept until its entry shows up;
-//   * s_pending counts entries that are queued or being expanded; when it reaches zero the window is drained, all warps
+//   * the high bits of s_pt count entries that are queued or being expanded (its low bits are the ring tail); when it reaches zero the window is drained, all warps
 //     leave the loop, and the CTA re-buckets the far pile exactly like the round-synchronous kernel;
 //   * an idle warp that has polled for about a second without the window draining gives the bundle up (watchdog);
 //   * the ring has far more slots (>= 1 024) than the CTA has ticket holders (128 groups), so a ticket can never meet the
@@ -17,6 +17,9 @@
 
 namespace dtl {
 
+#define PT_SHIFT 17
+#define PT_ONE_PENDING (1u << PT_SHIFT)
+#define PT_TAIL_MASK (PT_ONE_PENDING - 1u)
 #ifndef BND_ASYNC_SLEEP
 #define BND_ASYNC_SLEEP 40 /* ns an idle warp sleeps between two polls of its ring slots */
 #endif
@@ -28,7 +31,10 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
     constexpr int G = B / LPT;
     constexpr int PR = (BND_U + G - 1) / G;
     extern __shared__ int s_dyn[];
-    __shared__ int s_bundle, s_head, s_tail, s_pending, s_n_far, s_n_far2, s_overflow;
+    __shared__ int s_bundle, s_head, s_n_far, s_n_far2, s_overflow;
+    // {entries queued or in flight (bits 17..31), ring tail of this window (bits 0..16)}: ONE shared-memory atomic per push --
+    // same-address shared-memory atomics are what this kernel's throughput hangs on
+    __shared__ unsigned s_pt;
     __shared__ unsigned s_red[32];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -50,11 +56,14 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
 
     // publish one entry into the ring (any thread)
     auto push_near = [&](int node, int2 row) {
-        const int queued = atomicAdd(&s_pending, 1);
-        const int slot = atomicAdd(&s_tail, 1) & RMASK;
-        if (s_q[slot] != 0 || queued >= a.near_limit) { // the ring wrapped onto an unconsumed entry (or the test hook's limit)
+        const unsigned pt = atomicAdd(&s_pt, PT_ONE_PENDING + 1u);
+        const int queued = (int)(pt >> PT_SHIFT);
+        const int tail = (int)(pt & PT_TAIL_MASK);
+        const int slot = tail & RMASK;
+        // the ring wrapped onto an unconsumed entry, the test hook's limit, or the tail field is about to run out of bits
+        if (s_q[slot] != 0 || queued >= a.near_limit || tail >= (int)PT_TAIL_MASK - 4096) {
             s_overflow = 1;
-            atomicSub(&s_pending, 1);
+            atomicSub(&s_pt, PT_ONE_PENDING);
             return;
         }
         s_r[slot] = row;
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
         }
         for (int i = tid; i < n_words; i += BLOCK) s_state[i] = 0u;
         for (int i = tid; i < RING; i += BLOCK) s_q[i] = 0;
-        if (tid == 0) { s_head = 0; s_tail = 0; s_pending = 0; s_n_far = 0; s_n_far2 = 0; s_overflow = 0; }
+        if (tid == 0) { s_head = 0; s_pt = 0u; s_n_far = 0; s_n_far2 = 0; s_overflow = 0; }
         __syncthreads();
         if (tid < B) { // seed: every origin relaxes its own (unhidden) row once with label 0; the heads wait in the far pile
             const int task = __ldg(&a.bundle_tasks[bundle * B + tid]);
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
             if (mm == BND_DEAD_KEY) break;
             thr = key_of((unsigned long long)__double_as_longlong(__hiloint2double((int)mm, 0) + a.s.delta));
             if (thr <= mm) thr = mm + 1;
-            if (tid == 0) { s_head = 0; s_tail = 0; } // the ring is empty here: every published entry was consumed
+            if (tid == 0) { s_head = 0; s_pt = 0u; } // the ring is empty here: every published entry was consumed and finished
             __syncthreads();
             for (int base = 0; base < n_far; base += BLOCK / G) {
                 if (base + (tid & ~31) / G >= n_far) continue;
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                 bool reserved = false; // a producer holds this group's slot and is about to publish into it
                 if (g == 0) {
                     node1 = s_q[ticket & RMASK];
-                    reserved = node1 == 0 && ticket < *reinterpret_cast<volatile int*>(&s_tail);
+                    reserved = node1 == 0 && ticket < (int)(*reinterpret_cast<volatile unsigned*>(&s_pt) & PT_TAIL_MASK);
                 }
                 const unsigned ready = __ballot_sync(0xffffffffu, node1 != 0);
                 const unsigned soon = __ballot_sync(0xffffffffu, reserved);
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     // nothing for this warp yet: leave when the window is drained or the bundle is aborted, otherwise poll again.
                     // With some entries ready and others about to be published the warp polls once more, so that one pass of
                     // the instruction stream below serves all of them.
-                    const int pend = *reinterpret_cast<volatile int*>(&s_pending);
+                    const int pend = (int)(*reinterpret_cast<volatile unsigned*>(&s_pt) >> PT_SHIFT);
                     const int ovf = *reinterpret_cast<volatile int*>(&s_overflow);
                     if (ovf || (ready == 0u && pend == 0)) break;
                     if (soon == 0u) __nanosleep(BND_ASYNC_SLEEP);
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                         }
                 }
                 __syncwarp();
-                if (have && g == 0) atomicSub(&s_pending, 1); // after every push of this expansion
+                if (have && g == 0) atomicSub(&s_pt, PT_ONE_PENDING); // after every push of this expansion
             }
             __syncthreads();
             if (s_overflow) { failed = true; break; }
