@@ -490,7 +490,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     int B = 16;
     if (n < 16 * e->sm_count / 2) B = 8;
     if (n < 8 * e->sm_count / 2) B = 4;
-    if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 2 ? 2 : atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
+    if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
     b.s = a;
     b.B = B;
     b.lpt = 2; // origins per thread; 4 measured slower (fewer warps to hide the round trips)
@@ -509,7 +509,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     // 20 % faster than the round-synchronous one at the bench configuration; DTL_BUNDLE_ASYNC=0 selects the latter
     b.async = 0;
     const char* async_env = getenv("DTL_BUNDLE_ASYNC");
-    if ((B >= 8 || B == 2 || async_env) && !(async_env && atoi(async_env) == 0) && !getenv("DTL_BUNDLE_BLOCK") && !getenv("DTL_BUNDLE_LPT")) {
+    if (B >= 8 && !(async_env && atoi(async_env) == 0) && !getenv("DTL_BUNDLE_BLOCK") && !getenv("DTL_BUNDLE_LPT")) {
         b.async = 1;
         b.block = 1024; b.lpt = 2;
         int ring = 1;
