@@ -95,7 +95,7 @@ int dtl_comm_init(dtl_engine* e, const unsigned char id128[128]);
  * Returns the number of tasks (may exceed capacity; only `capacity` entries are written). */
 int dtl_plan_tasks(const dtl_problem* p, int rank, int world_size, int* at, int* tau, int* zone, int capacity);
 
-/* Host-only: groups `n` origin nodes into bundles of up to B (4, 8 or 16) neighbouring origins -- the groups the
+/* Host-only: groups `n` origin nodes into bundles of up to B (2, 4, 8 or 16) neighbouring origins -- the groups the
  * origin-bundle shortest-path kernel searches together: a k-d split of a two-landmark hop-distance embedding of the
  * forward star (row_ptr[n_nodes + 1], head[row_ptr[n_nodes]]).  Writes n_bundles * B entries (indices into `origins`,
  * -1 = empty slot; only the first `capacity` are written) and returns n_bundles.  Every origin appears exactly once and
