@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <chrono>
 #include <queue>
 #include <tuple>
 
@@ -169,10 +170,32 @@ struct dtl_engine {
     ncclComm_t comm = nullptr;
     bool local_shard = false; // world > 1 without a communicator: the caller reduces the shards (tests)
 
+    // Device memory: allocations up to 32 MB are carved out of 256 MB slabs (an engine makes ~80 of them; one cudaMalloc each
+    // costs more than the copies that fill them), larger ones get their own cudaMalloc.  Everything is freed in dtl_destroy.
+    char* slab = nullptr;
+    size_t slab_used = 0, slab_cap = 0;
     template <class T>
     int alloc(T** p, size_t n)
     {
         size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        if (bytes <= ((size_t)32 << 20)) {
+            const size_t need = (bytes + 255) & ~(size_t)255;
+            if (!slab || slab_used + need > slab_cap) {
+                void* q = nullptr;
+                const size_t cap = (size_t)256 << 20;
+                cudaError_t e = cudaMalloc(&q, cap);
+                if (e != cudaSuccess) {
+                    set_err("cudaMalloc of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+                    return -1;
+                }
+                allocs.push_back(q);
+                slab = (char*)q; slab_used = 0; slab_cap = cap;
+            }
+            *p = (T*)(slab + slab_used);
+            slab_used += need;
+            dev_bytes += need;
+            return 0;
+        }
         void* q = nullptr;
         cudaError_t e = cudaMalloc(&q, bytes);
         if (e != cudaSuccess) {
@@ -720,9 +743,21 @@ void dtl_destroy(dtl_engine* e)
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
+// DTL_CREATE_TRACE=1: wall-clock time between the sections of create_impl on stderr
+#define DTL_TRACE(what)                                                                                          \
+    do {                                                                                                         \
+        if (trace_on) {                                                                                          \
+            const auto now_ = std::chrono::steady_clock::now();                                                 \
+            fprintf(stderr, "dtl_create: %8.3f ms before \"%s\"\n", std::chrono::duration<double, std::milli>(now_ - trace_t).count(), what); \
+            trace_t = now_;                                                                                      \
+        }                                                                                                        \
+    } while (0)
+
 
 static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* opt)
 {
+    const bool trace_on = getenv("DTL_CREATE_TRACE") != nullptr;
+    auto trace_t = std::chrono::steady_clock::now();
     dtl_options o;
     if (opt) o = *opt; else dtl_default_options(&o);
     e->opt = o;
@@ -759,6 +794,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
             return -1;
         }
 
+    DTL_TRACE("tasks of this rank: origin zones are sha");
     // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
     std::vector<int> g_at, g_tau, g_zone;
     build_task_list(p, g_at, g_tau, g_zone);
@@ -782,6 +818,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
     if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
 
+    DTL_TRACE("OD cells of this rank (cells whose origi");
     // ---- OD cells of this rank (cells whose origin has no task never get columns in the reference either) ----
     std::vector<int> od_dest, od_at, od_tau, od_task;
     std::vector<double> od_vol;
@@ -811,6 +848,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
 
+    DTL_TRACE("network image");
     // ---- network image ----
     if (e->upload(&e->d_link_tag, p->link_tag, L)) return -1;
     if (e->upload(&e->d_link_from, p->link_from, L)) return -1;
@@ -867,6 +905,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_link_edge_ptrs, le.data(), le.size())) return -1;
     if (e->upload(&e->d_edges_ptrs, ed.data(), ed.size())) return -1;
 
+    DTL_TRACE("column pool");
     // ---- column pool ----
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -895,6 +934,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     CK(cudaMemset(e->d_counters, 0, 32));
     if (e->alloc(&e->d_task_counter, 1)) return -1;
 
+    DTL_TRACE("tree batch + SSSP workspace");
     // ---- tree batch + SSSP workspace ----
     const size_t per_tree = (size_t)N * 12;
     size_t tree_budget = o.tree_batch_bytes ? o.tree_batch_bytes : std::min<size_t>((size_t)24 << 30, free_b / 6);
@@ -928,6 +968,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_ws, (size_t)e->sssp_grid * e->ws_stride)) return -1;
     if (e->alloc(&e->d_tie_cand, (size_t)e->sssp_grid * e->tie_cap)) return -1;
 
+    DTL_TRACE("path-link arena: what is left, bounded b");
     // ---- path-link arena: what is left, bounded by the option ----
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t arena_bytes = o.column_arena_bytes ? o.column_arena_bytes : std::min<size_t>((size_t)6 << 30, free_b / 4);
@@ -937,6 +978,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     e->pool.arena_cap = (long long)(arena_bytes / sizeof(int));
     if (e->alloc(&e->pool.arena, (size_t)e->pool.arena_cap)) return -1;
     CK(cudaDeviceSynchronize());
+    DTL_TRACE("end");
     return 0;
 }
 
