@@ -798,7 +798,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
     std::vector<int> g_at, g_tau, g_zone;
     build_task_list(p, g_at, g_tau, g_zone);
-    std::map<long long, int> task_of; // (at,tau,zone) -> local task
+    std::vector<int> task_of((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
     for (size_t i = 0; i < g_at.size(); ++i)
         if (g_zone[i] % e->world == e->rank) {
             task_of[((long long)g_at[i] * T + g_tau[i]) * Z + g_zone[i]] = (int)e->task_at.size();
@@ -824,15 +824,20 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     std::vector<double> od_vol;
     std::vector<std::vector<int>> cells_of_task(n_tasks);
     for (int i = 0; i < p->n_od; ++i) {
+        if (p->od_o[i] < 0 || p->od_o[i] >= Z || p->od_d[i] < 0 || p->od_d[i] >= Z || p->od_at[i] < 0 || p->od_at[i] >= AT ||
+            p->od_tau[i] < 0 || p->od_tau[i] >= T) {
+            set_err("OD row %d: zone, agent type or period index out of range", i);
+            return -1;
+        }
         if (p->od_o[i] % e->world != e->rank) continue;
-        auto it = task_of.find(((long long)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]);
-        if (it == task_of.end()) continue;
+        const int task_i = task_of[((size_t)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]];
+        if (task_i < 0) continue;
         const int c = (int)e->cell_global.size();
         e->cell_global.push_back(i);
         od_dest.push_back(p->zone_centroid[p->od_d[i]]);
-        od_at.push_back(p->od_at[i]); od_tau.push_back(p->od_tau[i]); od_task.push_back(it->second);
+        od_at.push_back(p->od_at[i]); od_tau.push_back(p->od_tau[i]); od_task.push_back(task_i);
         od_vol.push_back(p->od_vol[i]);
-        cells_of_task[it->second].push_back(c);
+        cells_of_task[task_i].push_back(c);
     }
     e->n_cells = (int)e->cell_global.size();
     std::vector<int> task_cells;
