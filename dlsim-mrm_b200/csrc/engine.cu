@@ -535,6 +535,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     if (B >= 8 && !(async_env && atoi(async_env) == 0) && !getenv("DTL_BUNDLE_BLOCK") && !getenv("DTL_BUNDLE_LPT")) {
         b.async = 1;
         b.block = 1024; b.lpt = 2;
+        if (const char* env = getenv("DTL_BUNDLE_ASYNC_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024; // experiment hook
         int ring = 1;
         while ((size_t)2 * ring * 12 + fixed <= (size_t)226 * 1024 && 2 * ring <= 16384) ring *= 2;
         if (ring < 1024) { set_err("origin-bundle kernel: %d nodes leave no room for the shared-memory ring", e->N); return -1; }

@@ -356,16 +356,21 @@ size_t bundle_async_smem_bytes(int N, int ring)
     return words * sizeof(unsigned) + (size_t)ring * (sizeof(int2) + sizeof(int));
 }
 
+template <int BLOCK, int B>
+static void async_launch(const BundleLaunch& a, size_t smem, cudaStream_t st)
+{
+    cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sssp_bundle_async_kernel<BLOCK, B><<<a.grid, BLOCK, smem, st>>>(a);
+}
+
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st)
 {
     if (a.n_bundles == 0) return;
     const size_t smem = bundle_async_smem_bytes(a.s.N, a.cap_near);
     if (a.B == 8) {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sssp_bundle_async_kernel<1024, 8><<<a.grid, 1024, smem, st>>>(a);
+        a.block == 512 ? async_launch<512, 8>(a, smem, st) : a.block == 768 ? async_launch<768, 8>(a, smem, st) : async_launch<1024, 8>(a, smem, st);
     } else {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sssp_bundle_async_kernel<1024, 16><<<a.grid, 1024, smem, st>>>(a);
+        a.block == 512 ? async_launch<512, 16>(a, smem, st) : a.block == 768 ? async_launch<768, 16>(a, smem, st) : async_launch<1024, 16>(a, smem, st);
     }
 }
 
