@@ -19,7 +19,10 @@
  * Environment knobs for trace mode:
  *   DTL_TRACE_TREES=0,1,2    iterations whose per-origin label/predecessor arrays are dumped
  *   DTL_TRACE_ORIGIN_STRIDE  dump every n-th origin only (default 1)
- *   DTL_TRACE_LIGHT=1        skip all per-iteration array dumps (timing runs)
+ *   DTL_TRACE_LIGHT=1        skip all per-iteration link-state / cost dumps (timing runs; tree dumps of
+ *                            DTL_TRACE_TREES are still written, after the iteration's timed region)
+ *   DTL_TRACE_EDGE_ITERS=0   iterations that also run the Graph500-style edge count (default: iteration 0 only;
+ *                            the count is a diagnostic walk over every tree and is kept out of timed iterations)
  */
 #include "main_api.cpp"
 
@@ -228,6 +231,7 @@ int run_trace(int K, int CU, int B, const char* out_path)
 {
     const bool light = getenv("DTL_TRACE_LIGHT") && atoi(getenv("DTL_TRACE_LIGHT")) != 0;
     const std::set<int> tree_iters = parse_int_set(getenv("DTL_TRACE_TREES"));
+    const std::set<int> edge_iters = parse_int_set(getenv("DTL_TRACE_EDGE_ITERS") ? getenv("DTL_TRACE_EDGE_ITERS") : "0");
     const int stride = getenv("DTL_TRACE_ORIGIN_STRIDE") ? std::max(1, atoi(getenv("DTL_TRACE_ORIGIN_STRIDE"))) : 1;
     g_dump = fopen(out_path, "wb");
     if (!g_dump) { fprintf(stderr, "cannot open %s\n", out_path); return 2; }
@@ -290,7 +294,8 @@ int run_trace(int K, int CU, int B, const char* out_path)
            main_api.cpp:667-697 so the result does not depend on the thread count */
         std::vector<std::vector<double> > least(nets);
         for (int n = 0; n < nets; ++n) least[n].assign(g_NetworkForSP_vector[n]->m_origin_node_vector.size(), 0.0);
-        const bool dump_trees = !light && tree_iters.count(k) > 0;
+        const bool dump_trees = tree_iters.count(k) > 0;
+        const bool count_edges = edge_iters.count(k) > 0;
         std::vector<long long> th_edges(nthreads, 0);
 
         t0 = now_s();
@@ -308,10 +313,11 @@ int run_trace(int K, int CU, int B, const char* out_path)
                     least[net][oi] = p->backtrace_shortest_path_tree(assignment, k, oi, false);   /* :687 */
                     double c = omp_get_wtime();
                     th_sssp[tid] += b - a; th_bt[tid] += c - b;
-                    /* Graph500-style edge count: forward-star edges of reachable nodes after filters */
+                    /* Graph500-style edge count: forward-star edges of reachable nodes after filters (the reachable set does
+                       not depend on the costs, so one counted iteration gives the per-iteration figure) */
                     long long e = 0;
                     int oz = p->m_origin_zone_seq_no_vector[oi];
-                    for (int i = 0; i < N; ++i) {
+                    for (int i = 0; count_edges && i < N; ++i) {
                         if (!(p->m_node_label_cost[i] < MAX_LABEL_COST)) continue;
                         const CNodeForwardStar& fs = p->NodeForwardStarArray[i];
                         for (int j = 0; j < fs.OutgoingLinkSize; ++j) {
@@ -335,7 +341,10 @@ int run_trace(int K, int CU, int B, const char* out_path)
             }
         }
         t1 = now_s(); t_region += t1 - t0;
-        for (int t = 0; t < nthreads; ++t) counted_edges += th_edges[t];
+        if (count_edges) {
+            counted_edges = 0;
+            for (int t = 0; t < nthreads; ++t) counted_edges += th_edges[t];
+        }
 
         double least_total = 0;
         for (int pid = 0; pid < nblocks; ++pid)
