@@ -43,6 +43,7 @@ struct ForwardStar {
     int2* in_edges = nullptr; // [E] {from node, forward edge index}
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
     double delta = 1.0;       // current label window of the near/far SSSP
+    bool open_tags = false;   // a node that is not a hidden centroid row has a zone-tagged out-link
     std::vector<int> h_row_ptr;
     std::vector<int> h_to;      // [E] head node of every forward-star edge (host copy for the origin-bundle planner)
     mutable std::vector<float> h_embed; // [2N] landmark-distance coordinates of every node (filled on first use)
@@ -150,6 +151,7 @@ struct BundleLaunch {
     int B;                   // origins per bundle: 4, 8 or 16
     int lpt;                 // origins per thread: 2 or 4
     int async;               // 1: search without round barriers (kernels_sssp_bundle_async.cu; cap_near = ring size, a power of two)
+    int tagged;              // 1: zone-tagged out-links exist outside the hidden centroid rows (the search then checks tags per edge)
     int near_limit;          // async: entries queued or in flight above which the bundle gives up (<= ring size; test hook)
     int n_bundles;
     const int* bundle_tasks; // [n_bundles][B] batch-local task index, -1 = empty slot
@@ -159,8 +161,12 @@ struct BundleLaunch {
     int cap_near;            // shared-memory near queue: entries per buffer
     int* bundle_counter;     // device int, zeroed before launch
     int grid, block;
+    int slim;                // 1: the label -> tree pass leaves predecessors node-major in bp and writes no per-tree arrays
+    int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
+    int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
 };
-void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);
+void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);        // search + label -> tree pass
+void launch_sssp_bundle_finish(const BundleLaunch& a, cudaStream_t st); // the label -> tree pass alone
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st);
 size_t bundle_async_smem_bytes(int N, int ring);
 size_t bundle_smem_bytes(int N, int cap_near); // dynamic shared memory of one CTA: two queue bits per node + two near queues
@@ -180,6 +186,12 @@ struct ColumnLaunch {
     const int* batch_cells;            // OD cells (local) belonging to the batch tasks
     int n_batch_cells;
     const unsigned char* task_skip_backtrace; // [n_tasks] origin has no physical out-link (routing.h:428)
+    // node-major trees of an origin-bundle batch (slim label -> tree pass); used instead of labels / pred_link when bp != nullptr
+    const unsigned long long* bl; // [n_bundles][N][B]
+    const int2* bp;               // [n_bundles][N][B] {predecessor link, predecessor node}
+    const int* task_slot;         // [task_count] bundle * B + slot of a batch-local task
+    int B;
+    const int* batch_flag;        // non-zero: the batch is redone through the per-tree path, this launch does nothing
     int k;
     double* least_contrib;             // [n_od]
     int* error_flag;                   // bit0 arena overflow, bit1 column slots exhausted

@@ -152,10 +152,13 @@ struct dtl_engine {
     int2* d_bfar = nullptr;
     int bundle_grid = 0, bundle_cap_far = 0;
     int* d_bundle_counter = nullptr;
-    struct BundlePlan { int B = 0, n_bundles = 0; int* d_tasks = nullptr; };
+    struct BundlePlan { int B = 0, n_bundles = 0; int* d_tasks = nullptr; int* d_slots = nullptr; };
     std::map<std::tuple<int, int, int, int>, BundlePlan> bundle_plans; // (forward star, first task, tasks, B)
     int* d_bundle_tmp = nullptr;
     size_t bundle_tmp_cap = 0;
+    int2* d_bp = nullptr;       // node-major predecessor records of a bundle batch (slim label -> tree pass)
+    size_t bp_cap = 0;
+    int* d_batch_flag = nullptr;
     int last_sssp_variant = -1;
     double counted_edges_cached = -1;
 
@@ -323,6 +326,7 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
         bool all_tagged = row[i + 1] > row[i];
         for (int ei = row[i]; ei < row[i + 1] && all_tagged; ++ei) all_tagged = edges[ei].to < 0;
         rows[i] = all_tagged ? make_int2(row[i], row[i]) : make_int2(row[i], row[i + 1]);
+        for (int ei = row[i]; ei < row[i + 1] && !all_tagged; ++ei) f.open_tags = f.open_tags || edges[ei].to < 0;
     }
     if (e->upload(&f.row_ptr, row.data(), row.size())) return -1;
     if (e->upload(&f.rows, rows.data(), rows.size())) return -1;
@@ -469,15 +473,70 @@ static void kd_split(std::vector<int>& idx, int lo, int hi, int B, const float* 
     kd_split(idx, lo + left, hi, B, embed, origin, out);
 }
 
+// Origin zones -> ranks.  The reference deals zones to its memory blocks round-robin (zone % blocks, main_api.cpp:259); any
+// partition gives the same link volumes here (integer sums), so the zones of a rank are chosen to be NEIGHBOURS instead: a
+// recursive median split of the landmark embedding, parts equal to within one zone.  Neighbouring origins are what the
+// origin-bundle search shares work between (9.1 vs 9.8 ms per 1 000-tree shard, 7.4 vs 10.9 ms per 250-tree shard measured
+// in round 1).  DTL_SHARD=mod selects the round-robin rule.  Every rank computes the same partition from the same problem.
+static void split_zones(std::vector<int>& idx, int lo, int hi, int r0, int r1, const float* embed, const int* centroid, int* owner)
+{
+    if (r1 - r0 <= 1) {
+        for (int i = lo; i < hi; ++i) owner[idx[i]] = r0;
+        return;
+    }
+    const int rl = (r1 - r0) / 2;
+    const int left = (int)((long long)(hi - lo) * rl / (r1 - r0));
+    float mn[2] = { INFINITY, INFINITY }, mx[2] = { -INFINITY, -INFINITY };
+    for (int i = lo; i < hi; ++i)
+        for (int d = 0; d < 2; ++d) {
+            const float x = embed[2 * centroid[idx[i]] + d];
+            mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x);
+        }
+    const int dim = (mx[1] - mn[1]) > (mx[0] - mn[0]) ? 1 : 0;
+    std::nth_element(idx.begin() + lo, idx.begin() + lo + left, idx.begin() + hi, [&](int x, int y) {
+        const float cx = embed[2 * centroid[x] + dim], cy = embed[2 * centroid[y] + dim];
+        return cx < cy || (cx == cy && x < y);
+    });
+    split_zones(idx, lo, lo + left, r0, r0 + rl, embed, centroid, owner);
+    split_zones(idx, lo + left, hi, r0 + rl, r1, embed, centroid, owner);
+}
+
+static std::vector<int> zone_owners(const dtl_problem* p, int world)
+{
+    const int Z = p->n_zones, N = p->n_nodes, L = p->n_links;
+    std::vector<int> owner(Z, 0);
+    if (world <= 1) return owner;
+    const char* rule = getenv("DTL_SHARD");
+    if (rule && !strcmp(rule, "mod")) {
+        for (int z = 0; z < Z; ++z) owner[z] = z % world;
+        return owner;
+    }
+    ForwardStar f; // every link, whatever the agent type: only the shape of the network matters here
+    f.h_row_ptr.assign(N + 1, 0);
+    for (int l = 0; l < L; ++l) f.h_row_ptr[p->link_from[l] + 1]++;
+    for (int i = 0; i < N; ++i) f.h_row_ptr[i + 1] += f.h_row_ptr[i];
+    f.h_to.resize(L);
+    std::vector<int> cur(f.h_row_ptr.begin(), f.h_row_ptr.end() - 1);
+    for (int l = 0; l < L; ++l) f.h_to[cur[p->link_from[l]]++] = p->link_to[l];
+    ensure_embedding(f, N);
+    std::vector<int> idx; // zones that can carry trees first, the others are dealt with them (they cost nothing)
+    for (int z = 0; z < Z; ++z) idx.push_back(z);
+    split_zones(idx, 0, Z, 0, world, f.h_embed.data(), p->zone_centroid, owner.data());
+    return owner;
+}
+
 // bundles of the batch [0, n_tasks): returns a device array [n_bundles][B] of batch-local task indices
 static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* h_origin, int plan_key, int B,
-                        const int** d_tasks, int* n_bundles)
+                        const int** d_tasks, const int** d_slots, int* n_bundles)
 {
     const int fsi = (int)(&f - e->fs.data());
     const auto key = std::make_tuple(fsi, plan_key, n_tasks, B);
     if (plan_key >= 0) {
         auto it = e->bundle_plans.find(key);
-        if (it != e->bundle_plans.end()) { *d_tasks = it->second.d_tasks; *n_bundles = it->second.n_bundles; return 0; }
+        if (it != e->bundle_plans.end()) {
+            *d_tasks = it->second.d_tasks; *d_slots = it->second.d_slots; *n_bundles = it->second.n_bundles;
+            return 0;
+        }
     }
     ensure_embedding(f, e->N);
     std::vector<int> idx(n_tasks), out;
@@ -488,11 +547,15 @@ static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const 
         kd_split(idx, 0, n_tasks, B, f.h_embed.data(), h_origin, out);
     }
     const int nb = (int)out.size() / B;
+    const size_t n_out = out.size();
+    out.resize(n_out + (size_t)std::max(1, n_tasks), -1); // followed by the inverse map: task -> bundle * B + slot
+    for (size_t i = 0; i < n_out; ++i)
+        if (out[i] >= 0) out[n_out + out[i]] = (int)i;
     int* d = nullptr;
     if (plan_key >= 0) {
         if (e->alloc(&d, out.size())) return -1;
         dtl_engine::BundlePlan pl;
-        pl.B = B; pl.n_bundles = nb; pl.d_tasks = d;
+        pl.B = B; pl.n_bundles = nb; pl.d_tasks = d; pl.d_slots = d + n_out;
         e->bundle_plans[key] = pl;
     } else {
         if (e->bundle_tmp_cap < out.size()) {
@@ -503,11 +566,12 @@ static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const 
     }
     CK(cudaMemcpyAsync(d, out.data(), sizeof(int) * out.size(), cudaMemcpyHostToDevice, e->st));
     CK(cudaStreamSynchronize(e->st)); // `out` is pageable and local
-    *d_tasks = d; *n_bundles = nb;
+    *d_tasks = d; *d_slots = d + n_out; *n_bundles = nb;
     return 0;
 }
 
-static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLaunch& a, const int* h_origin, int plan_key, BundleLaunch& b)
+static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLaunch& a, const int* h_origin, int plan_key, bool slim,
+                              BundleLaunch& b, const int** d_slots)
 {
     const int n = a.n_tasks;
     int B = 16;
@@ -516,9 +580,10 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
     b.s = a;
     b.B = B;
+    b.tagged = f.open_tags || getenv("DTL_BUNDLE_TAGS") ? 1 : 0; // the env hook forces the per-edge tag check (tests)
     b.lpt = 2; // origins per thread; 4 measured slower (fewer warps to hide the round trips)
     if (const char* env = getenv("DTL_BUNDLE_LPT")) b.lpt = atoi(env) == 4 && B >= 8 ? 4 : 2;
-    if (plan_bundles(e, f, n, h_origin, plan_key, B, &b.bundle_tasks, &b.n_bundles)) return -1;
+    if (plan_bundles(e, f, n, h_origin, plan_key, B, &b.bundle_tasks, d_slots, &b.n_bundles)) return -1;
     b.block = 1024;
     if (const char* env = getenv("DTL_BUNDLE_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024;
     // shared memory of a CTA: two queue bits per node, the rest for the two near queues (12 bytes per entry)
@@ -556,6 +621,15 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
         if (e->alloc(&e->d_bl, need)) return -1; // the previous, smaller buffer stays allocated until dtl_destroy
         e->bl_cap = need;
     }
+    b.slim = slim ? 1 : 0;
+    if (slim) {
+        if (e->bp_cap < need) {
+            if (e->alloc(&e->d_bp, need)) return -1;
+            e->bp_cap = need;
+        }
+        if (!e->d_batch_flag && e->alloc(&e->d_batch_flag, 1)) return -1;
+    }
+    b.bp = e->d_bp; b.batch_flag = e->d_batch_flag;
     b.bl = e->d_bl; b.far = e->d_bfar; b.cap_far = e->bundle_cap_far;
     b.bundle_counter = e->d_bundle_counter;
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
@@ -617,17 +691,30 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     return a;
 }
 
-// run the SSSP kernel for one batch (trees land in d_labels/d_pred), replay tied origins
-int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, bool count_edges,
-                   int tree_off, const int* h_origin, int plan_key)
+// One batch of shortest-path trees.  sssp_launch_batch launches the search; sssp_complete_batch waits for it, recomputes the
+// trees whose queues overflowed and replays tied origins.  With `slim` (the caller only back-traces the trees) an origin-bundle
+// batch leaves its trees node-major (BundleLaunch::bp) and writes no per-tree arrays; `st.slim` tells whether that happened.
+struct BatchState {
+    SsspLaunch a{};
+    BundleLaunch b{};
+    const int* d_slots = nullptr;
+    bool bundle = false, slim = false;
+};
+
+int sssp_launch_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, int tree_off,
+                      const int* h_origin, int plan_key, bool want_slim, BatchState& bs)
 {
-    SsspLaunch a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
+    SsspLaunch& a = bs.a;
+    a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
     e->last_sssp_variant = a.smq;
-    if (a.smq == 2) { // origin bundles: one search per B neighbouring origins, then labels -> trees
-        BundleLaunch b{};
-        if (make_bundle_launch(e, f, a, h_origin, plan_key, b)) return -1;
+    bs.bundle = a.smq == 2;
+    bs.slim = bs.bundle && want_slim && !getenv("DTL_NO_SLIM_TREES");
+    if (bs.bundle) { // origin bundles: one search per B neighbouring origins, then labels -> trees
+        BundleLaunch& b = bs.b;
+        if (make_bundle_launch(e, f, a, h_origin, plan_key, bs.slim, b, &bs.d_slots)) return -1;
         const int ph = e->phase_begin(2);
         CK(cudaMemsetAsync(e->d_bundle_counter, 0, sizeof(int), e->st));
+        if (bs.slim) CK(cudaMemsetAsync(e->d_batch_flag, 0, sizeof(int), e->st));
         launch_sssp_bundle(b, e->st);
         if (b.async) e->last_sssp_variant = 3;
         e->phase_end(ph, 2);
@@ -638,6 +725,12 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
         e->phase_end(ph, 1);
     }
     CK(cudaGetLastError());
+    return 0;
+}
+
+int sssp_complete_batch(dtl_engine* e, BatchState& bs, int n_tasks, bool count_edges)
+{
+    SsspLaunch& a = bs.a;
     e->h_tie_nodes.resize(n_tasks);
     CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
@@ -693,6 +786,15 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
     }
     e->tasks_done += n_tasks;
     return 0;
+}
+
+// run the SSSP kernel for one batch (trees land in d_labels/d_pred), replay tied origins
+int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, bool count_edges,
+                   int tree_off, const int* h_origin, int plan_key)
+{
+    BatchState bs;
+    if (sssp_launch_batch(e, f, n_tasks, d_origin, d_zone, tree_off, h_origin, plan_key, false, bs)) return -1;
+    return sssp_complete_batch(e, bs, n_tasks, count_edges);
 }
 
 int check_flags(dtl_engine* e)
@@ -795,13 +897,18 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
             return -1;
         }
 
+    for (int z = 0; z < Z; ++z)
+        if (p->zone_centroid[z] < 0 || p->zone_centroid[z] >= N) { set_err("zone %d: centroid node outside [0, %d)", z, N); return -1; }
+    for (int l = 0; l < L; ++l)
+        if (p->link_tag[l] >= Z) { set_err("link %d: outgoing-connector zone tag %d outside [0, %d)", l, p->link_tag[l], Z); return -1; }
     DTL_TRACE("tasks of this rank: origin zones are sha");
     // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
     std::vector<int> g_at, g_tau, g_zone;
     build_task_list(p, g_at, g_tau, g_zone);
+    const std::vector<int> owner = zone_owners(p, e->world);
     std::vector<int> task_of((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
     for (size_t i = 0; i < g_at.size(); ++i)
-        if (g_zone[i] % e->world == e->rank) {
+        if (owner[g_zone[i]] == e->rank) {
             task_of[((long long)g_at[i] * T + g_tau[i]) * Z + g_zone[i]] = (int)e->task_at.size();
             e->task_at.push_back(g_at[i]); e->task_tau.push_back(g_tau[i]); e->task_zone.push_back(g_zone[i]);
         }
@@ -830,7 +937,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
             set_err("OD row %d: zone, agent type or period index out of range", i);
             return -1;
         }
-        if (p->od_o[i] % e->world != e->rank) continue;
+        if (owner[p->od_o[i]] != e->rank) continue;
         const int task_i = task_of[((size_t)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]];
         if (task_i < 0) continue;
         const int c = (int)e->cell_global.size();
@@ -1033,9 +1140,12 @@ int dtl_plan_tasks(const dtl_problem* p, int rank, int world_size, int* at, int*
     if (!p || world_size < 1 || rank < 0 || rank >= world_size) { set_err("bad arguments"); return -1; }
     std::vector<int> a, t, z;
     build_task_list(p, a, t, z);
+    for (int i = 0; i < p->n_zones; ++i)
+        if (p->zone_centroid[i] < 0 || p->zone_centroid[i] >= p->n_nodes) { set_err("zone %d: centroid node outside [0, %d)", i, p->n_nodes); return -1; }
+    const std::vector<int> owner = zone_owners(p, world_size);
     int n = 0;
     for (size_t i = 0; i < a.size(); ++i)
-        if (z[i] % world_size == rank) {
+        if (owner[z[i]] == rank) {
             if (n < capacity) {
                 if (at) at[n] = a[i];
                 if (tau) tau[n] = t[i];
@@ -1088,7 +1198,12 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         while (t1 < n_tasks && t1 - t0 < e->batch_tasks && fs_index(e, e->task_at[t1], e->task_tau[t1]) == fsi) ++t1;
         const int nb = t1 - t0;
         const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
-        if (run_sssp_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, want_count, tree_off, e->h_task_origin.data() + t0, t0)) return -1;
+        // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept or
+        // counted: both read the per-tree arrays)
+        BatchState bs;
+        if (sssp_launch_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, tree_off, e->h_task_origin.data() + t0, t0,
+                              !e->opt.keep_trees && !want_count, bs))
+            return -1;
         ColumnLaunch c{};
         c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
         c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
@@ -1099,10 +1214,35 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
         c.task_skip_backtrace = e->d_task_skip;
         c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
-        const int ph = e->phase_begin(4);
-        launch_backtrace(c, e->st);
-        e->phase_end(ph, 1);
-        CK(cudaGetLastError());
+        bool done = false;
+        if (bs.slim) {
+            // back-trace on the node-major trees; the kernel does nothing when the label -> tree pass flagged a tie or an
+            // overflowed bundle, and the batch is then redone through the per-tree path below
+            ColumnLaunch cs = c;
+            cs.bl = bs.b.bl; cs.bp = bs.b.bp; cs.task_slot = bs.d_slots; cs.B = bs.b.B; cs.batch_flag = e->d_batch_flag;
+            const int ph = e->phase_begin(4);
+            launch_backtrace(cs, e->st);
+            e->phase_end(ph, 1);
+            CK(cudaGetLastError());
+            int flag = 0;
+            CK(cudaMemcpyAsync(&flag, e->d_batch_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+            CK(cudaStreamSynchronize(e->st));
+            if (!flag) { done = true; e->tasks_done += nb; }
+            else {
+                bs.b.slim = 0; bs.slim = false;
+                const int ph2 = e->phase_begin(2);
+                launch_sssp_bundle_finish(bs.b, e->st);
+                e->phase_end(ph2, 1);
+                CK(cudaGetLastError());
+            }
+        }
+        if (!done) {
+            if (sssp_complete_batch(e, bs, nb, want_count)) return -1;
+            const int ph = e->phase_begin(4);
+            launch_backtrace(c, e->st);
+            e->phase_end(ph, 1);
+            CK(cudaGetLastError());
+        }
         t0 = t1;
     }
     e->trees_valid = e->opt.keep_trees != 0;

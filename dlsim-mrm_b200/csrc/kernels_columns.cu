@@ -84,10 +84,83 @@ __global__ void __launch_bounds__(128) backtrace_kernel(ColumnLaunch a)
     P.volume[base + slot] += volume;         // routing.h:619
 }
 
+// K2a on the node-major trees an origin-bundle batch leaves behind (bundle_finish_kernel<.., SLIM>): the record of a node row
+// holds the predecessor link AND the predecessor node, so a hop of the walk is ONE dependent 8-byte load (two in the
+// per-tree layout: pred_link, then link_from).  Same arithmetic and the same column pool updates as backtrace_kernel.
+__global__ void __launch_bounds__(128) backtrace_nm_kernel(ColumnLaunch a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_batch_cells) return;
+    if (*a.batch_flag) return;               // ties or an overflowed bundle: the host redoes the batch through the per-tree path
+    const int cell = a.batch_cells[t];
+    const int task = a.od_task[cell];
+    a.least_contrib[cell] = 0.0;
+    if (a.task_skip_backtrace[task]) return; // routing.h:428
+    const int N = a.N, L = a.L, B = a.B;
+    const int ts = a.task_slot[task - a.task_first];
+    const size_t row0 = (size_t)(ts / B) * N * B + (ts % B); // + node * B
+    const int2* pred = a.bp + row0;
+    const double od_volume = a.od_vol[cell];
+    if (!(od_volume > 0.000001)) return;     // routing.h:505
+    const int dest = a.od_dest_node[cell];
+    const float kp = (float)1 / (float)(a.k + 1); // routing.h:435
+    const double volume = od_volume * kp;    // routing.h:502
+
+    int2 rec = __ldg(&pred[(size_t)dest * B]);
+    if (rec.x >= 0) a.least_contrib[cell] = od_volume * __longlong_as_double((long long)__ldg(&a.bl[row0 + (size_t)dest * B])); // :517-520
+    unsigned node_sum = 0;
+    int n_nodes = 0, n_links = 0;
+    int cur = dest;
+    for (;;) {                               // routing.h:522-572
+        ++n_nodes;
+        node_sum += (unsigned)cur + (unsigned)rec.x;
+        if (rec.x < 0 || rec.x >= L) break;
+        ++n_links;
+        cur = rec.y;
+        if (cur < 0 || cur >= N) break;
+        rec = __ldg(&pred[(size_t)cur * B]);
+    }
+    atomicAdd(a.path_nodes, (unsigned long long)n_nodes);
+    if (n_nodes < 2) return;                 // routing.h:584
+    const int key = (int)node_sum;
+    const ColumnPool& P = a.pool;
+    const size_t base = (size_t)cell * P.cap;
+    int cnt = P.count[cell];
+    int slot = -1;
+    for (int j = 0; j < cnt; ++j)
+        if (P.node_sum[base + j] == key) { slot = j; break; }
+    if (slot < 0) {                          // routing.h:595-617 insert a new column
+        if (cnt >= P.cap) { atomicOr(a.error_flag, 2); return; }
+        const long long need = (n_links + 3) & ~3; // keep every column 16-byte aligned
+        const long long off = (long long)atomicAdd(P.arena_used, (unsigned long long)need);
+        if (off + need > P.arena_cap) { atomicOr(a.error_flag, 1); return; }
+        slot = cnt;
+        P.node_sum[base + slot] = key;
+        P.n_links[base + slot] = n_links;
+        P.n_nodes[base + slot] = n_nodes;
+        P.offset[base + slot] = off;
+        P.volume[base + slot] = 0.0;
+        P.cost[base + slot] = 0.0;
+        P.time[base + slot] = 0.0;
+        int* out = P.arena + off;
+        int w = n_links;
+        cur = dest;
+        while (w > 0) {
+            rec = __ldg(&pred[(size_t)cur * B]);
+            out[--w] = rec.x;
+            cur = rec.y;
+        }
+        for (int q = n_links; q < need; ++q) out[q] = -1;
+        P.count[cell] = cnt + 1;
+    }
+    P.volume[base + slot] += volume;         // routing.h:619
+}
+
 void launch_backtrace(const ColumnLaunch& a, cudaStream_t st)
 {
     if (a.n_batch_cells == 0) return;
-    backtrace_kernel<<<(a.n_batch_cells + 127) / 128, 128, 0, st>>>(a);
+    if (a.bp) backtrace_nm_kernel<<<(a.n_batch_cells + 127) / 128, 128, 0, st>>>(a);
+    else backtrace_kernel<<<(a.n_batch_cells + 127) / 128, 128, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------

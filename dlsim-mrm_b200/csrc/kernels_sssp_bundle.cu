@@ -382,12 +382,16 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 512 && LPT <= 2 ? 2 : 1) sssp_
 //   2. one group of B/2 threads per node (two origins per thread): the label rows of the node and of its upstream nodes are
 //      coalesced 16-byte loads, issued together; the tight in-edge is the predecessor (two tight upstream nodes = a tie, left to the serial replay);
 //   3. the tile is transposed through shared memory so that every tree receives TN consecutive labels / predecessors.
+// SLIM (the caller does not keep per-tree arrays: the assignment loop, which only back-traces the trees): step 3 is dropped and
+// the predecessors stay node-major next to the labels -- bp[node][B] records {predecessor link, predecessor node}, one
+// coalesced row per node -- for the node-major back-trace (kernels_columns.cu: backtrace_nm_kernel).  Order-dependent ties
+// and overflowed bundles raise a.batch_flag instead (the host then redoes the batch through the per-tree path).
 #define FIN_CAP 384 /* reverse-star records staged per tile (a tile with more falls back to global loads for the rest) */
-template <int B, int TN>
+template <int B, int TN, bool SLIM>
 __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
 {
-    __shared__ unsigned long long s_lab[B][TN + 1];
-    __shared__ int s_pred[B][TN + 1];
+    __shared__ unsigned long long s_lab[SLIM ? 1 : B][TN + 1];
+    __shared__ int s_pred[SLIM ? 1 : B][TN + 1];
     __shared__ int s_task[B];
     __shared__ int s_ptr[TN + 1];
     __shared__ double s_cost[FIN_CAP];
@@ -403,7 +407,10 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         task[t] = __ldg(&a.bundle_tasks[bundle * B + 2 * g + t]);
-        if (task[t] >= 0 && a.s.tie_nodes[task[t]] < 0) task[t] = -1; // the search of this bundle overflowed: the host re-runs its trees
+        if (task[t] >= 0 && a.s.tie_nodes[task[t]] < 0) { // the search of this bundle overflowed: the host re-runs its trees
+            task[t] = -1;
+            if (SLIM && tid < G && blockIdx.x == 0) atomicOr(a.batch_flag, 2);
+        }
         origin[t] = task[t] >= 0 ? __ldg(&a.s.task_origin[task[t]]) : -1;
         zone[t] = task[t] >= 0 ? __ldg(&a.s.task_zone[task[t]]) : -1;
     }
@@ -472,8 +479,16 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
         }
         if (multi0) { link0 = TIE_MARK; ++n_ties0; }
         if (multi1) { link1 = TIE_MARK; ++n_ties1; }
-        s_lab[2 * g][j] = lvb.x; s_lab[2 * g + 1][j] = lvb.y;
-        s_pred[2 * g][j] = link0; s_pred[2 * g + 1][j] = link1;
+        if (SLIM) {
+            reinterpret_cast<int4*>(a.bp + ((size_t)bundle * N + v) * B)[g] = make_int4(link0, first0, link1, first1);
+        } else {
+            s_lab[2 * g][j] = lvb.x; s_lab[2 * g + 1][j] = lvb.y;
+            s_pred[2 * g][j] = link0; s_pred[2 * g + 1][j] = link1;
+        }
+    }
+    if (SLIM) {
+        if (n_ties0 | n_ties1) atomicOr(a.batch_flag, 1);
+        return;
     }
     if (n_ties0) atomicAdd(&a.s.tie_nodes[task[0]], (int)n_ties0);
     if (n_ties1) atomicAdd(&a.s.tie_nodes[task[1]], (int)n_ties1);
@@ -507,7 +522,8 @@ static void finish_launch(const BundleLaunch& a, cudaStream_t st)
 {
     constexpr int TN = 64;
     const dim3 grid((a.s.N + TN - 1) / TN, a.n_bundles);
-    bundle_finish_kernel<B, TN><<<grid, 256, 0, st>>>(a);
+    if (a.slim) bundle_finish_kernel<B, TN, true><<<grid, 256, 0, st>>>(a);
+    else bundle_finish_kernel<B, TN, false><<<grid, 256, 0, st>>>(a);
 }
 
 template <int B, int LPT>
@@ -516,6 +532,17 @@ static void bundle_launch_block(const BundleLaunch& a, cudaStream_t st)
     if (a.block >= 1024) bundle_launch<1024, B, LPT>(a, st);
     else if (a.block >= 768) bundle_launch<768, B, LPT>(a, st);
     else bundle_launch<512, B, LPT>(a, st);
+}
+
+void launch_sssp_bundle_finish(const BundleLaunch& a, cudaStream_t st)
+{
+    if (a.n_bundles == 0) return;
+    switch (a.B) {
+    case 2: finish_launch<2>(a, st); break;
+    case 4: finish_launch<4>(a, st); break;
+    case 8: finish_launch<8>(a, st); break;
+    default: finish_launch<16>(a, st); break;
+    }
 }
 
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st)
@@ -528,12 +555,7 @@ void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st)
     case 8: a.lpt >= 4 ? bundle_launch_block<8, 4>(a, st) : bundle_launch_block<8, 2>(a, st); break;
     default: a.lpt >= 4 ? bundle_launch_block<16, 4>(a, st) : bundle_launch_block<16, 2>(a, st); break;
     }
-    switch (a.B) {
-    case 2: finish_launch<2>(a, st); break;
-    case 4: finish_launch<4>(a, st); break;
-    case 8: finish_launch<8>(a, st); break;
-    default: finish_launch<16>(a, st); break;
-    }
+    launch_sssp_bundle_finish(a, st);
 }
 
 } // namespace dtl

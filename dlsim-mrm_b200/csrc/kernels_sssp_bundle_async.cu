@@ -24,12 +24,12 @@ namespace dtl {
 #define BND_ASYNC_SLEEP 40 /* ns an idle warp sleeps between two polls of its ring slots */
 #endif
 
-template <int BLOCK, int B>
+template <int BLOCK, int B, bool TAGS>
 __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunch a)
 {
     constexpr int LPT = 2;
     constexpr int G = B / LPT;
-    constexpr int PR = (BND_U + G - 1) / G;
+    static_assert(BND_U == 4 && (G == 4 || G == 8), "a pass relaxes four out-edges per group of 4 or 8 lanes");
     extern __shared__ int s_dyn[];
     __shared__ int s_bundle, s_head, s_n_far, s_n_far2, s_overflow;
     // {entries queued or in flight (bits 17..31), ring tail of this window (bits 0..16)}: ONE shared-memory atomic per push --
@@ -40,7 +40,6 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
     const int lane = tid & 31;
     const int g = tid & (G - 1);
     const int gfirst = lane & ~(G - 1);
-    const unsigned gmask = ((1u << G) - 1u) << gfirst;
     const int N = a.s.N;
     const int RING = a.cap_near; // power of two
     const int RMASK = RING - 1;
@@ -220,101 +219,105 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     u = node1 - 1;
                     const volatile int* rr = reinterpret_cast<const volatile int*>(&s_r[ticket & RMASK]);
                     row.x = rr[0]; row.y = rr[1];
-                    __threadfence_block();
-                    s_q[ticket & RMASK] = 0; // the slot is free again
+                    // the slot is free again (no fence: shared-memory accesses of a thread are performed in order, and the slot is
+                    // not handed out again before the tail has gone round the whole ring)
+                    s_q[ticket & RMASK] = 0;
                     ticket = -1;
                     was = atomicAnd(&s_state[ST_WORD(u)], ~(3u << ST_SHIFT(u))) >> ST_SHIFT(u);
                 }
                 u = __shfl_sync(0xffffffffu, u, gfirst);
-                row.x = __shfl_sync(0xffffffffu, row.x, gfirst);
-                row.y = __shfl_sync(0xffffffffu, row.y, gfirst);
-                int e0 = row.x;
-                const int re = row.y;
+                int e0 = __shfl_sync(0xffffffffu, row.x, gfirst);
+                const int re = __shfl_sync(0xffffffffu, row.y, gfirst);
+                // edge records are loaded unconditionally (slots past the end of the row repeat its last edge and are masked out
+                // of the atomics): no predicated register moves in the instruction stream
+                const int elast = max(re - 1, 0);
                 double cost[BND_U];
                 int to[BND_U];
 #pragma unroll
                 for (int j = 0; j < BND_U; ++j) {
-                    cost[j] = 0.0; to[j] = 0;
-                    if (e0 + j < re) {
-                        const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[e0 + j]));
-                        cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
-                    }
+                    const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[min(e0 + j, elast)]));
+                    cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
                 }
                 was = __shfl_sync(0xffffffffu, was, gfirst) & 3u;
                 double lu[LPT];
-                unsigned act = 0;
+                bool act[LPT];
                 {
                     ulonglong2 lab = make_ulonglong2(INF_BITS, INF_BITS);
                     if (was) lab = __ldcg(reinterpret_cast<const ulonglong2*>(blg + (size_t)u * B));
                     lu[0] = __longlong_as_double((long long)lab.x);
                     lu[1] = __longlong_as_double((long long)lab.y);
-                    act = ((unsigned)(lab.x < INF_BITS) | (unsigned)(lab.y < INF_BITS) << 1) & has_task;
+                    act[0] = lab.x < INF_BITS && (has_task & 1u);
+                    act[1] = lab.y < INF_BITS && (has_task & 2u);
                 }
-                if (have) {
-                    if (g == 0) ++c_pops;
-                    c_relax += (unsigned)__popc(act) * (unsigned)(re - e0);
-                }
-                while (__any_sync(0xffffffffu, e0 < re)) {
+                c_pops += (unsigned)(have && g == 0);
+                c_relax += ((unsigned)act[0] + (unsigned)act[1]) * (unsigned)(re - e0);
+                // One pass relaxes up to BND_U out-edges of the group's node for the thread's two origins: all atomics are issued
+                // first (predicated, not branched; an atomic that is not issued "returns" its own candidate, i.e. no improvement);
+                // when they have returned, the group decides per edge whether the head improved for any origin and what its key
+                // is now, and the lane that owns the edge (lane 2j of a group of 8, lane j of a group of 4) queues the head.
+                for (;;) {
                     unsigned long long old[BND_U][LPT];
-                    int2 prow[PR];
-                    unsigned okm = 0;
 #pragma unroll
                     for (int j = 0; j < BND_U; ++j) {
-                        const bool valid = e0 + j < re;
-                        unsigned ok = valid ? act : 0u;
-                        if (to[j] < 0) { // routing.h:779-786
-                            to[j] &= 0x7fffffff;
-                            const int tag = __ldg(&a.s.link_tag[__ldg(&a.s.edges[e0 + j].link)]);
+                        bool ok[LPT];
 #pragma unroll
-                            for (int t = 0; t < LPT; ++t)
-                                if (tag != zone[t]) ok &= ~(1u << t);
+                        for (int t = 0; t < LPT; ++t) ok[t] = act[t] && e0 + j < re;
+                        if (TAGS) {
+                            if (to[j] < 0) { // routing.h:779-786
+                                const int tag = __ldg(&a.s.link_tag[__ldg(&a.s.edges[min(e0 + j, elast)].link)]);
+#pragma unroll
+                                for (int t = 0; t < LPT; ++t) ok[t] = ok[t] && tag == zone[t];
+                            }
+                            to[j] &= 0x7fffffff;
                         }
                         unsigned long long* const p = blg + (size_t)to[j] * B;
 #pragma unroll
-                        for (int t = 0; t < LPT; ++t) {
-                            old[j][t] = 0ULL;
-                            if ((ok >> t) & 1u) old[j][t] = atomicMin(p + t, (unsigned long long)__double_as_longlong(lu[t] + cost[j])); // routing.h:804,816
-                        }
-                        okm |= ok << (j * LPT);
-                        if (valid && g == (j % G)) prow[j / G] = __ldg(&a.s.rows[to[j]]);
+                        for (int t = 0; t < LPT; ++t)
+                            old[j][t] = atom_min_if(p + t, (unsigned long long)__double_as_longlong(lu[t] + cost[j]), ok[t]); // routing.h:804,816
                     }
+                    // the edge this lane queues: its head and the head's forward-star row (fetched in the shadow of the atomics)
+                    const int je = G == 8 ? g >> 1 : g;
+                    int myto = to[0];
+#pragma unroll
+                    for (int j = 1; j < BND_U; ++j) myto = je == j ? to[j] : myto;
+                    const bool owner = (G == 4 || (g & 1) == 0) && e0 + je < re;
+                    int2 prow = make_int2(0, 0);
+                    if (owner) prow = __ldg(&a.s.rows[myto]);
+                    unsigned impm = 0;
+                    unsigned nk[BND_U];
 #pragma unroll
                     for (int j = 0; j < BND_U; ++j) {
-                        bool imp = false;
-                        unsigned k = BND_DEAD_KEY;
+                        const unsigned long long cb0 = (unsigned long long)__double_as_longlong(lu[0] + cost[j]);
+                        const unsigned long long cb1 = (unsigned long long)__double_as_longlong(lu[1] + cost[j]);
+                        impm |= (unsigned)(old[j][0] > cb0 || old[j][1] > cb1) << j;
+                        nk[j] = min(min(key_of(old[j][0]), key_of(cb0)), min(key_of(old[j][1]), key_of(cb1)));
+                    }
 #pragma unroll
-                        for (int t = 0; t < LPT; ++t) {
-                            const unsigned long long cb = (unsigned long long)__double_as_longlong(lu[t] + cost[j]);
-                            if ((okm >> (j * LPT + t)) & 1u) {
-                                imp = imp || old[j][t] > cb;
-                                k = min(k, min(key_of(old[j][t]), key_of(cb)));
-                            }
-                        }
-                        const unsigned bal = __ballot_sync(0xffffffffu, imp);
-                        if (bal == 0u) continue;
-                        const unsigned key = group_min_u32<G>(k);
-                        if ((bal & gmask) && g == (j % G)) {
-                            const int w = ST_WORD(to[j]), sh = ST_SHIFT(to[j]);
+                    for (int o = G / 2; o > 0; o >>= 1) impm |= __shfl_xor_sync(0xffffffffu, impm, o);
+                    if (__any_sync(0xffffffffu, impm != 0u)) {
+                        const unsigned key = group_min_edges<G>(nk, g);
+                        if (owner && ((impm >> je) & 1u)) {
+                            const int w = ST_WORD(myto), sh = ST_SHIFT(myto);
                             if (key < thr) {
                                 const unsigned o = atomicOr(&s_state[w], 1u << sh);
-                                if (!((o >> sh) & 1u)) push_near(to[j], prow[j / G]);
+                                if (!((o >> sh) & 1u)) push_near(myto, prow);
                             } else {
                                 const unsigned o = atomicOr(&s_state[w], 2u << sh);
                                 if (!((o >> sh) & 3u)) {
                                     const int pos = atomicAdd(&s_n_far, 1);
-                                    if (pos < CAPF) q_far[pos] = make_int2(to[j], (int)key);
+                                    if (pos < CAPF) q_far[pos] = make_int2(myto, (int)key);
                                     else s_overflow = 1;
                                 }
                             }
                         }
                     }
                     e0 += BND_U;
+                    if (!__any_sync(0xffffffffu, e0 < re)) break; // rows of more than BND_U edges take another pass
 #pragma unroll
-                    for (int j = 0; j < BND_U; ++j)
-                        if (e0 + j < re) {
-                            const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[e0 + j]));
-                            cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
-                        }
+                    for (int j = 0; j < BND_U; ++j) {
+                        const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[min(e0 + j, elast)]));
+                        cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
+                    }
                 }
                 __syncwarp();
                 if (have && g == 0) atomicSub(&s_pt, PT_ONE_PENDING); // after every push of this expansion
@@ -359,8 +362,15 @@ size_t bundle_async_smem_bytes(int N, int ring)
 template <int BLOCK, int B>
 static void async_launch(const BundleLaunch& a, size_t smem, cudaStream_t st)
 {
-    cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sssp_bundle_async_kernel<BLOCK, B><<<a.grid, BLOCK, smem, st>>>(a);
+    // a.tagged: some node outside the hidden centroid rows has a zone-tagged out-link (routing.h:779-786 then has to be
+    // evaluated inside the edge loop); ordinary networks only tag the connectors that leave a centroid
+    if (a.tagged) {
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sssp_bundle_async_kernel<BLOCK, B, true><<<a.grid, BLOCK, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sssp_bundle_async_kernel<BLOCK, B, false><<<a.grid, BLOCK, smem, st>>>(a);
+    }
 }
 
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st)

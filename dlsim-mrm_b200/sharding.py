@@ -1,7 +1,9 @@
 """Host-side plumbing of the origin-sharded multi-GPU run (one process per GPU).
 
-Origin zones are dealt round-robin (zone % world_size == rank, mirroring the reference's zone % memory blocks,
-main_api.cpp:259); the only data-path collective -- the all-reduce of the fixed-point link-volume vector -- is issued
+Origin zones are partitioned into spatially contiguous blocks, one per rank (a recursive median split of a landmark
+embedding of the network, equal to within one zone; ``dtl_plan_tasks`` / ``engine.cu: zone_owners``).  The reference deals
+zones to its memory blocks round-robin (zone % blocks, main_api.cpp:259; ``DTL_SHARD=mod`` selects that rule); link volumes are
+integer sums and therefore identical for any partition.  The only data-path collective -- the all-reduce of the fixed-point link-volume vector -- is issued
 by the engine itself over NCCL.  What is here is the rendezvous around it: broadcasting the 128-byte NCCL id and
 reducing timings, over whatever torch.distributed backend the launcher initialised (nccl on GPUs, gloo in CPU tests).
 """

@@ -379,3 +379,55 @@ def test_small_queues_fall_back_to_worst_case_rerun(D, problems, golden, oracle_
         for i, z in enumerate(zones):
             rl, rpn, rpl, _, _ = o.sssp(fs, cost, int(z))
             assert np.array_equal(lab[i], rl) and np.array_equal(pl[i], rpl) and np.array_equal(pn[i], rpn)
+
+
+# ------------------------------------------------------------------------------------------------ node-major trees
+def _loop_vs_oracle(D, oracle_mod, p, K, CU=0):
+    """whole assignment loop WITHOUT kept trees (an origin-bundle batch then leaves its trees node-major and the back-trace walks
+    them there) against the oracle: columns bit-exact, link state within TOL"""
+    o = oracle_mod.Oracle(p)
+    with D.Engine(p, keep_trees=False, max_columns_per_od=K + 4) as e:
+        for k in range(K):
+            r, ro = e.iteration(k), o.iteration(k)
+            for key in ("sysTT", "least"):
+                assert abs(r[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (k, key, r, ro)
+            assert abs(r["gap"] - ro["gap"]) <= TOL * max(1.0, abs(ro["gap"]))
+        for n in range(CU):
+            r, ro = e.column_update(n), o.column_update(n)
+            assert abs(r["rel_gap_pct"] - ro["rel_gap_pct"]) <= TOL * max(1.0, abs(ro["rel_gap_pct"]))
+        e.finalize(K); o.finalize(K)
+        st, so = e.link_state(0), o.link_state(0)
+        assert rel_err(st["tt"], so["tt"]) <= TOL and rel_err(st["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
+        _compare_columns(e.columns(), o.columns())
+        return e.counters(), e.sssp_kernel
+
+
+@pytest.mark.parametrize("workload,kernel,tags", [("grid2k", "bundle16", 0), ("grid10k", "bundle16", 0), ("grid10k", "bundle16", 1),
+                                                  ("grid2k", "bundle", 0)])
+def test_node_major_trees_and_backtrace(D, oracle_mod, tmp_path, monkeypatch, workload, kernel, tags):
+    _force_kernel(monkeypatch, kernel)
+    if tags:
+        monkeypatch.setenv("DTL_BUNDLE_TAGS", "1")   # the search variant that checks zone tags per edge (routing.h:779-786)
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
+    p = D.read_gmns(str(tmp_path), 8)
+    c, used = _loop_vs_oracle(D, oracle_mod, p, 5, 2 if workload == "grid2k" else 0)
+    assert "bundle" in used and c["replayed"] == 0 and c["reruns"] == 0
+
+
+@pytest.mark.parametrize("name,K,CU", [("corridor_101", 6, 2), ("edge_cases", 6, 2), ("corridor_3_2p", 5, 2)])
+def test_node_major_trees_on_reference_datasets(D, problems, oracle_mod, monkeypatch, name, K, CU):
+    """agent-type filters, unreachable zones, two periods: several forward stars per iteration, ragged bundles"""
+    _force_kernel(monkeypatch, "bundle16")
+    c, used = _loop_vs_oracle(D, oracle_mod, problems(name), K, CU)
+    assert "bundle" in used
+
+
+def test_node_major_trees_fall_back_on_ties_and_overflow(D, oracle_mod, monkeypatch, problems):
+    """a tie or an overflowed bundle found by the label -> tree pass sends the batch through the per-tree path (replay / re-run)"""
+    _force_kernel(monkeypatch, "bundle16")
+    c, _ = _loop_vs_oracle(D, oracle_mod, _tie_grid(), 4)
+    assert c["replayed"] > 0
+    monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "4")
+    c, _ = _loop_vs_oracle(D, oracle_mod, problems("corridor_101"), 3)
+    assert c["reruns"] > 0

@@ -94,3 +94,79 @@ def test_sharded_engines_sum_to_the_same_fixed_point_volumes(D, grid):
     parts = [volumes(rank=r, world_size=2) for r in range(2)]
     assert whole.sum() > 0
     assert np.array_equal(parts[0] + parts[1], whole), "fixed-point volumes must not depend on the sharding"
+
+
+# ------------------------------------------------------------------------------------------------ against the reference itself
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _rel(a, b, floor):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), floor)))
+
+
+@pytest.fixture(scope="module")
+def full_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid100k_full_ref.npz"))
+    return g
+
+
+def test_generated_inputs_are_the_ones_the_golden_was_made_from(grid, full_golden):
+    import hashlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import workload_dir
+    d = workload_dir("grid100k")
+    for name, digest in zip(full_golden["input_files"], full_golden["input_sha256"]):
+        if str(name) == "settings.csv":
+            continue  # iteration counts are passed as arguments on both sides
+        h = hashlib.sha256(open(os.path.join(d, str(name)), "rb").read()).hexdigest()
+        assert h == str(digest), f"{name}: the seeded generator no longer writes the file the reference run read"
+
+
+@pytest.mark.parametrize("keep_trees", [True, False])
+def test_config5_matches_the_full_reference_run(D, grid, full_golden, keep_trees):
+    """tests/golden/grid100k_full_ref.npz is ONE complete run of the reference engine (oracle/_ref, all 2 000 origins, 20
+    iterations + 1 column-pool iteration; tests/golden/make_golden_full.py).  Bars: trees and path columns bit-exact; volumes,
+    travel times, gap within 1e-6 relative.  keep_trees=True compares the per-tree arrays of 55 origins at iterations 0, 2 and
+    19; keep_trees=False is the bench path (node-major trees, no per-tree arrays)."""
+    p, g = grid, full_golden
+    K, CU = int(g["K"]), int(g["CU"])
+    TOL = 1e-6
+    want = {}
+    for tag, digest in zip(g["tree_keys"], g["tree_sha256"]):
+        parts = dict(kv.split("=") for kv in str(tag).split(":"))
+        want.setdefault(int(parts["k"]), {})[int(parts["z"])] = str(digest)
+    assert sum(len(v) for v in want.values()) >= 50
+    with D.Engine(p, keep_trees=keep_trees, max_columns_per_od=K + 4) as e:
+        zone_task = {int(z): i for i, z in enumerate(e.task_zone)}
+        for k in range(K):
+            r = e.iteration(k)
+            ref = g["iter_rows"][k]
+            assert abs(r["sysTT"] - ref[1]) <= TOL * abs(ref[1]), (k, r, ref)
+            assert abs(r["least"] - ref[2]) <= TOL * abs(ref[2]), (k, r, ref)
+            assert abs(r["gap"] - ref[3]) <= TOL * max(1.0, abs(ref[3])), (k, r, ref)
+            if keep_trees and k in want:
+                for z, digest in want[k].items():
+                    lab, pn, pl = e.tree(zone_task[z])
+                    assert _sha(lab) + _sha(pl) + _sha(pn) == digest, f"iteration {k}, origin zone {z}: tree differs from the reference's"
+        for n in range(CU):
+            e.column_update(n)
+        sys_tt = e.finalize(K)
+        assert abs(sys_tt - float(g["final_sysTT"][0])) <= TOL * float(g["final_sysTT"][0])
+        st = e.link_state(0)
+        assert _rel(st["tt"], g["final_tt"], 1e-9) <= TOL
+        assert _rel(st["pce_volume"], g["final_pce_volume"], 1e-3) <= TOL
+        c = e.columns()
+        assert c["node_sum"].size == int(g["n_columns"]) and c["links"].size == int(g["n_column_links"])
+        assert _sha(c["node_sum"]) == str(g["col_node_sum_sha256"])
+        assert _sha(np.stack([p.od_o[c["od_index"]], p.od_d[c["od_index"]]])) == str(g["col_od_sha256"])
+        assert _sha(c["seq_no"]) == str(g["col_seq_sha256"])
+        assert _sha(c["links"]) == str(g["col_links_sha256"]), "path link sequences must be bit-exact"
+        assert _rel(c["volume"][::64], g["col_volume_sample"], 1e-6) <= TOL
+        assert abs(c["volume"].sum() - float(g["col_volume_sum"])) <= TOL * float(g["col_volume_sum"])
+        if not keep_trees:
+            assert "bundle" in e.sssp_kernel

@@ -27,13 +27,15 @@ def _worker(rank, world, port, out_dir):
     from dlsim_mrm_b200 import sharding
     p = D.read_gmns(os.path.join(FIXTURES, "corridor_101"), 4)
     at, tau, zone = D.plan_tasks(p, rank, world)
-    assert np.all(zone % world == rank)
+    os.environ["DTL_SHARD"] = "mod"                       # the reference's round-robin rule stays selectable
+    assert np.all(D.plan_tasks(p, rank, world)[2] % world == rank)
+    del os.environ["DTL_SHARD"]
     payload = bytes(range(128)) if rank == 0 else None
     got = sharding.broadcast_bytes(dist, payload, 128)
     assert got == bytes(range(128))
     # every rank contributes the Q31.32 volume of "its" origins; the integer sum must not depend on the split
     q = np.zeros(p.n_links, np.int64)
-    mine = np.flatnonzero(p.od_o % world == rank)
+    mine = np.flatnonzero(np.isin(p.od_o, zone))
     np.add.at(q, p.od_d[mine] % p.n_links, np.rint(p.od_vol[mine] * 2.0**32).astype(np.int64))
     total = sharding.sum_over_ranks(dist, q)
     t = sharding.max_over_ranks(dist, float(rank + 1))
@@ -53,6 +55,9 @@ def test_two_rank_plan_and_exact_reduction(native, problems, tmp_path):
     merged = np.sort(np.concatenate([key(q["at"], q["tau"], q["zone"]) for q in parts]))
     assert np.array_equal(merged, np.sort(key(*full)))           # disjoint cover of the single-GPU task list
     assert len(set(merged.tolist())) == merged.size
+    # spatial blocks: equal to within one zone, and every rank derives the same partition on its own
+    sizes = [np.unique(q["zone"]).size for q in parts]
+    assert max(sizes) - min(sizes) <= 1 + (p.n_zones - np.unique(full[2]).size)
     q = np.zeros(p.n_links, np.int64)
     np.add.at(q, p.od_d % p.n_links, np.rint(p.od_vol * 2.0**32).astype(np.int64))
     assert np.array_equal(parts[0]["total"], q) and np.array_equal(parts[1]["total"], q)
