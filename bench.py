@@ -4,13 +4,13 @@
 
 A "step" is one column-generation iteration of the assignment loop (VDF -> volume scatter + MSA decay ->
 all shortest-path trees -> tree back-trace / column update; reference main_api.cpp:589-728) over the whole
-network.  `--gpus N` shards origin zones over N ranks (zone % N), one process per GPU (torchrun); the only
-data-path collective is the all-reduce of the fixed-point link-volume vector.
+network.  `--gpus N` shards origin zones over N ranks (spatially contiguous blocks of zones), one process per GPU (torchrun);
+the only data-path collective is the all-reduce of the fixed-point link-volume vector.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid100k] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own OpenMP CPU path
-(oracle/_ref/dtalite_ref, the unmodified sources) on a bounded sample of the same workload.
+(oracle/_ref/dtalite_ref, the unmodified sources) on the same workload, all origin zones, for the same W + K iterations.
 """
 from __future__ import annotations
 
@@ -128,8 +128,9 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def reference_sample(workload: str, steps: int, warmup: int, n_origins: int | None = None):
-    """Run the reference's own CPU path (oracle/_ref/dtalite_ref trace mode, unmodified sources) on a bounded sample of
-    the workload: same network, demand of the first S origin zones only.  Returns per-iteration seconds of the
+    """Run the reference's own CPU path (oracle/_ref/dtalite_ref trace mode, unmodified sources) on the workload -- by default
+    the FULL demand (every origin zone: nothing is extrapolated; the bound on the CPU time is the number of iterations the
+    caller asks for), with `n_origins` the demand of the first S origin zones only.  Returns per-iteration seconds of the
     timed steps, the number of trees per iteration, the thread count and the sample description."""
     from oracle import binding as B
     if not os.path.exists(B.REF_BIN):
@@ -141,28 +142,35 @@ def reference_sample(workload: str, steps: int, warmup: int, n_origins: int | No
     except Exception:
         pass
     blocks = max(1, min(cores, 100))                     # number_of_memory_blocks = parallel width of the reference
-    S = n_origins or max(96, 2 * blocks)
+    S = n_origins or full_trees(workload)
     with tempfile.TemporaryDirectory(prefix="dtl_ref_") as tmp:
         for f in ("node.csv", "link.csv", "settings.csv"):
             os.symlink(os.path.join(src, f), os.path.join(tmp, f))
-        n_rows = 0
+        n_rows, trips = 0, 0.0
         with open(os.path.join(src, "demand.csv")) as fi, open(os.path.join(tmp, "demand.csv"), "w") as fo:
             fo.write(fi.readline())
             for line in fi:
                 if int(line.split(",", 1)[0]) <= S:
                     fo.write(line)
                     n_rows += 1
+                    trips += float(line.rsplit(",", 1)[1])
         t0 = time.time()
-        _, tm = B.run_reference(tmp, "trace", warmup + steps, 0, blocks, "dump.bin", env={"DTL_TRACE_LIGHT": "1"},
+        _, tm = B.run_reference(tmp, "trace", warmup + steps, 0, blocks, "dump.bin", env={"DTL_TRACE_LIGHT": "1", "DTL_TRACE_NO_COLUMNS": "1"},
                                 threads=blocks, timeout=3000)
         wall = time.time() - t0
     iters = tm["iter_s"][warmup:warmup + steps]
     trees = tm["n_sssp"] / tm["K"]
-    sample = (f"{workload}: full network, demand of origin zones 1..{S} only ({n_rows} OD rows, {trees:.0f} shortest-path trees "
-              f"per iteration), {warmup}+{steps} iterations, OMP threads = memory blocks = {blocks}; iteration time scaled by "
-              f"(trees in the full workload / trees in the sample)")
+    if S >= full_trees(workload):
+        sample = (f"{workload}: the whole workload ({n_rows} OD rows, {trees:.0f} shortest-path trees per iteration, nothing "
+                  f"extrapolated), iterations {warmup}..{warmup + steps - 1} of a {warmup}+{steps}-iteration run of oracle/_ref/dtalite_ref "
+                  f"(unmodified reference sources), OMP threads = memory blocks = {blocks}")
+    else:
+        sample = (f"{workload}: full network, demand of origin zones 1..{S} only ({n_rows} OD rows, {trees:.0f} shortest-path trees "
+                  f"per iteration), {warmup}+{steps} iterations, OMP threads = memory blocks = {blocks}; iteration time scaled by "
+                  f"(trees in the full workload / trees in the sample)")
     return dict(iter_s=iters, trees=trees, threads=int(tm["threads"]), blocks=blocks, sample=sample, wall_s=wall, io_s=tm["io_s"],
-                counted_edges_total=tm["counted_edges"], sssp_thread_s=tm["sssp_thread_s"], n_origins=S)
+                counted_edges_total=tm["counted_edges"] * tm["K"], sssp_thread_s=tm["sssp_thread_s"], n_origins=S, od_rows=n_rows,
+                trips=trips, nodes=tm["nodes"], links=tm["links"], zones=tm["zones"])
 
 
 def full_trees(workload: str) -> int:
@@ -184,8 +192,10 @@ def run_reference_arm(args, rank):
     sec = statistics.mean(r["iter_s"]) * scale
     value = 1.0 / sec
     out = {**base, "value": value, "ms_per_step": sec * 1e3,
-           "config": {"workload": args.workload, "nodes": 100172, "links": 300000, "zones": full_trees(args.workload),
-                      "sample": r["sample"]},
+           # same workload as the engine arm (its `config` keys; nodes / links without the centroids and connectors both sides add)
+           "config": {"workload": args.workload, "nodes": int(r["nodes"] - r["zones"]), "links": int(r["links"] - 2 * r["zones"]),
+                      "zones": int(r["zones"]), "od_rows": int(r["od_rows"]), "trips": round(r["trips"], 1), "agent_types": 1, "periods": 1,
+                      "first_timed_iteration": args.warmup, "sample": r["sample"]},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": r["sample"]},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
@@ -297,7 +307,7 @@ def run_engine_arm(args, rank, world, local_rank):
             "config": {"workload": args.workload, "nodes": int(p.n_nodes - p.n_zones), "links": int(p.n_links - 2 * p.n_zones),
                        "zones": int(p.n_zones), "od_rows": int(p.n_od), "trips": float(p.total_demand_volume),
                        "agent_types": int(p.n_agent_types), "periods": int(p.n_periods),
-                       "parallelism": f"origin zones sharded zone % {world}", "first_timed_iteration": W,
+                       "parallelism": f"origin zones sharded over {world} GPU(s) in spatially contiguous blocks", "first_timed_iteration": W,
                        "l2": "inputs larger than L2 (trees 2.4 GB + column pool per iteration vs 126 MB L2)"},
             "clocks": clocks,
             "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,

@@ -41,6 +41,8 @@ struct ForwardStar {
                               // entry reached over link l needs, in one 16-byte load
     int* in_ptr = nullptr;    // [N+1] reverse star (tie verification only)
     int2* in_edges = nullptr; // [E] {from node, forward edge index}
+    int2* rin4 = nullptr;     // [N][4] the first four in-edges of every node {from node, forward edge index}, {-1, 0} padding;
+                              // bit 30 of [v][3].y: the node has more than four (the rest is read through in_ptr / in_edges)
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
     double delta = 1.0;       // current label window of the near/far SSSP
     bool open_tags = false;   // a node that is not a hidden centroid row has a zone-tagged out-link
@@ -114,6 +116,7 @@ struct SsspLaunch {
     const Edge* edges;
     const int* in_ptr;
     const int2* in_edges;
+    const int2* rin4;        // [N][4] padded reverse star (ForwardStar::rin4)
     const int* link_tag;
     const int* link_from;
     int n_tasks;             // tasks in this batch
@@ -161,6 +164,7 @@ struct BundleLaunch {
     int cap_near;            // shared-memory near queue: entries per buffer
     int* bundle_counter;     // device int, zeroed before launch
     int grid, block;
+    int ctas_per_sm;         // async: resident CTAs per SM the kernel is compiled for (1, or 2 / 3 / 4 with the smaller CTA sizes)
     int slim;                // 1: the label -> tree pass leaves predecessors node-major in bp and writes no per-tree arrays
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
     int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
@@ -209,6 +213,7 @@ struct ScatterLaunch {
     unsigned long long* person_fix; // may be null (skipped inside the CG loop)
     int decay_k;                    // <0: none
     unsigned long long* link_refs;  // counter
+    int cell_stride;                // set by launch_scatter: warp w handles cell (w * cell_stride) % n_od
 };
 void launch_scatter(const ScatterLaunch& a, cudaStream_t st);
 

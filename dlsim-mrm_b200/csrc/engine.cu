@@ -339,6 +339,13 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
     if (e->upload(&f.edges, edges.data(), edges.size())) return -1;
     if (e->upload(&f.in_ptr, in_ptr.data(), in_ptr.size())) return -1;
     if (e->upload(&f.in_edges, in_edges.data(), in_edges.size())) return -1;
+    std::vector<int2> rin4((size_t)std::max(N, 1) * 4, make_int2(-1, 0));
+    for (int v = 0; v < N; ++v) {
+        const int n_in = in_ptr[v + 1] - in_ptr[v];
+        for (int q = 0; q < std::min(n_in, 4); ++q) rin4[(size_t)v * 4 + q] = in_edges[in_ptr[v] + q];
+        if (n_in > 4) rin4[(size_t)v * 4 + 3].y |= 0x40000000;
+    }
+    if (e->upload(&f.rin4, rin4.data(), rin4.size())) return -1;
     if (e->upload(&f.link_edge, link_edge.data(), link_edge.size())) return -1;
     return 0;
 }
@@ -575,8 +582,8 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
 {
     const int n = a.n_tasks;
     int B = 16;
-    if (n < 16 * e->sm_count / 2) B = 8;
-    if (n < 8 * e->sm_count / 2) B = 4;
+    if (n < 8 * e->sm_count) B = 8;     // fewer than 8 trees per SM: bundles of 8 so that every SM still gets one
+    if (n < 2 * e->sm_count) B = 4;     // (only when the kernel is forced: the round-synchronous search)
     if (const char* env = getenv("DTL_BUNDLE_B")) B = atoi(env) == 4 ? 4 : atoi(env) == 8 ? 8 : 16;
     b.s = a;
     b.B = B;
@@ -587,7 +594,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     b.block = 1024;
     if (const char* env = getenv("DTL_BUNDLE_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024;
     // shared memory of a CTA: two queue bits per node, the rest for the two near queues (12 bytes per entry)
-    const int ctas_per_sm = b.block <= 512 && b.lpt <= 2 ? 2 : 1;
+    int ctas_per_sm = b.block <= 512 && b.lpt <= 2 ? 2 : 1;
     const size_t smem_cta = (size_t)220 * 1024 / ctas_per_sm;
     const size_t fixed = bundle_smem_bytes(e->N, 0);
     b.cap_near = fixed + 24 * 64 <= smem_cta ? (int)std::min<size_t>(8192, (smem_cta - fixed) / 24) : 0;
@@ -599,10 +606,17 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     const char* async_env = getenv("DTL_BUNDLE_ASYNC");
     if (B >= 8 && !(async_env && atoi(async_env) == 0) && !getenv("DTL_BUNDLE_BLOCK") && !getenv("DTL_BUNDLE_LPT")) {
         b.async = 1;
-        b.block = 1024; b.lpt = 2;
-        if (const char* env = getenv("DTL_BUNDLE_ASYNC_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024; // experiment hook
+        b.block = 768; b.lpt = 2; // 768 threads x 80 registers: no spills; 8.3 against 8.7 ms per 2 000 trees with 1 024 x 64
+        ctas_per_sm = 1;
+        if (const char* env = getenv("DTL_BUNDLE_ASYNC_BLOCK")) { // experiment hook: "<threads>" or "<threads>x<CTAs per SM>"
+            int t = 1024, c = 1;
+            sscanf(env, "%dx%d", &t, &c);
+            const int ok[4][2] = { { 1024, 1 }, { 768, 1 }, { 512, 1 }, { 512, 2 } };
+            for (const auto& o2 : ok)
+                if (o2[0] == t && o2[1] == c) { b.block = t; ctas_per_sm = c; }
+        }
         int ring = 1;
-        while ((size_t)2 * ring * 12 + fixed <= (size_t)226 * 1024 && 2 * ring <= 16384) ring *= 2;
+        while ((size_t)2 * ring * 12 + fixed <= (size_t)226 * 1024 / ctas_per_sm - 1024 * (ctas_per_sm > 1) && 2 * ring <= 16384) ring *= 2;
         if (ring < 1024) { set_err("origin-bundle kernel: %d nodes leave no room for the shared-memory ring", e->N); return -1; }
         b.cap_near = ring; // far more slots than the 128 tickets the groups of a CTA can hold: a ticket never meets the slot of an older lap
         b.near_limit = ring;
@@ -610,11 +624,12 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
         if (!(e->opt.sssp_delta_factor > 0)) b.s.delta *= 1.5; // windows of 12 mean link costs: fewer block-wide re-bucketing steps
     }
     const int max_grid = e->sm_count * ctas_per_sm;
-    if (!e->d_bfar) {
-        e->bundle_grid = e->sm_count * 2;
+    b.ctas_per_sm = ctas_per_sm;
+    if (!e->d_bundle_counter && e->alloc(&e->d_bundle_counter, 1)) return -1;
+    if (e->bundle_grid < std::min(max_grid, b.n_bundles)) { // far piles of every resident CTA (an earlier, smaller buffer stays until dtl_destroy)
+        e->bundle_grid = max_grid;
         e->bundle_cap_far = 2 * e->N + 1024;
         if (e->alloc(&e->d_bfar, (size_t)e->bundle_grid * 2 * e->bundle_cap_far)) return -1;
-        if (e->alloc(&e->d_bundle_counter, 1)) return -1;
     }
     const size_t need = (size_t)b.n_bundles * B * e->N;
     if (e->bl_cap < need) {
@@ -636,23 +651,22 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     return 0;
 }
 
-// K1 has three kernels (DESIGN.md "K1").  Per launch:
-//   * origin bundles (kernels_sssp_bundle.cu) when the launch fills the GPU with bundles of 16 origins: a wave of bundles (one
-//     per SM) lasts about as long as 8.8 x #SM trees of the global-queue kernel, whatever the number of bundles in it, and
-//     the label -> tree pass costs ~15 % of a global-queue tree per tree (calibrated on the config-5 grid);
-//   * global-memory queues (kernels_sssp.cu) with many trees per SM otherwise: throughput of the SM;
-//   * shared-memory queues (kernels_sssp_smq.cu) with few trees per SM (an origin shard on one of several GPUs): a launch
-//     lasts as long as one tree, and short rounds with a big CTA per tree win.
+// K1 has three kernels (DESIGN.md "K1").  Per launch, by trees per SM:
+//   * origin bundles (kernels_sssp_bundle*.cu) from 4 trees per SM upwards: 16 origins per search from 8 trees per SM (every SM
+//     gets a bundle), 8 below.  A bundle keeps one SM busy for 5-7 ms whatever it holds, so this needs enough trees to hand
+//     every SM a bundle; measured on the config-5 grid per launch: 2 000 trees 8.3 ms, 1 000 trees 6.1 ms (bundles of 8;
+//     8.7 ms with the global-queue kernel), 500 trees 5.7 ms (5.2 ms with shared-memory queues);
+//   * shared-memory queues (kernels_sssp_smq.cu) below 4 trees per SM (an origin shard on one of 4 or 8 GPUs): one big CTA
+//     per tree, a launch lasts as long as one or two trees;
+//   * global-memory queues (kernels_sssp.cu): networks whose per-node queue bits do not fit in shared memory, explicit block
+//     sizes, and the worst-case re-run of trees whose queues overflowed.
 // DTL_SSSP_KERNEL=gq|smq|bundle forces one (tests, experiments).
 void choose_sssp_variant(dtl_engine* e, SsspLaunch& a)
 {
     const char* force = getenv("DTL_SSSP_KERNEL");
     const int per_sm = (a.n_run + e->sm_count - 1) / std::max(1, e->sm_count);
     int v = per_sm <= 4 && !e->opt.sssp_block_threads ? 1 : 0; // an explicit block size asks for the global-queue kernel
-    if (!e->opt.sssp_block_threads && !a.task_list) {
-        const int waves = ((a.n_run + 15) / 16 + e->sm_count - 1) / std::max(1, e->sm_count);
-        if (0.85 * a.n_run > 8.8 * e->sm_count * waves) v = 2;
-    }
+    if (!e->opt.sssp_block_threads && !a.task_list && a.n_run >= 4 * e->sm_count) v = 2;
     if (force && !strcmp(force, "gq")) v = 0;
     if (force && !strcmp(force, "smq")) v = 1;
     if (force && !strcmp(force, "bundle")) v = 2;
@@ -677,7 +691,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
                             int tree_off)
 {
     SsspLaunch a{};
-    a.N = e->N; a.row_ptr = f.row_ptr; a.rows = f.rows; a.link_info = f.link_info; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges;
+    a.N = e->N; a.row_ptr = f.row_ptr; a.rows = f.rows; a.link_info = f.link_info; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges; a.rin4 = f.rin4;
     a.link_tag = e->d_link_tag; a.link_from = e->d_link_from;
     a.n_tasks = n_tasks; a.n_run = n_tasks; a.task_list = nullptr; a.task_origin = d_origin; a.task_zone = d_zone;
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;

@@ -6,6 +6,8 @@
 // The column pool is a CSR of columns: fixed slots per OD cell (count, node_sum, n_links, offset, volume)
 // and one int32 arena of path links in origin->destination order.  All three kernels are HBM/L2 bound
 // gather/scatter work; algorithmic bytes per unit are listed in DESIGN.md.  Compiled with -fmad=false.
+#include <cstdlib>
+
 #include "dtl_internal.h"
 
 namespace dtl {
@@ -164,18 +166,20 @@ void launch_backtrace(const ColumnLaunch& a, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: one warp per OD cell; lanes stride over a column's links (coalesced 128-byte gathers from the
-// arena) and add the column's PCE volume to the per-link Q31.32 accumulators with integer atomics, so
-// the sums do not depend on the order columns are visited in -- across warps, launches or GPUs.
-// The addend is the reference's own  (double)(float)path_volume * pce  (assignment.h:87,127,140)
-// rounded once to 2^-32.
+// K3: one warp per OD cell.  A lane reads FOUR consecutive path links of a column per step (columns are 16-byte aligned in the
+// arena and padded with -1: one 16-byte load, 512 bytes per warp step) and adds the column's PCE volume to the per-link
+// Q31.32 accumulators with integer atomics, so the sums do not depend on the order columns are visited in -- across warps,
+// launches or GPUs.  The addend is the reference's own  (double)(float)path_volume * pce  (assignment.h:87,127,140)
+// rounded once to 2^-32.  Warps are dealt to cells with a stride (a.cell_stride, coprime to the number of cells): the
+// cells of one origin all run over the same first links, and neighbouring warps hammering the same accumulators serialise
+// in the L2 atomic units.
 template <bool PERSON>
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.pool.n_od) return;
-    const int cell = warp;
+    const int cell = (int)(((long long)warp * a.cell_stride) % a.pool.n_od);
     const ColumnPool& P = a.pool;
     const int cnt = P.count[cell];
     if (cnt == 0) return;
@@ -190,34 +194,86 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
     unsigned long long* per_at = PERSON ? per + (size_t)(1 + at) * a.L : nullptr;
     const size_t base = (size_t)cell * P.cap;
     unsigned long long refs = 0;
-    for (int j = 0; j < cnt; ++j) {
-        const double vol = P.volume[base + j];
-        const float f = (float)vol;                                  // assignment.h:87,127
-        const int n = P.n_links[base + j];
-        const int* links = P.arena + P.offset[base + j];
-        if (f != 0.0f) {
-            for (int q = lane; q < n; q += 32) {
-                const int l = __ldg(&links[q]);
-                const double x = f * (pce_same ? pce_u : __ldg(&pce[l])); // assignment.h:140
-                atomicAdd(&acc[l], (unsigned long long)__double2ll_rn(x * DTL_FIX_SCALE));
-                if (PERSON) {
-                    const unsigned long long y =
-                        (unsigned long long)__double2ll_rn(f * (occ_same ? occ_u : __ldg(&occ[l])) * DTL_FIX_SCALE);
-                    atomicAdd(&per[l], y);                           // assignment.h:141
-                    atomicAdd(&per_at[l], y);                        // assignment.h:142
+    // slot records of the cell's columns: lane j holds column j (cells have at most a few dozen columns)
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const int jm = min(32, cnt - j0);
+        double vol_l = 0.0;
+        int n_l = 0;
+        long long off_l = 0;
+        if (lane < jm) {
+            vol_l = P.volume[base + j0 + lane];
+            n_l = P.n_links[base + j0 + lane];
+            off_l = P.offset[base + j0 + lane];
+            if (a.decay_k >= 0)                                      // assignment.h:182-186 MSA self-reduction
+                P.volume[base + j0 + lane] = vol_l * ((double)a.decay_k / (double)(a.decay_k + 1));
+        }
+        // four columns per step: their link groups are requested together (a warp otherwise has ONE load in flight per column
+        // and spends its time waiting for it); a lane's first group covers columns of up to 128 links, longer ones take the tail loop
+        for (int j = 0; j < jm; j += 4) {
+            int4 v[4];
+            float f[4];
+            int n[4];
+            const int4* links[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int jj = (j + c) & 31;
+                const double vol = __shfl_sync(0xffffffffu, vol_l, jj);
+                n[c] = __shfl_sync(0xffffffffu, n_l, jj);
+                const long long off = __shfl_sync(0xffffffffu, off_l, jj);
+                f[c] = (float)vol;                                   // assignment.h:87,127
+                if (j + c >= jm) n[c] = 0;
+                refs += n[c];
+                if (f[c] == 0.0f) n[c] = 0;
+                links[c] = reinterpret_cast<const int4*>(P.arena + off);
+                v[c] = make_int4(-1, -1, -1, -1);
+                if (lane * 4 < n[c]) v[c] = __ldg(&links[c][lane]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const unsigned long long x_u = (unsigned long long)__double2ll_rn((double)f[c] * pce_u * DTL_FIX_SCALE);
+                const unsigned long long y_u = PERSON ? (unsigned long long)__double2ll_rn((double)f[c] * occ_u * DTL_FIX_SCALE) : 0ULL;
+                for (int q = lane;;) {
+                    const int ls[4] = { v[c].x, v[c].y, v[c].z, v[c].w };
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int l = ls[r];
+                        if (l < 0) continue;                         // padding of the last group / nothing for this lane
+                        const unsigned long long x =
+                            pce_same ? x_u : (unsigned long long)__double2ll_rn(f[c] * __ldg(&pce[l]) * DTL_FIX_SCALE); // assignment.h:140
+                        atomicAdd(&acc[l], x);
+                        if (PERSON) {
+                            const unsigned long long y =
+                                occ_same ? y_u : (unsigned long long)__double2ll_rn(f[c] * __ldg(&occ[l]) * DTL_FIX_SCALE);
+                            atomicAdd(&per[l], y);                   // assignment.h:141
+                            atomicAdd(&per_at[l], y);                // assignment.h:142
+                        }
+                    }
+                    q += 32;
+                    if (q * 4 >= n[c]) break;
+                    v[c] = __ldg(&links[c][q]);
                 }
             }
         }
-        refs += n;
-        if (a.decay_k >= 0 && lane == 0)                             // assignment.h:182-186 MSA self-reduction
-            P.volume[base + j] = vol * ((double)a.decay_k / (double)(a.decay_k + 1));
     }
     if (lane == 0) atomicAdd(a.link_refs, refs);
 }
 
-void launch_scatter(const ScatterLaunch& a, cudaStream_t st)
+static int coprime_stride(int n)
 {
-    if (a.pool.n_od == 0) return;
+    // a stride near n / golden ratio, coprime to n: consecutive warps get cells of different origins, every cell exactly once
+    if (n < 64) return 1;
+    int s = (int)(n * 0.6180339887498949);
+    auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+    while (gcd(s, n) != 1) ++s;
+    return s;
+}
+
+void launch_scatter(const ScatterLaunch& a0, cudaStream_t st)
+{
+    if (a0.pool.n_od == 0) return;
+    ScatterLaunch a = a0;
+    static const bool in_order = getenv("DTL_SCATTER_IN_ORDER") != nullptr; // experiment hook: cells in origin order
+    a.cell_stride = in_order ? 1 : coprime_stride(a.pool.n_od);
     const int blocks = (a.pool.n_od + 7) / 8;
     if (a.person_fix) scatter_kernel<true><<<blocks, 256, 0, st>>>(a);
     else scatter_kernel<false><<<blocks, 256, 0, st>>>(a);

@@ -13,6 +13,9 @@
 //     by the global-queue kernel, like any other overflow).
 // Correctness does not depend on the order of expansions (see kernels_sssp_bundle.cu): the protocol "clear the node's queue
 // bits, then read its label row" / "atomicMin, then set the bit and push" is unchanged.
+#include <cstdio>
+#include <cstdlib>
+
 #include "sssp_bundle_common.cuh"
 
 namespace dtl {
@@ -24,12 +27,22 @@ namespace dtl {
 #define BND_ASYNC_SLEEP 40 /* ns an idle warp sleeps between two polls of its ring slots */
 #endif
 
-template <int BLOCK, int B, bool TAGS>
-__global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunch a)
+// EPL = out-edges relaxed per lane and pass (4, 2 or 1).  A ring entry (one node) is served by a group of
+// G = (B / 2) * (4 / EPL) lanes: lane (es, op) of the group relaxes edges es*EPL .. es*EPL+EPL-1 of the node for origins 2*op and
+// 2*op+1.  Only EPL = 4 is instantiated: on average a warp pass serves 0.9 nodes at the bench configuration (24.5 M passes for
+// 21.7 M expansions), which suggested spreading a node over more lanes to shorten the serial instruction stream of a pass, but
+// the ready nodes come in bursts and the number of GROUPS a CTA has is what counts then -- measured per 2 000 trees with 1 024
+// threads: EPL = 4 (128 groups) 7.3 ms, EPL = 2 (64 groups) 7.7 ms, EPL = 1 (32 groups, one node per warp) 12.2 ms.
+template <int BLOCK, int B, int EPL, bool TAGS, int CPS>
+__global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLaunch a)
 {
     constexpr int LPT = 2;
-    constexpr int G = B / LPT;
-    static_assert(BND_U == 4 && (G == 4 || G == 8), "a pass relaxes four out-edges per group of 4 or 8 lanes");
+    constexpr int OPL = B / LPT;      // lanes that share an edge: one per pair of origins
+    constexpr int ESG = BND_U / EPL;  // edge subgroups of a group
+    constexpr int G = OPL * ESG;      // lanes per ring entry
+    constexpr int OWN = OPL / EPL;    // lanes of an edge subgroup that end up holding the same edge's key
+    static_assert(BND_U == 4 && (OPL == 4 || OPL == 8) && (EPL == 1 || EPL == 2 || EPL == 4) && G <= 32 && OWN >= 1,
+                  "a pass relaxes four out-edges per group");
     extern __shared__ int s_dyn[];
     __shared__ int s_bundle, s_head, s_n_far, s_n_far2, s_overflow;
     // {entries queued or in flight (bits 17..31), ring tail of this window (bits 0..16)}: ONE shared-memory atomic per push --
@@ -38,7 +51,9 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
     __shared__ unsigned s_red[32];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int g = tid & (G - 1);
+    const int g = tid & (G - 1);        // lane of the group: g == 0 pops the entry
+    const int op = g & (OPL - 1);       // origin pair of this lane
+    const int es = g / OPL;             // edge subgroup of this lane
     const int gfirst = lane & ~(G - 1);
     const int N = a.s.N;
     const int RING = a.cap_near; // power of two
@@ -83,12 +98,12 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
         unsigned has_task = 0;
 #pragma unroll
         for (int t = 0; t < LPT; ++t) {
-            const int task = __ldg(&a.bundle_tasks[bundle * B + g * LPT + t]);
-            zone[t] = task >= 0 ? __ldg(&a.s.task_zone[task]) : -1;
+            const int task = __ldg(&a.bundle_tasks[bundle * B + op * LPT + t]);
+            zone[t] = TAGS && task >= 0 ? __ldg(&a.s.task_zone[task]) : -1;
             has_task |= (unsigned)(task >= 0) << t;
         }
         unsigned long long* const bl = a.bl + (size_t)bundle * N * B;
-        unsigned long long* const blg = bl + g * LPT;
+        unsigned long long* const blg = bl + op * LPT;
 
         {
             ulonglong2* v = reinterpret_cast<ulonglong2*>(bl);
@@ -150,23 +165,25 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
             if (thr <= mm) thr = mm + 1;
             if (tid == 0) { s_head = 0; s_pt = 0u; } // the ring is empty here: every published entry was consumed and finished
             __syncthreads();
-            for (int base = 0; base < n_far; base += BLOCK / G) {
-                if (base + (tid & ~31) / G >= n_far) continue;
-                const int i = base + tid / G;
+            // one far entry per OPL lanes (the lanes of a group's first edge subgroup suffice: a label row is OPL 16-byte loads)
+            for (int base = 0; base < n_far; base += BLOCK / OPL) {
+                if (base + (tid & ~31) / OPL >= n_far) continue;
+                const int i = base + tid / OPL;
                 const bool have = i < n_far;
                 const int v = have ? q_far[i].x : 0;
                 const int w = ST_WORD(v), sh = ST_SHIFT(v);
+                const int ofirst = lane & ~(OPL - 1);
                 unsigned o = 0;
-                if (have && g == 0) o = atomicAnd(&s_state[w], ~(2u << sh)) >> sh;
-                o = __shfl_sync(0xffffffffu, o, gfirst);
+                if (have && op == 0) o = atomicAnd(&s_state[w], ~(2u << sh)) >> sh;
+                o = __shfl_sync(0xffffffffu, o, ofirst);
                 const bool live = (o & 2u) != 0;
                 unsigned k = BND_DEAD_KEY;
                 if (live) {
                     const ulonglong2 lab = __ldcg(reinterpret_cast<const ulonglong2*>(blg + (size_t)v * B));
                     k = min(key_of(lab.x), key_of(lab.y));
                 }
-                const unsigned key = group_min_u32<G>(k);
-                if (live && g == 0) {
+                const unsigned key = group_min_u32<OPL>(k);
+                if (live && op == 0) {
                     if (key < thr) {
                         const unsigned o2 = atomicOr(&s_state[w], 1u << sh);
                         if (!((o2 >> sh) & 1u)) push_near(v, __ldg(&a.s.rows[v]));
@@ -226,15 +243,15 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     was = atomicAnd(&s_state[ST_WORD(u)], ~(3u << ST_SHIFT(u))) >> ST_SHIFT(u);
                 }
                 u = __shfl_sync(0xffffffffu, u, gfirst);
-                int e0 = __shfl_sync(0xffffffffu, row.x, gfirst);
+                int e0 = __shfl_sync(0xffffffffu, row.x, gfirst) + es * EPL; // first edge of this lane's subgroup
                 const int re = __shfl_sync(0xffffffffu, row.y, gfirst);
                 // edge records are loaded unconditionally (slots past the end of the row repeat its last edge and are masked out
                 // of the atomics): no predicated register moves in the instruction stream
                 const int elast = max(re - 1, 0);
-                double cost[BND_U];
-                int to[BND_U];
+                double cost[EPL];
+                int to[EPL];
 #pragma unroll
-                for (int j = 0; j < BND_U; ++j) {
+                for (int j = 0; j < EPL; ++j) {
                     const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[min(e0 + j, elast)]));
                     cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
                 }
@@ -250,15 +267,15 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     act[1] = lab.y < INF_BITS && (has_task & 2u);
                 }
                 c_pops += (unsigned)(have && g == 0);
-                c_relax += ((unsigned)act[0] + (unsigned)act[1]) * (unsigned)(re - e0);
-                // One pass relaxes up to BND_U out-edges of the group's node for the thread's two origins: all atomics are issued
-                // first (predicated, not branched; an atomic that is not issued "returns" its own candidate, i.e. no improvement);
-                // when they have returned, the group decides per edge whether the head improved for any origin and what its key
-                // is now, and the lane that owns the edge (lane 2j of a group of 8, lane j of a group of 4) queues the head.
+                if (es == 0) c_relax += ((unsigned)act[0] + (unsigned)act[1]) * (unsigned)max(re - e0, 0);
+                // One pass relaxes up to BND_U out-edges of the group's node, EPL of them per lane, for the lane's two origins: all
+                // atomics are issued first (an atomic that is not issued "returns" its own candidate, i.e. no improvement); when
+                // they have returned, the lanes of an edge subgroup decide per edge whether the head improved for any origin and
+                // what its key is now, and one lane per edge queues the head.
                 for (;;) {
-                    unsigned long long old[BND_U][LPT];
+                    unsigned long long old[EPL][LPT];
 #pragma unroll
-                    for (int j = 0; j < BND_U; ++j) {
+                    for (int j = 0; j < EPL; ++j) {
                         bool ok[LPT];
 #pragma unroll
                         for (int t = 0; t < LPT; ++t) ok[t] = act[t] && e0 + j < re;
@@ -276,26 +293,26 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                             old[j][t] = atom_min_if(p + t, (unsigned long long)__double_as_longlong(lu[t] + cost[j]), ok[t]); // routing.h:804,816
                     }
                     // the edge this lane queues: its head and the head's forward-star row (fetched in the shadow of the atomics)
-                    const int je = G == 8 ? g >> 1 : g;
+                    const int je = op / OWN; // index among this lane's EPL edges
                     int myto = to[0];
 #pragma unroll
-                    for (int j = 1; j < BND_U; ++j) myto = je == j ? to[j] : myto;
-                    const bool owner = (G == 4 || (g & 1) == 0) && e0 + je < re;
+                    for (int j = 1; j < EPL; ++j) myto = je == j ? to[j] : myto;
+                    const bool owner = (op % OWN) == 0 && e0 + je < re;
                     int2 prow = make_int2(0, 0);
                     if (owner) prow = __ldg(&a.s.rows[myto]);
                     unsigned impm = 0;
-                    unsigned nk[BND_U];
+                    unsigned nk[EPL];
 #pragma unroll
-                    for (int j = 0; j < BND_U; ++j) {
+                    for (int j = 0; j < EPL; ++j) {
                         const unsigned long long cb0 = (unsigned long long)__double_as_longlong(lu[0] + cost[j]);
                         const unsigned long long cb1 = (unsigned long long)__double_as_longlong(lu[1] + cost[j]);
                         impm |= (unsigned)(old[j][0] > cb0 || old[j][1] > cb1) << j;
                         nk[j] = min(min(key_of(old[j][0]), key_of(cb0)), min(key_of(old[j][1]), key_of(cb1)));
                     }
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) impm |= __shfl_xor_sync(0xffffffffu, impm, o);
+                    for (int o = OPL / 2; o > 0; o >>= 1) impm |= __shfl_xor_sync(0xffffffffu, impm, o);
                     if (__any_sync(0xffffffffu, impm != 0u)) {
-                        const unsigned key = group_min_edges<G>(nk, g);
+                        const unsigned key = subgroup_min_edges<OPL, EPL>(nk, op);
                         if (owner && ((impm >> je) & 1u)) {
                             const int w = ST_WORD(myto), sh = ST_SHIFT(myto);
                             if (key < thr) {
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(BLOCK, 1) sssp_bundle_async_kernel(BundleLaunc
                     e0 += BND_U;
                     if (!__any_sync(0xffffffffu, e0 < re)) break; // rows of more than BND_U edges take another pass
 #pragma unroll
-                    for (int j = 0; j < BND_U; ++j) {
+                    for (int j = 0; j < EPL; ++j) {
                         const int4 v = __ldg(reinterpret_cast<const int4*>(&a.s.edges[min(e0 + j, elast)]));
                         cost[j] = __hiloint2double(v.y, v.x); to[j] = v.z;
                     }
@@ -359,17 +376,39 @@ size_t bundle_async_smem_bytes(int N, int ring)
     return words * sizeof(unsigned) + (size_t)ring * (sizeof(int2) + sizeof(int));
 }
 
-template <int BLOCK, int B>
+template <int BLOCK, int B, int EPL, int CPS>
 static void async_launch(const BundleLaunch& a, size_t smem, cudaStream_t st)
 {
     // a.tagged: some node outside the hidden centroid rows has a zone-tagged out-link (routing.h:779-786 then has to be
     // evaluated inside the edge loop); ordinary networks only tag the connectors that leave a centroid
     if (a.tagged) {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sssp_bundle_async_kernel<BLOCK, B, true><<<a.grid, BLOCK, smem, st>>>(a);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS><<<a.grid, BLOCK, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sssp_bundle_async_kernel<BLOCK, B, false><<<a.grid, BLOCK, smem, st>>>(a);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        static bool said = false;
+        if (!said && getenv("DTL_BUNDLE_DEBUG")) {
+            said = true;
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, BLOCK, smem);
+            fprintf(stderr, "async bundle search: %d threads x %d CTAs/SM asked, %d edges per lane, occupancy %d CTAs/SM, %zu B dynamic smem, grid %d, %d bundles of %d\n",
+                    BLOCK, CPS, EPL, occ, smem, a.grid, a.n_bundles, B);
+        }
+        sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS><<<a.grid, BLOCK, smem, st>>>(a);
+    }
+}
+
+template <int B, int EPL>
+static void async_launch_b(const BundleLaunch& a, size_t smem, cudaStream_t st)
+{
+    // CTA size x resident CTAs per SM: one big CTA per SM, or two smaller ones (each with its own bundle, ring and queue bits)
+    switch (a.block * 10 + a.ctas_per_sm) {
+    case 5122: async_launch<512, B, EPL, 2>(a, smem, st); break;
+    case 5121: async_launch<512, B, EPL, 1>(a, smem, st); break;
+    case 7681: async_launch<768, B, EPL, 1>(a, smem, st); break;
+    default: async_launch<1024, B, EPL, 1>(a, smem, st); break;
     }
 }
 
@@ -377,11 +416,8 @@ void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st)
 {
     if (a.n_bundles == 0) return;
     const size_t smem = bundle_async_smem_bytes(a.s.N, a.cap_near);
-    if (a.B == 8) {
-        a.block == 512 ? async_launch<512, 8>(a, smem, st) : a.block == 768 ? async_launch<768, 8>(a, smem, st) : async_launch<1024, 8>(a, smem, st);
-    } else {
-        a.block == 512 ? async_launch<512, 16>(a, smem, st) : a.block == 768 ? async_launch<768, 16>(a, smem, st) : async_launch<1024, 16>(a, smem, st);
-    }
+    if (a.B == 8) async_launch_b<8, 4>(a, smem, st);
+    else async_launch_b<16, 4>(a, smem, st);
 }
 
 } // namespace dtl

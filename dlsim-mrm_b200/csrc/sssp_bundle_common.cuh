@@ -57,28 +57,30 @@ __device__ __forceinline__ unsigned group_min_u32(unsigned v)
     return v;
 }
 
-// Group-wide minimum of four values per lane, transposed: after log2(G) exchange steps the lane holds the minimum, over the
-// G lanes of its group, of the value with index (g >> 1) for G = 8 and index g for G = 4 -- each step halves the values a
-// lane still carries (4 shuffles for G = 8 instead of the 12 of four separate butterfly reductions).
-template <int G>
-__device__ __forceinline__ unsigned group_min_edges(const unsigned (&v)[4], int g)
+// Minimum over the OPL lanes of an edge subgroup of EPL values per lane, transposed: every exchange step halves the values a
+// lane still carries until one is left, then the remaining steps are a plain butterfly.  Lane `op` ends up with the minimum of
+// value index op / (OPL / EPL) (the high bits of op pick the value), e.g. 4 shuffles instead of 12 for EPL = 4, OPL = 8.
+template <int OPL, int EPL>
+__device__ __forceinline__ unsigned subgroup_min_edges(const unsigned (&v)[EPL], int op)
 {
-    static_assert(G == 4 || G == 8, "groups of 4 or 8 lanes");
-    unsigned a0, a1;
-    if (G == 8) {
-        const bool hi = (g & 4) != 0;
-        a0 = min(hi ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 4));
-        a1 = min(hi ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 4));
-        const bool h2 = (g & 2) != 0;
-        unsigned b = min(h2 ? a1 : a0, __shfl_xor_sync(0xffffffffu, h2 ? a0 : a1, 2));
-        return min(b, __shfl_xor_sync(0xffffffffu, b, 1));
-    } else {
-        const bool hi = (g & 2) != 0;
-        a0 = min(hi ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2));
-        a1 = min(hi ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2));
-        const bool h1 = (g & 1) != 0;
-        return min(h1 ? a1 : a0, __shfl_xor_sync(0xffffffffu, h1 ? a0 : a1, 1));
+    static_assert((OPL == 4 || OPL == 8) && (EPL == 1 || EPL == 2 || EPL == 4) && EPL <= OPL, "lanes per edge, edges per lane");
+    unsigned w[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) w[j] = v[j];
+    int n = EPL;
+#pragma unroll
+    for (int o = OPL / 2; o > 0; o >>= 1) {
+        if (n > 1) {
+            const bool hi = (op & o) != 0;
+            n >>= 1;
+#pragma unroll
+            for (int j = 0; j < EPL / 2; ++j)
+                if (j < n) w[j] = min(hi ? w[j + n] : w[j], __shfl_xor_sync(0xffffffffu, hi ? w[j] : w[j + n], o));
+        } else {
+            w[0] = min(w[0], __shfl_xor_sync(0xffffffffu, w[0], o));
+        }
     }
+    return w[0];
 }
 
 } // namespace dtl
