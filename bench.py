@@ -278,7 +278,22 @@ def run_engine_arm(args, rank, world, local_rank):
     achieved = BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (sssp_ms_launch / 1e3) / 1e9
     gteps = rows[-1]["counted_edges"] * K / (max_over_ranks(tm["ms"]["sssp"]) / 1e3) / 1e9
     dev_bytes = e.device_bytes
+    # every rank must hold the same all-reduced integers, and they must be the single-GPU ones (committed table)
+    import hashlib
+    vol_sha = hashlib.sha256(e.volume_fixed(0).tobytes()).hexdigest()
+    tag = float(int(vol_sha[:12], 16))
+    same_on_all_ranks = max_over_ranks(tag) == tag and -max_over_ranks(-tag) == tag
+    golden_sha = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "grid100k_volume_digests.json")) as f:
+            golden_sha = json.load(f)["digests"].get(str(W + K)) if args.workload == "grid100k" else None
+    except Exception:
+        pass
     e.close()
+    if not same_on_all_ranks:
+        raise SystemExit(f"bench.py: rank {rank} holds link volumes {vol_sha[:16]}.. that differ from another rank's")
+    if golden_sha is not None and golden_sha != vol_sha:
+        raise SystemExit(f"bench.py: link volumes after {W + K} iterations ({vol_sha[:16]}..) differ from the single-GPU golden ({golden_sha[:16]}..)")
 
     # ---- end to end through the C ABI with host buffers: image upload + K iterations + result read-back ----
     barrier()
@@ -325,6 +340,8 @@ def run_engine_arm(args, rank, world, local_rank):
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},
             "counted_edges_per_step": rows[-1]["counted_edges"],
             "relative_gap_last": rows[-1]["gap"],
+            "volume_digest": {"sha256": vol_sha, "iterations": W + K, "same_on_all_ranks": bool(same_on_all_ranks),
+                              "matches_single_gpu_golden": None if golden_sha is None else golden_sha == vol_sha},
             "device_gib": dev_bytes / 2**30, "read_gmns_s": read_s, "e2e_create_s": create_s, "e2e_total_s": e2e_s,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -102,6 +102,7 @@ struct VdfLaunch {
     const double* volume_override; // non-null: use this volume instead of pce+preload (KAT entry)
     bool detail;
     bool write_cost;
+    int* error_flag;               // bit 2: a generalized link cost is negative (not supported by the label-correcting kernels)
 };
 void launch_vdf(const VdfLaunch& a, cudaStream_t st);
 void launch_model_speed(int T, int L, int tau, const VdfParams& p, const LinkState& s, int first_slot, int n_slots,

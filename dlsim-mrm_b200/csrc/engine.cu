@@ -14,6 +14,7 @@
 #include <map>
 #include <numeric>
 #include <chrono>
+#include <thread>
 #include <queue>
 #include <tuple>
 
@@ -50,6 +51,8 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load()
     {
@@ -65,6 +68,8 @@ struct Nccl {
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        CommAbort = (decltype(CommAbort))dlsym(h, "ncclCommAbort");
+        CommGetAsyncError = (decltype(CommGetAsyncError))dlsym(h, "ncclCommGetAsyncError");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_err("libnccl lacks a required symbol"); return false; }
         return true;
     }
@@ -113,7 +118,8 @@ struct dtl_engine {
     double2* d_link_cost = nullptr;                    // [T*AT*L] K2b workspace
     float* d_vot = nullptr;
     double *d_block_sums = nullptr, *d_scalars = nullptr, *d_volume_tmp = nullptr;
-    double* h_scalars = nullptr; // pinned [16]
+    double* h_scalars = nullptr; // [16] scalar read-backs
+    double h_scalars_buf[16] = { 0 };
     ColumnPool pool{};
     int* d_error_flag = nullptr;
     double *d_least = nullptr, *d_od_sums = nullptr;
@@ -161,6 +167,8 @@ struct dtl_engine {
     int* d_batch_flag = nullptr;
     int last_sssp_variant = -1;
     double counted_edges_cached = -1;
+    std::thread embed_thread;        // landmark embeddings of the forward stars (bundle planner), computed behind dtl_create
+    std::vector<float> h_embed_all;  // embedding of the whole network when the zone partition needed one (world_size > 1)
 
     // timing
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
@@ -171,6 +179,7 @@ struct dtl_engine {
     double tasks_done = 0, reruns = 0;
 
     ncclComm_t comm = nullptr;
+    std::string comm_key;     // key of `comm` in the process-wide table (dtl_comm_init)
     bool local_shard = false; // world > 1 without a communicator: the caller reduces the shards (tests)
 
     // Device memory: allocations up to 32 MB are carved out of 256 MB slabs (an engine makes ~80 of them; one cudaMalloc each
@@ -282,17 +291,28 @@ void build_task_list(const dtl_problem* p, std::vector<int>& at_out, std::vector
                 if (visited[((size_t)at * T + tau) * Z + z]) { at_out.push_back(at); tau_out.push_back(tau); zone_out.push_back(z); }
 }
 
-int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
+// Host image of one forward star, built without any CUDA call (a worker thread builds it while the link arrays are uploaded).
+struct FsHost {
+    std::vector<int> row, link_edge, in_ptr;
+    std::vector<Edge> edges;
+    std::vector<int2> in_edges, rows, rin4;
+    std::vector<int4> link_info;
+};
+
+void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int tau, FsHost& h)
 {
     ForwardStar& f = e->fs[fs_index(e, at, tau)];
     const int N = e->N, L = e->L;
     const unsigned char* allowed = p->allowed + ((size_t)tau * e->AT + at) * L;
-    std::vector<int> row(N + 1, 0), link_edge(L, -1);
+    std::vector<int>& row = h.row;
+    std::vector<int>& link_edge = h.link_edge;
+    row.assign(N + 1, 0); link_edge.assign(L, -1);
     for (int l = 0; l < L; ++l)
         if (allowed[l]) row[p->link_from[l] + 1]++;
     for (int i = 0; i < N; ++i) row[i + 1] += row[i];
     const int E = row[N];
-    std::vector<Edge> edges(std::max(E, 1));
+    std::vector<Edge>& edges = h.edges;
+    edges.resize(std::max(E, 1));
     std::vector<int> cur(row.begin(), row.end() - 1);
     double cost_sum = 0;
     long long cost_n = 0;
@@ -306,10 +326,12 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
             const double c = p->fftt[(size_t)tau * L + l];
             if (c > 1e-3) { cost_sum += c; ++cost_n; }
         }
-    std::vector<int> in_ptr(N + 1, 0);
+    std::vector<int>& in_ptr = h.in_ptr;
+    in_ptr.assign(N + 1, 0);
     for (int ei = 0; ei < E; ++ei) in_ptr[(edges[ei].to & 0x7fffffff) + 1]++;
     for (int i = 0; i < N; ++i) in_ptr[i + 1] += in_ptr[i];
-    std::vector<int2> in_edges(std::max(E, 1));
+    std::vector<int2>& in_edges = h.in_edges;
+    in_edges.resize(std::max(E, 1));
     std::vector<int> icur(in_ptr.begin(), in_ptr.end() - 1);
     for (int u = 0; u < N; ++u)
         for (int ei = row[u]; ei < row[u + 1]; ++ei) in_edges[icur[edges[ei].to & 0x7fffffff]++] = make_int2(u, ei);
@@ -319,7 +341,8 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
     for (int ei = 0; ei < E; ++ei) f.h_to[ei] = edges[ei].to & 0x7fffffff;
     const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
     f.delta = factor * (cost_n ? cost_sum / (double)cost_n : 1.0);
-    std::vector<int2> rows(std::max(N, 1));
+    std::vector<int2>& rows = h.rows;
+    rows.resize(std::max(N, 1));
     for (int i = 0; i < N; ++i) {
         // a node whose out-edges are all zone-tagged connectors (a centroid) is expanded only as the origin of its own
         // tree (routing.h:779-786); the kernel reads the origin's row from row_ptr, so every other lookup sees an empty row
@@ -328,34 +351,94 @@ int build_forward_star(dtl_engine* e, const dtl_problem* p, int at, int tau)
         rows[i] = all_tagged ? make_int2(row[i], row[i]) : make_int2(row[i], row[i + 1]);
         for (int ei = row[i]; ei < row[i + 1] && !all_tagged; ++ei) f.open_tags = f.open_tags || edges[ei].to < 0;
     }
-    if (e->upload(&f.row_ptr, row.data(), row.size())) return -1;
-    if (e->upload(&f.rows, rows.data(), rows.size())) return -1;
-    std::vector<int4> link_info(std::max(L, 1));
+    h.link_info.resize(std::max(L, 1));
     for (int l = 0; l < L; ++l) {
         const int2 r = rows[p->link_to[l]];
-        link_info[l] = make_int4(p->link_from[l], r.x, r.y, 0);
+        h.link_info[l] = make_int4(p->link_from[l], r.x, r.y, 0);
     }
-    if (e->upload(&f.link_info, link_info.data(), link_info.size())) return -1;
-    if (e->upload(&f.edges, edges.data(), edges.size())) return -1;
-    if (e->upload(&f.in_ptr, in_ptr.data(), in_ptr.size())) return -1;
-    if (e->upload(&f.in_edges, in_edges.data(), in_edges.size())) return -1;
-    std::vector<int2> rin4((size_t)std::max(N, 1) * 4, make_int2(-1, 0));
+    h.rin4.assign((size_t)std::max(N, 1) * 4, make_int2(-1, 0));
     for (int v = 0; v < N; ++v) {
         const int n_in = in_ptr[v + 1] - in_ptr[v];
-        for (int q = 0; q < std::min(n_in, 4); ++q) rin4[(size_t)v * 4 + q] = in_edges[in_ptr[v] + q];
-        if (n_in > 4) rin4[(size_t)v * 4 + 3].y |= 0x40000000;
+        for (int q = 0; q < std::min(n_in, 4); ++q) h.rin4[(size_t)v * 4 + q] = in_edges[in_ptr[v] + q];
+        if (n_in > 4) h.rin4[(size_t)v * 4 + 3].y |= 0x40000000;
     }
-    if (e->upload(&f.rin4, rin4.data(), rin4.size())) return -1;
-    if (e->upload(&f.link_edge, link_edge.data(), link_edge.size())) return -1;
+}
+
+int upload_forward_star(dtl_engine* e, int at, int tau, const FsHost& h)
+{
+    ForwardStar& f = e->fs[fs_index(e, at, tau)];
+    if (e->upload(&f.row_ptr, h.row.data(), h.row.size())) return -1;
+    if (e->upload(&f.rows, h.rows.data(), h.rows.size())) return -1;
+    if (e->upload(&f.link_info, h.link_info.data(), h.link_info.size())) return -1;
+    if (e->upload(&f.edges, h.edges.data(), h.edges.size())) return -1;
+    if (e->upload(&f.in_ptr, h.in_ptr.data(), h.in_ptr.size())) return -1;
+    if (e->upload(&f.in_edges, h.in_edges.data(), h.in_edges.size())) return -1;
+    if (e->upload(&f.rin4, h.rin4.data(), h.rin4.size())) return -1;
+    if (e->upload(&f.link_edge, h.link_edge.data(), h.link_edge.size())) return -1;
     return 0;
 }
 
-int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt)
+// ---- multi-GPU failure handling -------------------------------------------------------------------------------------------
+// Raw NCCL has no watchdog: a rank that leaves the iteration early (a CUDA error, an exhausted column arena) would leave its
+// peers blocked in their next collective for ever.  Three measures: (1) the soft error flags are all-reduced (max) at the end
+// of every iteration, so every rank stops at the same point with the same message; (2) a rank that fails hard aborts the
+// communicator on its way out; (3) every wait on the stream of an engine with a communicator polls, watches
+// ncclCommGetAsyncError and gives up -- aborting the communicator -- after DTL_NCCL_TIMEOUT_S seconds (default 120).
+std::map<std::string, ncclComm_t>& comm_table()
+{
+    static std::map<std::string, ncclComm_t> comms;
+    return comms;
+}
+
+void comm_abort(dtl_engine* e)
+{
+    if (!e->comm) return;
+    if (g_nccl.CommAbort) g_nccl.CommAbort(e->comm);
+    comm_table().erase(e->comm_key);
+    e->comm = nullptr;
+    e->local_shard = false; // later collectives of this engine fail with "dtl_comm_init was not called" instead of hanging
+}
+
+int sync_stream(dtl_engine* e)
+{
+    if (!e->comm) {
+        CK(cudaStreamSynchronize(e->st));
+        return 0;
+    }
+    static const double limit_s = getenv("DTL_NCCL_TIMEOUT_S") ? atof(getenv("DTL_NCCL_TIMEOUT_S")) : 120.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long spins = 0;; ++spins) {
+        const cudaError_t q = cudaStreamQuery(e->st);
+        if (q == cudaSuccess) return 0;
+        if (q != cudaErrorNotReady) {
+            set_err("CUDA error %s while waiting for the stream: %s", cudaGetErrorName(q), cudaGetErrorString(q));
+            comm_abort(e);
+            return -1;
+        }
+        if ((spins & 1023) == 1023) {
+            ncclResult_t ar = ncclSuccess;
+            if (g_nccl.CommGetAsyncError && g_nccl.CommGetAsyncError(e->comm, &ar) == ncclSuccess && ar != ncclSuccess && ar != ncclInProgress) {
+                set_err("NCCL reported an asynchronous error (%s): a peer rank failed", g_nccl.GetErrorString ? g_nccl.GetErrorString(ar) : "?");
+                comm_abort(e);
+                return -1;
+            }
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (waited > limit_s) {
+                set_err("a collective did not complete within %.0f s (DTL_NCCL_TIMEOUT_S): a peer rank left the iteration", limit_s);
+                comm_abort(e);
+                return -1;
+            }
+            if (waited > 0.002) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
+}
+
+int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum)
 {
     if (e->world <= 1 || e->local_shard) return 0;
-    if (!e->comm) { set_err("world_size > 1 but dtl_comm_init was not called"); return -1; }
+    if (!e->comm) { set_err("world_size > 1 but dtl_comm_init was not called (or the communicator was aborted after a failure)"); return -1; }
     const int ph = e->phase_begin(6);
-    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, ncclSum, e->comm, e->st);
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, op, e->comm, e->st);
     e->phase_end(ph);
     if (r != ncclSuccess) { set_err("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return -1; }
     return 0;
@@ -370,7 +453,7 @@ int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_ove
     a.link_edge = e->d_link_edge_ptrs; a.edges = e->d_edges_ptrs;
     a.block_sums = e->d_block_sums; a.sys_tt = e->d_scalars + 0;
     a.volume_override = volume_override;
-    a.detail = detail; a.write_cost = write_cost;
+    a.detail = detail; a.write_cost = write_cost; a.error_flag = e->d_error_flag;
     const int ph = e->phase_begin(0);
     launch_vdf(a, e->st);
     e->phase_end(ph, 2);
@@ -508,7 +591,7 @@ static void split_zones(std::vector<int>& idx, int lo, int hi, int r0, int r1, c
     split_zones(idx, lo + left, hi, r0 + rl, r1, embed, centroid, owner);
 }
 
-static std::vector<int> zone_owners(const dtl_problem* p, int world)
+static std::vector<int> zone_owners(const dtl_problem* p, int world, std::vector<float>* embed_out = nullptr)
 {
     const int Z = p->n_zones, N = p->n_nodes, L = p->n_links;
     std::vector<int> owner(Z, 0);
@@ -529,6 +612,7 @@ static std::vector<int> zone_owners(const dtl_problem* p, int world)
     std::vector<int> idx; // zones that can carry trees first, the others are dealt with them (they cost nothing)
     for (int z = 0; z < Z; ++z) idx.push_back(z);
     split_zones(idx, 0, Z, 0, world, f.h_embed.data(), p->zone_centroid, owner.data());
+    if (embed_out) *embed_out = std::move(f.h_embed);
     return owner;
 }
 
@@ -545,6 +629,7 @@ static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const 
             return 0;
         }
     }
+    if (e->embed_thread.joinable()) e->embed_thread.join();
     ensure_embedding(f, e->N);
     std::vector<int> idx(n_tasks), out;
     std::iota(idx.begin(), idx.end(), 0);
@@ -572,7 +657,7 @@ static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const 
         d = e->d_bundle_tmp;
     }
     CK(cudaMemcpyAsync(d, out.data(), sizeof(int) * out.size(), cudaMemcpyHostToDevice, e->st));
-    CK(cudaStreamSynchronize(e->st)); // `out` is pageable and local
+    if (sync_stream(e)) return -1; // `out` is pageable and local
     *d_tasks = d; *d_slots = d + n_out; *n_bundles = nb;
     return 0;
 }
@@ -590,7 +675,11 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     b.tagged = f.open_tags || getenv("DTL_BUNDLE_TAGS") ? 1 : 0; // the env hook forces the per-edge tag check (tests)
     b.lpt = 2; // origins per thread; 4 measured slower (fewer warps to hide the round trips)
     if (const char* env = getenv("DTL_BUNDLE_LPT")) b.lpt = atoi(env) == 4 && B >= 8 ? 4 : 2;
+    const auto plan_t0 = std::chrono::steady_clock::now();
     if (plan_bundles(e, f, n, h_origin, plan_key, B, &b.bundle_tasks, d_slots, &b.n_bundles)) return -1;
+    if (getenv("DTL_CREATE_TRACE"))
+        fprintf(stderr, "bundle plan (%d trees, bundles of %d): %.3f ms\n", n, B,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - plan_t0).count());
     b.block = 1024;
     if (const char* env = getenv("DTL_BUNDLE_BLOCK")) b.block = atoi(env) == 512 ? 512 : atoi(env) == 768 ? 768 : 1024;
     // shared memory of a CTA: two queue bits per node, the rest for the two near queues (12 bytes per entry)
@@ -646,6 +735,9 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     }
     b.bp = e->d_bp; b.batch_flag = e->d_batch_flag;
     b.bl = e->d_bl; b.far = e->d_bfar; b.cap_far = e->bundle_cap_far;
+    if (getenv("DTL_CREATE_TRACE"))
+        fprintf(stderr, "bundle launch set up (plan + buffers): %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - plan_t0).count());
     b.bundle_counter = e->d_bundle_counter;
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
     return 0;
@@ -747,7 +839,7 @@ int sssp_complete_batch(dtl_engine* e, BatchState& bs, int n_tasks, bool count_e
     SsspLaunch& a = bs.a;
     e->h_tie_nodes.resize(n_tasks);
     CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     std::vector<int> rerun;
     for (int i = 0; i < n_tasks; ++i)
         if (e->h_tie_nodes[i] < 0) rerun.push_back(i);
@@ -770,7 +862,7 @@ int sssp_complete_batch(dtl_engine* e, BatchState& bs, int n_tasks, bool count_e
         e->phase_end(ph2, 1);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e->h_tie_nodes.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost, e->st));
-        CK(cudaStreamSynchronize(e->st));
+        if (sync_stream(e)) return -1;
         e->reruns += (double)rerun.size();
         for (int i : rerun)
             if (e->h_tie_nodes[i] < 0) { set_err("SSSP work queue overflow with worst-case capacities (internal bound violated)"); return -1; }
@@ -791,7 +883,7 @@ int sssp_complete_batch(dtl_engine* e, BatchState& bs, int n_tasks, bool count_e
         launch_sssp_replay(a, e->d_replay_tasks, n, e->d_replay_status, e->d_replay_next, e->st);
         e->phase_end(ph3, 1);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(e->st));
+        if (sync_stream(e)) return -1;
         done += n;
     }
     if (count_edges) {
@@ -811,15 +903,22 @@ int run_sssp_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* 
     return sssp_complete_batch(e, bs, n_tasks, count_edges);
 }
 
-int check_flags(dtl_engine* e)
+int check_flags(dtl_engine* e, bool collective = false)
 {
     int flag = 0;
     SsspStats s{};
+    // inside the assignment loop every rank sees the worst flag of any rank and stops at the same point (integer max: exact)
+    if (collective && all_reduce(e, e->d_error_flag, 1, ncclInt32, ncclMax)) return -1;
     CK(cudaMemcpyAsync(&flag, e->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     if (flag & 1) { set_err("column arena exhausted (%lld path links): raise dtl_options.column_arena_bytes", e->pool.arena_cap); return -1; }
     if (flag & 2) { set_err("an OD cell needs more than %d columns: raise dtl_options.max_columns_per_od", e->pool.cap); return -1; }
+    if (flag & 4) {
+        set_err("a generalized link cost (travel time + penalty + LR price + toll / VOT * 60) is negative: not supported, the "
+                "shortest-path kernels order labels by their FP64 bit pattern (reference routing.h:229-231 accepts it)");
+        return -1;
+    }
     (void)s; // queue overflows are handled per batch by re-running those trees with worst-case queues
     return 0;
 }
@@ -850,13 +949,13 @@ void dtl_default_options(dtl_options* o)
 void dtl_destroy(dtl_engine* e)
 {
     if (!e) return;
+    if (e->embed_thread.joinable()) e->embed_thread.join();
     cudaSetDevice(e->dev);
     if (e->st) cudaStreamSynchronize(e->st);
     e->resolve_timing();
     for (cudaEvent_t ev : e->free_events) cudaEventDestroy(ev);
     // e->comm is shared and lives as long as the process (see dtl_comm_init)
     for (void* p : e->allocs) cudaFree(p);
-    if (e->h_scalars) cudaFreeHost(e->h_scalars);
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -886,11 +985,11 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     }
     if (o.device >= 0) CK(cudaSetDevice(o.device));
     CK(cudaGetDevice(&e->dev));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, e->dev));
-    e->sm_count = prop.multiProcessorCount;
+    DTL_TRACE("device selected");
+    CK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->dev)); // (cudaGetDeviceProperties costs milliseconds)
     CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-    CK(cudaMallocHost(&e->h_scalars, 16 * sizeof(double)));
+    DTL_TRACE("stream");
+    e->h_scalars = e->h_scalars_buf; // pageable: a 16-byte read-back per iteration does not pay for pinning memory (2.7 ms)
 
     e->N = p->n_nodes; e->L = p->n_links; e->Z = p->n_zones; e->AT = p->n_agent_types; e->T = p->n_periods;
     e->B = std::max(1, p->memory_blocks);
@@ -915,11 +1014,20 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         if (p->zone_centroid[z] < 0 || p->zone_centroid[z] >= N) { set_err("zone %d: centroid node outside [0, %d)", z, N); return -1; }
     for (int l = 0; l < L; ++l)
         if (p->link_tag[l] >= Z) { set_err("link %d: outgoing-connector zone tag %d outside [0, %d)", l, p->link_tag[l], Z); return -1; }
+    // the host images of the forward stars are built by a worker thread while this thread partitions the demand and uploads
+    // the link arrays (no CUDA call and no error path inside the worker)
+    e->fs.resize((size_t)AT * T);
+    std::vector<FsHost> fsh((size_t)AT * T);
+    std::thread fs_thread([&]() {
+        for (int at = 0; at < AT; ++at)
+            for (int tau = 0; tau < T; ++tau) build_forward_star_host(e, p, at, tau, fsh[fs_index(e, at, tau)]);
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } fs_joiner{ fs_thread };
     DTL_TRACE("tasks of this rank: origin zones are sha");
     // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
     std::vector<int> g_at, g_tau, g_zone;
     build_task_list(p, g_at, g_tau, g_zone);
-    const std::vector<int> owner = zone_owners(p, e->world);
+    const std::vector<int> owner = zone_owners(p, e->world, &e->h_embed_all);
     std::vector<int> task_of((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
     for (size_t i = 0; i < g_at.size(); ++i)
         if (owner[g_zone[i]] == e->rank) {
@@ -1018,24 +1126,37 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_block_sums, vdf_blocks((int)TL) + 1)) return -1;
     if (e->alloc(&e->d_scalars, 16)) return -1;
     if (e->alloc(&e->d_volume_tmp, TL)) return -1;
+    DTL_TRACE("link arrays uploaded");
 
-    e->fs.resize((size_t)AT * T);
+    fs_thread.join();
+    DTL_TRACE("forward stars built (worker thread)");
     int maxE = 0;
     for (int at = 0; at < AT; ++at)
         for (int tau = 0; tau < T; ++tau) {
-            if (build_forward_star(e, p, at, tau)) return -1;
+            if (upload_forward_star(e, at, tau, fsh[fs_index(e, at, tau)])) return -1;
             maxE = std::max(maxE, e->fs[fs_index(e, at, tau)].n_edges);
         }
+    fsh.clear();
+    // the bundle planner's landmark embeddings (three or four breadth-first searches per forward star) are computed behind
+    // the rest of dtl_create and joined by the first bundle plan
+    e->embed_thread = std::thread([e, L]() {
+        for (ForwardStar& f : e->fs) {
+            if (!e->h_embed_all.empty() && f.n_edges == L) f.h_embed = e->h_embed_all; // same graph as the zone partition's
+            else ensure_embedding(f, e->N);
+        }
+    });
     std::vector<int*> le(AT * T);
     std::vector<Edge*> ed(AT * T);
     for (int i = 0; i < AT * T; ++i) { le[i] = e->fs[i].link_edge; ed[i] = e->fs[i].edges; }
     if (e->upload(&e->d_link_edge_ptrs, le.data(), le.size())) return -1;
     if (e->upload(&e->d_edges_ptrs, ed.data(), ed.size())) return -1;
+    DTL_TRACE("forward stars");
 
     DTL_TRACE("column pool");
     // ---- column pool ----
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
+    DTL_TRACE("cudaMemGetInfo");
     e->pool.n_od = e->n_cells;
     e->pool.cap = std::max(1, o.max_columns_per_od);
     const size_t slots = (size_t)e->n_cells * e->pool.cap;
@@ -1188,8 +1309,9 @@ int dtl_comm_init(dtl_engine* e, const unsigned char id128[128])
     if (!g_nccl.load()) return -1;
     CK(cudaSetDevice(e->dev));
     // communicators are process-lifetime objects keyed by their id: a second engine of the same run re-uses it
-    static std::map<std::string, ncclComm_t> comms;
+    std::map<std::string, ncclComm_t>& comms = comm_table();
     const std::string key((const char*)id128, 128);
+    e->comm_key = key;
     auto it = comms.find(key);
     if (it != comms.end()) { e->comm = it->second; return 0; }
     ncclUniqueId id;
@@ -1240,7 +1362,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
             CK(cudaGetLastError());
             int flag = 0;
             CK(cudaMemcpyAsync(&flag, e->d_batch_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
-            CK(cudaStreamSynchronize(e->st));
+            if (sync_stream(e)) return -1;
             if (!flag) { done = true; e->tasks_done += nb; }
             else {
                 bs.b.slim = 0; bs.slim = false;
@@ -1263,7 +1385,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
     return 0;
 }
 
-int dtl_iteration(dtl_engine* e, int k, double row[5])
+static int iteration_impl(dtl_engine* e, int k, double row[5])
 {
     CK(cudaSetDevice(e->dev));
     const int ph7 = e->phase_begin(7);
@@ -1279,17 +1401,17 @@ int dtl_iteration(dtl_engine* e, int k, double row[5])
         // counted edges: reachability does not change between iterations, so count once
         unsigned long long ce = 0;
         CK(cudaMemcpyAsync(&ce, &e->d_stats->counted_edges, 8, cudaMemcpyDeviceToHost, e->st));
-        CK(cudaStreamSynchronize(e->st));
+        if (sync_stream(e)) return -1;
         e->h_scalars[8] = (double)ce;
         CK(cudaMemcpyAsync(e->d_scalars + 2, e->h_scalars + 8, 8, cudaMemcpyHostToDevice, e->st));
         if (all_reduce(e, e->d_scalars + 2, 1, ncclFloat64)) return -1;
         CK(cudaMemcpyAsync(e->h_scalars + 8, e->d_scalars + 2, 8, cudaMemcpyDeviceToHost, e->st));
-        CK(cudaStreamSynchronize(e->st));
+        if (sync_stream(e)) return -1;
         e->counted_edges_cached = e->h_scalars[8];
     }
     CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
     e->phase_end(ph7, 0);
-    if (check_flags(e)) return -1;
+    if (check_flags(e, true)) return -1;
     e->resolve_timing();
     const double sysTT = e->h_scalars[0], least = e->h_scalars[1];
     if (row) {
@@ -1303,7 +1425,15 @@ int dtl_iteration(dtl_engine* e, int k, double row[5])
     return 0;
 }
 
-int dtl_column_update(dtl_engine* e, int n, double row[4])
+// a rank that fails inside the loop aborts the communicator on its way out, so that its peers' collectives end (see comm_abort)
+int dtl_iteration(dtl_engine* e, int k, double row[5])
+{
+    const int rc = iteration_impl(e, k, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
+
+static int column_update_impl(dtl_engine* e, int n, double row[4])
 {
     CK(cudaSetDevice(e->dev));
     const int ph7 = e->phase_begin(7);
@@ -1322,7 +1452,7 @@ int dtl_column_update(dtl_engine* e, int n, double row[4])
     if (all_reduce(e, e->d_scalars + 4, 4, ncclFloat64)) return -1;
     CK(cudaMemcpyAsync(e->h_scalars + 4, e->d_scalars + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
     e->phase_end(ph7, 0);
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     e->resolve_timing();
     if (row) {
         const double gap = e->h_scalars[4], cost = e->h_scalars[5], time = e->h_scalars[6], dem = e->h_scalars[7];
@@ -1334,17 +1464,31 @@ int dtl_column_update(dtl_engine* e, int n, double row[4])
     return 0;
 }
 
-int dtl_finalize(dtl_engine* e, int K, double* sys_tt)
+int dtl_column_update(dtl_engine* e, int n, double row[4])
+{
+    const int rc = column_update_impl(e, n, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
+
+static int finalize_impl(dtl_engine* e, int K, double* sys_tt)
 {
     (void)K;
     CK(cudaSetDevice(e->dev));
     if (do_scatter(e, -1, true)) return -1;                            // main_api.cpp:752
     if (do_vdf(e, true, true, nullptr)) return -1;                     // main_api.cpp:759
     CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     e->resolve_timing();
     if (sys_tt) *sys_tt = e->h_scalars[0];
     return 0;
+}
+
+int dtl_finalize(dtl_engine* e, int K, double* sys_tt)
+{
+    const int rc = finalize_impl(e, K, sys_tt);
+    if (rc) comm_abort(e);
+    return rc;
 }
 
 int dtl_run_assignment(dtl_engine* e, int K, int CU, double* iter_rows, double* cu_rows)
@@ -1374,7 +1518,7 @@ static int fetch_fixed(dtl_engine* e, double* dst, const unsigned long long* src
 {
     std::vector<long long> tmp(e->L);
     CK(cudaMemcpyAsync(tmp.data(), src, sizeof(long long) * e->L, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     for (int l = 0; l < e->L; ++l) dst[l] = (double)tmp[l] * (1.0 / DTL_FIX_SCALE);
     return 0;
 }
@@ -1387,7 +1531,7 @@ int dtl_get_link_state(dtl_engine* e, int tau, double* tt, double* pce_volume, d
     if (fetch(e, tt, e->ls.tt, tau) || fetch(e, link_volume, e->ls.link_volume, tau) || fetch(e, doc, e->ls.doc, tau) ||
         fetch(e, voc, e->ls.voc, tau) || fetch(e, P, e->ls.P, tau) || fetch(e, vt2, e->ls.vt2, tau))
         return -1;
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     if (pce_volume && fetch_fixed(e, pce_volume, e->ls.pce_fix + (size_t)tau * e->L)) return -1;
     if (person_volume && fetch_fixed(e, person_volume, e->ls.person_fix + (size_t)tau * (1 + e->AT) * e->L)) return -1;
     return 0;
@@ -1398,7 +1542,7 @@ int dtl_get_volume_fixed(dtl_engine* e, int tau, long long* q)
     if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
     CK(cudaSetDevice(e->dev));
     CK(cudaMemcpyAsync(q, e->ls.pce_fix + (size_t)tau * e->L, sizeof(long long) * e->L, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     return 0;
 }
 
@@ -1418,7 +1562,7 @@ int dtl_get_link_detail(dtl_engine* e, int tau, double* avg_queue_speed, double*
         fetch(e, Q_mu, e->ls.Q_mu, tau) || fetch(e, Q_gamma, e->ls.Q_gamma, tau) || fetch(e, t0, e->ls.t0, tau) ||
         fetch(e, t3, e->ls.t3, tau) || fetch(e, severe, e->ls.severe_P, tau))
         return -1;
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     return 0;
 }
 
@@ -1445,7 +1589,7 @@ int dtl_get_gen_cost(dtl_engine* e, int at, int tau, double* cost)
     const ForwardStar& f = e->fs[fs_index(e, at, tau)];
     std::vector<Edge> ed(std::max(1, f.n_edges));
     CK(cudaMemcpyAsync(ed.data(), f.edges, sizeof(Edge) * f.n_edges, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     for (int l = 0; l < e->L; ++l) cost[l] = 0.0;
     for (int i = 0; i < f.n_edges; ++i) cost[ed[i].link] = ed[i].cost;
     return 0;
@@ -1471,7 +1615,7 @@ static int pool_to_host(dtl_engine* e, PoolHost& h)
     CK(cudaMemcpyAsync(h.volume.data(), e->pool.volume, s * 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(h.cost.data(), e->pool.cost, s * 8, cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(h.time.data(), e->pool.time, s * 8, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     return 0;
 }
 
@@ -1632,7 +1776,7 @@ int dtl_vdf(dtl_engine* e, int tau, const double* volume, double* tt, double* do
     CK(cudaMemcpyAsync(e->d_volume_tmp, e->ls.link_volume, sizeof(double) * (size_t)e->T * e->L, cudaMemcpyDeviceToDevice, e->st));
     CK(cudaMemcpyAsync(e->d_volume_tmp + (size_t)tau * e->L, volume, sizeof(double) * e->L, cudaMemcpyHostToDevice, e->st));
     if (do_vdf(e, true, false, e->d_volume_tmp)) return -1;
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     e->resolve_timing();
     return dtl_get_link_state(e, tau, tt, nullptr, nullptr, nullptr, doc, voc, P, vt2);
 }
@@ -1641,7 +1785,7 @@ int dtl_scatter(dtl_engine* e, int decay_k)
 {
     CK(cudaSetDevice(e->dev));
     if (do_scatter(e, decay_k, true)) return -1;
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     e->resolve_timing();
     return 0;
 }
@@ -1667,7 +1811,7 @@ int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pr
 int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset)
 {
     CK(cudaSetDevice(e->dev));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     e->resolve_timing();
     if (ms) memcpy(ms, e->ms, sizeof(e->ms));
     if (counts) memcpy(counts, e->launches, sizeof(e->launches));
@@ -1678,7 +1822,7 @@ int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset)
 int dtl_get_counters(dtl_engine* e, double c[10], int reset)
 {
     CK(cudaSetDevice(e->dev));
-    CK(cudaStreamSynchronize(e->st));
+    if (sync_stream(e)) return -1;
     SsspStats s{};
     unsigned long long ctr[4] = { 0 };
     CK(cudaMemcpy(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost));

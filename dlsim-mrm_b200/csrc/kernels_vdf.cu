@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(VDF_THREADS) vdf_kernel(VdfLaunch a)
                 if (e >= 0) {
                     const size_t ai = ((size_t)tau * a.AT + at) * a.L + l;
                     // routing.h:229-231: tt + penalty + LR_price + toll / VOT(float) * 60
-                    a.edges[fs][e].cost = c.tt + pen + a.lr_price[ai] + a.toll[ai] / a.vot[at] * 60;
+                    const double gc = c.tt + pen + a.lr_price[ai] + a.toll[ai] / a.vot[at] * 60;
+                    a.edges[fs][e].cost = gc;
+                    // K1 orders labels by their FP64 bit pattern, which is only valid for non-negative sums: a negative (or NaN)
+                    // generalized cost -- a negative penalty, toll or LR price larger than the travel time -- is refused
+                    if (!(gc >= 0.0)) atomicOr(a.error_flag, 4);
                 }
             }
         }
