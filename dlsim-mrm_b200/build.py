@@ -43,7 +43,7 @@ def _stale(target: str, deps) -> bool:
 
 
 def build_variant(name: str, sssp_flags, verbose: bool = False) -> str:
-    """Experiment helper: a copy of the library with extra nvcc flags on kernels_sssp*.cu -> lib/variants/<name>.so
+    """Experiment helper: a copy of the library with extra nvcc flags on kernels_*.cu -> lib/variants/<name>.so
     (selected at run time with DTL_LIB=<path>)."""
     vdir = os.path.join(LIB_DIR, "variants")
     odir = os.path.join(vdir, "obj_" + name)
@@ -51,7 +51,7 @@ def build_variant(name: str, sssp_flags, verbose: bool = False) -> str:
     objs = []
     for s in [x for x in sources() if os.path.basename(x) != "main.cpp"]:
         o = os.path.join(odir, os.path.basename(s) + ".o")
-        extra = list(sssp_flags) if os.path.basename(s).startswith("kernels_sssp") else []
+        extra = list(sssp_flags) if os.path.basename(s).startswith("kernels_") else []
         cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose and extra else []) + \
             ["-x", "cu" if s.endswith(".cu") else "c++", "-c", s, "-o", o]
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

@@ -167,6 +167,9 @@ struct BundleLaunch {
     int grid, block;
     int ctas_per_sm;         // async: resident CTAs per SM the kernel is compiled for (1, or 2 / 3 / 4 with the smaller CTA sizes)
     int slim;                // 1: the label -> tree pass leaves predecessors node-major in bp and writes no per-tree arrays
+    int fuse_pred;           // slim + async: the search kernel runs the label -> predecessor pass itself -- every CTA that has no
+                             // (more) bundle to search takes tiles of the bundles that are finished (work[] below)
+    int* work;               // fuse_pred: [1 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters}
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
     int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
 };

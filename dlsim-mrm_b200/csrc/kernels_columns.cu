@@ -173,8 +173,11 @@ void launch_backtrace(const ColumnLaunch& a, cudaStream_t st)
 // rounded once to 2^-32.  Warps are dealt to cells with a stride (a.cell_stride, coprime to the number of cells): the
 // cells of one origin all run over the same first links, and neighbouring warps hammering the same accumulators serialise
 // in the L2 atomic units.
+#ifndef SCATTER_MIN_BLOCKS
+#define SCATTER_MIN_BLOCKS 4
+#endif
 template <bool PERSON>
-__global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
+__global__ void __launch_bounds__(256, PERSON ? 3 : SCATTER_MIN_BLOCKS) scatter_kernel(ScatterLaunch a)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -228,10 +231,43 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
                 v[c] = make_int4(-1, -1, -1, -1);
                 if (lane * 4 < n[c]) v[c] = __ldg(&links[c][lane]);
             }
+            // first link group of the four columns: the columns of a cell are alternative paths of ONE origin-destination pair
+            // and share their first links position by position, so a lane often holds the same link in several columns --
+            // their addends are summed before the atomic (integer sums: the same bits)
+            unsigned long long x_u[4], y_u[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const unsigned long long x_u = (unsigned long long)__double2ll_rn((double)f[c] * pce_u * DTL_FIX_SCALE);
-                const unsigned long long y_u = PERSON ? (unsigned long long)__double2ll_rn((double)f[c] * occ_u * DTL_FIX_SCALE) : 0ULL;
+                x_u[c] = (unsigned long long)__double2ll_rn((double)f[c] * pce_u * DTL_FIX_SCALE);
+                y_u[c] = PERSON ? (unsigned long long)__double2ll_rn((double)f[c] * occ_u * DTL_FIX_SCALE) : 0ULL;
+            }
+            if (pce_same && (!PERSON || occ_same)) {
+                const int ls[4][4] = { { v[0].x, v[0].y, v[0].z, v[0].w }, { v[1].x, v[1].y, v[1].z, v[1].w },
+                                       { v[2].x, v[2].y, v[2].z, v[2].w }, { v[3].x, v[3].y, v[3].z, v[3].w } };
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    int l[4] = { ls[0][r], ls[1][r], ls[2][r], ls[3][r] };
+                    unsigned long long x[4] = { x_u[0], x_u[1], x_u[2], x_u[3] };
+                    unsigned long long y[4] = { y_u[0], y_u[1], y_u[2], y_u[3] };
+#pragma unroll
+                    for (int c = 3; c > 0; --c)
+#pragma unroll
+                        for (int c2 = 0; c2 < c; ++c2)
+                            if (l[c] >= 0 && l[c] == l[c2]) { x[c2] += x[c]; y[c2] += y[c]; l[c] = -1; }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (l[c] < 0) continue;                      // padding, nothing for this lane, or merged into an earlier column
+                        atomicAdd(&acc[l[c]], x[c]);
+                        if (PERSON) {
+                            atomicAdd(&per[l[c]], y[c]);             // assignment.h:141
+                            atomicAdd(&per_at[l[c]], y[c]);          // assignment.h:142
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = make_int4(-1, -1, -1, -1);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 for (int q = lane;;) {
                     const int ls[4] = { v[c].x, v[c].y, v[c].z, v[c].w };
 #pragma unroll
@@ -239,11 +275,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterLaunch a)
                         const int l = ls[r];
                         if (l < 0) continue;                         // padding of the last group / nothing for this lane
                         const unsigned long long x =
-                            pce_same ? x_u : (unsigned long long)__double2ll_rn(f[c] * __ldg(&pce[l]) * DTL_FIX_SCALE); // assignment.h:140
+                            pce_same ? x_u[c] : (unsigned long long)__double2ll_rn(f[c] * __ldg(&pce[l]) * DTL_FIX_SCALE); // assignment.h:140
                         atomicAdd(&acc[l], x);
                         if (PERSON) {
                             const unsigned long long y =
-                                occ_same ? y_u : (unsigned long long)__double2ll_rn(f[c] * __ldg(&occ[l]) * DTL_FIX_SCALE);
+                                occ_same ? y_u[c] : (unsigned long long)__double2ll_rn(f[c] * __ldg(&occ[l]) * DTL_FIX_SCALE);
                             atomicAdd(&per[l], y);                   // assignment.h:141
                             atomicAdd(&per_at[l], y);                // assignment.h:142
                         }

@@ -505,87 +505,14 @@ __global__ void __launch_bounds__(256, 4) bundle_finish_kernel(BundleLaunch a)
     }
 }
 
-// The node-major label -> predecessor pass of the assignment loop (trees are only back-traced, no per-tree arrays): a group
-// of B/2 lanes per node, two origins per lane.  The node's first four in-edges come as one 32-byte record (ForwardStar::rin4),
-// their edge records and the label rows of the upstream nodes are all requested at once, and the group writes one coalesced
-// row of {predecessor link, predecessor node} records.  The tight in-edge is the predecessor (label[u] + cost == label[v] in
-// exact FP64; of parallel links from one node the first in scan order); two tight upstream nodes are an order-dependent tie
-// and, like an overflowed bundle, raise a.batch_flag: the host then redoes the batch through bundle_finish_kernel.
+#ifndef PRED_MIN_BLOCKS
+#define PRED_MIN_BLOCKS 4
+#endif
 template <int B>
-__global__ void __launch_bounds__(256) bundle_pred_kernel(BundleLaunch a)
+__global__ void __launch_bounds__(256, PRED_MIN_BLOCKS) bundle_pred_kernel(BundleLaunch a)
 {
-    constexpr int G = B / 2;
-    constexpr int NODES = 256 / G;     // nodes per block and step
-    constexpr int STEPS = 8;
-    const int tid = threadIdx.x;
-    const int g = tid & (G - 1);
-    const int N = a.s.N;
-    const int bundle = blockIdx.y;
-    int task[2], origin[2], zone[2];
-    bool bad = false;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        task[t] = __ldg(&a.bundle_tasks[bundle * B + 2 * g + t]);
-        if (task[t] >= 0 && a.s.tie_nodes[task[t]] < 0) { task[t] = -1; bad = true; }
-        origin[t] = task[t] >= 0 ? __ldg(&a.s.task_origin[task[t]]) : -1;
-        zone[t] = task[t] >= 0 ? __ldg(&a.s.task_zone[task[t]]) : -1;
-    }
-    if (bad && blockIdx.x == 0 && tid < G) atomicOr(a.batch_flag, 2);
-    const ulonglong2* const bl2 = reinterpret_cast<const ulonglong2*>(a.bl + (size_t)bundle * N * B) + g;
-    int4* const out = reinterpret_cast<int4*>(a.bp + (size_t)bundle * N * B) + g;
-    bool tie = false;
-    const int v_end = min(N, (blockIdx.x + 1) * NODES * STEPS);
-    for (int v = blockIdx.x * NODES * STEPS + tid / G; v < v_end; v += NODES) {
-        const ulonglong2 lvb = __ldg(bl2 + (size_t)v * G);
-        const int4 r01 = __ldg(reinterpret_cast<const int4*>(a.s.rin4 + (size_t)v * 4));
-        const int4 r23 = __ldg(reinterpret_cast<const int4*>(a.s.rin4 + (size_t)v * 4) + 1);
-        const int from[4] = { r01.x, r01.z, r23.x, r23.z };
-        const int eidx[4] = { r01.y, r01.w, r23.y, r23.w & 0x3fffffff };
-        ulonglong2 lub[4];
-        int4 ed[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            lub[q] = make_ulonglong2(INF_BITS, INF_BITS);
-            ed[q] = make_int4(0, 0, 0, 0);
-            if (from[q] >= 0) {
-                lub[q] = __ldg(bl2 + (size_t)from[q] * G);
-                ed[q] = __ldg(reinterpret_cast<const int4*>(&a.s.edges[eidx[q]]));
-            }
-        }
-        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0];
-        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1];
-        const double lv0 = __longlong_as_double((long long)lvb.x), lv1 = __longlong_as_double((long long)lvb.y);
-        int first0 = -1, first1 = -1, link0 = DTL_NO_PRED, link1 = DTL_NO_PRED;
-        auto consider = [&](int u, double cost, int link, bool tagged, ulonglong2 lu) {
-            bool ok0 = need0 && lu.x < INF_BITS, ok1 = need1 && lu.y < INF_BITS;
-            if (tagged) { // routing.h:779-786
-                const int tag = __ldg(&a.s.link_tag[link]);
-                ok0 = ok0 && tag == zone[0];
-                ok1 = ok1 && tag == zone[1];
-            }
-            if (ok0 && __longlong_as_double((long long)lu.x) + cost == lv0) {
-                if (first0 < 0) { first0 = u; link0 = link; }
-                else if (u != first0) tie = true;
-            }
-            if (ok1 && __longlong_as_double((long long)lu.y) + cost == lv1) {
-                if (first1 < 0) { first1 = u; link1 = link; }
-                else if (u != first1) tie = true;
-            }
-        };
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (from[q] >= 0) consider(from[q], __hiloint2double(ed[q].y, ed[q].x), ed[q].w, ed[q].z < 0, lub[q]);
-        if (r23.w & 0x40000000) { // more than four in-edges: the rest through the reverse star
-            const int j1 = __ldg(&a.s.in_ptr[v + 1]);
-            for (int jj = __ldg(&a.s.in_ptr[v]) + 4; jj < j1; ++jj) {
-                const int2 ie = __ldg(&a.s.in_edges[jj]);
-                const Edge e2 = ld_edge(&a.s.edges[ie.y]);
-                consider(ie.x, e2.cost, e2.link, e2.to < 0, __ldg(bl2 + (size_t)ie.x * G));
-            }
-        }
-        out[(size_t)v * G] = make_int4(link0, first0, link1, first1);
-    }
-    if (tie) atomicOr(a.batch_flag, 1);
+    constexpr int per_block = 256 / (B / 2) * 8;
+    bundle_pred_nodes<B, 256, false>(a, blockIdx.y, blockIdx.x * per_block, min(a.s.N, (blockIdx.x + 1) * per_block), blockIdx.x == 0);
 }
 
 template <int B>
@@ -643,6 +570,10 @@ void launch_sssp_bundle_finish(const BundleLaunch& a, cudaStream_t st)
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st)
 {
     if (a.n_bundles == 0) return;
+    if (a.async && a.slim && a.fuse_pred) { // the search kernel also runs the label -> predecessor pass (CTAs without a bundle)
+        launch_sssp_bundle_async_search(a, st);
+        return;
+    }
     if (a.async) launch_sssp_bundle_async_search(a, st); // experiment: no round barriers inside a label window
     else
     switch (a.B) {

@@ -358,6 +358,39 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
             }
             if (tid == 0) atomicAdd(&a.s.stats->overflow, 1ULL);
         }
+        if (a.fuse_pred) { // the bundle's labels are final: hand it to the label -> predecessor pass below (any CTA)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(&a.work[1 + atomicAdd(&a.work[0], 1)], bundle);
+        }
+    }
+    // ---- label -> predecessor pass of the finished bundles, by every CTA that has nothing left to search: the CTAs beyond
+    // the number of bundles from the start, the others as their bundle finishes (bundles differ by some 10 % in search time).
+    // Bundles are taken in the order they finished, tiles of a bundle from a counter.
+    if (a.fuse_pred) {
+        constexpr int TILE = BLOCK / (B / 2) * 8;
+        const int n_tiles = (N + TILE - 1) / TILE;
+        int* const done = a.work + 1;
+        int* const tile_counter = a.work + 1 + a.n_bundles;
+        for (int i = 0; i < a.n_bundles; ++i) {
+            __syncthreads();
+            if (tid == 0) {
+                int b;
+                while ((b = *reinterpret_cast<volatile int*>(&done[i])) < 0) __nanosleep(400);
+                s_bundle = b;
+            }
+            __syncthreads();
+            const int b = s_bundle;
+            __threadfence();
+            for (;;) {
+                __syncthreads();
+                if (tid == 0) s_head = atomicAdd(&tile_counter[b], 1);
+                __syncthreads();
+                const int tile = s_head;
+                if (tile >= n_tiles) break;
+                bundle_pred_nodes<B, BLOCK, true>(a, b, tile * TILE, min(N, (tile + 1) * TILE), tile == 0);
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         c_relax += __shfl_xor_sync(0xffffffffu, c_relax, o);
