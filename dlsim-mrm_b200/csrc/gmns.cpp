@@ -43,6 +43,9 @@ struct StopError : std::runtime_error {
 // CSV dialect of the reference's CDTACSVParser (utils.cpp:233-470, utils.h:115-221): header names are
 // left-trimmed of blanks, later duplicates win, a line containing '[' opens a section and is its header,
 // an empty line ends ReadRecord loops, quoted fields may contain commas.
+// The whole file is read into memory once; a record's fields are views into that buffer (commas and the line end are
+// overwritten with NULs so that strtod / strtol run on the field in place): no per-field std::string, which is what the
+// reader of a 300 000-row link.csv used to spend its time on.  Lines with quotes take the general splitter.
 class Csv {
 public:
     bool first_line_header = true;
@@ -52,64 +55,120 @@ public:
     bool open(const std::string& path)
     {
         file = path;
-        in_.open(path.c_str());
-        if (!in_.is_open()) return false;
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        buf_.clear();
+        char chunk[1 << 16];
+        size_t n;
+        while ((n = fread(chunk, 1, sizeof(chunk), f)) > 0) buf_.append(chunk, n);
+        fclose(f);
+        buf_.push_back('\n'); // sentinel: the last line always ends inside the buffer
+        pos_ = 0;
+        end_ = buf_.size() - 1;
+        open_ = true;
         if (first_line_header) {
             std::string s;
-            std::getline(in_, s);
+            getline_buf(s);
             set_header(s);
         }
         return true;
     }
-    void close() { in_.close(); }
+    void close() { open_ = false; buf_.clear(); }
+
+    // a slice of a file that was read elsewhere (whole lines), with that file's header line: what a worker thread parses
+    void open_text(const char* begin, const char* end, const std::string& header_line, const std::string& path)
+    {
+        file = path;
+        buf_.assign(begin, end);
+        buf_.push_back('\n');
+        pos_ = 0;
+        end_ = buf_.size() - 1;
+        open_ = true;
+        set_header(header_line);
+    }
+    static bool read_file(const std::string& path, std::string& out)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        out.clear();
+        char chunk[1 << 16];
+        size_t n;
+        while ((n = fread(chunk, 1, sizeof(chunk), f)) > 0) out.append(chunk, n);
+        fclose(f);
+        return true;
+    }
 
     bool read_record()
     {
-        values_.clear();
-        if (!in_.is_open()) return false;
-        std::string s;
-        std::getline(in_, s);
-        if (s.empty()) return false;
-        values_ = split(s);
+        fields_.clear();
+        if (!open_ || pos_ >= end_) return false; // std::getline at end of file leaves the string empty
+        char* b = &buf_[pos_];
+        char* e = (char*)memchr(b, '\n', end_ + 1 - pos_);
+        pos_ = (size_t)(e - &buf_[0]) + 1;
+        if (e == b) return false;                 // an empty line ends ReadRecord loops (utils.cpp:290-312)
+        if (memchr(b, '"', (size_t)(e - b))) {    // quoted fields: general splitter, fields kept in side strings
+            quoted_ = split(std::string(b, e));
+            for (std::string& q : quoted_) fields_.push_back({ &q[0], (int)q.size() });
+            for (size_t i = 0; i < quoted_.size(); ++i)
+                if (quoted_[i].empty()) fields_[i] = { empty_, 0 };
+            return true;
+        }
+        *e = '\0';
+        char* p = b;
+        for (;;) {
+            char* c = (char*)memchr(p, ',', (size_t)(e - p));
+            if (!c) {
+                if (p < e) fields_.push_back({ p, (int)(e - p) });
+                break;
+            }
+            *c = '\0';
+            fields_.push_back({ p, (int)(c - p) });
+            p = c + 1;
+        }
+        if (e[-1] == '\0' && e > b) fields_.push_back({ empty_, 0 }); // the line ended with a comma: one more, empty, field
         return true;
     }
 
     // sectioned settings.csv: returns false only at end of file
     bool read_record_section()
     {
-        values_.clear();
-        if (!in_.is_open()) return false;
+        fields_.clear();
+        if (!open_) return false;
         std::string s;
-        std::getline(in_, s);
+        const bool more = getline_buf(s);
         if (!s.empty()) {
             if (s.find('[') != std::string::npos) {
                 std::vector<std::string> v = split(s);
                 if (!v.empty()) section = v[0];
                 set_header(s);
-                std::getline(in_, s);
+                getline_buf(s);
             }
-            values_ = split(s);
+            quoted_ = split(s);
+            for (std::string& q : quoted_) {
+                if (q.empty()) fields_.push_back({ empty_, 0 });
+                else fields_.push_back({ &q[0], (int)q.size() });
+            }
             return true;
         }
-        return !in_.eof();
+        return more;
     }
 
     bool has(const std::string& name) const { return index_.count(name) != 0; }
 
     bool get(const std::string& name, std::string& value, bool required = true)
     {
-        const std::string* s = raw(name, required);
+        const Field* s = raw(name, required);
         if (!s) return false;
-        value = *s;
+        value.assign(s->p, (size_t)s->n);
         return true;
     }
     template <class T>
     bool get(const std::string& name, T& value, bool required = true, bool nonnegative = true)
     {
-        const std::string* s = raw(name, required);
+        const Field* s = raw(name, required);
         if (!s) return false;
         T v;
-        if (!parse(s->c_str(), v)) return false;
+        if (!parse(s->p, v)) return false;
         if (required && nonnegative && v < 0) v = 0;
         value = v;
         return true;
@@ -119,28 +178,45 @@ public:
     template <class T>
     bool get(const char* name, T& value, bool required = true, bool nonnegative = true)
     {
-        const std::string* s = raw_cached(name, required);
+        const Field* s = raw_cached(name, required);
         if (!s) return false;
         T v;
-        if (!parse(s->c_str(), v)) return false;
+        if (!parse(s->p, v)) return false;
         if (required && nonnegative && v < 0) v = 0;
         value = v;
         return true;
     }
     bool get(const char* name, std::string& value, bool required = true)
     {
-        const std::string* s = raw_cached(name, required);
+        const Field* s = raw_cached(name, required);
         if (!s) return false;
-        value = *s;
+        value.assign(s->p, (size_t)s->n);
         return true;
     }
     bool has(const char* name) const { return index_.count(name) != 0; }
 
 private:
-    std::ifstream in_;
+    struct Field { char* p; int n; }; // NUL-terminated view into buf_ (or into quoted_)
+    std::string buf_;
+    size_t pos_ = 0, end_ = 0;
+    bool open_ = false;
+    char empty_[1] = { 0 };
     std::map<std::string, int> index_;
-    std::vector<std::string> values_;
+    std::vector<Field> fields_;
+    std::vector<std::string> quoted_;
     std::vector<std::pair<const char*, int>> cache_; // literal address -> column index (-1: no such column); reset with the header
+
+    // std::getline over the buffer: false once the end of the file has been reached (the string is empty then)
+    bool getline_buf(std::string& s)
+    {
+        s.clear();
+        if (pos_ >= end_) return false;
+        const char* b = &buf_[pos_];
+        const char* e = (const char*)memchr(b, '\n', end_ + 1 - pos_);
+        s.assign(b, e);
+        pos_ = (size_t)(e - &buf_[0]) + 1;
+        return pos_ < end_ || true;
+    }
 
     // the stream extraction the reference's parser performs (operator>> of an istringstream), without the stream:
     // leading white space skipped, the longest valid prefix converted, failure when nothing converts
@@ -162,7 +238,7 @@ private:
         v = (int)x;
         return true;
     }
-    const std::string* raw_cached(const char* name, bool required)
+    const Field* raw_cached(const char* name, bool required)
     {
         int col = -2;
         for (const auto& c : cache_)
@@ -176,9 +252,9 @@ private:
             if (required) stop(std::string("Field ") + name + " in file " + file + " does not exist. Please check the file.");
             return nullptr;
         }
-        if (values_.empty() || col >= (int)values_.size()) return nullptr;
-        const std::string& s = values_[col];
-        return s.empty() ? nullptr : &s;
+        if (fields_.empty() || col >= (int)fields_.size()) return nullptr;
+        const Field& s = fields_[col];
+        return s.n == 0 ? nullptr : &s;
     }
 
     void set_header(const std::string& line)
@@ -192,16 +268,16 @@ private:
             index_[b == std::string::npos ? std::string() : names[i].substr(b)] = (int)i;
         }
     }
-    const std::string* raw(const std::string& name, bool required)
+    const Field* raw(const std::string& name, bool required)
     {
         auto it = index_.find(name);
         if (it == index_.end()) {
             if (required) stop("Field " + name + " in file " + file + " does not exist. Please check the file.");
             return nullptr;
         }
-        if (values_.empty() || it->second >= (int)values_.size()) return nullptr;
-        const std::string& s = values_[it->second];
-        return s.empty() ? nullptr : &s;
+        if (fields_.empty() || it->second >= (int)fields_.size()) return nullptr;
+        const Field& s = fields_[it->second];
+        return s.n == 0 ? nullptr : &s;
     }
     static std::vector<std::string> split(const std::string& line)
     {
@@ -482,8 +558,12 @@ void read_network(dtl_gmns& g)
             for (int at = 0; at < AT; ++at) n_toll[(size_t)tau * AT + at] = "VDF_toll" + g.agents[at].name + pid;
         }
         const std::string n_ref = "VDF_ref_link_volume" + std::to_string(g.periods[0].id);
-        p.open(g.dir + "/link.csv");
-        int type_warnings = 0;
+        // The rows of link.csv are independent of each other except for one thing (the first ten link types that [link_type]
+        // does not define are registered in row order), so the file is cut into slices of whole lines that worker threads parse
+        // into their own vectors, appended in slice order afterwards; a file with an unknown link type is re-read serially.
+        auto parse_rows = [&](Csv& p, dtl_gmns& out, std::vector<std::vector<PerPeriod>>& lp_out, std::map<int, LinkType>& link_types,
+                              bool serial, bool& unknown_type) {
+            int type_warnings = 0;
         while (p.read_record()) {
             long from_id = -1, to_id = -1;
             if (!p.get("from_node_id", from_id)) continue;
@@ -504,6 +584,7 @@ void read_network(dtl_gmns& g)
             int link_type_in = 2, link_type = 2; // CLink(): link_type 2, DTA.h:1105
             p.get("link_type", link_type_in, false);
             if (!link_types.count(link_type_in)) {
+                if (!serial) { unknown_type = true; return; } // registering a type depends on the row order: the caller re-reads serially
                 if (type_warnings < 10) { // the reference registers the unknown type (first ten only) but leaves the link at type 2
                     LinkType e; e.id = link_type_in;
                     link_types[link_type_in] = e;
@@ -578,14 +659,84 @@ void read_network(dtl_gmns& g)
             p.get("tmc", tmc, false);
             int tmc_cid = -1, tmc_seq = -1;
             if (!tmc.empty()) { tmc_cid = 1; tmc_seq = 1; p.get("tmc_corridor_id", tmc_cid, false); p.get("tmc_road_sequence", tmc_seq, false); }
-            g.link_from.push_back(from); g.link_to.push_back(to); g.link_tag.push_back(tag);
-            g.link_id.push_back(id); g.geometry.push_back(geometry); g.link_type_code.push_back(type_code); g.vdf_code.push_back(vdf_code);
-            g.tmc_code.push_back(tmc); g.tmc_corridor_name.push_back(tmc_name); g.tmc_corridor_id.push_back(tmc_cid);
-            g.tmc_road_sequence.push_back(tmc_seq); g.link_type.push_back(link_type); g.link_vdf_type.push_back(lt.vdf_type);
-            g.meso_link_id.push_back(meso >= 0 ? meso : -1);
-            g.free_speed.push_back(free_speed); g.cutoff_speed.push_back((float)cutoff); g.dist_km.push_back(length_m / 1000.0);
-            g.dist_mile.push_back(dist); g.fftt_min.push_back(length_m / 1609.0 / free_speed * 60); g.ref_volume.push_back(ref_vol);
-            lp.push_back(std::move(per));
+            out.link_from.push_back(from); out.link_to.push_back(to); out.link_tag.push_back(tag);
+            out.link_id.push_back(id); out.geometry.push_back(geometry); out.link_type_code.push_back(type_code); out.vdf_code.push_back(vdf_code);
+            out.tmc_code.push_back(tmc); out.tmc_corridor_name.push_back(tmc_name); out.tmc_corridor_id.push_back(tmc_cid);
+            out.tmc_road_sequence.push_back(tmc_seq); out.link_type.push_back(link_type); out.link_vdf_type.push_back(lt.vdf_type);
+            out.meso_link_id.push_back(meso >= 0 ? meso : -1);
+            out.free_speed.push_back(free_speed); out.cutoff_speed.push_back((float)cutoff); out.dist_km.push_back(length_m / 1000.0);
+            out.dist_mile.push_back(dist); out.fftt_min.push_back(length_m / 1609.0 / free_speed * 60); out.ref_volume.push_back(ref_vol);
+            lp_out.push_back(std::move(per));
+        }
+        };
+        auto append = [&](dtl_gmns& o, std::vector<std::vector<PerPeriod>>& lo) {
+#define APP(f) g.f.insert(g.f.end(), std::make_move_iterator(o.f.begin()), std::make_move_iterator(o.f.end()))
+            APP(link_from); APP(link_to); APP(link_tag); APP(link_id); APP(geometry); APP(link_type_code); APP(vdf_code); APP(tmc_code);
+            APP(tmc_corridor_name); APP(tmc_corridor_id); APP(tmc_road_sequence); APP(link_type); APP(link_vdf_type); APP(meso_link_id);
+            APP(free_speed); APP(cutoff_speed); APP(dist_km); APP(dist_mile); APP(fftt_min); APP(ref_volume);
+#undef APP
+            lp.insert(lp.end(), std::make_move_iterator(lo.begin()), std::make_move_iterator(lo.end()));
+        };
+        std::string text;
+        Csv::read_file(g.dir + "/link.csv", text);
+        const size_t h_end = std::min(text.find('\n'), text.size());
+        const std::string header = text.substr(0, h_end);
+        const char* body = text.data() + std::min(h_end + 1, text.size());
+        const char* body_end = text.data() + text.size();
+        {   // an empty line ends the reference's ReadRecord loop: nothing after it is read
+            const char* q = body;
+            while (q < body_end) {
+                const char* nl = (const char*)memchr(q, '\n', (size_t)(body_end - q));
+                if (nl == q) { body_end = q; break; }
+                if (!nl) break;
+                q = nl + 1;
+            }
+        }
+        unsigned n_thr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (const char* env = getenv("DTL_IO_THREADS")) n_thr = (unsigned)std::max(1, atoi(env));
+        if ((size_t)(body_end - body) < ((size_t)1 << 20)) n_thr = 1;
+        bool redo_serial = n_thr == 1;
+        if (n_thr > 1) {
+            std::vector<const char*> cut(n_thr + 1, body_end);
+            cut[0] = body;
+            for (unsigned i = 1; i < n_thr; ++i) {
+                const char* q = body + (size_t)(body_end - body) * i / n_thr;
+                q = std::max(q, cut[i - 1]);
+                const char* nl = (const char*)memchr(q, '\n', (size_t)(body_end - q));
+                cut[i] = nl ? nl + 1 : body_end;
+            }
+            std::vector<dtl_gmns> outs(n_thr);
+            std::vector<std::vector<std::vector<PerPeriod>>> lps(n_thr);
+            std::vector<std::string> errs(n_thr);
+            std::vector<char> unknown(n_thr, 0);
+            std::vector<std::thread> pool;
+            for (unsigned i = 0; i < n_thr; ++i)
+                pool.emplace_back([&, i]() {
+                    try {
+                        Csv p;
+                        p.open_text(cut[i], cut[i + 1], header, g.dir + "/link.csv");
+                        std::map<int, LinkType> types = link_types;
+                        bool unk = false;
+                        parse_rows(p, outs[i], lps[i], types, false, unk);
+                        unknown[i] = unk;
+                    } catch (const StopError& e) { errs[i] = e.what(); }
+                });
+            for (auto& t : pool) t.join();
+            for (unsigned i = 0; i < n_thr; ++i) {
+                if (!errs[i].empty()) stop(errs[i]);
+                redo_serial = redo_serial || unknown[i];
+            }
+            if (!redo_serial)
+                for (unsigned i = 0; i < n_thr; ++i) append(outs[i], lps[i]);
+        }
+        if (redo_serial) {
+            Csv p;
+            p.open_text(body, body_end, header, g.dir + "/link.csv");
+            dtl_gmns out;
+            std::vector<std::vector<PerPeriod>> lo;
+            bool unk = false;
+            parse_rows(p, out, lo, link_types, true, unk);
+            append(out, lo);
         }
     }
     // ---- link_qvdf.csv defaults, input.h:2153-2300 (no per-link overrides supported) ----

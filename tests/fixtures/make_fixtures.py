@@ -17,6 +17,10 @@
                  only way out is closed to one agent type (that agent type's tree stops at the first node), a zone without
                  any demand, parallel links between one node pair, demand rows that the reader must skip (o == d, unknown
                  zone, zero volume) and a volume below the 1e-6 back-trace threshold
+  toll_signal    AUTHORED: the edge_cases grid with per-agent-type tolls (VDF_toll{agent}1), link penalties (VDF_penalty1), values of
+                 time of 7.5 and 31.25 $/h (toll / VOT * 60 with a float VOT, routing.h:229-231, DTA.h:1157) and signalised links
+                 (cycle_length >= 1 with start/end green times and a saturation flow rate: the signal branch of the VDF with
+                 its float roundings, VDF.h:204-210)
   asu_qvdf       dataset/2_ASU/network (BASELINE.json configs[2]): link.csv verbatim; node.csv with AUTHORED zone ids
                  on every 27th node (the dataset ships without zones); AUTHORED demand and settings with
                  vdf_type=qvdf on every link type, so the queue VDF branch is exercised
@@ -148,6 +152,38 @@ def edge_cases():
         ",,1,0.1\n")
 
 
+def toll_signal():
+    """edge_cases' network and demand + toll / penalty / signal columns in link.csv and other values of time"""
+    src = os.path.join(HERE, "edge_cases")
+    dst = os.path.join(HERE, "toll_signal")
+    os.makedirs(dst, exist_ok=True)
+    for n in ("node.csv", "demand.csv"):
+        shutil.copy(os.path.join(src, n), os.path.join(dst, n))
+    with open(os.path.join(src, "link.csv")) as f:
+        rows = list(csv.reader(f))
+    hdr = rows[0] + ["VDF_tollauto1", "VDF_tolltruck1", "VDF_penalty1", "cycle_length", "start_green_time", "end_green_time",
+                     "saturation_flow_rate"]
+    out = [hdr]
+    for k, r in enumerate(rows[1:], 1):
+        toll_auto = f"{0.25 * (k % 4):.2f}" if k % 3 == 0 else "0"
+        toll_truck = f"{0.8 + 0.1 * (k % 5):.2f}" if k % 3 == 0 or k % 7 == 0 else "0"
+        penalty = f"{0.35 * (1 + k % 3):.2f}" if k % 5 == 0 else "0"
+        if k % 4 == 1:      # signalised: 90 s cycle, green from 5 s to 40-55 s
+            sig = ["90", "5", str(40 + 5 * (k % 4)), str(1700 + 50 * (k % 3))]
+        elif k % 11 == 0:   # a cycle without green times: the whole cycle counts as green, red time 1 s (input.h:3599-3605)
+            sig = ["60", "", "", "1900"]
+        else:
+            sig = ["", "", "", ""]
+        out.append(r + [toll_auto, toll_truck, penalty] + sig)
+    with open(os.path.join(dst, "link.csv"), "w") as f:
+        for r in out:
+            f.write(",".join(r) + "\n")
+    s = open(os.path.join(src, "settings.csv")).read()
+    s = s.replace(",auto,passenger,,10,0,1,1", ",auto,passenger,,7.5,0,1,1").replace(",truck,truck,,25,0,2.5,1", ",truck,truck,,31.25,0,2.5,1")
+    assert "7.5" in s and "31.25" in s
+    open(os.path.join(dst, "settings.csv"), "w").write(s)
+
+
 def asu_qvdf():
     src = "dataset/2_ASU/network"
     dst = os.path.join(HERE, "asu_qvdf")
@@ -204,5 +240,6 @@ if __name__ == "__main__":
     corridor_3()
     corridor_3_2p()
     edge_cases()
+    toll_signal()
     asu_qvdf()
     print("fixtures written under", HERE)

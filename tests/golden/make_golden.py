@@ -125,7 +125,8 @@ def reference_output_files(name, K, CU, multi_period=False):
 
 if __name__ == "__main__":
     for name_, K_, CU_, mp_ in (("two_corridor", 20, 0, False), ("corridor_3", 20, 20, False), ("edge_cases", 10, 4, False),
-                                ("corridor_3_2p", 12, 6, True)):
+                                ("corridor_3_2p", 12, 6, True), ("toll_signal", 10, 4, False), ("corridor_101", 20, 5, False),
+                                ("asu_qvdf", 20, 3, False)):
         reference_output_files(name_, K_, CU_, mp_)
     copy_lines(os.path.join(REF, "src/test_case_01_two_corridor/final_summary.csv"), 35, 58,
                os.path.join(OUT, "two_corridor_final_summary.txt"))
@@ -138,3 +139,4 @@ if __name__ == "__main__":
     # two demand periods + allowed_uses filter; needs the MAX_TIMEPERIODS = 4 build of the reference (oracle/build_ref.sh)
     run_case("corridor_3_2p", 12, 6, range(12), None, multi_period=True)
     run_case("edge_cases", 10, 4, range(10), None)        # authored corner cases: unreachable zones, closed links, skipped demand rows
+    run_case("toll_signal", 10, 4, range(10), None)       # authored: tolls, penalties, values of time, signalised links

@@ -205,7 +205,7 @@ def _sfx(tau):
 
 
 @pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_101", 20, 5), ("corridor_3", 20, 20),
-                                       ("corridor_3_2p", 12, 6), ("edge_cases", 10, 4), ("asu_qvdf", 20, 3)])
+                                       ("corridor_3_2p", 12, 6), ("edge_cases", 10, 4), ("toll_signal", 10, 4), ("asu_qvdf", 20, 3)])
 def test_assignment_matches_oracle_and_reference(D, problems, golden, oracle_mod, name, K, CU):
     p, g = problems(name), golden(name)
     o = oracle_mod.Oracle(p)

@@ -9,7 +9,7 @@ import pytest
 from conftest import FIXTURES
 
 
-@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "corridor_3_2p", "edge_cases", "asu_qvdf"])
+@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "corridor_3_2p", "edge_cases", "toll_signal", "asu_qvdf"])
 def test_reader_image_is_bit_identical_to_reference(problems, golden, name):
     p, g = problems(name), golden(name)
     N, L, Z, AT, T = (int(x) for x in g["meta"])

@@ -61,7 +61,7 @@ def _sfx(tau):
     return "" if tau == 0 else f":tau={tau}"
 
 
-@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "corridor_3_2p", "edge_cases", "asu_qvdf"])
+@pytest.mark.parametrize("name", ["two_corridor", "corridor_101", "corridor_3", "corridor_3_2p", "edge_cases", "toll_signal", "asu_qvdf"])
 def test_oracle_matches_reference_engine_state(problems, golden, oracle_mod, name):
     p, g = problems(name), golden(name)
     K, CU = int(g["K"]), int(g["CU"])

@@ -62,7 +62,8 @@ assert lib.network_assignment(1, int(sys.argv[2]), int(sys.argv[3]), 0, 0, 0, 4)
 """
 
 
-@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_3", 20, 20), ("edge_cases", 10, 4), ("corridor_3_2p", 12, 6)])
+@pytest.mark.parametrize("name,K,CU", [("two_corridor", 20, 0), ("corridor_3", 20, 20), ("edge_cases", 10, 4), ("corridor_3_2p", 12, 6),
+                                       ("toll_signal", 10, 4), ("asu_qvdf", 20, 3)])
 def test_output_files_match_the_reference(native, tmp_path, name, K, CU):
     """network_assignment(1, K, CU, 0, 0, 0, 4) through the C ABI, in the dataset directory, like a ctypes caller of the
     reference's library; the golden files come from the same call on the reference."""
