@@ -44,6 +44,7 @@ struct ForwardStar {
     int2* rin4 = nullptr;     // [N][4] the first four in-edges of every node {from node, forward edge index}, {-1, 0} padding;
                               // bit 30 of [v][3].y: the node has more than four (the rest is read through in_ptr / in_edges)
     int* link_edge = nullptr; // [L] forward edge index of a link, -1 when the agent type may not use it
+    const int* d_tail = nullptr; // [L] the node a link leaves in the search direction; null: link_from (forward search)
     double delta = 1.0;       // current label window of the near/far SSSP
     bool open_tags = false;   // a node that is not a hidden centroid row has a zone-tagged out-link
     std::vector<int> h_row_ptr;

@@ -108,6 +108,8 @@ struct dtl_engine {
     double* d_od_vol = nullptr;
 
     std::vector<ForwardStar> fs; // [AT*T], index at*T+tau
+    std::vector<ForwardStar> bstar; // [T] stars of the backward search from a destination (dtl_backward_trees), built on first use
+    int* d_link_to = nullptr;
     int** d_link_edge_ptrs = nullptr;
     Edge** d_edges_ptrs = nullptr;
     int *d_link_tag = nullptr, *d_link_from = nullptr;
@@ -301,16 +303,18 @@ struct FsHost {
     std::vector<int4> link_info;
 };
 
-void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int tau, FsHost& h)
+// The star of a search direction: `tail` / `head` are link_from / link_to for the forward search (routing.h:257-352) and
+// swapped for the backward search from a destination (routing.h:1009-1273: the in-links of a node in insertion order);
+// `allowed` may be null (every link), `tag` may be null (no zone-tagged links in this star); `fftt` seeds the label window.
+void build_star_host(dtl_engine* e, ForwardStar& f, const int* tail, const int* head, const int* tag, const unsigned char* allowed,
+                     const double* fftt, FsHost& h)
 {
-    ForwardStar& f = e->fs[fs_index(e, at, tau)];
     const int N = e->N, L = e->L;
-    const unsigned char* allowed = p->allowed + ((size_t)tau * e->AT + at) * L;
     std::vector<int>& row = h.row;
     std::vector<int>& link_edge = h.link_edge;
     row.assign(N + 1, 0); link_edge.assign(L, -1);
     for (int l = 0; l < L; ++l)
-        if (allowed[l]) row[p->link_from[l] + 1]++;
+        if (!allowed || allowed[l]) row[tail[l] + 1]++;
     for (int i = 0; i < N; ++i) row[i + 1] += row[i];
     const int E = row[N];
     std::vector<Edge>& edges = h.edges;
@@ -319,13 +323,13 @@ void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int ta
     double cost_sum = 0;
     long long cost_n = 0;
     for (int l = 0; l < L; ++l) // out-links of a node in insertion order == ascending link seq no
-        if (allowed[l]) {
-            const int ei = cur[p->link_from[l]]++;
-            edges[ei].to = p->link_to[l] | (p->link_tag[l] >= 0 ? 0x80000000 : 0);
+        if (!allowed || allowed[l]) {
+            const int ei = cur[tail[l]]++;
+            edges[ei].to = head[l] | (tag && tag[l] >= 0 ? 0x80000000 : 0);
             edges[ei].link = l;
             edges[ei].cost = 0.0;
             link_edge[l] = ei;
-            const double c = p->fftt[(size_t)tau * L + l];
+            const double c = fftt[l];
             if (c > 1e-3) { cost_sum += c; ++cost_n; }
         }
     std::vector<int>& in_ptr = h.in_ptr;
@@ -355,8 +359,8 @@ void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int ta
     }
     h.link_info.resize(std::max(L, 1));
     for (int l = 0; l < L; ++l) {
-        const int2 r = rows[p->link_to[l]];
-        h.link_info[l] = make_int4(p->link_from[l], r.x, r.y, 0);
+        const int2 r = rows[head[l]];
+        h.link_info[l] = make_int4(tail[l], r.x, r.y, 0);
     }
     h.rin4.assign((size_t)std::max(N, 1) * 4, make_int2(-1, 0));
     for (int v = 0; v < N; ++v) {
@@ -366,9 +370,14 @@ void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int ta
     }
 }
 
-int upload_forward_star(dtl_engine* e, int at, int tau, const FsHost& h)
+void build_forward_star_host(dtl_engine* e, const dtl_problem* p, int at, int tau, FsHost& h)
 {
-    ForwardStar& f = e->fs[fs_index(e, at, tau)];
+    build_star_host(e, e->fs[fs_index(e, at, tau)], p->link_from, p->link_to, p->link_tag, p->allowed + ((size_t)tau * e->AT + at) * e->L,
+                    p->fftt + (size_t)tau * e->L, h);
+}
+
+int upload_star(dtl_engine* e, ForwardStar& f, const FsHost& h)
+{
     if (e->upload(&f.row_ptr, h.row.data(), h.row.size())) return -1;
     if (e->upload(&f.rows, h.rows.data(), h.rows.size())) return -1;
     if (e->upload(&f.link_info, h.link_info.data(), h.link_info.size())) return -1;
@@ -379,6 +388,8 @@ int upload_forward_star(dtl_engine* e, int at, int tau, const FsHost& h)
     if (e->upload(&f.link_edge, h.link_edge.data(), h.link_edge.size())) return -1;
     return 0;
 }
+
+int upload_forward_star(dtl_engine* e, int at, int tau, const FsHost& h) { return upload_star(e, e->fs[fs_index(e, at, tau)], h); }
 
 // ---- multi-GPU failure handling -------------------------------------------------------------------------------------------
 // Raw NCCL has no watchdog: a rank that leaves the iteration early (a CUDA error, an exhausted column arena) would leave its
@@ -799,7 +810,7 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
 {
     SsspLaunch a{};
     a.N = e->N; a.row_ptr = f.row_ptr; a.rows = f.rows; a.link_info = f.link_info; a.edges = f.edges; a.in_ptr = f.in_ptr; a.in_edges = f.in_edges; a.rin4 = f.rin4;
-    a.link_tag = e->d_link_tag; a.link_from = e->d_link_from;
+    a.link_tag = e->d_link_tag; a.link_from = f.d_tail ? f.d_tail : e->d_link_from;
     a.n_tasks = n_tasks; a.n_run = n_tasks; a.task_list = nullptr; a.task_origin = d_origin; a.task_zone = d_zone;
     a.labels = e->d_labels + (size_t)tree_off * e->N; a.pred_link = e->d_pred + (size_t)tree_off * e->N;
     a.tie_nodes = e->d_tie_nodes;
@@ -1700,12 +1711,11 @@ int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, in
 }
 
 // ---- kernel-level entry points -----------------------------------------------------------------
-int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int* zones, int n, double* labels, int* pred_node,
-                   int* pred_link, int* tie_nodes, double stats[6])
+// n one-to-all trees on star `f` from the nodes `origin` (zones: the zone whose tagged out-links the tree may use, per tree);
+// h_tail[l] = the node a link leaves in the search direction (the predecessor node of a node reached over l)
+static int trees_on_star(dtl_engine* e, ForwardStar& f, const double* cost, const std::vector<int>& origin, const int* zones, int n,
+                         const std::vector<int>& h_tail, double* labels, int* pred_node, int* pred_link, int* tie_nodes, double stats[6])
 {
-    if (tau < 0 || tau >= e->T || at < 0 || at >= e->AT) { set_err("index out of range"); return -1; }
-    CK(cudaSetDevice(e->dev));
-    ForwardStar& f = e->fs[fs_index(e, at, tau)];
     const int N = e->N;
     if (cost) { // known-answer mode: caller-supplied generalized costs
         std::vector<Edge> ed(std::max(1, f.n_edges));
@@ -1719,11 +1729,6 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
         CK(cudaMemcpy(f.edges, ed.data(), sizeof(Edge) * f.n_edges, cudaMemcpyHostToDevice));
         const double factor = e->opt.sssp_delta_factor > 0 ? e->opt.sssp_delta_factor : 8.0;
         f.delta = factor * (cnt ? sum / (double)cnt : 1.0);
-    }
-    std::vector<int> origin(n);
-    for (int i = 0; i < n; ++i) {
-        if (zones[i] < 0 || zones[i] >= e->Z) { set_err("zone %d out of range", zones[i]); return -1; }
-        origin[i] = e->h_zone_centroid[zones[i]];
     }
     int *d_origin = nullptr, *d_zone = nullptr;
     CK(cudaMalloc(&d_origin, sizeof(int) * std::max(1, n)));
@@ -1756,7 +1761,7 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
             for (size_t i = 0; i < (size_t)nb * N; ++i) {
                 const int pl = hp[i];
                 if (pred_link) pred_link[(size_t)b0 * N + i] = pl;
-                if (pred_node) pred_node[(size_t)b0 * N + i] = pl >= 0 ? e->h_link_from[pl] : DTL_NO_PRED;
+                if (pred_node) pred_node[(size_t)b0 * N + i] = pl >= 0 ? h_tail[pl] : DTL_NO_PRED;
             }
         }
     }
@@ -1786,6 +1791,52 @@ int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int
     }
     e->trees_valid = false;
     return 0;
+}
+
+int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int* zones, int n, double* labels, int* pred_node,
+                   int* pred_link, int* tie_nodes, double stats[6])
+{
+    if (tau < 0 || tau >= e->T || at < 0 || at >= e->AT) { set_err("index out of range"); return -1; }
+    CK(cudaSetDevice(e->dev));
+    std::vector<int> origin(std::max(0, n));
+    for (int i = 0; i < n; ++i) {
+        if (zones[i] < 0 || zones[i] >= e->Z) { set_err("zone %d out of range", zones[i]); return -1; }
+        origin[i] = e->h_zone_centroid[zones[i]];
+    }
+    return trees_on_star(e, e->fs[fs_index(e, at, tau)], cost, origin, zones, n, e->h_link_from, labels, pred_node, pred_link, tie_nodes, stats);
+}
+
+// Backward one-to-all search from destination nodes: NetworkForSP::optimal_backward_label_correcting_from_destination
+// (routing.h:1009-1273).  The star of the search is every node's in-link list in insertion order
+// (g_node_vector[].m_incoming_link_seq_no_vector: no agent-type filter), without the links that carry an outgoing-connector
+// zone tag (routing.h:1104-1108) and without the links rt_allowed rules out (RT_allowed_use, routing.h:1119); the cost of a
+// link is avg_travel_time + RT_waiting_time (routing.h:1148).  The same K1 kernels run on it -- a label is now the least cost
+// from the node TO the destination, pred_node the next node downstream, pred_link the link to take.
+int dtl_backward_trees(dtl_engine* e, int tau, const double* cost, const unsigned char* rt_allowed, const int* dest_nodes, int n,
+                       double* labels, int* pred_node, int* pred_link, int* tie_nodes, double stats[6])
+{
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    const int L = e->L;
+    for (int i = 0; i < n; ++i)
+        if (dest_nodes[i] < 0 || dest_nodes[i] >= e->N) { set_err("destination node %d out of range", dest_nodes[i]); return -1; }
+    if (e->bstar.empty()) e->bstar.resize(e->T);
+    ForwardStar* f = &e->bstar[tau];
+    ForwardStar masked; // a caller-supplied RT_allowed_use mask changes the star: built for this call only
+    std::vector<double> h_tt(L);
+    CK(cudaMemcpy(h_tt.data(), e->ls.tt + (size_t)tau * L, sizeof(double) * L, cudaMemcpyDeviceToHost));
+    if (rt_allowed || !f->row_ptr) {
+        std::vector<unsigned char> keep(L);
+        for (int l = 0; l < L; ++l) keep[l] = e->h_link_tag[l] < 0 && (!rt_allowed || rt_allowed[l]);
+        if (rt_allowed) f = &masked;
+        FsHost h;
+        build_star_host(e, *f, e->h_link_to.data(), e->h_link_from.data(), nullptr, keep.data(), h_tt.data(), h);
+        if (upload_star(e, *f, h)) return -1; // (device memory of a masked star stays with the engine until dtl_destroy)
+        if (!e->d_link_to && e->upload(&e->d_link_to, e->h_link_to.data(), (size_t)L)) return -1;
+        f->d_tail = e->d_link_to;
+    }
+    std::vector<int> origin(dest_nodes, dest_nodes + std::max(0, n)), zones(std::max(1, n), 0);
+    return trees_on_star(e, *f, cost ? cost : h_tt.data(), origin, zones.data(), n, e->h_link_to, labels, pred_node, pred_link, tie_nodes, stats);
 }
 
 int dtl_vdf(dtl_engine* e, int tau, const double* volume, double* tt, double* doc, double* voc, double* P, double* vt2)

@@ -84,6 +84,7 @@ def load_library(path: str | None = None):
     L.dtl_num_column_links.argtypes = [vp]
     L.dtl_get_columns.argtypes = [vp] * 10
     L.dtl_sssp_trees.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp]
+    L.dtl_backward_trees.argtypes = [vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     L.dtl_vdf.argtypes = [vp, ci] + [vp] * 6
     L.dtl_scatter.argtypes = [vp, ci]
     L.dtl_get_tree.argtypes = [vp, ci, vp, vp, vp]
@@ -321,6 +322,21 @@ class Engine:
         stats = np.zeros(6)
         self._ck(self.lib.dtl_sssp_trees(self.h, at, tau, _ptr(cost_a), _ptr(zones), n, _ptr(lab), _ptr(pn), _ptr(pl),
                                          _ptr(ties), _ptr(stats)))
+        st = dict(ms=stats[0], counted_edges=stats[1], relaxations=stats[2], pops=stats[3], rounds=stats[4],
+                  replayed=stats[5])
+        return lab, pn, pl, ties[:n], st
+
+    def backward_trees(self, tau: int, dest_nodes, cost=None, rt_allowed=None):
+        """Backward search from destination nodes (``optimal_backward_label_correcting_from_destination``, ``routing.h:1009``)."""
+        dest = np.ascontiguousarray(dest_nodes, np.int32)
+        n, N = dest.size, self.problem.n_nodes
+        cost_a = None if cost is None else np.ascontiguousarray(cost, np.float64)
+        mask = None if rt_allowed is None else np.ascontiguousarray(rt_allowed, np.uint8)
+        lab = np.zeros((n, N)); pn = np.zeros((n, N), np.int32); pl = np.zeros((n, N), np.int32)
+        ties = np.zeros(max(n, 1), np.int32)
+        stats = np.zeros(6)
+        self._ck(self.lib.dtl_backward_trees(self.h, tau, _ptr(cost_a), _ptr(mask), _ptr(dest), n, _ptr(lab), _ptr(pn), _ptr(pl),
+                                             _ptr(ties), _ptr(stats)))
         st = dict(ms=stats[0], counted_edges=stats[1], relaxations=stats[2], pops=stats[3], rounds=stats[4],
                   replayed=stats[5])
         return lab, pn, pl, ties[:n], st

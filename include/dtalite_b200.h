@@ -152,6 +152,16 @@ int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, in
  * stats (may be NULL): { device ms, counted edges, relaxations, queue pops, rounds, replayed origins } */
 int dtl_sssp_trees(dtl_engine* e, int at, int tau, const double* cost, const int* zones, int n, double* labels,
                    int* pred_node, int* pred_link, int* tie_nodes, double stats[6]);
+/* Backward one-to-all search from n destination nodes; replaces
+ * NetworkForSP::optimal_backward_label_correcting_from_destination (routing.h:1009-1273), the search the reference's
+ * real-time-information layer runs per destination zone centroid (main_api.cpp:293-321, assignment.h:1386-1414).
+ * The star is every node's in-link list without the links that carry an outgoing-connector zone tag (routing.h:1104) and
+ * without the links whose rt_allowed[l] == 0 (RT_allowed_use, routing.h:1119; NULL = all allowed).  cost: [L] host
+ * array of avg_travel_time + RT_waiting_time (routing.h:1148), or NULL for the engine's current travel times of period tau.
+ * labels [n][N] = least cost from every node TO the destination, pred_node [n][N] = next node downstream,
+ * pred_link [n][N] = link to take; tie_nodes and stats as for dtl_sssp_trees. */
+int dtl_backward_trees(dtl_engine* e, int tau, const double* cost, const unsigned char* rt_allowed, const int* dest_nodes,
+                       int n, double* labels, int* pred_node, int* pred_link, int* tie_nodes, double stats[6]);
 /* Elementwise link performance; replaces CPeriod_VDF::calculate_travel_time_based_on_QVDF
  * (VDF.h:139) over all links of period tau for the given volumes [L]. */
 int dtl_vdf(dtl_engine* e, int tau, const double* volume, double* tt, double* doc, double* voc, double* P,

@@ -138,6 +138,8 @@ class Oracle:
         L.orc_sssp.restype = C.c_longlong
         L.orc_sssp.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
         L.orc_vdf_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_backward_sssp.restype = C.c_longlong
+        L.orc_backward_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         self.problem = problem
         self._keep = dict(problem.arrays)
         cp = _OrcProblem()
@@ -232,6 +234,14 @@ class Oracle:
         pops = self.lib.orc_sssp(C.byref(self._cp), _ptr(rp), _ptr(cl_), _ptr(ct_), _ptr(cost), int(origin_zone),
                                  _ptr(label), _ptr(pn), _ptr(pl), C.byref(relax))
         return label, pn, pl, int(pops), int(relax.value)
+
+    def backward_sssp(self, cost, dest_node: int, rt_allowed=None):
+        N = self.problem.n_nodes
+        cost = np.ascontiguousarray(cost, np.float64)
+        mask = None if rt_allowed is None else np.ascontiguousarray(rt_allowed, np.uint8)
+        label = np.zeros(N); pn = np.zeros(N, np.int32); pl = np.zeros(N, np.int32)
+        pops = self.lib.orc_backward_sssp(C.byref(self._cp), _ptr(cost), None if mask is None else _ptr(mask), int(dest_node), _ptr(label), _ptr(pn), _ptr(pl))
+        return label, pn, pl, int(pops)
 
     def vdf_link(self, tau: int, link: int, volume: float, want_speed: bool = False):
         out = _VdfOut()

@@ -208,6 +208,59 @@ long long orc_sssp(const orc_problem* p, const int* row_ptr, const int* col_link
     return pops;
 }
 
+/* NetworkForSP::optimal_backward_label_correcting_from_destination, routing.h:1009-1273: the same deque rule, scanning the
+ * in-links of the popped node (g_node_vector[].m_incoming_link_seq_no_vector: every link, in insertion order == ascending
+ * link seq no, no agent-type filter) */
+long long orc_backward_sssp(const orc_problem* p, const double* cost, const unsigned char* rt_allowed, int dest_node,
+                            double* label, int* pred_node, int* pred_link)
+{
+    const int N = p->n_nodes, L = p->n_links;
+    int* in_ptr = (int*)calloc((size_t)N + 1, sizeof(int));
+    int* in_link = (int*)malloc(sizeof(int) * (size_t)(L > 0 ? L : 1));
+    int* cursor = (int*)malloc(sizeof(int) * ((size_t)N + 1));
+    int* status = (int*)malloc(sizeof(int) * (size_t)N);
+    int* next = (int*)malloc(sizeof(int) * (size_t)N);
+    for (int l = 0; l < L; ++l) in_ptr[p->link_to[l] + 1]++;
+    for (int i = 0; i < N; ++i) in_ptr[i + 1] += in_ptr[i];
+    memcpy(cursor, in_ptr, sizeof(int) * ((size_t)N + 1));
+    for (int l = 0; l < L; ++l) in_link[cursor[p->link_to[l]]++] = l;
+    long long pops = 0;
+    for (int i = 0; i < N; ++i) {                                                         /* :1042-1051 */
+        status[i] = 0; label[i] = ORC_MAX_LABEL_COST; pred_link[i] = ORC_NO_PRED; pred_node[i] = ORC_NO_PRED;
+    }
+    label[dest_node] = 0.0;                                                               /* :1055 */
+    int front = dest_node, tail = dest_node;                                              /* :1064-1065 */
+    next[dest_node] = -1;
+    while (front != -1) {                                                                 /* :1074 */
+        int to = front;                                                                   /* :1077-1082 */
+        front = next[to];
+        next[to] = -1;
+        status[to] = 2;
+        ++pops;
+        for (int j = in_ptr[to]; j < in_ptr[to + 1]; ++j) {                               /* :1094 */
+            int l = in_link[j], from = p->link_from[l];
+            if (p->link_tag[l] >= 0) continue;                                            /* :1104-1108 */
+            if (rt_allowed && !rt_allowed[l]) continue;                                   /* :1119 */
+            double c = label[to] + cost[l];                                               /* :1148 */
+            if (c < label[from]) {                                                        /* :1162 */
+                label[from] = c; pred_node[from] = to; pred_link[from] = l;               /* :1170-1174 */
+                if (status[from] == 0) {                                                  /* :1183-1201 push back */
+                    if (front == -1) { front = from; tail = from; next[from] = -1; }
+                    else { next[tail] = from; next[from] = -1; tail = from; }
+                    status[from] = 1;
+                }
+                if (status[from] == 2) {                                                  /* :1203-1219 push front */
+                    if (front == -1) { next[from] = -1; front = from; tail = from; }
+                    else { next[from] = front; front = from; }
+                    status[from] = 1;
+                }
+            }
+        }
+    }
+    free(in_ptr); free(in_link); free(cursor); free(status); free(next);
+    return pops;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 static double** alloc2(int n, int m)
 {

@@ -91,6 +91,12 @@ void orc_forward_star(const orc_problem* p, int at, int tau, int* row_ptr /*[N+1
 long long orc_sssp(const orc_problem* p, const int* row_ptr, const int* col_link, const int* col_to,
                    const double* cost /*[L]*/, int origin_zone, double* label, int* pred_node, int* pred_link,
                    long long* relaxations);
+/* backward deque label-correcting search from a destination node over the in-link lists
+ * (NetworkForSP::optimal_backward_label_correcting_from_destination, routing.h:1009-1273).
+ * cost [L] = avg_travel_time + RT_waiting_time; rt_allowed [L] or NULL (RT_allowed_use).
+ * label = least cost to the destination, pred_node = next node downstream.  Returns the pops. */
+long long orc_backward_sssp(const orc_problem* p, const double* cost, const unsigned char* rt_allowed, int dest_node,
+                            double* label, int* pred_node, int* pred_link);
 /* VDF for one (link, period) slot given the volume to be assigned (VDF.h:139-367) */
 typedef struct orc_vdf_out {
     double tt, doc, voc, P, vt2, avg_queue_speed, avg_speed_bpr, Q_mu, Q_gamma, t0, t3, severe_congestion_P,

@@ -22,6 +22,8 @@
  *   DTL_TRACE_LIGHT=1        skip all per-iteration link-state / cost dumps (timing runs; tree dumps of
  *                            DTL_TRACE_TREES are still written, after the iteration's timed region)
  *   DTL_TRACE_NO_COLUMNS=1   skip the final dump of the column pool (timing runs: 1.4 GB on the config-5 grid)
+ *   DTL_TRACE_BACKWARD=n     also dump the backward tree (optimal_backward_label_correcting_from_destination) of every n-th
+ *                            zone centroid on the final travel times, per agent type and period
  *   DTL_TRACE_EDGE_ITERS=0   iterations that also run the Graph500-style edge count (default: iteration 0 only;
  *                            the count is a diagnostic walk over every tree and is kept out of timed iterations)
  */
@@ -392,6 +394,28 @@ int run_trace(int K, int CU, int B, const char* out_path)
     std::vector<double> fin = { final_sysTT };
     dump_f64("final_sysTT", fin);
     if (!(getenv("DTL_TRACE_NO_COLUMNS") && atoi(getenv("DTL_TRACE_NO_COLUMNS")) != 0)) dump_columns(":final");
+    if (getenv("DTL_TRACE_BACKWARD")) {
+        /* the real-time-information layer's per-destination search (main_api.cpp:293-321, assignment.h:1386-1414) on the final
+           travel times: one NetworkForSP per (agent type, period), destination = every n-th zone centroid */
+        const int bstride = std::max(1, atoi(getenv("DTL_TRACE_BACKWARD")));
+        const int Zn = (int)g_zone_vector.size();
+        for (int at = 0; at < (int)assignment.g_AgentTypeVector.size(); ++at)
+            for (int tau = 0; tau < (int)assignment.g_DemandPeriodVector.size(); ++tau) {
+                NetworkForSP* p = new NetworkForSP();
+                p->m_agent_type_no = at; p->m_tau = tau;
+                p->AllocateMemory(assignment.g_number_of_nodes, assignment.g_number_of_links, assignment.g_number_of_analysis_districts);
+                float now_min = 1000.0f;
+                for (int z = 0; z < Zn; z += bstride) {
+                    p->m_RT_dest_node = g_zone_vector[z].node_seq_no; p->m_RT_dest_zone = z;
+                    now_min += 10.0f + assignment.g_info_updating_freq_in_min; /* routing.h:1011: only runs when the clock has advanced */
+                    p->optimal_backward_label_correcting_from_destination(0, &assignment, now_min, z, p->m_RT_dest_node, -1, 0);
+                    std::string s = ":at=" + std::to_string(at) + ":tau=" + std::to_string(tau) + ":z=" + std::to_string(z);
+                    dump_rec("bw_label" + s, DT_F64, p->m_node_label_cost, N);
+                    dump_rec("bw_pred_node" + s, DT_I32, p->m_node_predecessor, N);
+                    dump_rec("bw_pred_link" + s, DT_I32, p->m_link_predecessor, N);
+                }
+            }
+    }
     assignment.summary_file.flush();
 
     double s_sssp = 0, s_bt = 0;

@@ -103,6 +103,33 @@ def run_case(name, K, CU, tree_iters, full_tree_zones, multi_period=False):
     print(name, "->", os.path.getsize(os.path.join(OUT, f"{name}_ref.npz")) // 1024, "KiB")
 
 
+def run_backward(cases):
+    """backward trees (optimal_backward_label_correcting_from_destination, routing.h:1009) of the reference on the final travel
+    times of a K-iteration run -> backward_ref.npz: the cost array, SHA-256 of every dumped tree, full arrays of a few"""
+    out = {}
+    for name, K, stride, full in cases:
+        src = os.path.join(ROOT, "tests", "fixtures", name)
+        with tempfile.TemporaryDirectory() as tmp:
+            for f in os.listdir(src):
+                shutil.copy(os.path.join(src, f), tmp)
+            B.run_reference(tmp, "trace", K, 0, 4, "dump.bin", env={"DTL_TRACE_BACKWARD": str(stride), "DTL_TRACE_NO_COLUMNS": "1"}, threads=4)
+            d = B.load_dump(os.path.join(tmp, "dump.bin"))
+        out[f"{name}:K"] = np.int32(K)
+        out[f"{name}:cost"] = d["tt:final:tau=0"]  # avg_travel_time after the final VDF pass; RT_waiting_time is 0 without the simulator
+        keys, shas = [], []
+        for key in sorted(k for k in d if k.startswith("bw_label:")):
+            tag = key[len("bw_label:"):]
+            keys.append(tag)
+            shas.append(sha(d["bw_label:" + tag]) + sha(d["bw_pred_link:" + tag]) + sha(d["bw_pred_node:" + tag]))
+            if int(tag.split("z=")[1]) in full and ":at=0:" in tag:
+                for part in ("label", "pred_link", "pred_node"):
+                    out[f"{name}:{part}:{tag}"] = d[f"bw_{part}:{tag}"]
+        out[f"{name}:keys"] = np.array(keys)
+        out[f"{name}:sha256"] = np.array(shas)
+    np.savez_compressed(os.path.join(OUT, "backward_ref.npz"), **out)
+    print("backward trees ->", os.path.getsize(os.path.join(OUT, "backward_ref.npz")) // 1024, "KiB")
+
+
 def reference_output_files(name, K, CU, multi_period=False):
     """link_performance.csv / route_assignment.csv as the reference's own network_assignment() writes them
     (harness mode "golden": the unmodified entry point, main_api.cpp:499) -> tests/golden/outputs/."""
@@ -124,6 +151,10 @@ def reference_output_files(name, K, CU, multi_period=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "backward":
+        run_backward((("two_corridor", 20, 1, (0, 1)), ("edge_cases", 10, 1, (0, 3)), ("corridor_101", 20, 3, (0, 45)),
+                      ("toll_signal", 10, 2, (2,))))
+        sys.exit(0)
     for name_, K_, CU_, mp_ in (("two_corridor", 20, 0, False), ("corridor_3", 20, 20, False), ("edge_cases", 10, 4, False),
                                 ("corridor_3_2p", 12, 6, True), ("toll_signal", 10, 4, False), ("corridor_101", 20, 5, False),
                                 ("asu_qvdf", 20, 3, False)):
