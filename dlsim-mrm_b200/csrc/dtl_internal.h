@@ -217,6 +217,8 @@ struct ScatterLaunch {
     unsigned long long* pce_fix;
     unsigned long long* person_fix; // may be null (skipped inside the CG loop)
     int decay_k;                    // <0: none
+    const unsigned char* decay_at;  // [AT] or null: the decay applies only to columns of agent types with a non-zero entry (SA
+                                    // stage: only users with real-time information are re-routed, assignment.h:150-176)
     unsigned long long* link_refs;  // counter
     int cell_stride;                // set by launch_scatter: warp w handles cell (w * cell_stride) % n_od
 };
@@ -234,6 +236,12 @@ struct PoolUpdateLaunch {
     int n;                 // column-pool iteration index
     double* od_sums;       // [n_od][4]: gap, cost, time, demand contributions
     double2* link_cost;    // [T*AT*L] workspace: {travel time, generalized first-order cost} per (tau, at, link)
+    // sensitivity-analysis stage (assignment.h:699-713, 828-846): flow only shifts in OD cells of agent types with real-time
+    // information that have a column over a link with a supply-side lane change
+    int sa;                          // 1: SA rules
+    const signed char* design_flag;  // [T*L] -1 = lanes changed by the scenario
+    const int* rt_info;              // [AT]
+    unsigned char* od_impact;        // [n_od] sticky flag of the cell
 };
 void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st);
 

@@ -108,6 +108,15 @@ struct dtl_engine {
     double* d_od_vol = nullptr;
 
     std::vector<ForwardStar> fs; // [AT*T], index at*T+tau
+    // sensitivity-analysis stage (dtl_sa_*)
+    std::vector<int> sa_rt_info;           // [AT] real_time_information of the agent types
+    std::vector<int> sa_tau, sa_link;      // supply-side lane changes
+    std::vector<double> sa_lanes;
+    bool sa_mode = false;                  // trees_and_columns only visits the agent types with real-time information
+    unsigned char *d_sa_decay_at = nullptr, *d_od_impact = nullptr;
+    signed char* d_design_flag = nullptr;
+    int* d_rt_info = nullptr;
+    std::vector<std::vector<double>> sa_hist_time, sa_hist_volume; // per SA column-pool iteration: path time / volume of every slot
     std::vector<ForwardStar> bstar; // [T] stars of the backward search from a destination (dtl_backward_trees), built on first use
     int* d_link_to = nullptr;
     int** d_link_edge_ptrs = nullptr;
@@ -474,7 +483,7 @@ int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_ove
     return 0;
 }
 
-int do_scatter(dtl_engine* e, int decay_k, bool person)
+int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false)
 {
     const size_t TL = (size_t)e->T * e->L;
     const int ph = e->phase_begin(1);
@@ -486,6 +495,7 @@ int do_scatter(dtl_engine* e, int decay_k, bool person)
     a.pce_uni = e->d_pce_uni; a.occ_uni = e->d_occ_uni;
     a.pce_fix = e->ls.pce_fix; a.person_fix = person ? e->ls.person_fix : nullptr;
     a.decay_k = decay_k; a.link_refs = e->d_counters + 0;
+    a.decay_at = sa ? e->d_sa_decay_at : nullptr;
     launch_scatter(a, e->st);
     e->phase_end(ph, 1);
     CK(cudaGetLastError());
@@ -1364,6 +1374,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         int t1 = t0;
         while (t1 < n_tasks && t1 - t0 < e->batch_tasks && fs_index(e, e->task_at[t1], e->task_tau[t1]) == fsi) ++t1;
         const int nb = t1 - t0;
+        if (e->sa_mode && e->sa_rt_info[e->task_at[t0]] != 1) { t0 = t1; continue; } // main_api.cpp:987-994
         const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
         // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept or
         // counted: both read the per-tree arrays)
@@ -1464,17 +1475,20 @@ int dtl_iteration(dtl_engine* e, int k, double row[5])
     return rc;
 }
 
-static int column_update_impl(dtl_engine* e, int n, double row[4])
+static int column_update_impl(dtl_engine* e, int n, double row[4], bool sa = false)
 {
     CK(cudaSetDevice(e->dev));
     const int ph7 = e->phase_begin(7);
-    if (do_scatter(e, -1, false)) return -1;                           // assignment.h:575
-    if (do_vdf(e, false, true, nullptr)) return -1;                    // assignment.h:593
+    // SA stage: the link state this call leaves is what the writers print after the stage, so person volumes and the detail
+    // outputs of the VDF are kept up to date as well
+    if (do_scatter(e, -1, sa, sa)) return -1;                          // assignment.h:575
+    if (do_vdf(e, sa, true, nullptr)) return -1;                       // assignment.h:593
     PoolUpdateLaunch a{};
     a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
     a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.od_vol = e->d_od_vol;
     a.tt = e->ls.tt; a.penalty = e->vp.penalty; a.toll = e->d_toll; a.vot = e->d_vot; a.n = n; a.od_sums = e->d_od_sums;
     a.link_cost = e->d_link_cost;
+    a.sa = sa ? 1 : 0; a.design_flag = e->d_design_flag; a.rt_info = e->d_rt_info; a.od_impact = e->d_od_impact;
     const int ph5 = e->phase_begin(5);
     launch_pool_update(a, e->st);
     for (int j = 0; j < 4; ++j) launch_sum(e->d_od_sums + j, e->n_cells, 4, e->d_scalars + 4 + j, e->st);
@@ -1502,6 +1516,102 @@ int dtl_column_update(dtl_engine* e, int n, double row[4])
     return rc;
 }
 
+// ---- sensitivity-analysis stage: main_api.cpp:771-1042 -------------------------------------------------------------------
+// What is covered: supply-side "sa" lane changes (scenario_API.h:152-160, applied at main_api.cpp:779-794), the column
+// re-generation loop that re-routes the agent types with real-time information (:864-1034: K4, K3 with the per-agent-type decay
+// rule, K1 + K2a for their origins only) and the column-pool iterations under the SA rules (:1040, assignment.h:643-846).
+// Not covered: dms scenario rows / information zones / g_column_pool_route_modification, demand-side scenario factors.
+static int sa_configure_impl(dtl_engine* e, const int* rt_info, int n_changes, const int* tau, const int* link, const double* lanes)
+{
+    CK(cudaSetDevice(e->dev));
+    e->sa_rt_info.assign(rt_info, rt_info + e->AT);
+    for (int i = 0; i < n_changes; ++i)
+        if (tau[i] < 0 || tau[i] >= e->T || link[i] < 0 || link[i] >= e->L) { set_err("lane change %d: period or link out of range", i); return -1; }
+    e->sa_tau.assign(tau, tau + n_changes); e->sa_link.assign(link, link + n_changes); e->sa_lanes.assign(lanes, lanes + n_changes);
+    const size_t TL = (size_t)e->T * e->L;
+    std::vector<signed char> flag(std::max<size_t>(1, TL), 0);
+    for (int i = 0; i < n_changes; ++i) flag[(size_t)tau[i] * e->L + link[i]] = -1;
+    std::vector<unsigned char> decay(std::max(1, e->AT));
+    for (int at = 0; at < e->AT; ++at) decay[at] = rt_info[at] == 1;
+    if (!e->d_design_flag) {
+        if (e->alloc(&e->d_design_flag, TL) || e->alloc(&e->d_sa_decay_at, (size_t)e->AT) || e->alloc(&e->d_rt_info, (size_t)e->AT) ||
+            e->alloc(&e->d_od_impact, (size_t)std::max(1, e->n_cells)))
+            return -1;
+    }
+    CK(cudaMemcpy(e->d_design_flag, flag.data(), TL, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_sa_decay_at, decay.data(), (size_t)e->AT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_rt_info, e->sa_rt_info.data(), sizeof(int) * e->AT, cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->d_od_impact, 0, (size_t)std::max(1, e->n_cells)));
+    e->sa_hist_time.clear(); e->sa_hist_volume.clear();
+    return 0;
+}
+
+static int sa_begin_impl(dtl_engine* e, double* sys_tt)
+{
+    CK(cudaSetDevice(e->dev));
+    if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
+    for (size_t i = 0; i < e->sa_link.size(); ++i) {                   // main_api.cpp:779-794
+        const size_t a = (size_t)e->sa_tau[i] * e->L + e->sa_link[i];
+        bool seen = false; // two rows for one (period, link): the flag is set once, the last row's lanes count
+        for (size_t j = i + 1; j < e->sa_link.size(); ++j) seen = seen || (e->sa_tau[j] == e->sa_tau[i] && e->sa_link[j] == e->sa_link[i]);
+        if (seen) continue;
+        double nl = 0, cap = 0;
+        CK(cudaMemcpy(&nl, e->vp.nlanes + a, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&cap, e->vp.cap + a, 8, cudaMemcpyDeviceToHost));
+        const float old_lanes = (float)nl;                              // :786
+        nl = (double)(float)e->sa_lanes[i];                             // :787 (sa_lanes_change is parsed as a float)
+        cap *= nl / std::max(0.00001, (double)old_lanes);               // :788
+        CK(cudaMemcpy(e->vp.nlanes + a, &nl, 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->vp.cap + a, &cap, 8, cudaMemcpyHostToDevice));
+        if (nl < 0.01) { const double f = 1440; CK(cudaMemcpy(e->vp.fftt + a, &f, 8, cudaMemcpyHostToDevice)); } // :789-790
+    }
+    if (do_vdf(e, false, true, nullptr)) return -1;                    // :857
+    CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    if (sync_stream(e)) return -1;
+    e->resolve_timing();
+    if (sys_tt) *sys_tt = e->h_scalars[0];
+    return 0;
+}
+
+static int sa_iteration_impl(dtl_engine* e, int it, double row[2])
+{
+    CK(cudaSetDevice(e->dev));
+    if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
+    const int ph7 = e->phase_begin(7);
+    // (person volumes and the detail outputs of the VDF are refreshed too: with S = 0 this is the state the writers print)
+    if (do_vdf(e, true, true, nullptr)) return -1;                     // main_api.cpp:897
+    if (do_scatter(e, it, true, true)) return -1;                      // :913
+    e->sa_mode = true;
+    const int rc = trees_and_columns(e, it, false);                    // :966-1018
+    e->sa_mode = false;
+    if (rc) return -1;
+    CK(cudaMemcpyAsync(e->h_scalars, e->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    e->phase_end(ph7, 0);
+    if (check_flags(e, true)) return -1;
+    e->resolve_timing();
+    if (row) {
+        const float denom = 1 > e->total_demand ? (float)1 : e->total_demand; // :1027
+        row[0] = e->h_scalars[0];
+        row[1] = e->h_scalars[0] / denom;
+    }
+    return 0;
+}
+
+static int sa_column_update_impl(dtl_engine* e, int n, double row[4])
+{
+    if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
+    if (column_update_impl(e, n, row, true)) return -1;
+    // path_time_per_iteration_SA_map / path_volume_per_iteration_SA_map (assignment.h:741, 896-900): what route_assignment.csv
+    // prints per SA iteration
+    const size_t s = (size_t)e->n_cells * e->pool.cap;
+    e->sa_hist_time.emplace_back(s); e->sa_hist_volume.emplace_back(s);
+    if (s) {
+        CK(cudaMemcpy(e->sa_hist_time.back().data(), e->pool.time, s * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(e->sa_hist_volume.back().data(), e->pool.volume, s * 8, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
 static int finalize_impl(dtl_engine* e, int K, double* sys_tt)
 {
     (void)K;
@@ -1522,6 +1632,28 @@ int dtl_finalize(dtl_engine* e, int K, double* sys_tt)
     return rc;
 }
 
+int dtl_sa_configure(dtl_engine* e, const int* rt_info, int n_changes, const int* sa_tau, const int* sa_link, const double* sa_lanes)
+{
+    return sa_configure_impl(e, rt_info, std::max(0, n_changes), sa_tau, sa_link, sa_lanes);
+}
+int dtl_sa_begin(dtl_engine* e, double* sys_tt)
+{
+    const int rc = sa_begin_impl(e, sys_tt);
+    if (rc) comm_abort(e);
+    return rc;
+}
+int dtl_sa_iteration(dtl_engine* e, int it, double row[2])
+{
+    const int rc = sa_iteration_impl(e, it, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
+int dtl_sa_column_update(dtl_engine* e, int n, double row[4])
+{
+    const int rc = sa_column_update_impl(e, n, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
 int dtl_run_assignment(dtl_engine* e, int K, int CU, double* iter_rows, double* cu_rows)
 {
     for (int k = 0; k < K; ++k) {
@@ -1703,6 +1835,39 @@ int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, in
             if (links) {
                 memcpy(links + l_out, arena.data() + h.offset[base + j], sizeof(int) * h.n_links[base + j]);
                 l_out += h.n_links[base + j];
+            }
+            ++c_out;
+        }
+    }
+    return 0;
+}
+
+// per-column records of the SA stage in dtl_get_columns order: od_impact = the cell's OD_impact_flag / at_od_impacted flag
+// (assignment.h:699-713), hist_time / hist_volume [n_iterations][n_columns] = path travel time / volume after each
+// dtl_sa_column_update (n_iterations = calls so far; may be NULL)
+int dtl_sa_get_columns(dtl_engine* e, unsigned char* od_impact, int* n_iterations, double* hist_time, double* hist_volume)
+{
+    CK(cudaSetDevice(e->dev));
+    PoolHost h;
+    if (pool_to_host(e, h)) return -1;
+    std::vector<unsigned char> imp(std::max(1, e->n_cells), 0);
+    if (e->d_od_impact) CK(cudaMemcpy(imp.data(), e->d_od_impact, (size_t)e->n_cells, cudaMemcpyDeviceToHost));
+    const size_t n_it = e->sa_hist_time.size();
+    if (n_iterations) *n_iterations = (int)n_it;
+    long long n_cols = 0;
+    for (int c = 0; c < e->n_cells; ++c) n_cols += h.count[c];
+    long long c_out = 0;
+    std::vector<int> order;
+    for (int c = 0; c < e->n_cells; ++c) {
+        const size_t base = (size_t)c * e->pool.cap;
+        order.resize(h.count[c]);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return h.node_sum[base + x] < h.node_sum[base + y]; });
+        for (int j : order) {
+            if (od_impact) od_impact[c_out] = imp[c];
+            for (size_t q = 0; q < n_it; ++q) {
+                if (hist_time) hist_time[q * n_cols + c_out] = e->sa_hist_time[q][base + j];
+                if (hist_volume) hist_volume[q * n_cols + c_out] = e->sa_hist_volume[q][base + j];
             }
             ++c_out;
         }

@@ -26,6 +26,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dtalite_b200.h"
@@ -373,6 +374,14 @@ struct dtl_gmns {
     std::vector<unsigned char> allowed;
     int path_output = 1;
     int sa_iterations = 0;
+    // supply_side_scenario.csv rows of type "sa" (scenario_API.h:152-160): lanes of (period, link) during the sensitivity analysis
+    std::vector<int> sa_tau, sa_link;
+    std::vector<double> sa_lanes;
+    std::vector<signed char> design_flag;  // [T*L] network_design_flag: -1 on the links of the sa rows
+    // link state recorded before the sensitivity-analysis stage (g_record_corridor_performance_summary(0), output.h:52-98):
+    // [T*L] vehicle volume, speed, DOC, P -- the *_before columns of link_performance.csv; empty = not recorded
+    std::vector<double> before_volume, before_speed, before_doc, before_P;
+    bool sa_stage = false;                 // the stage ran: per-column flags and per-iteration records are printed
 };
 
 namespace {
@@ -894,6 +903,44 @@ void bind_problem(dtl_gmns& g, int blocks)
     q.origin_demand = g.origin_demand.data();
 }
 
+// g_load_supply_side_scenario_file, scenario_API.h:53-190: rows of type "sa" change the lanes of a link for the
+// sensitivity-analysis stage; "dms" rows (information zones, route splicing) are not supported.
+void read_scenario(dtl_gmns& g)
+{
+    Csv p;
+    if (!p.open(g.dir + "/supply_side_scenario.csv")) return;
+    std::map<int, int> node_seq;
+    for (size_t i = 0; i < g.node_id.size(); ++i)
+        if (!node_seq.count(g.node_id[i])) node_seq[g.node_id[i]] = (int)i;
+    std::map<std::pair<int, int>, int> link_of; // m_to_node_2_link_seq_no_map: the last link between two nodes
+    for (size_t l = 0; l < g.link_from.size(); ++l) link_of[{ g.link_from[l], g.link_to[l] }] = (int)l;
+    while (p.read_record()) {
+        int from_id = 0, to_id = 0;
+        if (!p.get("from_node_id", from_id)) continue;
+        if (!p.get("to_node_id", to_id)) continue;
+        if (from_id == 0 && to_id == 0) continue;
+        auto fi = node_seq.find(from_id), ti = node_seq.find(to_id);
+        if (fi == node_seq.end() || ti == node_seq.end()) continue;
+        auto li = link_of.find({ fi->second, ti->second });
+        if (li == link_of.end()) continue;
+        std::string period, type;
+        p.get("demand_period", period, false);
+        int tau = 0;
+        for (size_t t = 0; t < g.periods.size(); ++t)
+            if (g.periods[t].name == period) tau = (int)t;
+        p.get("scenario_type", type, false);
+        if (type == "sa") {
+            float lanes = 0;
+            p.get("lanes", lanes, false);
+            g.sa_tau.push_back(tau); g.sa_link.push_back(li->second); g.sa_lanes.push_back(lanes);
+            if (g.design_flag.empty()) g.design_flag.assign(g.periods.size() * g.link_from.size(), 0);
+            g.design_flag[(size_t)tau * g.link_from.size() + li->second] = -1;
+        } else if (type == "dms") {
+            stop("supply_side_scenario.csv: scenario_type dms (information zones, route modification) is not supported");
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -917,6 +964,7 @@ dtl_gmns* dtl_gmns_read(const char* dir, int number_of_memory_blocks)
         read_demand(*g);
         phase("demand files");
         read_output_configuration(*g);
+        read_scenario(*g);
         bind_problem(*g, number_of_memory_blocks);
         phase("problem image");
     } catch (const StopError& e) {
@@ -930,6 +978,20 @@ dtl_gmns* dtl_gmns_read(const char* dir, int number_of_memory_blocks)
 const dtl_problem* dtl_gmns_problem(const dtl_gmns* g) { return g ? &g->prob : nullptr; }
 void dtl_gmns_free(dtl_gmns* g) { delete g; }
 const char* dtl_gmns_last_error(void) { return g_io_err.c_str(); }
+
+int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link, double* sa_lanes, int capacity)
+{
+    if (!g) return -1;
+    if (rt_info)
+        for (size_t at = 0; at < g->agents.size(); ++at) rt_info[at] = g->agents[at].rt_info;
+    const int n = (int)g->sa_link.size();
+    for (int i = 0; i < std::min(n, capacity); ++i) {
+        if (sa_tau) sa_tau[i] = g->sa_tau[i];
+        if (sa_link) sa_link[i] = g->sa_link[i];
+        if (sa_lanes) sa_lanes[i] = g->sa_lanes[i];
+    }
+    return n;
+}
 
 int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id)
 {
@@ -1057,8 +1119,13 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
     auto format_link = [&](int i, std::string& out) {
         if (g.link_type[i] == -1) return; // virtual connectors
         float total_vehicle_volume = 0;
-        for (int tau = 0; tau < T; ++tau) total_vehicle_volume += pce[tau][i] + g.preload[(size_t)tau * L + i];
-        if (total_vehicle_volume < 0.001) return;
+        int scenario_code_count = 0;
+        for (int tau = 0; tau < T; ++tau) {                           // output.h:587-598
+            if (!g.before_volume.empty()) total_vehicle_volume += g.before_volume[(size_t)tau * L + i];
+            total_vehicle_volume += pce[tau][i] + g.preload[(size_t)tau * L + i];
+            if (!g.design_flag.empty() && g.design_flag[(size_t)tau * L + i] == -1) scenario_code_count += 2;
+        }
+        if (scenario_code_count == 0 && total_vehicle_volume < 0.001) return;
         for (int tau = 0; tau < T; ++tau) {
             if (g.periods[tau].n_files == 0) continue;
             const size_t k = (size_t)tau * L + i;
@@ -1112,15 +1179,18 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                 }
                 appendf(out, "%.3f,", sum / std::max(1, cnt));
             }
-            appendf(out, "%s,", "");
-            // base case / after the sensitivity-analysis stage (g_record_corridor_performance_summary, output.h:60-98).  Without
-            // a supply-side scenario that stage only recomputes volumes and times from the final columns (main_api.cpp:772-1072),
-            // which is the state dtl_finalize leaves: both records are the final state and the differences are zero.
-            const double vb = vehicle_volume, sb = spd, db = doc[tau][i], pb = P[tau][i];
-            appendf(out, "%.3f,%.3f,%.3f,", vb, vb, vb - vb);
-            appendf(out, "%.3f,%.3f,%.3f,", sb, sb, sb - sb);
-            appendf(out, "%.3f,%.3f,%.3f,", db, db, db - db);
-            appendf(out, "%.3f,%.3f,%.3f,", pb, pb, pb - pb);
+            appendf(out, "%s,", !g.design_flag.empty() && g.design_flag[k] == -1 ? "sa" : "");
+            // base case / after the sensitivity-analysis stage (g_record_corridor_performance_summary, output.h:52-98): the
+            // "before" record is taken between the assignment and the stage (network_assignment below), the "after" record is
+            // the state being written.  Without the stage both are the final state and the differences are zero.
+            const double va = vehicle_volume, sa = spd, da = doc[tau][i], pa = P[tau][i];
+            const bool rec = !g.before_volume.empty();
+            const double vb = rec ? g.before_volume[k] : va, sb = rec ? g.before_speed[k] : sa, db = rec ? g.before_doc[k] : da,
+                         pb = rec ? g.before_P[k] : pa;
+            appendf(out, "%.3f,%.3f,%.3f,", vb, va, va - vb);
+            appendf(out, "%.3f,%.3f,%.3f,", sb, sa, sa - sb);
+            appendf(out, "%.3f,%.3f,%.3f,", db, da, da - db);
+            appendf(out, "%.3f,%.3f,%.3f,", pb, pa, pa - pb);
             appendf(out, "period-based\n");
         }
     };
@@ -1206,6 +1276,33 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         for (int it = 0; it <= g.sa_iterations; ++it) { snprintf(b, sizeof b, "%f,", -1.0); sa_cols += b; }
         for (int it = 0; it <= g.sa_iterations; ++it) { snprintf(b, sizeof b, "%f,", 0.0); sa_cols += b; }
     }
+    // Sensitivity-analysis records (only when the stage ran): per column the path travel time and volume after every SA column-pool
+    // iteration (path_time_per_iteration_SA_map / path_volume_per_iteration_SA_map, assignment.h:741, 896-900), the cell's
+    // at_od_impacted flag (assignment.h:699-713), and the flags g_classification_in_column_pool (assignment.h:930-1010) and
+    // g_column_pool_route_modification (assignment.h:1176-1180) derive from the links with a lane change.
+    int n_hist = 0;
+    std::vector<unsigned char> at_impact(od_index.size(), 0), path_impact(od_index.size(), 0);
+    std::vector<double> hist_time, hist_volume;
+    std::map<std::tuple<int, int, int>, int> od_impact_regular; // (o, d, tau) -> a cell of an agent type without information is impacted
+    if (g.sa_stage) {
+        if (dtl_sa_get_columns(e, at_impact.data(), &n_hist, nullptr, nullptr)) { fclose(f); return -1; }
+        hist_time.assign((size_t)std::max(1, n_hist) * od_index.size(), 0.0);
+        hist_volume.assign((size_t)std::max(1, n_hist) * od_index.size(), 0.0);
+        if (dtl_sa_get_columns(e, nullptr, nullptr, hist_time.data(), hist_volume.data())) { fclose(f); return -1; }
+        if (!g.design_flag.empty())
+            for (long long c = 0; c < nc; ++c) {
+                const int cell = od_index[c], at = g.od_at[cell], tau = g.od_tau[cell];
+                bool passes = false;
+                for (long long q = first_link[c]; q < first_link[c + 1] && !passes; ++q) passes = g.design_flag[(size_t)tau * L + links[q]] == -1;
+                if (!passes) continue;
+                if (g.agents[at].rt_info == 0) {
+                    path_impact[c] = 1;
+                    od_impact_regular[std::make_tuple(g.od_o[cell], g.od_d[cell], tau)] = 1;
+                } else if (g.agents[at].rt_info == 2 && !(volume[c] < 0.00001)) {
+                    path_impact[c] = 1;
+                }
+            }
+    }
     auto format_row = [&](long long oc, int count, std::string& out) {
         const int cell = od_index[oc];
         const int o = g.od_o[cell], d = g.od_d[cell], at = g.od_at[cell], tau = g.od_tau[cell];
@@ -1227,7 +1324,9 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         char b[1024];
         const int nb = snprintf(b, sizeof b, ",%d,%d,%d,%d,%d,%d->%d,%d,%d,%s,%s,%d,%s,%s,%.4f,%d,%d,%d,%d,%d,%.1f,%d,%.1f,%.4f,%.4f,%.4f,%.4f,%.4f,",
                                 count, g.zone_id[o], g.zone_id[d], o, d, g.zone_id[o], g.zone_id[d], seq[oc], seq[oc] + 1, "", "", 0,
-                                g.agents[at].name.c_str(), g.periods[tau].name.c_str(), vol, 0, 0, 0, 0, 0, path_toll, m_nodes - 2,
+                                g.agents[at].name.c_str(), g.periods[tau].name.c_str(), vol, 0, 0,
+                                g.sa_stage && od_impact_regular.count(std::make_tuple(o, d, tau)) ? 1 : 0, (int)at_impact[oc], (int)path_impact[oc],
+                                path_toll, m_nodes - 2,
                                 (double)path_tt, path_tt, path_tt_no_access, dist, dist_km, dist_ml);
         out.append(b, std::min<size_t>(nb > 0 ? nb : 0, sizeof b - 1));
         // nodes: origin centroid, then the head of every link; the virtual first/last connector is stripped
@@ -1235,7 +1334,21 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         out += ',';
         for (int q = 1; q + 1 < m_links; ++q) out += link_seq[pl[q]];
         out += ',';
-        out += sa_cols;
+        if (n_hist == 0) out += sa_cols;
+        else {                                                        // output.h:1367-1390
+            char hb[64];
+            for (int it = 0; it <= g.sa_iterations; ++it) {
+                snprintf(hb, sizeof hb, "%f,", it < n_hist ? hist_time[(size_t)it * od_index.size() + oc] : -1.0);
+                out += hb;
+            }
+            double prev = 0;
+            for (int it = 0; it <= g.sa_iterations; ++it) {
+                const double v = it < n_hist ? hist_volume[(size_t)it * od_index.size() + oc] : 0.0;
+                snprintf(hb, sizeof hb, "%f,", v - prev);
+                out += hb;
+                prev = v;
+            }
+        }
         if (volume[oc] >= 5 || count < 3000) {
             out += "\"LINESTRING (";
             for (int q = 0; q + 1 < m_links; ++q) {
@@ -1292,11 +1405,16 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     dtl_gmns* g = dtl_gmns_read(".", number_of_memory_blocks);
     if (!g) fail(g_io_err);
     const double s_read = since(t_start);
-    if (sensitivity_analysis_iterations > 0) fail("supply-side scenario analysis is outside the accelerated path (sensitivity_analysis_iterations must be 0)");
     g->sa_iterations = std::max(0, sensitivity_analysis_iterations);
+    const int S = g->sa_iterations;
+    // stage II (main_api.cpp:771-1042) always runs in the reference; it only changes anything when an agent type has real-time
+    // information, a supply-side scenario changes lanes, or SA iterations are asked for
+    bool any_rt = false;
+    for (const AgentType& a : g->agents) any_rt = any_rt || a.rt_info == 1;
+    const bool sa_stage = any_rt || !g->sa_link.empty() || S > 0;
     dtl_options opt;
     dtl_default_options(&opt);
-    opt.max_columns_per_od = std::max(4, column_generation_iterations + 4);
+    opt.max_columns_per_od = std::max(4, column_generation_iterations + 4) + (sa_stage ? S + 1 : 0);
     const auto t_create = clk::now();
     dtl_engine* e = dtl_create(dtl_gmns_problem(g), &opt);
     if (!e) fail(dtl_last_error());
@@ -1326,6 +1444,51 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     }
     double sys = 0;
     if (dtl_finalize(e, column_generation_iterations, &sys)) fail(dtl_last_error()); // main_api.cpp:748-759
+    if (sa_stage) {
+        const int L = g->prob.n_links, T = g->prob.n_periods, AT = g->prob.n_agent_types;
+        // the "before" record of every link (g_record_corridor_performance_summary(assignment, 0), main_api.cpp:776)
+        g->before_volume.assign((size_t)T * L, 0.0); g->before_speed.assign((size_t)T * L, 0.0);
+        g->before_doc.assign((size_t)T * L, 0.0); g->before_P.assign((size_t)T * L, 0.0);
+        std::vector<double> tt(L), pce(L), doc(L), P(L);
+        for (int tau = 0; tau < T; ++tau) {
+            if (dtl_get_link_state(e, tau, tt.data(), pce.data(), nullptr, nullptr, doc.data(), nullptr, P.data(), nullptr)) fail(dtl_last_error());
+            for (int i = 0; i < L; ++i) {
+                const size_t k = (size_t)tau * L + i;
+                float spd = g->free_speed[i];                          // output.h:67-69
+                if (tt[i] > 0.001f) spd = g->free_speed[i] / std::max(0.000001, tt[i]) * g->fftt[k];
+                const float vehicle_volume = pce[i] + g->preload[k];
+                g->before_volume[k] = vehicle_volume; g->before_speed[k] = spd; g->before_doc[k] = doc[i]; g->before_P[k] = P[i];
+            }
+        }
+        std::vector<int> rt(AT);
+        for (int at = 0; at < AT; ++at) rt[at] = g->agents[at].rt_info;
+        if (dtl_sa_configure(e, rt.data(), (int)g->sa_link.size(), g->sa_tau.data(), g->sa_link.data(), g->sa_lanes.data())) fail(dtl_last_error());
+        if (dtl_sa_begin(e, nullptr)) fail(dtl_last_error());          // main_api.cpp:779-794, 857
+        for (size_t i = 0; i < g->sa_link.size(); ++i) {               // the same lane changes on the host image the writers print
+            bool later = false;
+            for (size_t j = i + 1; j < g->sa_link.size(); ++j) later = later || (g->sa_tau[j] == g->sa_tau[i] && g->sa_link[j] == g->sa_link[i]);
+            if (later) continue;
+            const size_t k = (size_t)g->sa_tau[i] * L + g->sa_link[i];
+            const float old_lanes = (float)g->nlanes[k];
+            g->nlanes[k] = (double)(float)g->sa_lanes[i];
+            g->cap[k] *= g->nlanes[k] / std::max(0.00001, (double)old_lanes);
+            if (g->nlanes[k] < 0.01) g->fftt[k] = 1440;
+        }
+        for (int it = 0; it <= S; ++it) {                              // main_api.cpp:864-1034
+            double row[2];
+            if (dtl_sa_iteration(e, it, row)) fail(dtl_last_error());
+            if (it == 0) summary << "Sensitivity analysis stage" << std::endl << ",Iteration,Avg Travel Time(min)" << std::endl;
+            summary << it << "," << row[1] << "," << std::endl;
+        }
+        summary << "column updating" << std::endl;                    // main_api.cpp:1040, assignment.h:1057
+        for (int n = 0; n < S; ++n) {
+            double row[4];
+            if (dtl_sa_column_update(e, n, row)) fail(dtl_last_error());
+            summary << "column updating: iteration= " << n << ", avg travel time = " << row[0] << "(min), optimization obj = " << row[1]
+                    << ",Relative_gap=" << row[2] << " %" << std::endl;
+        }
+        g->sa_stage = true;
+    }
     const double s_loop = since(t_loop);
     const auto t_write = clk::now();
     if (dtl_gmns_write_outputs(g, e, ".")) fail(g_io_err.empty() ? dtl_last_error() : g_io_err);

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256, PERSON ? 3 : SCATTER_MIN_BLOCKS) scatter_
             vol_l = P.volume[base + j0 + lane];
             n_l = P.n_links[base + j0 + lane];
             off_l = P.offset[base + j0 + lane];
-            if (a.decay_k >= 0)                                      // assignment.h:182-186 MSA self-reduction
+            if (a.decay_k >= 0 && (!a.decay_at || a.decay_at[at]))   // assignment.h:182-186 MSA self-reduction (:150-176 in the SA stage)
                 P.volume[base + j0 + lane] = vol_l * ((double)a.decay_k / (double)(a.decay_k + 1));
         }
         // four columns per step: their link groups are requested together (a warp otherwise has ONE load in flight per column
@@ -344,10 +344,16 @@ __global__ void __launch_bounds__(128) pool_column_cost_kernel(PoolUpdateLaunch 
     const int n = P.n_links[slot];
     const int4* links = reinterpret_cast<const int4*>(P.arena + P.offset[slot]);
     double path_cost = 0, path_time = 0;
+    const bool watch = a.sa && a.rt_info[a.od_at[cell]] == 1;          // assignment.h:699-713
+    const signed char* flag = a.design_flag + (size_t)a.od_tau[cell] * a.L;
+    bool impacted = false;
     for (int q = 0; q < n; q += 4) {
         const int4 v = __ldg(&links[q >> 2]);
         const int ls[4] = { v.x, v.y, v.z, v.w };
         double2 c[4];
+        if (watch)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) impacted = impacted || (q + r < n && flag[ls[r]] == -1);
 #pragma unroll
         for (int r = 0; r < 4; ++r) // the four gathers of a 16-byte group of link ids are issued together
             c[r] = q + r < n ? __ldg(&lc[ls[r]]) : make_double2(0.0, 0.0);
@@ -357,6 +363,7 @@ __global__ void __launch_bounds__(128) pool_column_cost_kernel(PoolUpdateLaunch 
     }
     P.cost[slot] = path_cost;
     P.time[slot] = path_time;
+    if (impacted) a.od_impact[cell] = 1;
 }
 
 __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
@@ -407,6 +414,7 @@ __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
                 double shift = stepsz * mxd(0.0000, rel);                // :808
                 if (rel > 3 * 60) shift = v;                             // :811
                 if (shift > v) shift = v;                                // :816
+                if (a.sa && !a.od_impact[cell]) shift = 0;               // :828-846
                 const double nv = mxd(0.0, v - shift);                   // :851
                 P.volume[base + j] = nv;
                 switched += (v - nv);                                    // :859

@@ -86,6 +86,12 @@ def load_library(path: str | None = None):
     L.dtl_sssp_trees.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp]
     L.dtl_backward_trees.argtypes = [vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     L.dtl_vdf.argtypes = [vp, ci] + [vp] * 6
+    L.dtl_sa_configure.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.dtl_sa_begin.argtypes = [vp, vp]
+    L.dtl_sa_iteration.argtypes = [vp, ci, vp]
+    L.dtl_sa_column_update.argtypes = [vp, ci, vp]
+    L.dtl_sa_get_columns.argtypes = [vp, vp, vp, vp, vp]
+    L.dtl_gmns_scenario.argtypes = [vp, vp, vp, vp, vp, ci]
     L.dtl_scatter.argtypes = [vp, ci]
     L.dtl_get_tree.argtypes = [vp, ci, vp, vp, vp]
     L.dtl_get_timing.argtypes = [vp, vp, vp, ci]
@@ -164,6 +170,13 @@ def read_gmns(directory: str, memory_blocks: int = 4) -> Problem:
         zone_id = np.zeros(Z, np.int32)
         L.dtl_gmns_ids(h, _ptr(node_id), _ptr(zone_id))
         q.node_id, q.zone_id = node_id, zone_id
+        # sensitivity-analysis inputs: [agent_type] real_time_info and the "sa" rows of supply_side_scenario.csv
+        rt = np.zeros(max(A, 1), np.int32)
+        n_sa = L.dtl_gmns_scenario(h, _ptr(rt), None, None, None, 0)
+        sa_tau, sa_link, sa_lanes = np.zeros(max(n_sa, 1), np.int32), np.zeros(max(n_sa, 1), np.int32), np.zeros(max(n_sa, 1))
+        L.dtl_gmns_scenario(h, None, _ptr(sa_tau), _ptr(sa_link), _ptr(sa_lanes), n_sa)
+        q.rt_info = rt[:A].copy()
+        q.sa_changes = [(int(sa_tau[i]), int(sa_link[i]), float(sa_lanes[i])) for i in range(n_sa)]
         return q.finalize()
     finally:
         L.dtl_gmns_free(h)
@@ -340,6 +353,38 @@ class Engine:
         st = dict(ms=stats[0], counted_edges=stats[1], relaxations=stats[2], pops=stats[3], rounds=stats[4],
                   replayed=stats[5])
         return lab, pn, pl, ties[:n], st
+
+    # ---- sensitivity-analysis stage (main_api.cpp:771-1042) ----
+    def sa_configure(self, rt_info, changes=()):
+        rt = np.ascontiguousarray(rt_info, np.int32)
+        tau = np.ascontiguousarray([c[0] for c in changes] or [0], np.int32)
+        link = np.ascontiguousarray([c[1] for c in changes] or [0], np.int32)
+        lanes = np.ascontiguousarray([c[2] for c in changes] or [0.0], np.float64)
+        self._ck(self.lib.dtl_sa_configure(self.h, _ptr(rt), len(changes), _ptr(tau), _ptr(link), _ptr(lanes)))
+
+    def sa_begin(self) -> float:
+        s = C.c_double(0)
+        self._ck(self.lib.dtl_sa_begin(self.h, C.byref(s)))
+        return s.value
+
+    def sa_iteration(self, it: int) -> dict:
+        row = np.zeros(2)
+        self._ck(self.lib.dtl_sa_iteration(self.h, int(it), _ptr(row)))
+        return dict(sysTT=row[0], avg_tt=row[1])
+
+    def sa_column_update(self, n: int) -> dict:
+        row = np.zeros(4)
+        self._ck(self.lib.dtl_sa_column_update(self.h, int(n), _ptr(row)))
+        return dict(avg_tt=row[0], total_gap=row[1], rel_gap_pct=row[2], demand=row[3])
+
+    def sa_columns(self) -> dict:
+        n = int(self.lib.dtl_num_columns(self.h))
+        n_it = C.c_int(0)
+        imp = np.zeros(max(n, 1), np.uint8)
+        self._ck(self.lib.dtl_sa_get_columns(self.h, _ptr(imp), C.byref(n_it), None, None))
+        ht = np.zeros((max(n_it.value, 1), max(n, 1))); hv = np.zeros((max(n_it.value, 1), max(n, 1)))
+        self._ck(self.lib.dtl_sa_get_columns(self.h, None, None, _ptr(ht), _ptr(hv)))
+        return dict(od_impact=imp[:n], time=ht[:n_it.value, :n], volume=hv[:n_it.value, :n])
 
     def vdf(self, tau: int, volume) -> dict:
         L = self.problem.n_links

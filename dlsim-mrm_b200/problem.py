@@ -54,6 +54,9 @@ class Problem:
     # optional identifiers kept for writers / debugging (not used by the engine)
     node_id: np.ndarray | None = None
     zone_id: np.ndarray | None = None
+    # sensitivity-analysis inputs (not part of dtl_problem): real_time_info per agent type, "sa" lane changes (tau, link, lanes)
+    rt_info: np.ndarray | None = None
+    sa_changes: list | None = None
 
     def __getattr__(self, name):
         arrs = self.__dict__.get("arrays", {})

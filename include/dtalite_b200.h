@@ -142,6 +142,24 @@ long long dtl_num_column_links(dtl_engine* e);
 int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, int* n_links, int* n_nodes,
                     double* volume, double* cost, double* time, int* links);
 
+/* ---- sensitivity-analysis stage: stage II of network_assignment, main_api.cpp:771-1042 ----
+ * Covered: supply-side "sa" lane changes (scenario_API.h:152-160) and the re-routing of the agent types with real-time
+ * information; dms scenario rows / information zones / route modification and demand-side scenario factors are not.
+ * Call order: dtl_sa_configure (any time after dtl_create), the assignment (dtl_iteration..., dtl_finalize), dtl_sa_begin,
+ * dtl_sa_iteration(0..S), dtl_sa_column_update(0..S-1).
+ *   dtl_sa_configure     rt_info [AT] = real_time_information of the agent types (0 none, 1 real-time, 2 dms; DTA.h:486);
+ *                        n_changes lane changes (period, link, lanes)
+ *   dtl_sa_begin         applies the lane changes (main_api.cpp:779-794) and refreshes the travel times (:857)
+ *   dtl_sa_iteration     one column re-generation iteration (:864-1034): K4, K3 (only columns of agent types with real-time
+ *                        information are decayed, assignment.h:150-176), K1 + K2a for their origins; row = { sysTT, avg travel time }
+ *   dtl_sa_column_update one column-pool iteration under the SA rules (assignment.h:699-713, 828-846); row as dtl_column_update
+ *   dtl_sa_get_columns   per column, in dtl_get_columns order: the cell's impact flag and the per-iteration path time / volume */
+int dtl_sa_configure(dtl_engine* e, const int* rt_info, int n_changes, const int* sa_tau, const int* sa_link, const double* sa_lanes);
+int dtl_sa_begin(dtl_engine* e, double* sys_tt);
+int dtl_sa_iteration(dtl_engine* e, int it, double row[2]);
+int dtl_sa_column_update(dtl_engine* e, int n, double row[4]);
+int dtl_sa_get_columns(dtl_engine* e, unsigned char* od_impact, int* n_iterations, double* hist_time, double* hist_volume);
+
 /* ---- kernel-level entry points (known-answer tests, benchmarks) ---- */
 
 /* Batched many-source SSSP; replaces NetworkForSP::optimal_label_correcting (routing.h:633) for
@@ -199,6 +217,10 @@ void dtl_gmns_free(dtl_gmns* g);
 const char* dtl_gmns_last_error(void);
 /* identifiers for writers / tests: node_id [N], zone_id [Z], link_id strings are not exposed */
 int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id);
+/* what the sensitivity-analysis stage needs beyond dtl_problem: rt_info [AT] = [agent_type] real_time_info (input.h:2652-2658:
+ * 0 none, 1 real-time information, 2 dms) and the "sa" rows of supply_side_scenario.csv (scenario_API.h:152-160) as
+ * (period, link, lanes) triples.  Returns the number of sa rows (at most `capacity` are copied) or -1. */
+int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link, double* sa_lanes, int capacity);
 /* settings.csv [assignment] as flash_dta.cpp:171-242 derives them: out = { CG iterations, CU iterations,
  * ODME iterations, SA iterations, simulation iterations, memory blocks } */
 int dtl_gmns_assignment_settings(const char* dir, int out[6]);

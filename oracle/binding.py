@@ -138,6 +138,12 @@ class Oracle:
         L.orc_sssp.restype = C.c_longlong
         L.orc_sssp.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
         L.orc_vdf_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_sa_configure.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_sa_lane_change.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.orc_sa_begin.restype = C.c_double
+        L.orc_sa_begin.argtypes = [C.c_void_p]
+        L.orc_sa_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_sa_column_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_backward_sssp.restype = C.c_longlong
         L.orc_backward_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         self.problem = problem
@@ -235,6 +241,26 @@ class Oracle:
                                  _ptr(label), _ptr(pn), _ptr(pl), C.byref(relax))
         return label, pn, pl, int(pops), int(relax.value)
 
+    # ---- sensitivity-analysis stage (main_api.cpp:771-1042) ----
+    def sa_configure(self, rt_info, changes=()):
+        rt = np.ascontiguousarray(rt_info, np.int32)
+        self.lib.orc_sa_configure(self.h, _ptr(rt))
+        for tau, link, lanes in changes:
+            self.lib.orc_sa_lane_change(self.h, int(tau), int(link), float(lanes))
+
+    def sa_begin(self) -> float:
+        return float(self.lib.orc_sa_begin(self.h))
+
+    def sa_iteration(self, it: int):
+        row = np.zeros(3)
+        self.lib.orc_sa_iteration(self.h, int(it), _ptr(row))
+        return dict(sysTT=row[0], avg_tt=row[1], least=row[2])
+
+    def sa_column_update(self, n: int):
+        row = np.zeros(4)
+        self.lib.orc_sa_column_update(self.h, int(n), _ptr(row))
+        return dict(avg_tt=row[0], total_gap=row[1], rel_gap_pct=row[2], demand=row[3])
+
     def backward_sssp(self, cost, dest_node: int, rt_allowed=None):
         N = self.problem.n_nodes
         cost = np.ascontiguousarray(cost, np.float64)
@@ -254,7 +280,7 @@ class Oracle:
 
 
 def run_reference(workdir: str, mode: str, K: int, CU: int, B: int, out: str | None = None, env: dict | None = None,
-                  timeout: float = 3600, threads: int | None = None, multi_period: bool = False):
+                  timeout: float = 3600, threads: int | None = None, multi_period: bool = False, extra_args=None):
     """Run oracle/_ref/dtalite_ref in ``workdir`` (stdin closed: the reference blocks on getchar()
     when it stops on an error, utils.cpp:41-46).  Returns (stdout_text, timing_dict_or_None)."""
     import json
@@ -266,7 +292,7 @@ def run_reference(workdir: str, mode: str, K: int, CU: int, B: int, out: str | N
         e["OMP_NUM_THREADS"] = str(threads)
     if env:
         e.update(env)
-    cmd = [ref_bin, mode, str(K), str(CU), str(B)] + ([out] if out else [])
+    cmd = [ref_bin, mode, str(K), str(CU), str(B)] + ([out] if out else []) + list(extra_args or [])
     r = subprocess.run(cmd, cwd=workdir, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        env=e, timeout=timeout)
     text = r.stdout.decode(errors="replace")

@@ -55,6 +55,13 @@ struct orc_state {
     /* capture */
     double* cap_label;
     int *cap_pn, *cap_pl;
+    /* sensitivity-analysis stage (main_api.cpp:771-1042) */
+    orc_problem pm;            /* the problem with this state's own fftt / cap / nlanes (the sa lane change edits them) */
+    double *m_fftt, *m_cap, *m_nlanes;
+    int* rt_info;              /* [AT] real_time_information, DTA.h:486 */
+    double* sa_lanes;          /* [T][L] sa_lanes_change */
+    signed char* design_flag;  /* [T][L] network_design_flag, VDF.h:419 */
+    unsigned char* od_impact;  /* [n_od] OD_impact_flag && at_od_impacted_flag_map[at] of the cell (assignment.h:699-713) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -352,6 +359,16 @@ orc_state* orc_create(const orc_problem* p)
     s->tmp_links = (int*)malloc(sizeof(int) * (N + 1));
     s->n_out_unfiltered = (int*)calloc(N, sizeof(int));
     for (int l = 0; l < L; ++l) s->n_out_unfiltered[p->link_from[l]]++;
+    s->pm = *p;
+    const size_t TL = (size_t)T * L;
+    s->m_fftt = (double*)malloc(sizeof(double) * (TL + 1)); memcpy(s->m_fftt, p->fftt, sizeof(double) * TL);
+    s->m_cap = (double*)malloc(sizeof(double) * (TL + 1)); memcpy(s->m_cap, p->cap, sizeof(double) * TL);
+    s->m_nlanes = (double*)malloc(sizeof(double) * (TL + 1)); memcpy(s->m_nlanes, p->nlanes, sizeof(double) * TL);
+    s->pm.fftt = s->m_fftt; s->pm.cap = s->m_cap; s->pm.nlanes = s->m_nlanes;
+    s->rt_info = (int*)calloc(AT > 0 ? AT : 1, sizeof(int));
+    s->sa_lanes = (double*)calloc(TL + 1, sizeof(double));
+    s->design_flag = (signed char*)calloc(TL + 1, 1);
+    s->od_impact = (unsigned char*)calloc((size_t)(p->n_od > 0 ? p->n_od : 1), 1);
     return s;
 }
 
@@ -373,6 +390,7 @@ void orc_destroy(orc_state* s)
     free(s->pool); free(s->od_first);
     free(s->label); free(s->pred_node); free(s->pred_link); free(s->status); free(s->next);
     free(s->tmp_nodes); free(s->tmp_links); free(s->n_out_unfiltered);
+    free(s->m_fftt); free(s->m_cap); free(s->m_nlanes); free(s->rt_info); free(s->sa_lanes); free(s->design_flag); free(s->od_impact);
     free(s);
 }
 
@@ -393,7 +411,7 @@ void orc_set_tree_capture(orc_state* s, double* labels, int* pred_node, int* pre
  * main_api.cpp:404-435 */
 static double vdf_pass(orc_state* s)
 {
-    const orc_problem* p = s->p;
+    const orc_problem* p = &s->pm;
     for (int l = 0; l < s->L; ++l)
         for (int tau = 0; tau < s->T; ++tau) {
             double v = s->pce_vol[tau][l] + p->preload[(size_t)tau * s->L + l] + 0.0 /* sa_volume */; /* :413 */
@@ -409,7 +427,9 @@ static double vdf_pass(orc_state* s)
 }
 
 /* g_reset_and_update_link_volume_based_on_columns, assignment.h:53-195 (stage-1 branch) */
-static void scatter_pass(orc_state* s, int iteration_index, int self_reducing)
+static void scatter_pass_sa(orc_state* s, int iteration_index, int self_reducing, int sa);
+static void scatter_pass(orc_state* s, int iteration_index, int self_reducing) { scatter_pass_sa(s, iteration_index, self_reducing, 0); }
+static void scatter_pass_sa(orc_state* s, int iteration_index, int self_reducing, int sa)
 {
     const orc_problem* p = s->p;
     const int L = s->L, AT = s->AT, T = s->T;
@@ -435,6 +455,10 @@ static void scatter_pass(orc_state* s, int iteration_index, int self_reducing)
                     s->person_vol[tau][l] += f * occ[l];                                  /* :141 */
                     s->person_vol_at[tau * AT + at][l] += f * occ[l];                     /* :142 */
                 }
+                /* :150-176 in the SA stage only users with real-time information are re-routed: a column of an agent type
+                   without information keeps its volume, and so does a DMS user's whose origin is not an information zone
+                   (information zones come with dms scenario rows, which this restatement does not cover) */
+                if (sa && s->rt_info[at] != 1) continue;
                 if (self_reducing)                                                        /* :182-186 */
                     c->volume = c->volume * ((double)iteration_index / (double)(iteration_index + 1));
             }
@@ -518,13 +542,12 @@ static int task_index(const orc_state* s, int at, int tau, int zone)
     return -1;
 }
 
-/* one column-generation iteration, main_api.cpp:589-728 */
-void orc_iteration(orc_state* s, int k, double row[5])
+/* the shortest-path region of an iteration: main_api.cpp:667-697 (stage 1) and :966-1018 (SA stage: only the origins of agent
+ * types with real-time information are searched and back-traced, :987-994) */
+static double sp_region(orc_state* s, int k, int sa, long long* counted_out)
 {
     const orc_problem* p = s->p;
     const int N = s->N, L = s->L, AT = s->AT, T = s->T, B = p->memory_blocks;
-    double sysTT = vdf_pass(s);                                                           /* :606 */
-    scatter_pass(s, k, 1);                                                                /* :618 */
     double least_total = 0;
     long long counted_edges = 0;
     for (int pid = 0; pid < s->n_blocks; ++pid)                                           /* :667 */
@@ -537,6 +560,7 @@ void orc_iteration(orc_state* s, int k, double row[5])
             float vot = p->vot[n->at];
             for (int oi = 0; oi < n->n_origins; ++oi) {
                 int oz = n->zones[oi];
+                if (sa && s->rt_info[n->at] != 1) continue;                               /* main_api.cpp:987-994 */
                 /* UpdateGeneralizedLinkCost, routing.h:229-231 */
                 for (int l = 0; l < L; ++l) {
                     size_t a = ((size_t)n->tau * AT + n->at) * L + l;
@@ -561,18 +585,30 @@ void orc_iteration(orc_state* s, int k, double row[5])
                 least_total += backtrace(s, n->at, n->tau, oz, k);                        /* :687-693 */
             }
         }
+    if (counted_out) *counted_out = counted_edges;
+    return least_total;
+}
+
+/* one column-generation iteration, main_api.cpp:589-728 */
+void orc_iteration(orc_state* s, int k, double row[5])
+{
+    const orc_problem* p = s->p;
+    double sysTT = vdf_pass(s);                                                           /* :606 */
+    scatter_pass(s, k, 1);                                                                /* :618 */
+    long long counted_edges = 0;
+    double least_total = sp_region(s, k, 0, &counted_edges);
     double gap = (sysTT - least_total) / dmax(0.00001, least_total);                      /* :711 */
     float denom = 1 > p->total_demand_volume ? (float)1 : p->total_demand_volume;         /* :716 max(1, float) */
     row[0] = sysTT; row[1] = least_total; row[2] = gap; row[3] = sysTT / denom; row[4] = (double)counted_edges;
 }
 
 /* g_update_gradient_cost_and_assigned_flow_in_column_pool, assignment.h:565-928 (stage 2, no SA) */
-void orc_column_update(orc_state* s, int n, double row[4])
+static void column_update_impl(orc_state* s, int n, double row[4], int sa)
 {
     const orc_problem* p = s->p;
     const int L = s->L, AT = s->AT;
     double total_gap = 0, total_cost = 0, total_time = 0, total_demand = 0;
-    scatter_pass(s, n, 0);                                                                /* :575 */
+    scatter_pass_sa(s, n, 0, sa);                                                         /* :575 */
     vdf_pass(s);                                                                          /* :593 */
     for (int i = 0; i < p->n_od; ++i) {                                                   /* o, d, at, tau */
         orc_colvec* cv = &s->pool[i];
@@ -584,6 +620,9 @@ void orc_column_update(orc_state* s, int n, double row[4])
         for (int j = 0; j < cv->n; ++j) {                                                 /* :690-767 */
             orc_column* c = &cv->c[j];
             double path_toll = 0, path_cost = 0, path_time = 0;
+            if (sa && s->rt_info[at] == 1)                                                /* :699-713 */
+                for (int q = 0; q < c->n_links; ++q)
+                    if (s->design_flag[(size_t)tau * L + c->links[q]] == -1) { s->od_impact[i] = 1; break; }
             for (int q = 0; q < c->n_links; ++q) {
                 int l = c->links[q];
                 size_t a = ((size_t)tau * AT + at) * L + l;
@@ -611,6 +650,7 @@ void orc_column_update(orc_state* s, int n, double row[4])
                 double shift = step * dmax(0.0000, rel);                                  /* :808 */
                 if (rel > 3 * 60) shift = c->volume;                                      /* :811 */
                 if (shift > c->volume) shift = c->volume;                                 /* :816 */
+                if (sa && !s->od_impact[i]) shift = 0;                                    /* :828-846 */
                 c->volume = dmax(0.0, c->volume - shift);                                 /* :851 */
                 switched += (prev - c->volume);                                           /* :859 */
             }
@@ -625,6 +665,49 @@ void orc_column_update(orc_state* s, int n, double row[4])
     row[2] = total_gap * 100.0 / dmax(0.00001, total_cost);                               /* :911 */
     row[3] = total_demand;
 }
+
+void orc_column_update(orc_state* s, int n, double row[4]) { column_update_impl(s, n, row, 0); }
+
+/* ---- sensitivity-analysis stage, main_api.cpp:771-1042 (supply-side `sa` lane changes and re-routing of the agent types
+ * with real-time information; dms scenario rows / information zones / demand-side factors are not covered) ---- */
+void orc_sa_configure(orc_state* s, const int* rt_info) { memcpy(s->rt_info, rt_info, sizeof(int) * s->AT); }
+
+/* a supply_side_scenario.csv row of type "sa", scenario_API.h:152-160 */
+void orc_sa_lane_change(orc_state* s, int tau, int link, double lanes)
+{
+    s->sa_lanes[(size_t)tau * s->L + link] = (double)(float)lanes;
+    s->design_flag[(size_t)tau * s->L + link] = -1;
+}
+
+/* main_api.cpp:779-794 (the lane changes take effect) and :857 (VDF pass); returns the system travel time */
+double orc_sa_begin(orc_state* s)
+{
+    for (int l = 0; l < s->L; ++l)
+        for (int tau = 0; tau < s->T; ++tau) {
+            size_t a = (size_t)tau * s->L + l;
+            if (s->design_flag[a] != -1) continue;
+            double old_lanes = s->m_nlanes[a];                                            /* :786 float old_lanes */
+            float old_f = (float)old_lanes;
+            s->m_nlanes[a] = s->sa_lanes[a];                                              /* :787 */
+            s->m_cap[a] *= s->m_nlanes[a] / dmax(0.00001, (double)old_f);                 /* :788 */
+            if (s->m_nlanes[a] < 0.01) s->m_fftt[a] = 1440;                               /* :789-790 */
+        }
+    return vdf_pass(s);
+}
+
+/* one column re-generation iteration, main_api.cpp:864-1034.  row = { sysTT, avg travel time, least_total } */
+void orc_sa_iteration(orc_state* s, int it, double row[3])
+{
+    const orc_problem* p = s->p;
+    double sysTT = vdf_pass(s);                                                           /* :897 */
+    scatter_pass_sa(s, it, 1, 1);                                                         /* :913 */
+    double least_total = sp_region(s, it, 1, NULL);                                       /* :966-1018 */
+    float denom = 1 > p->total_demand_volume ? (float)1 : p->total_demand_volume;         /* :1027 */
+    row[0] = sysTT; row[1] = sysTT / denom; row[2] = least_total;
+}
+
+/* g_update_gradient_cost_and_assigned_flow_in_column_pool with the SA flag (main_api.cpp:1040, assignment.h:565-928) */
+void orc_sa_column_update(orc_state* s, int n, double row[4]) { column_update_impl(s, n, row, 1); }
 
 double orc_finalize(orc_state* s, int K)
 {

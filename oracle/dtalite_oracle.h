@@ -69,6 +69,15 @@ void orc_column_update(orc_state* s, int n, double row[4]);
 /* Final scatter (no decay) + VDF, main_api.cpp:748-759.  Returns system travel time. */
 double orc_finalize(orc_state* s, int K);
 
+/* ---- sensitivity-analysis stage (main_api.cpp:771-1042): supply-side "sa" lane changes + re-routing of the agent types
+ * with real-time information.  Call order: orc_sa_configure, orc_sa_lane_change*, [stage 1/2 + orc_finalize], orc_sa_begin,
+ * orc_sa_iteration(0..S), orc_sa_column_update(0..S-1). ---- */
+void orc_sa_configure(orc_state* s, const int* rt_info /* [AT] real_time_information: 0 none, 1 rt, 2 dms */);
+void orc_sa_lane_change(orc_state* s, int tau, int link, double lanes);
+double orc_sa_begin(orc_state* s);
+void orc_sa_iteration(orc_state* s, int it, double row[3]); /* { sysTT, avg travel time, least system TT of the re-routed origins } */
+void orc_sa_column_update(orc_state* s, int n, double row[4]);
+
 /* state read-back; per-period arrays of length L */
 void orc_get_link_state(const orc_state* s, int tau, double* tt, double* pce_volume, double* person_volume,
                         double* link_volume, double* doc, double* voc, double* P, double* vt2);

@@ -13,6 +13,9 @@
  * static-initialisation time, DTA.h:858-876):
  *   dtalite_ref golden K CU B      -> calls network_assignment(1,K,CU,0,0,0,B) verbatim
  *                                      (main_api.cpp:499) and exits.
+ *   dtalite_ref golden_dump K CU B out S -> network_assignment(1,K,CU,0,S,0,B) verbatim (S sensitivity-analysis iterations:
+ *                                      supply_side_scenario.csv lane changes, re-routing of the agent types with real-time
+ *                                      information, main_api.cpp:771-1042), then dumps the state it leaves in the globals.
  *   dtalite_ref trace  K CU B out  -> re-drives stage 1 / stage 2 of network_assignment
  *                                      (main_api.cpp:505-759) by calling the reference's own
  *                                      functions in the same order, dumping state to <out>.
@@ -440,7 +443,7 @@ int run_trace(int K, int CU, int B, const char* out_path)
 int main(int argc, char** argv)
 {
     if (argc < 5) {
-        fprintf(stderr, "usage: %s golden|trace K CU B [out.bin]\n", argv[0]);
+        fprintf(stderr, "usage: %s golden|trace|golden_dump K CU B [out.bin] [S]\n", argv[0]);
         return 2;
     }
     std::string mode = argv[1];
@@ -448,6 +451,58 @@ int main(int argc, char** argv)
     if (mode == "golden") {
         network_assignment(1, K, CU, 0, 0, 0, B);
         return 0;
+    }
+    if (mode == "golden_dump") {
+        /* the unmodified entry point with a sensitivity-analysis stage of S iterations (main_api.cpp:771-1042), then the state
+           it leaves in the reference's globals: dtalite_ref golden_dump K CU B out.bin S */
+        const char* out = argc >= 6 ? argv[5] : "ref_trace.bin";
+        const int S = argc >= 7 ? atoi(argv[6]) : 0;
+        network_assignment(1, K, CU, 0, S, 0, B);
+        g_dump = fopen(out, "wb");
+        if (!g_dump) { fprintf(stderr, "cannot open %s\n", out); return 2; }
+        dump_network();
+        const int L = (int)g_link_vector.size(), AT = (int)assignment.g_AgentTypeVector.size(), T = (int)assignment.g_DemandPeriodVector.size();
+        std::vector<int> rt(AT);
+        for (int at = 0; at < AT; ++at) rt[at] = assignment.g_AgentTypeVector[at].real_time_information;
+        dump_i32("agent_rt_info", rt);
+        for (int tau = 0; tau < T; ++tau) {
+            std::vector<int> flag(L);
+            std::vector<double> lanes(L), nl(L), cap(L), fftt(L);
+            for (int l = 0; l < L; ++l) {
+                const CPeriod_VDF& v = g_link_vector[l].VDF_period[tau];
+                flag[l] = v.network_design_flag; lanes[l] = v.sa_lanes_change; nl[l] = v.nlanes; cap[l] = v.BPR_period_capacity; fftt[l] = v.FFTT;
+            }
+            std::string sfx = ":tau=" + std::to_string(tau);
+            dump_i32("design_flag" + sfx, flag); dump_f64("sa_lanes" + sfx, lanes);
+            dump_f64("sa_nlanes_after" + sfx, nl); dump_f64("sa_cap_after" + sfx, cap); dump_f64("sa_fftt_after" + sfx, fftt);
+        }
+        dump_link_state(":final");
+        dump_columns(":final");
+        {   /* per-column and per-cell flags of the SA stage, in dump_columns order */
+            const int Z = (int)g_zone_vector.size();
+            std::vector<int> impacted, sa_flag, od_impact, at_impact;
+            for (int o = 0; o < Z; ++o) {
+                int so = g_zone_vector[o].sindex; if (so < 0) continue;
+                for (int d = 0; d < Z; ++d) {
+                    int sd = g_zone_vector[d].sindex; if (sd < 0) continue;
+                    for (int at = 0; at < AT; ++at) for (int tau = 0; tau < T; ++tau) {
+                        CColumnVector& cv = assignment.g_column_pool[so][sd][at][tau];
+                        if (!(cv.od_volume > 0)) continue;
+                        for (auto it = cv.path_node_sequence_map.begin(); it != cv.path_node_sequence_map.end(); ++it) {
+                            impacted.push_back(it->second.impacted_path_flag);
+                            sa_flag.push_back(it->second.b_sensitivity_analysis_flag ? 1 : 0);
+                            od_impact.push_back(cv.OD_impact_flag);
+                            at_impact.push_back(cv.at_od_impacted_flag_map.count(at) ? 1 : 0);
+                        }
+                    }
+                }
+            }
+            dump_i32("col_impacted_path_flag:final", impacted); dump_i32("col_sa_flag:final", sa_flag);
+            dump_i32("col_od_impact_flag:final", od_impact); dump_i32("col_at_od_impacted:final", at_impact);
+        }
+        fclose(g_dump); g_dump = nullptr;
+        fflush(NULL);
+        _exit(0);
     }
     if (mode == "trace") {
         const char* out = argc >= 6 ? argv[5] : "ref_trace.bin";

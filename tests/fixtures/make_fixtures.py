@@ -184,6 +184,27 @@ def toll_signal():
     open(os.path.join(dst, "settings.csv"), "w").write(s)
 
 
+def sa_corridor():
+    """3-corridor network with the agent types of dataset/4_101_corridor (p without information, rt with real-time information,
+    dms) and a supply_side_scenario.csv that takes lanes away from two motorway links: the sensitivity-analysis stage
+    (main_api.cpp:771-1042)"""
+    src = os.path.join(HERE, "corridor_3")
+    dst = os.path.join(HERE, "sa_corridor")
+    os.makedirs(dst, exist_ok=True)
+    for n in ("node.csv", "demand.csv", "link.csv"):
+        shutil.copy(os.path.join(src, n), os.path.join(dst, n))
+    s = open(os.path.join(src, "settings.csv")).read()
+    s = s.replace("[agent_type],agent_type,name,,vot,flow_type,pce,person_occupancy\n,sov,passenger,,10,0,1,1\n,hov,HOV2,,15,0,1,2\n",
+                  "[agent_type],agent_type,name,,vot,flow_type,pce,person_occupancy,real_time_info\n,p,passenger,,10,0,1,1,0\n"
+                  ",rt,passenger,,10,0,1,1,1\n,dms,passenger,,10,0,1,1,2\n")
+    s = s.replace(",1,demand.csv,,column,AM,sov,6.4\n,2,demand.csv,,column,AM,hov,1.6\n",
+                  ",1,demand.csv,,column,AM,p,4.8\n,2,demand.csv,,column,AM,rt,2.4\n,3,demand.csv,,column,AM,dms,0.8\n")
+    assert ",rt,passenger" in s and "AM,rt,2.4" in s
+    open(os.path.join(dst, "settings.csv"), "w").write(s)
+    with open(os.path.join(dst, "supply_side_scenario.csv"), "w") as f:
+        f.write("scenario_type,from_node_id,to_node_id,lanes,demand_period\nsa,4,5,0.5,AM\nsa,5,6,1,AM\n")
+
+
 def asu_qvdf():
     src = "dataset/2_ASU/network"
     dst = os.path.join(HERE, "asu_qvdf")
@@ -241,5 +262,6 @@ if __name__ == "__main__":
     corridor_3_2p()
     edge_cases()
     toll_signal()
+    sa_corridor()
     asu_qvdf()
     print("fixtures written under", HERE)

@@ -130,6 +130,53 @@ def run_backward(cases):
     print("backward trees ->", os.path.getsize(os.path.join(OUT, "backward_ref.npz")) // 1024, "KiB")
 
 
+def run_sa(cases):
+    """sensitivity-analysis stage (main_api.cpp:771-1042): the state the UNMODIFIED network_assignment(1, K, CU, 0, S, 0, 4)
+    leaves in the reference's globals (harness mode golden_dump) -> sa_ref.npz; its output files -> outputs/<name>_sa<S>_*.csv"""
+    out = {}
+    os.makedirs(os.path.join(OUT, "outputs"), exist_ok=True)
+    for name, K, CU, S in cases:
+        src = os.path.join(ROOT, "tests", "fixtures", name)
+        key = f"{name}:S={S}"
+        with tempfile.TemporaryDirectory() as tmp:
+            for f in os.listdir(src):
+                shutil.copy(os.path.join(src, f), tmp)
+            B.run_reference(tmp, "golden_dump", K, CU, 4, "dump.bin", threads=4, extra_args=[str(S)])
+            d = B.load_dump(os.path.join(tmp, "dump.bin"))
+            for f in ("link_performance", "route_assignment"):
+                if name == "corridor_101" and S > 0:
+                    continue  # 30 MB of text per run: the state of this case is pinned through sa_ref.npz only
+                dst = os.path.join(OUT, "outputs", f"{name}_sa{S}_{f}.csv")
+                shutil.copy(os.path.join(tmp, f + ".csv"), dst)
+                if os.path.getsize(dst) > (1 << 20):  # large files are committed gzip-compressed
+                    import gzip
+                    with open(dst, "rb") as fi, gzip.GzipFile(dst + ".gz", "wb", 9, mtime=0) as fo:
+                        shutil.copyfileobj(fi, fo)
+                    os.remove(dst)
+            with open(os.path.join(tmp, "final_summary.csv")) as f, open(os.path.join(OUT, "outputs", f"{name}_sa{S}_final_summary_rows.txt"), "w") as o:
+                seen = False
+                for line in f:
+                    seen = seen or line.startswith("Iteration, CPU Running Time")
+                    if seen and (line[:1].isdigit() and line.count(",") in (2, 4) or line.startswith("column updating: iteration")
+                                 or line.startswith("Sensitivity analysis stage")):
+                        o.write(line)
+        out[f"{key}:K_CU_S"] = np.array([K, CU, S], np.int32)
+        out[f"{key}:rt_info"] = d["agent_rt_info"]
+        for k2 in ("design_flag", "sa_lanes", "sa_nlanes_after", "sa_cap_after", "sa_fftt_after"):
+            out[f"{key}:{k2}"] = d[f"{k2}:tau=0"]
+        for k2 in ("tt", "pce_volume", "person_volume", "doc", "P"):
+            out[f"{key}:final_{k2}"] = d[f"{k2}:final:tau=0"]
+        for k2 in ("col_o", "col_d", "col_at", "col_node_sum", "col_seq", "col_nlinks", "col_volume", "col_cost", "col_time",
+                   "col_impacted_path_flag", "col_sa_flag", "col_od_impact_flag", "col_at_od_impacted"):
+            out[f"{key}:{k2}"] = d[k2 + ":final"]
+        links = d["col_links:final"]
+        if links.size <= 100000:
+            out[f"{key}:col_links"] = links
+        out[f"{key}:col_links_sha256"] = np.array(sha(links))
+    np.savez_compressed(os.path.join(OUT, "sa_ref.npz"), **out)
+    print("sensitivity analysis ->", os.path.getsize(os.path.join(OUT, "sa_ref.npz")) // 1024, "KiB")
+
+
 def reference_output_files(name, K, CU, multi_period=False):
     """link_performance.csv / route_assignment.csv as the reference's own network_assignment() writes them
     (harness mode "golden": the unmodified entry point, main_api.cpp:499) -> tests/golden/outputs/."""
@@ -151,13 +198,15 @@ def reference_output_files(name, K, CU, multi_period=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sa":
+        run_sa((("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0), ("corridor_101", 20, 5, 2)))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward":
         run_backward((("two_corridor", 20, 1, (0, 1)), ("edge_cases", 10, 1, (0, 3)), ("corridor_101", 20, 3, (0, 45)),
                       ("toll_signal", 10, 2, (2,))))
         sys.exit(0)
     for name_, K_, CU_, mp_ in (("two_corridor", 20, 0, False), ("corridor_3", 20, 20, False), ("edge_cases", 10, 4, False),
-                                ("corridor_3_2p", 12, 6, True), ("toll_signal", 10, 4, False), ("corridor_101", 20, 5, False),
-                                ("asu_qvdf", 20, 3, False)):
+                                ("corridor_3_2p", 12, 6, True), ("toll_signal", 10, 4, False), ("asu_qvdf", 20, 3, False)):
         reference_output_files(name_, K_, CU_, mp_)
     copy_lines(os.path.join(REF, "src/test_case_01_two_corridor/final_summary.csv"), 35, 58,
                os.path.join(OUT, "two_corridor_final_summary.txt"))
