@@ -245,6 +245,29 @@ struct PoolUpdateLaunch {
 };
 void launch_pool_update(const PoolUpdateLaunch& a, cudaStream_t st);
 
+// ODME (kernels_odme.cu): reference ODME.h:91-516, assignment.h:263-563
+struct OdmeLaunch {
+    int L, T, AT;
+    ColumnPool pool;
+    const int *od_at, *od_tau;
+    const double* tt;               // [T*L] current link travel times
+    const double* link_volume;      // [T*L] PCE volume + preload as the last VDF pass stored it
+    const float *at_pce, *at_occ;   // [AT] agent-type PCE / person occupancy (float)
+    unsigned long long* pce_fix;    // [T*L]
+    unsigned long long* person_fix; // [T*(1+AT)*L]
+    double* od_sums;                // [n_od][4] {demand, travel time, UE gap, -}
+    const double* obs;              // [T*L] observed count, 0 = none
+    const int* ub;                  // [T*L] upper_bound_flag
+    double* est_dev;                // [T*L] est_count_dev
+    int n_sensors;
+    const int* sensor_idx;          // [n_sensors] tau * L + link, in (link, tau) order
+    double* sensor_dev;             // [n_sensors] est_count_dev of the sensors, for the host-side summary row
+};
+void launch_odme_stats(const OdmeLaunch& a, cudaStream_t st);
+void launch_odme_scatter(const OdmeLaunch& a, cudaStream_t st);
+void launch_odme_dev(const OdmeLaunch& a, cudaStream_t st);
+void launch_odme_update(const OdmeLaunch& a, cudaStream_t st);
+
 // deterministic sum of n doubles with stride `stride` starting at `in` -> out[0]
 void launch_sum(const double* in, long long n, int stride, double* out, cudaStream_t st);
 

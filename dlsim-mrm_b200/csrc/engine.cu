@@ -117,6 +117,14 @@ struct dtl_engine {
     signed char* d_design_flag = nullptr;
     int* d_rt_info = nullptr;
     std::vector<std::vector<double>> sa_hist_time, sa_hist_volume; // per SA column-pool iteration: path time / volume of every slot
+    // ODME (dtl_odme_*)
+    bool odme_ready = false;
+    double *d_obs = nullptr, *d_est_dev = nullptr, *d_sensor_dev = nullptr;
+    int *d_ub = nullptr, *d_sensor_idx = nullptr;
+    float *d_at_pce = nullptr, *d_at_occ = nullptr;
+    std::vector<int> odme_sensor_idx;      // tau * L + link of the links with a count, in (link, tau) order
+    std::vector<double> odme_obs;          // [T*L]
+    std::vector<int> odme_ub;              // [T*L]
     std::vector<ForwardStar> bstar; // [T] stars of the backward search from a destination (dtl_backward_trees), built on first use
     int* d_link_to = nullptr;
     int** d_link_edge_ptrs = nullptr;
@@ -1612,6 +1620,127 @@ static int sa_column_update_impl(dtl_engine* e, int n, double row[4])
     return 0;
 }
 
+// ---- ODME: Assignment::Demand_ODME, ODME.h:91-516 ------------------------------------------------------------------------
+static OdmeLaunch make_odme_launch(dtl_engine* e)
+{
+    OdmeLaunch a{};
+    a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool; a.od_at = e->d_od_at; a.od_tau = e->d_od_tau;
+    a.tt = e->ls.tt; a.link_volume = e->ls.link_volume; a.at_pce = e->d_at_pce; a.at_occ = e->d_at_occ;
+    a.pce_fix = e->ls.pce_fix; a.person_fix = e->ls.person_fix; a.od_sums = e->d_od_sums;
+    a.obs = e->d_obs; a.ub = e->d_ub; a.est_dev = e->d_est_dev;
+    a.n_sensors = (int)e->odme_sensor_idx.size(); a.sensor_idx = e->d_sensor_idx; a.sensor_dev = e->d_sensor_dev;
+    return a;
+}
+
+static int odme_configure_impl(dtl_engine* e, const float* at_pce, const float* at_occ, int n, const int* tau, const int* link,
+                               const float* count, const int* ub)
+{
+    CK(cudaSetDevice(e->dev));
+    const size_t TL = (size_t)e->T * e->L;
+    e->odme_obs.assign(std::max<size_t>(1, TL), 0.0);
+    e->odme_ub.assign(std::max<size_t>(1, TL), 1);                     // CPeriod_VDF(): upper_bound_flag 1, VDF.h:60
+    for (int i = 0; i < n; ++i) {                                      // ODME.h:156-175, rows in file order
+        if (tau[i] < 0 || tau[i] >= e->T || link[i] < 0 || link[i] >= e->L) { set_err("measurement %d: period or link out of range", i); return -1; }
+        const size_t a = (size_t)tau[i] * e->L + link[i];
+        if (e->odme_obs[a] >= 1) {
+            if (ub[i] == 0) { e->odme_obs[a] = count[i]; e->odme_ub[a] = ub[i]; } // an actual count overwrites, an upper bound does not
+        } else {
+            e->odme_obs[a] = count[i]; e->odme_ub[a] = ub[i];
+        }
+    }
+    e->odme_sensor_idx.clear();
+    for (int l = 0; l < e->L; ++l)                                     // the order of the summary sums, assignment.h:465-469
+        for (int t = 0; t < e->T; ++t)
+            if (e->odme_obs[(size_t)t * e->L + l] >= 1) e->odme_sensor_idx.push_back(t * e->L + l);
+    if (!e->d_obs) {
+        if (e->alloc(&e->d_obs, TL) || e->alloc(&e->d_est_dev, TL) || e->alloc(&e->d_ub, TL) || e->alloc(&e->d_at_pce, (size_t)e->AT) ||
+            e->alloc(&e->d_at_occ, (size_t)e->AT))
+            return -1;
+    }
+    if (e->alloc(&e->d_sensor_idx, e->odme_sensor_idx.size()) || e->alloc(&e->d_sensor_dev, e->odme_sensor_idx.size())) return -1;
+    CK(cudaMemcpy(e->d_obs, e->odme_obs.data(), TL * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_ub, e->odme_ub.data(), TL * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->d_est_dev, 0, TL * 8));
+    CK(cudaMemcpy(e->d_at_pce, at_pce, sizeof(float) * e->AT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_at_occ, at_occ, sizeof(float) * e->AT, cudaMemcpyHostToDevice));
+    if (!e->odme_sensor_idx.empty())
+        CK(cudaMemcpy(e->d_sensor_idx, e->odme_sensor_idx.data(), sizeof(int) * e->odme_sensor_idx.size(), cudaMemcpyHostToDevice));
+    e->odme_ready = true;
+    return 0;
+}
+
+// g_reset_and_update_link_volume_based_on_ODME_columns, assignment.h:263-563
+static int odme_scatter_impl(dtl_engine* e, int s, double row[8])
+{
+    (void)s;
+    CK(cudaSetDevice(e->dev));
+    if (!e->odme_ready) { set_err("dtl_odme_configure has not been called"); return -1; }
+    const size_t TL = (size_t)e->T * e->L;
+    const OdmeLaunch a = make_odme_launch(e);
+    const int ph5 = e->phase_begin(5);
+    launch_odme_stats(a, e->st);                                       // on the link times of the previous pass (:378-430)
+    for (int j = 0; j < 3; ++j) launch_sum(e->d_od_sums + j, e->n_cells, 4, e->d_scalars + 4 + j, e->st);
+    e->phase_end(ph5, 5);
+    CK(cudaGetLastError());
+    if (all_reduce(e, e->d_scalars + 4, 3, ncclFloat64)) return -1;
+    const int ph1 = e->phase_begin(1);
+    CK(cudaMemsetAsync(e->ls.pce_fix, 0, TL * sizeof(unsigned long long), e->st));
+    CK(cudaMemsetAsync(e->ls.person_fix, 0, TL * (1 + e->AT) * sizeof(unsigned long long), e->st));
+    launch_odme_scatter(a, e->st);                                     // :433-457
+    e->phase_end(ph1, 1);
+    CK(cudaGetLastError());
+    if (all_reduce(e, e->ls.pce_fix, TL, ncclUint64)) return -1;
+    if (all_reduce(e, e->ls.person_fix, TL * (1 + e->AT), ncclUint64)) return -1;
+    if (do_vdf(e, true, true, nullptr)) return -1;                     // :467
+    launch_odme_dev(a, e->st);                                         // :476
+    CK(cudaGetLastError());
+    const size_t ns = e->odme_sensor_idx.size();
+    std::vector<double> dev(std::max<size_t>(1, ns));
+    if (ns) CK(cudaMemcpyAsync(dev.data(), e->d_sensor_dev, ns * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(e->h_scalars + 4, e->d_scalars + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+    if (sync_stream(e)) return -1;
+    e->resolve_timing();
+    // the summary sums of the reference: float accumulators, links in ascending order (:465-515)
+    float total_gap = 0, sub_link = 0, sub_system = 0;
+    int n_links = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        const int idx = e->odme_sensor_idx[i];
+        const double d = dev[i], obs = e->odme_obs[idx];
+        if (e->odme_ub[idx] == 0 || d > 0) {
+            total_gap += abs((int)d);                                  // :491: abs() binds to the int overload in the reference
+            sub_link += fabs(d / obs);
+            sub_system += d / obs;
+        }
+        n_links += 1;
+    }
+    if (row) {
+        const double demand = e->h_scalars[4], time = e->h_scalars[5], ue = e->h_scalars[6];
+        const int denom = std::max(1, n_links);
+        row[0] = sub_link / denom;                                     // :560
+        row[1] = sub_system / denom;                                   // :561
+        row[2] = total_gap / denom;
+        row[3] = time / std::max(0.1, demand);
+        row[4] = ue / std::max(0.00001, demand);
+        row[5] = ue / std::max(0.00001, time) * 100;
+        row[6] = demand;
+        row[7] = n_links;
+    }
+    return 0;
+}
+
+static int odme_update_impl(dtl_engine* e)
+{
+    CK(cudaSetDevice(e->dev));
+    if (!e->odme_ready) { set_err("dtl_odme_configure has not been called"); return -1; }
+    const int ph5 = e->phase_begin(5);
+    launch_odme_update(make_odme_launch(e), e->st);                    // ODME.h:262-488
+    e->phase_end(ph5, 1);
+    CK(cudaGetLastError());
+    if (sync_stream(e)) return -1;
+    e->resolve_timing();
+    return 0;
+}
+
 static int finalize_impl(dtl_engine* e, int K, double* sys_tt)
 {
     (void)K;
@@ -1630,6 +1759,59 @@ int dtl_finalize(dtl_engine* e, int K, double* sys_tt)
     const int rc = finalize_impl(e, K, sys_tt);
     if (rc) comm_abort(e);
     return rc;
+}
+
+int dtl_odme_configure(dtl_engine* e, const float* at_pce, const float* at_occ, int n, const int* tau, const int* link, const float* count,
+                       const int* upper_bound_flag)
+{
+    return odme_configure_impl(e, at_pce, at_occ, std::max(0, n), tau, link, count, upper_bound_flag);
+}
+int dtl_odme_scatter(dtl_engine* e, int s, double row[8])
+{
+    const int rc = odme_scatter_impl(e, s, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
+int dtl_odme_update(dtl_engine* e)
+{
+    const int rc = odme_update_impl(e);
+    if (rc) comm_abort(e);
+    return rc;
+}
+// the ODME loop of the reference (ODME.h:240-260, 490-512): scatter, stop when the link MAPE has grown by more than 0.01 after
+// five iterations, path-flow step; one more scatter at the end.  rows (may be NULL): [n_iterations + 1][8], the last row is
+// the closing scatter; *n_done = iterations whose path-flow step ran
+int dtl_odme_run(dtl_engine* e, int n_iterations, double* rows, int* n_done)
+{
+    double prev_gap = 9999999;
+    int done = 0;
+    for (int s = 0; s < n_iterations; ++s) {
+        double row[8];
+        if (dtl_odme_scatter(e, s, row)) return -1;
+        if (rows) memcpy(rows + (size_t)s * 8, row, sizeof(row));
+        const double gap_increase = row[0] - prev_gap;
+        if (s >= 5 && gap_increase > 0.01) break;
+        prev_gap = row[0];
+        if (dtl_odme_update(e)) return -1;
+        done = s + 1;
+    }
+    double row[8];
+    if (dtl_odme_scatter(e, n_iterations, row)) return -1;
+    if (rows) memcpy(rows + (size_t)n_iterations * 8, row, sizeof(row));
+    if (n_done) *n_done = done;
+    return 0;
+}
+// observed count, upper-bound flag and count deviation of every link of a period (host arrays of length L, may be NULL)
+int dtl_odme_get(dtl_engine* e, int tau, double* obs_count, int* upper_bound_flag, double* est_count_dev)
+{
+    if (!e->odme_ready) { set_err("dtl_odme_configure has not been called"); return -1; }
+    if (tau < 0 || tau >= e->T) { set_err("period %d out of range", tau); return -1; }
+    CK(cudaSetDevice(e->dev));
+    const size_t off = (size_t)tau * e->L;
+    if (obs_count) memcpy(obs_count, e->odme_obs.data() + off, sizeof(double) * e->L);
+    if (upper_bound_flag) memcpy(upper_bound_flag, e->odme_ub.data() + off, sizeof(int) * e->L);
+    if (est_count_dev) CK(cudaMemcpy(est_count_dev, e->d_est_dev + off, sizeof(double) * e->L, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int dtl_sa_configure(dtl_engine* e, const int* rt_info, int n_changes, const int* sa_tau, const int* sa_link, const double* sa_lanes)

@@ -377,11 +377,17 @@ struct dtl_gmns {
     // supply_side_scenario.csv rows of type "sa" (scenario_API.h:152-160): lanes of (period, link) during the sensitivity analysis
     std::vector<int> sa_tau, sa_link;
     std::vector<double> sa_lanes;
+    // measurement.csv rows of type "link" (ODME.h:100-178), one entry per (row, period) in file order
+    std::vector<int> ms_tau, ms_link, ms_ub;
+    std::vector<float> ms_count;
+    std::vector<double> obs_count;         // [T*L] the record a link ends up with (0 = none) and its upper_bound_flag: what the writers print
+    std::vector<int> obs_ub;
     std::vector<signed char> design_flag;  // [T*L] network_design_flag: -1 on the links of the sa rows
     // link state recorded before the sensitivity-analysis stage (g_record_corridor_performance_summary(0), output.h:52-98):
     // [T*L] vehicle volume, speed, DOC, P -- the *_before columns of link_performance.csv; empty = not recorded
     std::vector<double> before_volume, before_speed, before_doc, before_P;
     bool sa_stage = false;                 // the stage ran: per-column flags and per-iteration records are printed
+    bool odme_ran = false;                 // ODME ran: link_performance.csv prints the count columns of the links with a record
 };
 
 namespace {
@@ -941,6 +947,47 @@ void read_scenario(dtl_gmns& g)
     }
 }
 
+// the "link" rows of measurement.csv, Assignment::Demand_ODME, ODME.h:100-178
+void read_measurements(dtl_gmns& g)
+{
+    Csv p;
+    if (!p.open(g.dir + "/measurement.csv")) return;
+    std::map<int, int> node_seq;
+    for (size_t i = 0; i < g.node_id.size(); ++i)
+        if (!node_seq.count(g.node_id[i])) node_seq[g.node_id[i]] = (int)i;
+    std::map<std::pair<int, int>, int> link_of; // m_to_node_2_link_seq_no_map: the last link between two nodes
+    for (size_t l = 0; l < g.link_from.size(); ++l) link_of[{ g.link_from[l], g.link_to[l] }] = (int)l;
+    const size_t L = g.link_from.size();
+    g.obs_count.assign(g.periods.size() * L, 0.0);
+    g.obs_ub.assign(g.periods.size() * L, 1); // CPeriod_VDF(): upper_bound_flag 1, VDF.h:60
+    while (p.read_record()) {
+        std::string type;
+        p.get("measurement_type", type, false);
+        if (type != "link") continue; // (the production / attraction branches of the reference sit inside the link branch: dead code)
+        int from_id = 0, to_id = 0;
+        if (!p.get("from_node_id", from_id)) continue;
+        if (!p.get("to_node_id", to_id)) continue;
+        auto fi = node_seq.find(from_id), ti = node_seq.find(to_id);
+        if (fi == node_seq.end() || ti == node_seq.end()) continue;
+        float count = -1;
+        for (size_t tau = 0; tau < g.periods.size(); ++tau) {
+            int ub = 0;
+            if (g.periods[tau].n_files == 0) continue;
+            p.get("count" + std::to_string(g.periods[tau].id), count, true, false);
+            p.get("upper_bound_flag" + std::to_string(g.periods[tau].id), ub, true, false);
+            auto li = link_of.find({ fi->second, ti->second });
+            if (li == link_of.end()) continue;
+            g.ms_tau.push_back((int)tau); g.ms_link.push_back(li->second); g.ms_count.push_back(count); g.ms_ub.push_back(ub);
+            const size_t a = tau * L + li->second;                 // ODME.h:156-175
+            if (g.obs_count[a] >= 1) {
+                if (ub == 0) { g.obs_count[a] = count; g.obs_ub[a] = ub; }
+            } else {
+                g.obs_count[a] = count; g.obs_ub[a] = ub;
+            }
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -965,6 +1012,7 @@ dtl_gmns* dtl_gmns_read(const char* dir, int number_of_memory_blocks)
         phase("demand files");
         read_output_configuration(*g);
         read_scenario(*g);
+        read_measurements(*g);
         bind_problem(*g, number_of_memory_blocks);
         phase("problem image");
     } catch (const StopError& e) {
@@ -989,6 +1037,23 @@ int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link
         if (sa_tau) sa_tau[i] = g->sa_tau[i];
         if (sa_link) sa_link[i] = g->sa_link[i];
         if (sa_lanes) sa_lanes[i] = g->sa_lanes[i];
+    }
+    return n;
+}
+
+int dtl_gmns_measurements(const dtl_gmns* g, float* at_pce, float* at_occ, int* ms_tau, int* ms_link, float* ms_count, int* ms_ub, int capacity)
+{
+    if (!g) return -1;
+    for (size_t at = 0; at < g->agents.size(); ++at) {
+        if (at_pce) at_pce[at] = (float)g->agents[at].pce; // float PCE_ratio = g_AgentTypeVector[at].PCE, assignment.h:308
+        if (at_occ) at_occ[at] = (float)g->agents[at].occ;
+    }
+    const int n = (int)g->ms_link.size();
+    for (int i = 0; i < std::min(n, capacity); ++i) {
+        if (ms_tau) ms_tau[i] = g->ms_tau[i];
+        if (ms_link) ms_link[i] = g->ms_link[i];
+        if (ms_count) ms_count[i] = g->ms_count[i];
+        if (ms_ub) ms_ub[i] = g->ms_ub[i];
     }
     return n;
 }
@@ -1152,7 +1217,12 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                     g.tmc_road_sequence[i], -1, g.link_type[i], g.link_type_code[i].c_str(), g.vdf_code[i].c_str(),
                     g.periods[tau].time_period.c_str());
             appendf(out, "%.3f,%.3f,%.3f,", vehicle_volume, g.ref_volume[i], ref_diff);
-            appendf(out, ",,,,");
+            if (g.odme_ran && g.obs_count[k] >= 1) {                   // output.h:682-692
+                const double vbef = g.before_volume.empty() ? (double)vehicle_volume : g.before_volume[k];
+                appendf(out, "%.3f,%.3f,%d,%.3f,", vbef, g.obs_count[k], g.obs_ub[k], g.obs_count[k] - vbef);
+            } else {
+                appendf(out, ",,,,");
+            }
             appendf(out, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", preload, person_volume, avg_tt, spd, speed_ratio, voc[tau][i],
                     doc[tau][i], g.cap_lane[k], 0.0, 0.0);
             appendf(out, "%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,", 0.0 / std::max(1.0f, vehicle_volume), g.qdf[k], g.nlanes[k],
@@ -1397,7 +1467,6 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
         log << m << "\nProgram stops." << std::endl;
         exit(2);
     };
-    if (ODME_iterations > 0) fail("ODME is outside the accelerated path (ODME_iterations must be 0)");
     if (simulation_iterations > 0) fail("the mesoscopic simulator is outside the accelerated path (simulation_iterations must be 0)");
     using clk = std::chrono::steady_clock;
     const auto t_start = clk::now();
@@ -1444,8 +1513,53 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     }
     double sys = 0;
     if (dtl_finalize(e, column_generation_iterations, &sys)) fail(dtl_last_error()); // main_api.cpp:748-759
-    if (sa_stage) {
-        const int L = g->prob.n_links, T = g->prob.n_periods, AT = g->prob.n_agent_types;
+    summary << "Step 4.3: OD estimation " << std::endl;              // main_api.cpp:761-769 (mode dta)
+    if (ODME_iterations >= 1) {                                       // Assignment::Demand_ODME, ODME.h:91-516
+        const int AT = g->prob.n_agent_types;
+        std::vector<float> apce(AT), aocc(AT);
+        for (int at = 0; at < AT; ++at) { apce[at] = (float)g->agents[at].pce; aocc[at] = (float)g->agents[at].occ; }
+        if (dtl_odme_configure(e, apce.data(), aocc.data(), (int)g->ms_link.size(), g->ms_tau.data(), g->ms_link.data(), g->ms_count.data(),
+                               g->ms_ub.data()))
+            fail(dtl_last_error());
+        summary << "ODME stage" << std::endl;
+        {   // sensor_count of the reference only counts records that overwrite an earlier one (ODME.h:158-164)
+            int sensor_count = 0;
+            std::vector<double> seen((size_t)g->prob.n_periods * g->prob.n_links, 0.0);
+            for (size_t i = 0; i < g->ms_link.size(); ++i) {
+                double& o = seen[(size_t)g->ms_tau[i] * g->prob.n_links + g->ms_link[i]];
+                if (o >= 1) { if (g->ms_ub[i] == 0) { o = g->ms_count[i]; ++sensor_count; } }
+                else o = g->ms_count[i];
+            }
+            summary << "ODME stage: # of sensors =," << sensor_count << std::endl;
+        }
+        auto odme_row = [&](int s2, const double* r) {                // assignment.h:539-546
+            // (the two percentages are float products in the reference)
+            summary << "ODME #" << s2 << ", link MAE= " << r[2] << ",link_MAPE: " << (float)r[0] * 100 << "%,system_MPE: " << (float)r[1] * 100
+                    << "%,avg_tt = " << r[3] << "(min) " << ",UE gap =" << r[4] << "(min)" << " = (" << r[5] << " %)" << std::endl;
+        };
+        double prev_gap = 9999999;
+        for (int s2 = 0; s2 < ODME_iterations; ++s2) {                // ODME.h:240-260
+            double row[8];
+            if (dtl_odme_scatter(e, s2, row)) fail(dtl_last_error());
+            odme_row(s2, row);
+            const double gap_increase = row[0] - prev_gap;
+            if (s2 >= 5 && gap_increase > 0.01) {
+                summary << "ODME stage terminates with gap increase = " << gap_increase * 100 << "% at iteration = " << s2 << std::endl;
+                break;
+            }
+            prev_gap = row[0];
+            if (dtl_odme_update(e)) fail(dtl_last_error());
+        }
+        double row[8];
+        if (dtl_odme_scatter(e, ODME_iterations, row)) fail(dtl_last_error()); // ODME.h:510-512
+        odme_row(ODME_iterations, row);
+        g->odme_ran = true;
+    } else {
+        summary << "ODME stage" << std::endl;
+    }
+    summary << ",# of ODME_iterations=," << ODME_iterations << std::endl;
+    if (sa_stage || g->odme_ran) {
+        const int L = g->prob.n_links, T = g->prob.n_periods;
         // the "before" record of every link (g_record_corridor_performance_summary(assignment, 0), main_api.cpp:776)
         g->before_volume.assign((size_t)T * L, 0.0); g->before_speed.assign((size_t)T * L, 0.0);
         g->before_doc.assign((size_t)T * L, 0.0); g->before_P.assign((size_t)T * L, 0.0);
@@ -1460,6 +1574,9 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
                 g->before_volume[k] = vehicle_volume; g->before_speed[k] = spd; g->before_doc[k] = doc[i]; g->before_P[k] = P[i];
             }
         }
+    }
+    if (sa_stage) {
+        const int L = g->prob.n_links, AT = g->prob.n_agent_types;
         std::vector<int> rt(AT);
         for (int at = 0; at < AT; ++at) rt[at] = g->agents[at].rt_info;
         if (dtl_sa_configure(e, rt.data(), (int)g->sa_link.size(), g->sa_tau.data(), g->sa_link.data(), g->sa_lanes.data())) fail(dtl_last_error());

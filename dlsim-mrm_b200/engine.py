@@ -86,12 +86,18 @@ def load_library(path: str | None = None):
     L.dtl_sssp_trees.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp]
     L.dtl_backward_trees.argtypes = [vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     L.dtl_vdf.argtypes = [vp, ci] + [vp] * 6
+    L.dtl_odme_configure.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp]
+    L.dtl_odme_scatter.argtypes = [vp, ci, vp]
+    L.dtl_odme_update.argtypes = [vp]
+    L.dtl_odme_run.argtypes = [vp, ci, vp, vp]
+    L.dtl_odme_get.argtypes = [vp, ci, vp, vp, vp]
     L.dtl_sa_configure.argtypes = [vp, vp, ci, vp, vp, vp]
     L.dtl_sa_begin.argtypes = [vp, vp]
     L.dtl_sa_iteration.argtypes = [vp, ci, vp]
     L.dtl_sa_column_update.argtypes = [vp, ci, vp]
     L.dtl_sa_get_columns.argtypes = [vp, vp, vp, vp, vp]
     L.dtl_gmns_scenario.argtypes = [vp, vp, vp, vp, vp, ci]
+    L.dtl_gmns_measurements.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci]
     L.dtl_scatter.argtypes = [vp, ci]
     L.dtl_get_tree.argtypes = [vp, ci, vp, vp, vp]
     L.dtl_get_timing.argtypes = [vp, vp, vp, ci]
@@ -177,6 +183,14 @@ def read_gmns(directory: str, memory_blocks: int = 4) -> Problem:
         L.dtl_gmns_scenario(h, None, _ptr(sa_tau), _ptr(sa_link), _ptr(sa_lanes), n_sa)
         q.rt_info = rt[:A].copy()
         q.sa_changes = [(int(sa_tau[i]), int(sa_link[i]), float(sa_lanes[i])) for i in range(n_sa)]
+        # ODME inputs: agent-type PCE / occupancy (float) and the link rows of measurement.csv
+        pce, occ = np.zeros(max(A, 1), np.float32), np.zeros(max(A, 1), np.float32)
+        n_ms = L.dtl_gmns_measurements(h, _ptr(pce), _ptr(occ), None, None, None, None, 0)
+        m_tau, m_link, m_ub = (np.zeros(max(n_ms, 1), np.int32) for _ in range(3))
+        m_cnt = np.zeros(max(n_ms, 1), np.float32)
+        L.dtl_gmns_measurements(h, None, None, _ptr(m_tau), _ptr(m_link), _ptr(m_cnt), _ptr(m_ub), n_ms)
+        q.at_pce, q.at_occ = pce[:A].copy(), occ[:A].copy()
+        q.sensors = [(int(m_tau[i]), int(m_link[i]), float(m_cnt[i]), int(m_ub[i])) for i in range(n_ms)]
         return q.finalize()
     finally:
         L.dtl_gmns_free(h)
@@ -353,6 +367,37 @@ class Engine:
         st = dict(ms=stats[0], counted_edges=stats[1], relaxations=stats[2], pops=stats[3], rounds=stats[4],
                   replayed=stats[5])
         return lab, pn, pl, ties[:n], st
+
+    # ---- ODME (Assignment::Demand_ODME, ODME.h:91-516) ----
+    ODME_ROW = ("gap", "system_gap", "link_mae", "avg_tt", "ue_gap", "ue_gap_pct", "demand", "links_with_data")
+
+    def odme_configure(self, at_pce, at_occ, sensors=()):
+        a = np.ascontiguousarray(at_pce, np.float32); b = np.ascontiguousarray(at_occ, np.float32)
+        tau = np.ascontiguousarray([s[0] for s in sensors] or [0], np.int32)
+        link = np.ascontiguousarray([s[1] for s in sensors] or [0], np.int32)
+        cnt = np.ascontiguousarray([s[2] for s in sensors] or [0], np.float32)
+        ub = np.ascontiguousarray([s[3] for s in sensors] or [0], np.int32)
+        self._ck(self.lib.dtl_odme_configure(self.h, _ptr(a), _ptr(b), len(sensors), _ptr(tau), _ptr(link), _ptr(cnt), _ptr(ub)))
+
+    def odme_scatter(self, s: int) -> dict:
+        row = np.zeros(8)
+        self._ck(self.lib.dtl_odme_scatter(self.h, int(s), _ptr(row)))
+        return dict(zip(self.ODME_ROW, row))
+
+    def odme_update(self):
+        self._ck(self.lib.dtl_odme_update(self.h))
+
+    def odme_run(self, n: int):
+        rows = np.zeros((n + 1, 8))
+        done = C.c_int(0)
+        self._ck(self.lib.dtl_odme_run(self.h, int(n), _ptr(rows), C.byref(done)))
+        return rows, done.value
+
+    def odme_state(self, tau: int = 0) -> dict:
+        L = self.problem.n_links
+        obs, ub, dev = np.zeros(L), np.zeros(L, np.int32), np.zeros(L)
+        self._ck(self.lib.dtl_odme_get(self.h, tau, _ptr(obs), _ptr(ub), _ptr(dev)))
+        return dict(obs_count=obs, upper_bound_flag=ub, est_count_dev=dev)
 
     # ---- sensitivity-analysis stage (main_api.cpp:771-1042) ----
     def sa_configure(self, rt_info, changes=()):

@@ -142,6 +142,25 @@ long long dtl_num_column_links(dtl_engine* e);
 int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, int* n_links, int* n_nodes,
                     double* volume, double* cost, double* time, int* links);
 
+/* ---- ODME: OD demand estimation against link counts, Assignment::Demand_ODME (ODME.h:91-516) and its scatter
+ * g_reset_and_update_link_volume_based_on_ODME_columns (assignment.h:263-563).  Runs on the column pool the assignment left.
+ *   dtl_odme_configure  at_pce / at_occ [AT] = agent-type PCE / person occupancy as floats (assignment.h:308-309); n "link"
+ *                       rows of measurement.csv in file order (period, link, count, upper_bound_flag; ODME.h:140-178)
+ *   dtl_odme_scatter    column volumes -> link volumes with the ODME addend, VDF pass, count deviations; row = { link MAPE / 100
+ *                       (the convergence gap), system MPE / 100, link MAE, avg travel time, UE gap per unit of demand, UE gap %,
+ *                       total demand, links with a count }
+ *   dtl_odme_update     the path-flow gradient step (ODME.h:262-488)
+ *   dtl_odme_run        the whole loop with the reference's stopping rule; rows [n_iterations + 1][8]
+ *   dtl_odme_get        per link of a period: count, upper-bound flag, count deviation
+ * Volumes are integer (Q31.32) sums as in the assignment: independent of the visiting order and of the GPU count, within 2^-33
+ * per addend of the reference's serial FP64 sums. */
+int dtl_odme_configure(dtl_engine* e, const float* at_pce, const float* at_occ, int n, const int* tau, const int* link,
+                       const float* count, const int* upper_bound_flag);
+int dtl_odme_scatter(dtl_engine* e, int s, double row[8]);
+int dtl_odme_update(dtl_engine* e);
+int dtl_odme_run(dtl_engine* e, int n_iterations, double* rows, int* n_done);
+int dtl_odme_get(dtl_engine* e, int tau, double* obs_count, int* upper_bound_flag, double* est_count_dev);
+
 /* ---- sensitivity-analysis stage: stage II of network_assignment, main_api.cpp:771-1042 ----
  * Covered: supply-side "sa" lane changes (scenario_API.h:152-160) and the re-routing of the agent types with real-time
  * information; dms scenario rows / information zones / route modification and demand-side scenario factors are not.
@@ -221,6 +240,11 @@ int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id);
  * 0 none, 1 real-time information, 2 dms) and the "sa" rows of supply_side_scenario.csv (scenario_API.h:152-160) as
  * (period, link, lanes) triples.  Returns the number of sa rows (at most `capacity` are copied) or -1. */
 int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link, double* sa_lanes, int capacity);
+/* ODME inputs: the agent types' PCE / person occupancy as floats (assignment.h:308-309) and the "link" rows of measurement.csv
+ * (ODME.h:100-178), one entry per (row, demand period) in file order: (period, link, count, upper_bound_flag).  Returns the
+ * number of entries (at most `capacity` are copied) or -1. */
+int dtl_gmns_measurements(const dtl_gmns* g, float* at_pce, float* at_occ, int* ms_tau, int* ms_link, float* ms_count, int* ms_ub,
+                          int capacity);
 /* settings.csv [assignment] as flash_dta.cpp:171-242 derives them: out = { CG iterations, CU iterations,
  * ODME iterations, SA iterations, simulation iterations, memory blocks } */
 int dtl_gmns_assignment_settings(const char* dir, int out[6]);

@@ -144,6 +144,10 @@ class Oracle:
         L.orc_sa_begin.argtypes = [C.c_void_p]
         L.orc_sa_iteration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_sa_column_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_odme_configure.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_odme_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
+        L.orc_odme_scatter.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_odme_update.argtypes = [C.c_void_p]
         L.orc_backward_sssp.restype = C.c_longlong
         L.orc_backward_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         self.problem = problem
@@ -260,6 +264,23 @@ class Oracle:
         row = np.zeros(4)
         self.lib.orc_sa_column_update(self.h, int(n), _ptr(row))
         return dict(avg_tt=row[0], total_gap=row[1], rel_gap_pct=row[2], demand=row[3])
+
+    # ---- ODME (ODME.h:91-516) ----
+    ODME_ROW = ("gap", "system_gap", "link_mae", "avg_tt", "ue_gap", "ue_gap_pct", "demand", "links_with_data")
+
+    def odme_configure(self, at_pce, at_occ, sensors=()):
+        a = np.ascontiguousarray(at_pce, np.float32); b = np.ascontiguousarray(at_occ, np.float32)
+        self.lib.orc_odme_configure(self.h, _ptr(a), _ptr(b))
+        for tau, link, count, ub in sensors:
+            self.lib.orc_odme_sensor(self.h, int(tau), int(link), float(count), int(ub))
+
+    def odme_scatter(self, s: int):
+        row = np.zeros(8)
+        self.lib.orc_odme_scatter(self.h, int(s), _ptr(row))
+        return dict(zip(self.ODME_ROW, row))
+
+    def odme_update(self):
+        self.lib.orc_odme_update(self.h)
 
     def backward_sssp(self, cost, dest_node: int, rt_allowed=None):
         N = self.problem.n_nodes

@@ -62,6 +62,11 @@ struct orc_state {
     double* sa_lanes;          /* [T][L] sa_lanes_change */
     signed char* design_flag;  /* [T][L] network_design_flag, VDF.h:419 */
     unsigned char* od_impact;  /* [n_od] OD_impact_flag && at_od_impacted_flag_map[at] of the cell (assignment.h:699-713) */
+    /* ODME (ODME.h:91-516) */
+    double* obs_count;         /* [T][L] VDF_period.obs_count, 0 = no data */
+    int* ub_flag;              /* [T][L] upper_bound_flag (default 1, VDF.h:60) */
+    double* est_dev;           /* [T][L] est_count_dev */
+    float *at_pce, *at_occ;    /* [AT] agent-type PCE / OCC as the ODME scatter uses them (float, assignment.h:308-309) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -369,6 +374,13 @@ orc_state* orc_create(const orc_problem* p)
     s->sa_lanes = (double*)calloc(TL + 1, sizeof(double));
     s->design_flag = (signed char*)calloc(TL + 1, 1);
     s->od_impact = (unsigned char*)calloc((size_t)(p->n_od > 0 ? p->n_od : 1), 1);
+    s->obs_count = (double*)calloc(TL + 1, sizeof(double));
+    s->ub_flag = (int*)malloc(sizeof(int) * (TL + 1));
+    for (size_t i = 0; i < TL; ++i) s->ub_flag[i] = 1;
+    s->est_dev = (double*)calloc(TL + 1, sizeof(double));
+    s->at_pce = (float*)calloc(AT > 0 ? AT : 1, sizeof(float));
+    s->at_occ = (float*)calloc(AT > 0 ? AT : 1, sizeof(float));
+    for (int at = 0; at < AT; ++at) { s->at_pce[at] = 1; s->at_occ[at] = 1; }
     return s;
 }
 
@@ -391,6 +403,7 @@ void orc_destroy(orc_state* s)
     free(s->label); free(s->pred_node); free(s->pred_link); free(s->status); free(s->next);
     free(s->tmp_nodes); free(s->tmp_links); free(s->n_out_unfiltered);
     free(s->m_fftt); free(s->m_cap); free(s->m_nlanes); free(s->rt_info); free(s->sa_lanes); free(s->design_flag); free(s->od_impact);
+    free(s->obs_count); free(s->ub_flag); free(s->est_dev); free(s->at_pce); free(s->at_occ);
     free(s);
 }
 
@@ -708,6 +721,132 @@ void orc_sa_iteration(orc_state* s, int it, double row[3])
 
 /* g_update_gradient_cost_and_assigned_flow_in_column_pool with the SA flag (main_api.cpp:1040, assignment.h:565-928) */
 void orc_sa_column_update(orc_state* s, int n, double row[4]) { column_update_impl(s, n, row, 1); }
+
+/* ---- ODME: Assignment::Demand_ODME, ODME.h:91-516 ---- */
+void orc_odme_configure(orc_state* s, const float* at_pce, const float* at_occ)
+{
+    memcpy(s->at_pce, at_pce, sizeof(float) * s->AT);
+    memcpy(s->at_occ, at_occ, sizeof(float) * s->AT);
+}
+
+/* one "link" row of measurement.csv for one period, ODME.h:140-178: an actual count overwrites what is there, an upper bound
+ * does not overwrite an existing record */
+void orc_odme_sensor(orc_state* s, int tau, int link, float count, int upper_bound_flag)
+{
+    size_t a = (size_t)tau * s->L + link;
+    if (s->obs_count[a] >= 1) {
+        if (upper_bound_flag == 0) { s->obs_count[a] = count; s->ub_flag[a] = upper_bound_flag; }
+    } else {
+        s->obs_count[a] = count; s->ub_flag[a] = upper_bound_flag;
+    }
+}
+
+/* g_reset_and_update_link_volume_based_on_ODME_columns, assignment.h:263-563 (one thread: the order of the sums is the
+ * loop order).  row = { gap (link MAPE / 100), system_gap, link MAE, avg_tt, UE gap per unit of demand, UE gap %, demand, links with data } */
+void orc_odme_scatter(orc_state* s, int iteration_no, double row[8])
+{
+    const orc_problem* p = s->p;
+    const int L = s->L, AT = s->AT, T = s->T;
+    float total_gap = 0, sub_total_gap_link_count = 0, sub_total_system_gap_count = 0;           /* :265-268 */
+    double total_cost = 0, total_time = 0, total_demand = 0, total_ue_gap = 0;
+    (void)iteration_no; (void)total_cost;
+    for (int tau = 0; tau < T; ++tau) {                                                   /* :281-293 */
+        memset(s->pce_vol[tau], 0, sizeof(double) * L);
+        memset(s->person_vol[tau], 0, sizeof(double) * L);
+        for (int at = 0; at < AT; ++at) memset(s->person_vol_at[tau * AT + at], 0, sizeof(double) * L);
+    }
+    for (int at = 0; at < AT; ++at) {                                                     /* :302 at, o, d, tau */
+        float PCE_ratio = s->at_pce[at], OCC_ratio = s->at_occ[at];                       /* :308-309 */
+        for (int i = 0; i < p->n_od; ++i) {
+            if (p->od_at[i] != at) continue;
+            int tau = p->od_tau[i];
+            orc_colvec* cv = &s->pool[i];
+            double least_cost = 999999;                                                   /* :347 */
+            int least_seq = -1;
+            for (int j = 0; j < cv->n; ++j) {                                             /* :370-409 */
+                orc_column* c = &cv->c[j];
+                total_demand += c->volume;
+                double path_time = 0;
+                for (int q = 0; q < c->n_links; ++q) path_time += s->tt[tau][c->links[q]];
+                c->toll = 0; c->time = path_time;
+                total_time += c->time * c->volume;
+                if (cv->n == 1) break;                                                    /* :393-396 */
+                if (path_time < least_cost) { least_cost = path_time; least_seq = c->seq_no; }
+                total_cost += c->time * c->volume;
+            }
+            if (cv->n >= 2)                                                               /* :411-430 */
+                for (int j = 0; j < cv->n; ++j) {
+                    orc_column* c = &cv->c[j];
+                    if (c->seq_no != least_seq) total_ue_gap += (c->time - least_cost) * c->volume;
+                }
+            for (int j = 0; j < cv->n; ++j) {                                             /* :433-457 */
+                orc_column* c = &cv->c[j];
+                float f = (float)c->volume;
+                for (int q = 0; q < c->n_links; ++q) {
+                    int l = c->links[q];
+                    s->pce_vol[tau][l] += f * PCE_ratio;                                  /* float product, :449 */
+                    s->person_vol[tau][l] += f * OCC_ratio;
+                    s->person_vol_at[tau * AT + at][l] += f;                              /* :451 pure volume */
+                }
+            }
+        }
+    }
+    int total_link_count = 0;
+    vdf_pass(s);                                                                          /* :467 per link, same function */
+    for (int l = 0; l < L; ++l)                                                           /* :465-515 */
+        for (int tau = 0; tau < T; ++tau) {
+            size_t a = (size_t)tau * L + l;
+            if (!(s->obs_count[a] >= 1)) continue;
+            double dev = s->pce_vol[tau][l] + s->pm.preload[a] - s->obs_count[a];         /* :476 */
+            s->est_dev[a] = dev;
+            if (s->ub_flag[a] == 0 || dev > 0) {                                          /* :489-507 */
+                total_gap += abs((int)dev);                                               /* :491 abs() binds to the int overload here */
+                sub_total_gap_link_count += fabs(dev / s->obs_count[a]);
+                sub_total_system_gap_count += dev / s->obs_count[a];
+            }
+            total_link_count += 1;
+        }
+    int denom = total_link_count > 1 ? total_link_count : 1;
+    row[0] = sub_total_gap_link_count / denom;                                            /* :560 */
+    row[1] = sub_total_system_gap_count / denom;                                          /* :561 */
+    row[2] = total_gap / denom;
+    row[3] = total_time / dmax(0.1, total_demand);
+    row[4] = total_ue_gap / dmax(0.00001, total_demand);
+    row[5] = total_ue_gap / dmax(0.00001, total_time) * 100;
+    row[6] = total_demand;
+    row[7] = total_link_count;
+}
+
+/* the path-flow step of one ODME iteration, ODME.h:262-488 */
+void orc_odme_update(orc_state* s)
+{
+    const orc_problem* p = s->p;
+    const int L = s->L;
+    for (int i = 0; i < p->n_od; ++i) {
+        orc_colvec* cv = &s->pool[i];
+        int tau = p->od_tau[i];
+        for (int j = 0; j < cv->n; ++j) {                                                 /* :349-470 */
+            orc_column* c = &cv->c[j];
+            float path_gradient_cost = 0;
+            for (int q = 0; q < c->n_links; ++q) {                                        /* :396-421 */
+                size_t a = (size_t)tau * L + c->links[q];
+                if (s->obs_count[a] >= 1) {
+                    if (s->ub_flag[a] == 0) path_gradient_cost += s->est_dev[a];
+                    if (s->ub_flag[a] == 1 && s->est_dev[a] > 0) path_gradient_cost += s->est_dev[a];
+                }
+            }
+            c->cost = path_gradient_cost;                                                 /* :426 */
+            float step_size = 0.05;                                                       /* :428 */
+            double weight = 1;
+            double ue_gap = 0; /* weight 0: never contributes */
+            double change = step_size * (weight * c->cost + (1 - weight) * ue_gap);       /* :434 */
+            float lo = c->volume * 0.1 * (-1), hi = c->volume * 0.1;                      /* :439-440 */
+            if (change < lo) change = lo;
+            if (change > hi) change = hi;
+            c->volume = dmax(1.0, c->volume - change);                                    /* :449 */
+        }
+    }
+}
 
 double orc_finalize(orc_state* s, int K)
 {

@@ -78,6 +78,14 @@ double orc_sa_begin(orc_state* s);
 void orc_sa_iteration(orc_state* s, int it, double row[3]); /* { sysTT, avg travel time, least system TT of the re-routed origins } */
 void orc_sa_column_update(orc_state* s, int n, double row[4]);
 
+/* ---- ODME: Assignment::Demand_ODME, ODME.h:91-516, and its scatter
+ * g_reset_and_update_link_volume_based_on_ODME_columns, assignment.h:263-563.  Loop of the reference: for s in 0..n-1:
+ * gap = scatter(s); stop if s >= 5 and gap - prev_gap > 0.01; update(); then one more scatter(n). ---- */
+void orc_odme_configure(orc_state* s, const float* at_pce, const float* at_occ);
+void orc_odme_sensor(orc_state* s, int tau, int link, float count, int upper_bound_flag);
+void orc_odme_scatter(orc_state* s, int iteration_no, double row[8]);
+void orc_odme_update(orc_state* s);
+
 /* state read-back; per-period arrays of length L */
 void orc_get_link_state(const orc_state* s, int tau, double* tt, double* pce_volume, double* person_volume,
                         double* link_volume, double* doc, double* voc, double* P, double* vt2);

@@ -13,7 +13,7 @@
  * static-initialisation time, DTA.h:858-876):
  *   dtalite_ref golden K CU B      -> calls network_assignment(1,K,CU,0,0,0,B) verbatim
  *                                      (main_api.cpp:499) and exits.
- *   dtalite_ref golden_dump K CU B out S -> network_assignment(1,K,CU,0,S,0,B) verbatim (S sensitivity-analysis iterations:
+ *   dtalite_ref golden_dump K CU B out S [ODME] -> network_assignment(1,K,CU,0,S,0,B) verbatim (S sensitivity-analysis iterations:
  *                                      supply_side_scenario.csv lane changes, re-routing of the agent types with real-time
  *                                      information, main_api.cpp:771-1042), then dumps the state it leaves in the globals.
  *   dtalite_ref trace  K CU B out  -> re-drives stage 1 / stage 2 of network_assignment
@@ -457,7 +457,8 @@ int main(int argc, char** argv)
            it leaves in the reference's globals: dtalite_ref golden_dump K CU B out.bin S */
         const char* out = argc >= 6 ? argv[5] : "ref_trace.bin";
         const int S = argc >= 7 ? atoi(argv[6]) : 0;
-        network_assignment(1, K, CU, 0, S, 0, B);
+        const int ODME = argc >= 8 ? atoi(argv[7]) : 0; /* OD demand estimation iterations (measurement.csv, ODME.h:91-516) */
+        network_assignment(1, K, CU, ODME, S, 0, B);
         g_dump = fopen(out, "wb");
         if (!g_dump) { fprintf(stderr, "cannot open %s\n", out); return 2; }
         dump_network();
@@ -465,6 +466,9 @@ int main(int argc, char** argv)
         std::vector<int> rt(AT);
         for (int at = 0; at < AT; ++at) rt[at] = assignment.g_AgentTypeVector[at].real_time_information;
         dump_i32("agent_rt_info", rt);
+        std::vector<double> apce(AT), aocc(AT);
+        for (int at = 0; at < AT; ++at) { apce[at] = assignment.g_AgentTypeVector[at].PCE; aocc[at] = assignment.g_AgentTypeVector[at].OCC; }
+        dump_f64("agent_pce", apce); dump_f64("agent_occ", aocc);
         for (int tau = 0; tau < T; ++tau) {
             std::vector<int> flag(L);
             std::vector<double> lanes(L), nl(L), cap(L), fftt(L);
@@ -473,6 +477,13 @@ int main(int argc, char** argv)
                 flag[l] = v.network_design_flag; lanes[l] = v.sa_lanes_change; nl[l] = v.nlanes; cap[l] = v.BPR_period_capacity; fftt[l] = v.FFTT;
             }
             std::string sfx = ":tau=" + std::to_string(tau);
+            std::vector<double> obs(L), dev(L);
+            std::vector<int> ub(L);
+            for (int l = 0; l < L; ++l) {
+                const CPeriod_VDF& v = g_link_vector[l].VDF_period[tau];
+                obs[l] = v.obs_count; dev[l] = v.est_count_dev; ub[l] = v.upper_bound_flag;
+            }
+            dump_f64("obs_count" + sfx, obs); dump_f64("est_count_dev" + sfx, dev); dump_i32("upper_bound_flag" + sfx, ub);
             dump_i32("design_flag" + sfx, flag); dump_f64("sa_lanes" + sfx, lanes);
             dump_f64("sa_nlanes_after" + sfx, nl); dump_f64("sa_cap_after" + sfx, cap); dump_f64("sa_fftt_after" + sfx, fftt);
         }

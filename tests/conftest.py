@@ -24,8 +24,20 @@ def native():
     return engine.load_library()
 
 
+def stage_fixture(name, dst):
+    """tests/fixtures/<base> copied into dst, then the files of tests/fixtures/overlays/<name> for names like "<base>+odme" """
+    import shutil
+    base = name.split("+")[0]
+    for f in os.listdir(os.path.join(FIXTURES, base)):
+        shutil.copy(os.path.join(FIXTURES, base, f), dst)
+    if "+" in name:
+        ov = os.path.join(FIXTURES, "overlays", name)
+        for f in os.listdir(ov):
+            shutil.copy(os.path.join(ov, f), dst)
+
+
 @pytest.fixture(scope="session")
-def problems(native):
+def problems(native, tmp_path_factory):
     """GMNS fixtures read through the native reader (pinned against the reference in test_gmns_reader.py)."""
     import dlsim_mrm_b200 as D
     cache = {}
@@ -33,7 +45,11 @@ def problems(native):
     def get(name, blocks=4):
         key = (name, blocks)
         if key not in cache:
-            cache[key] = D.read_gmns(os.path.join(FIXTURES, name), blocks)
+            d = os.path.join(FIXTURES, name)
+            if "+" in name:
+                d = str(tmp_path_factory.mktemp("fixture"))
+                stage_fixture(name, d)
+            cache[key] = D.read_gmns(d, blocks)
         return cache[key]
     return get
 

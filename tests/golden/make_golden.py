@@ -130,6 +130,49 @@ def run_backward(cases):
     print("backward trees ->", os.path.getsize(os.path.join(OUT, "backward_ref.npz")) // 1024, "KiB")
 
 
+def stage_fixture(name, dst):
+    """copies tests/fixtures/<base> into dst, then the files of tests/fixtures/overlays/<name> for names like "<base>+odme" """
+    base = name.split("+")[0]
+    for f in os.listdir(os.path.join(ROOT, "tests", "fixtures", base)):
+        shutil.copy(os.path.join(ROOT, "tests", "fixtures", base, f), dst)
+    if "+" in name:
+        ov = os.path.join(ROOT, "tests", "fixtures", "overlays", name)
+        for f in os.listdir(ov):
+            shutil.copy(os.path.join(ov, f), dst)
+
+
+def run_odme(cases):
+    """OD demand estimation (Assignment::Demand_ODME, ODME.h:91-516) followed by the SA stage with 0 iterations: the state the
+    UNMODIFIED network_assignment(1, K, CU, ODME, 0, 0, 4) leaves (harness mode golden_dump, ONE OpenMP thread: the reference's
+    ODME scatter sums link volumes inside a parallel loop, so only a single-thread run is reproducible to the bit)"""
+    out = {}
+    for name, K, CU, n_odme in cases:
+        key = f"{name}:ODME={n_odme}"
+        with tempfile.TemporaryDirectory() as tmp:
+            stage_fixture(name, tmp)
+            B.run_reference(tmp, "golden_dump", K, CU, 4, "dump.bin", threads=1, extra_args=["0", str(n_odme)])
+            d = B.load_dump(os.path.join(tmp, "dump.bin"))
+            small = os.path.getsize(os.path.join(tmp, "route_assignment.csv")) < (1 << 20)
+            for f in ("link_performance", "route_assignment"):
+                if small:
+                    shutil.copy(os.path.join(tmp, f + ".csv"), os.path.join(OUT, "outputs", f"{name}_odme{n_odme}_{f}.csv"))
+            with open(os.path.join(tmp, "final_summary.csv")) as f, open(os.path.join(OUT, "outputs", f"{name}_odme{n_odme}_final_summary_rows.txt"), "w") as o:
+                for line in f:
+                    if line.startswith("ODME"):
+                        o.write(line)
+        out[f"{key}:K_CU_ODME"] = np.array([K, CU, n_odme], np.int32)
+        for k2 in ("obs_count", "upper_bound_flag", "est_count_dev"):
+            out[f"{key}:{k2}"] = d[f"{k2}:tau=0"]
+        out[f"{key}:agent_pce"] = d["agent_pce"]; out[f"{key}:agent_occ"] = d["agent_occ"]
+        for k2 in ("tt", "pce_volume", "person_volume"):
+            out[f"{key}:final_{k2}"] = d[f"{k2}:final:tau=0"]
+        for k2 in ("col_node_sum", "col_seq", "col_volume", "col_cost", "col_time"):
+            out[f"{key}:{k2}"] = d[k2 + ":final"]
+        out[f"{key}:col_links_sha256"] = np.array(sha(d["col_links:final"]))
+    np.savez_compressed(os.path.join(OUT, "odme_ref.npz"), **out)
+    print("ODME ->", os.path.getsize(os.path.join(OUT, "odme_ref.npz")) // 1024, "KiB")
+
+
 def run_sa(cases):
     """sensitivity-analysis stage (main_api.cpp:771-1042): the state the UNMODIFIED network_assignment(1, K, CU, 0, S, 0, 4)
     leaves in the reference's globals (harness mode golden_dump) -> sa_ref.npz; its output files -> outputs/<name>_sa<S>_*.csv"""
@@ -198,6 +241,9 @@ def reference_output_files(name, K, CU, multi_period=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "odme":
+        run_odme((("sa_corridor+odme", 20, 5, 12), ("corridor_101+odme", 20, 5, 20)))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sa":
         run_sa((("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0), ("corridor_101", 20, 5, 2)))
         sys.exit(0)
