@@ -51,3 +51,19 @@ def test_assignment_settings(native):
     out = (C.c_int * 6)()
     assert native.dtl_gmns_assignment_settings(os.path.join(FIXTURES, "two_corridor").encode(), out) == 0
     assert list(out) == [20, 0, 0, 0, 0, 4]
+
+
+def test_parallel_link_parse_gives_the_same_image(native, monkeypatch):
+    """link.csv is cut into slices of whole lines that worker threads parse; the image must not depend on
+    the number of slices -- including a count that does not divide the file evenly"""
+    import dlsim_mrm_b200 as D
+    d = os.path.join(FIXTURES, "corridor_101")          # link.csv: 2 MB, above the 1 MiB threshold of the parallel path
+    assert os.path.getsize(os.path.join(d, "link.csv")) > (1 << 20)
+    images = []
+    for threads in ("1", "7", "16"):
+        monkeypatch.setenv("DTL_IO_THREADS", threads)
+        images.append(D.read_gmns(d, 4))
+    for other in images[1:]:
+        assert other.n_links == images[0].n_links and other.n_nodes == images[0].n_nodes
+        for name, a in images[0].arrays.items():
+            assert np.array_equal(a, other.arrays[name], equal_nan=a.dtype.kind == "f"), name

@@ -61,11 +61,13 @@ def _worker(rank, world, out_dir, mode):
     np.savez(os.path.join(out_dir, f"{mode}_rank{rank}.npz"), **res)
 
 
-@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-def test_two_ranks_all_reduce_the_single_gpu_volumes(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_all_reduce_the_single_gpu_volumes(tmp_path, world):
+    """BASELINE.json config 4 origin-sharded over 2, 4 and 8 GPUs (99 zones x 3 agent types: 12-13 zones per GPU at 8)"""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import dlsim_mrm_b200 as D
-    world = 2
     mp.spawn(_worker, args=(world, str(tmp_path), "ok"), nprocs=world, join=True)
     parts = [np.load(tmp_path / f"ok_rank{r}.npz") for r in range(world)]
     assert all(str(q["error"]) == "" for q in parts), [str(q["error"]) for q in parts]
