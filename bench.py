@@ -304,7 +304,7 @@ def run_engine_arm(args, rank, world, local_rank):
     for k in range(K):
         e2.iteration(k)
     e2.finalize(K)
-    st = e2.link_state(0)
+    st = e2.link_state(0, fields=("tt", "pce_volume"))   # the result of the assignment: link travel times and volumes
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = sum(a.nbytes for a in p.arrays.values())

@@ -7,10 +7,12 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <map>
 #include <numeric>
 #include <chrono>
@@ -1067,16 +1069,37 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     // the link arrays (no CUDA call and no error path inside the worker)
     e->fs.resize((size_t)AT * T);
     std::vector<FsHost> fsh((size_t)AT * T);
-    std::thread fs_thread([&]() {
+    // (the same thread goes on to the bundle planner's landmark embeddings -- three or four breadth-first searches per forward
+    // star -- and is joined by the first bundle plan; the zone partition of a multi-GPU run computes its own embedding on this
+    // thread first, so the worker only reads e->h_embed_all after `owners_ready`)
+    std::promise<void> stars_built, owners_ready;
+    std::future<void> stars_future = stars_built.get_future();
+    std::shared_future<void> owners_future = owners_ready.get_future().share();
+    bool owners_signalled = false;
+    e->embed_thread = std::thread([e, p, AT, T, L, &fsh, &stars_built, owners_future]() {
         for (int at = 0; at < AT; ++at)
             for (int tau = 0; tau < T; ++tau) build_forward_star_host(e, p, at, tau, fsh[fs_index(e, at, tau)]);
+        stars_built.set_value();
+        owners_future.wait();
+        for (ForwardStar& f : e->fs) {
+            if (!e->h_embed_all.empty() && f.n_edges == L) f.h_embed = e->h_embed_all; // same graph as the zone partition's
+            else ensure_embedding(f, e->N);
+        }
     });
-    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } fs_joiner{ fs_thread };
+    // an early return must not take `fsh` and the promises away from under the worker: it touches them only until it has
+    // signalled `stars_built` (afterwards it works on the engine alone, and dtl_destroy joins it)
+    bool stars_waited = false;
+    struct Joiner {
+        std::promise<void>& pr; bool& owners_done; std::future<void>& stars; bool& stars_done;
+        ~Joiner() { if (!owners_done) pr.set_value(); if (!stars_done) stars.wait(); }
+    } fs_joiner{ owners_ready, owners_signalled, stars_future, stars_waited };
     DTL_TRACE("tasks of this rank: origin zones are sha");
     // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
     std::vector<int> g_at, g_tau, g_zone;
     build_task_list(p, g_at, g_tau, g_zone);
     const std::vector<int> owner = zone_owners(p, e->world, &e->h_embed_all);
+    owners_ready.set_value();
+    owners_signalled = true;
     std::vector<int> task_of((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
     for (size_t i = 0; i < g_at.size(); ++i)
         if (owner[g_zone[i]] == e->rank) {
@@ -1099,51 +1122,81 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
 
     DTL_TRACE("OD cells of this rank (cells whose origi");
     // ---- OD cells of this rank (cells whose origin has no task never get columns in the reference either) ----
-    std::vector<int> od_dest, od_at, od_tau, od_task;
+    // The cell arrays are put together by a second worker thread (two passes over the OD rows: count per task, then fill) while
+    // this thread uploads the link arrays; they are uploaded when it is done.
+    std::vector<int> od_dest, od_at, od_tau, od_task, task_cells;
     std::vector<double> od_vol;
-    std::vector<std::vector<int>> cells_of_task(n_tasks);
-    for (int i = 0; i < p->n_od; ++i) {
-        if (p->od_o[i] < 0 || p->od_o[i] >= Z || p->od_d[i] < 0 || p->od_d[i] >= Z || p->od_at[i] < 0 || p->od_at[i] >= AT ||
-            p->od_tau[i] < 0 || p->od_tau[i] >= T) {
-            set_err("OD row %d: zone, agent type or period index out of range", i);
-            return -1;
-        }
-        if (owner[p->od_o[i]] != e->rank) continue;
-        const int task_i = task_of[((size_t)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]];
-        if (task_i < 0) continue;
-        const int c = (int)e->cell_global.size();
-        e->cell_global.push_back(i);
-        od_dest.push_back(p->zone_centroid[p->od_d[i]]);
-        od_at.push_back(p->od_at[i]); od_tau.push_back(p->od_tau[i]); od_task.push_back(task_i);
-        od_vol.push_back(p->od_vol[i]);
-        cells_of_task[task_i].push_back(c);
-    }
-    e->n_cells = (int)e->cell_global.size();
-    std::vector<int> task_cells;
+    int bad_od_row = -1;
     e->task_cell_ptr.assign(n_tasks + 1, 0);
-    for (int t = 0; t < n_tasks; ++t) {
-        task_cells.insert(task_cells.end(), cells_of_task[t].begin(), cells_of_task[t].end());
-        e->task_cell_ptr[t + 1] = (int)task_cells.size();
-    }
-    if (e->upload(&e->d_od_dest, od_dest.data(), e->n_cells)) return -1;
-    if (e->upload(&e->d_od_at, od_at.data(), e->n_cells)) return -1;
-    if (e->upload(&e->d_od_tau, od_tau.data(), e->n_cells)) return -1;
-    if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
-    if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
-    if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
+    std::thread cells_thread([&]() {
+        std::vector<int> task_i_of(p->n_od, -1);
+        size_t n_keep = 0;
+        for (int i = 0; i < p->n_od; ++i) {
+            if (p->od_o[i] < 0 || p->od_o[i] >= Z || p->od_d[i] < 0 || p->od_d[i] >= Z || p->od_at[i] < 0 || p->od_at[i] >= AT ||
+                p->od_tau[i] < 0 || p->od_tau[i] >= T) {
+                bad_od_row = i;
+                return;
+            }
+            if (owner[p->od_o[i]] != e->rank) continue;
+            const int t = task_of[((size_t)p->od_at[i] * T + p->od_tau[i]) * Z + p->od_o[i]];
+            if (t < 0) continue;
+            task_i_of[i] = t;
+            e->task_cell_ptr[t + 1]++;
+            ++n_keep;
+        }
+        for (int t = 0; t < n_tasks; ++t) e->task_cell_ptr[t + 1] += e->task_cell_ptr[t];
+        std::vector<int> cur(e->task_cell_ptr.begin(), e->task_cell_ptr.end() - 1);
+        e->cell_global.resize(n_keep); od_dest.resize(n_keep); od_at.resize(n_keep); od_tau.resize(n_keep); od_task.resize(n_keep);
+        od_vol.resize(n_keep); task_cells.resize(n_keep);
+        int c = 0;
+        for (int i = 0; i < p->n_od; ++i) {
+            const int t = task_i_of[i];
+            if (t < 0) continue;
+            e->cell_global[c] = i;
+            od_dest[c] = p->zone_centroid[p->od_d[i]];
+            od_at[c] = p->od_at[i]; od_tau[c] = p->od_tau[i]; od_task[c] = t; od_vol[c] = p->od_vol[i];
+            task_cells[cur[t]++] = c;
+            ++c;
+        }
+    });
+    struct ThreadJoiner { std::thread& t; ~ThreadJoiner() { if (t.joinable()) t.join(); } } cells_joiner{ cells_thread };
 
     DTL_TRACE("network image");
-    // ---- network image ----
-    if (e->upload(&e->d_link_tag, p->link_tag, L)) return -1;
-    if (e->upload(&e->d_link_from, p->link_from, L)) return -1;
+    // ---- network image: device arrays are allocated here, the copies (about sixty megabytes of pageable host memory on the
+    // config-5 grid, ~30 arrays) are issued by three threads -- a pageable copy is bounded by the host-side staging of the
+    // calling thread, not by the link ----
+    struct CopyJob { void* dst; const void* src; size_t bytes; };
+    std::vector<CopyJob> jobs;
+    auto up = [&](auto** dst, const auto* src, size_t n) -> int {
+        if (e->alloc(dst, n)) return -1;
+        if (n) jobs.push_back(CopyJob{ (void*)*dst, (const void*)src, n * sizeof(**dst) });
+        return 0;
+    };
+    if (up(&e->d_link_tag, p->link_tag, (size_t)L)) return -1;
+    if (up(&e->d_link_from, p->link_from, (size_t)L)) return -1;
     const size_t TL = (size_t)T * L, TAL = (size_t)T * AT * L;
-#define UPV(field) if (e->upload(&e->vp.field, p->field, TL)) return -1
+#define UPV(field) if (up(&e->vp.field, p->field, TL)) return -1
     UPV(fftt); UPV(cap); UPV(alpha); UPV(beta); UPV(vf); UPV(vc); UPV(nlanes); UPV(cap_lane); UPV(qdf); UPV(preload);
     UPV(penalty); UPV(Q_alpha); UPV(Q_beta); UPV(Q_cd); UPV(Q_n); UPV(Q_cp); UPV(Q_s); UPV(t2); UPV(L_h); UPV(start_h);
     UPV(end_h); UPV(plf); UPV(cycle_length); UPV(red_time); UPV(sat_flow); UPV(vdf_type);
 #undef UPV
-    if (e->upload(&e->d_pce, p->pce, TAL)) return -1;
-    if (e->upload(&e->d_occ, p->occ, TAL)) return -1;
+    if (up(&e->d_pce, p->pce, TAL)) return -1;
+    if (up(&e->d_occ, p->occ, TAL)) return -1;
+    if (up(&e->d_toll, p->toll, TAL)) return -1;
+    if (up(&e->d_lr, p->lr_price, TAL)) return -1;
+    {
+        std::atomic<size_t> next{ 0 };
+        std::atomic<int> failed{ 0 };
+        auto worker = [&]() {
+            if (cudaSetDevice(e->dev) != cudaSuccess) { failed = 1; return; }
+            for (size_t j; (j = next.fetch_add(1)) < jobs.size();)
+                if (cudaMemcpy(jobs[j].dst, jobs[j].src, jobs[j].bytes, cudaMemcpyHostToDevice) != cudaSuccess) failed = 1;
+        };
+        std::thread h1(worker), h2(worker);
+        worker();
+        h1.join(); h2.join();
+        if (failed) { set_err("uploading the network image failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    }
     { // per (tau, at): the PCE / occupancy when all links share it (K3 then skips the gather), NaN otherwise
         std::vector<double> pu((size_t)T * AT), ou((size_t)T * AT);
         for (int ta = 0; ta < T * AT; ++ta) {
@@ -1158,8 +1211,6 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         if (e->upload(&e->d_occ_uni, ou.data(), ou.size())) return -1;
         if (e->alloc(&e->d_link_cost, TAL)) return -1;
     }
-    if (e->upload(&e->d_toll, p->toll, TAL)) return -1;
-    if (e->upload(&e->d_lr, p->lr_price, TAL)) return -1;
     if (e->upload(&e->d_vot, p->vot, AT)) return -1;
     if (e->alloc(&e->ls.pce_fix, TL)) return -1;
     if (e->alloc(&e->ls.person_fix, TL * (1 + AT))) return -1;
@@ -1176,8 +1227,19 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_scalars, 16)) return -1;
     if (e->alloc(&e->d_volume_tmp, TL)) return -1;
     DTL_TRACE("link arrays uploaded");
+    cells_thread.join();
+    if (bad_od_row >= 0) { set_err("OD row %d: zone, agent type or period index out of range", bad_od_row); return -1; }
+    e->n_cells = (int)e->cell_global.size();
+    if (e->upload(&e->d_od_dest, od_dest.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_at, od_at.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_tau, od_tau.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
+    if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
+    DTL_TRACE("OD cells uploaded");
 
-    fs_thread.join();
+    stars_future.wait();
+    stars_waited = true;
     DTL_TRACE("forward stars built (worker thread)");
     int maxE = 0;
     for (int at = 0; at < AT; ++at)
@@ -1186,14 +1248,6 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
             maxE = std::max(maxE, e->fs[fs_index(e, at, tau)].n_edges);
         }
     fsh.clear();
-    // the bundle planner's landmark embeddings (three or four breadth-first searches per forward star) are computed behind
-    // the rest of dtl_create and joined by the first bundle plan
-    e->embed_thread = std::thread([e, L]() {
-        for (ForwardStar& f : e->fs) {
-            if (!e->h_embed_all.empty() && f.n_edges == L) f.h_embed = e->h_embed_all; // same graph as the zone partition's
-            else ensure_embedding(f, e->N);
-        }
-    });
     std::vector<int*> le(AT * T);
     std::vector<Edge*> ed(AT * T);
     for (int i = 0; i < AT * T; ++i) { le[i] = e->fs[i].link_edge; ed[i] = e->fs[i].edges; }

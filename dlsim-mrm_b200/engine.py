@@ -291,12 +291,13 @@ class Engine:
         return it[:K], cu[:CU]
 
     # -- state
-    def link_state(self, tau: int = 0) -> dict:
+    def link_state(self, tau: int = 0, fields=None) -> dict:
+        """per-link state of a period; ``fields`` selects the arrays to read back (default: all eight)"""
         L = self.problem.n_links
         names = ("tt", "pce_volume", "person_volume", "link_volume", "doc", "voc", "P", "vt2")
-        arrs = [np.zeros(L) for _ in names]
+        arrs = [np.empty(L) if fields is None or n in fields else None for n in names]
         self._ck(self.lib.dtl_get_link_state(self.h, tau, *[_ptr(a) for a in arrs]))
-        return dict(zip(names, arrs))
+        return {n: a for n, a in zip(names, arrs) if a is not None}
 
     def volume_fixed(self, tau: int = 0) -> np.ndarray:
         q = np.zeros(self.problem.n_links, np.int64)
