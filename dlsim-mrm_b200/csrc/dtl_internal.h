@@ -174,6 +174,7 @@ struct BundleLaunch {
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
     int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
 };
+void launch_count_edges_nm(const BundleLaunch& a, cudaStream_t st);     // Graph500 edge count on the node-major labels of a bundle batch
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);        // search + label -> tree pass
 void launch_sssp_bundle_finish(const BundleLaunch& a, cudaStream_t st); // the label -> tree pass alone
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st);

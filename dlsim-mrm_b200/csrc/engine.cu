@@ -1094,41 +1094,38 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         ~Joiner() { if (!owners_done) pr.set_value(); if (!stars_done) stars.wait(); }
     } fs_joiner{ owners_ready, owners_signalled, stars_future, stars_waited };
     DTL_TRACE("tasks of this rank: origin zones are sha");
-    // ---- tasks of this rank: origin zones are sharded zone % world == rank (reference: zone % blocks) ----
-    std::vector<int> g_at, g_tau, g_zone;
-    build_task_list(p, g_at, g_tau, g_zone);
-    const std::vector<int> owner = zone_owners(p, e->world, &e->h_embed_all);
-    owners_ready.set_value();
-    owners_signalled = true;
-    std::vector<int> task_of((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
-    for (size_t i = 0; i < g_at.size(); ++i)
-        if (owner[g_zone[i]] == e->rank) {
-            task_of[((long long)g_at[i] * T + g_tau[i]) * Z + g_zone[i]] = (int)e->task_at.size();
-            e->task_at.push_back(g_at[i]); e->task_tau.push_back(g_tau[i]); e->task_zone.push_back(g_zone[i]);
-        }
-    const int n_tasks = (int)e->task_at.size();
-    std::vector<int> origin(n_tasks);
-    std::vector<unsigned char> skip(n_tasks, 0);
-    std::vector<int> n_out(N, 0);
-    for (int l = 0; l < L; ++l) n_out[p->link_from[l]]++;
-    for (int i = 0; i < n_tasks; ++i) {
-        origin[i] = p->zone_centroid[e->task_zone[i]];
-        skip[i] = n_out[origin[i]] == 0; // routing.h:428
-    }
-    e->h_task_origin = origin;
-    if (e->upload(&e->d_task_origin, origin.data(), n_tasks)) return -1;
-    if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
-    if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
-
-    DTL_TRACE("OD cells of this rank (cells whose origi");
-    // ---- OD cells of this rank (cells whose origin has no task never get columns in the reference either) ----
-    // The cell arrays are put together by a second worker thread (two passes over the OD rows: count per task, then fill) while
-    // this thread uploads the link arrays; they are uploaded when it is done.
-    std::vector<int> od_dest, od_at, od_tau, od_task, task_cells;
+    // ---- tasks and OD cells of this rank ----
+    // Origin zones are sharded over the ranks in spatial blocks (zone_owners; the reference deals zone % blocks); cells whose
+    // origin has no task never get columns in the reference either.  The partition (with more than one rank: four breadth-first
+    // searches), the task list and the cell arrays (two passes over the OD rows: count per task, then fill) are put together by
+    // a second worker thread while this thread uploads the link arrays; they are uploaded when it is done.
+    std::vector<int> owner, task_of, origin, od_dest, od_at, od_tau, od_task, task_cells;
+    std::vector<unsigned char> skip;
     std::vector<double> od_vol;
-    int bad_od_row = -1;
-    e->task_cell_ptr.assign(n_tasks + 1, 0);
+    int bad_od_row = -1, n_tasks = 0;
     std::thread cells_thread([&]() {
+        std::vector<int> g_at, g_tau, g_zone;
+        build_task_list(p, g_at, g_tau, g_zone);
+        owner = zone_owners(p, e->world, &e->h_embed_all);
+        owners_ready.set_value();
+        owners_signalled = true;
+        task_of.assign((size_t)AT * T * Z, -1); // (at,tau,zone) -> local task
+        for (size_t i = 0; i < g_at.size(); ++i)
+            if (owner[g_zone[i]] == e->rank) {
+                task_of[((long long)g_at[i] * T + g_tau[i]) * Z + g_zone[i]] = (int)e->task_at.size();
+                e->task_at.push_back(g_at[i]); e->task_tau.push_back(g_tau[i]); e->task_zone.push_back(g_zone[i]);
+            }
+        n_tasks = (int)e->task_at.size();
+        origin.assign(n_tasks, 0);
+        skip.assign(n_tasks, 0);
+        std::vector<int> n_out(N, 0);
+        for (int l = 0; l < L; ++l) n_out[p->link_from[l]]++;
+        for (int i = 0; i < n_tasks; ++i) {
+            origin[i] = p->zone_centroid[e->task_zone[i]];
+            skip[i] = n_out[origin[i]] == 0; // routing.h:428
+        }
+        e->h_task_origin = origin;
+        e->task_cell_ptr.assign(n_tasks + 1, 0);
         std::vector<int> task_i_of(p->n_od, -1);
         size_t n_keep = 0;
         for (int i = 0; i < p->n_od; ++i) {
@@ -1229,6 +1226,9 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     DTL_TRACE("link arrays uploaded");
     cells_thread.join();
     if (bad_od_row >= 0) { set_err("OD row %d: zone, agent type or period index out of range", bad_od_row); return -1; }
+    if (e->upload(&e->d_task_origin, origin.data(), n_tasks)) return -1;
+    if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
+    if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
     e->n_cells = (int)e->cell_global.size();
     if (e->upload(&e->d_od_dest, od_dest.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_at, od_at.data(), e->n_cells)) return -1;
@@ -1438,11 +1438,11 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         const int nb = t1 - t0;
         if (e->sa_mode && e->sa_rt_info[e->task_at[t0]] != 1) { t0 = t1; continue; } // main_api.cpp:987-994
         const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
-        // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept or
-        // counted: both read the per-tree arrays)
+        // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept:
+        // dtl_get_tree reads the per-tree arrays)
         BatchState bs;
         if (sssp_launch_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, tree_off, e->h_task_origin.data() + t0, t0,
-                              !e->opt.keep_trees && !want_count, bs))
+                              !e->opt.keep_trees, bs))
             return -1;
         ColumnLaunch c{};
         c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
@@ -1467,7 +1467,11 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
             int flag = 0;
             CK(cudaMemcpyAsync(&flag, e->d_batch_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
             if (sync_stream(e)) return -1;
-            if (!flag) { done = true; e->tasks_done += nb; }
+            if (!flag) {
+                done = true;
+                e->tasks_done += nb;
+                if (want_count) { launch_count_edges_nm(bs.b, e->st); CK(cudaGetLastError()); } // counted on the node-major labels
+            }
             else {
                 bs.b.slim = 0; bs.slim = false;
                 const int ph2 = e->phase_begin(2);

@@ -445,4 +445,38 @@ void launch_count_edges(const SsspLaunch& a, cudaStream_t st)
     count_edges_kernel<<<148 * 8, 256, 0, st>>>(a);
 }
 
+// the same count on the node-major labels of an origin-bundle batch (the trees were never written per tree): one thread per
+// (bundle, node) walks the node's row once for all B origins of the bundle
+__global__ void count_edges_nm_kernel(BundleLaunch a)
+{
+    const int N = a.s.N, B = a.B;
+    unsigned long long cnt = 0;
+    const size_t total = (size_t)a.n_bundles * N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int bundle = (int)(idx / N);
+        const int u = (int)(idx - (size_t)bundle * N);
+        const unsigned long long* row = a.bl + idx * B;
+        unsigned reached = 0;
+        for (int o = 0; o < B; ++o)
+            if (a.bundle_tasks[bundle * B + o] >= 0 && __longlong_as_double((long long)row[o]) < DTL_MAX_LABEL_COST) reached |= 1u << o;
+        if (!reached) continue;
+        const int n_reached = __popc(reached);
+        for (int e = a.s.row_ptr[u]; e < a.s.row_ptr[u + 1]; ++e) {
+            const Edge ed = ld_edge(&a.s.edges[e]);
+            if (ed.to >= 0) { cnt += n_reached; continue; }
+            const int tag = a.s.link_tag[ed.link];                     // routing.h:779-786: only the origin zone may use it
+            for (int o = 0; o < B; ++o)
+                if (((reached >> o) & 1u) && a.s.task_zone[a.bundle_tasks[bundle * B + o]] == tag) ++cnt;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&a.s.stats->counted_edges, cnt);
+}
+
+void launch_count_edges_nm(const BundleLaunch& a, cudaStream_t st)
+{
+    if (a.n_bundles == 0) return;
+    count_edges_nm_kernel<<<148 * 8, 256, 0, st>>>(a);
+}
+
 } // namespace dtl

@@ -11,10 +11,14 @@ import dlsim_mrm_b200 as D  # noqa: E402
 from bench import ensure_workload  # noqa: E402
 
 p = D.read_gmns(ensure_workload("grid100k"), 8)
+WORLD = int(sys.argv[1]) if len(sys.argv) > 1 else 1   # > 1: one rank of a sharded run in shard-only mode (no collective)
+RANK = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 for rep in range(2):
     torch.cuda.synchronize()
     t = [time.perf_counter()]
-    e = D.Engine(p, max_columns_per_od=24)
+    e = D.Engine(p, max_columns_per_od=24, rank=RANK, world_size=WORLD)
+    if WORLD > 1:
+        e.comm_init(None)
     torch.cuda.synchronize(); t.append(time.perf_counter())
     for k in range(10):
         e.iteration(k)
