@@ -243,7 +243,7 @@ def run_engine_arm(args, rank, world, local_rank):
     def make_engine():
         # the dense-OD variant stores ~200 path links per column for 4 M OD cells: give the path-link arena what it needs
         arena = (40 << 30) // max(1, world) if args.workload.endswith("_dense") else 0
-        e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 4,
+        e = D.Engine(p, device=local_rank, rank=rank, world_size=world, max_columns_per_od=K + W + 8,
                      delta_factor=args.delta, block_threads=args.block, ctas_per_sm=args.ctas, column_arena_bytes=arena)
         if world > 1:
             e.comm_init(uid)
@@ -289,6 +289,12 @@ def run_engine_arm(args, rank, world, local_rank):
             golden_sha = json.load(f)["digests"].get(str(W + K)) if args.workload == "grid100k" else None
     except Exception:
         pass
+    # the scatter runs beside K1 inside the timed steps; its duration ALONE (and that of the other kernels) comes from three more
+    # iterations with every kernel on one stream
+    e.set_overlap(False); e.timing(reset=True); e.counters(reset=True)
+    for k in range(3):
+        e.iteration(W + K + k)
+    tm1, ctr1 = e.timing(), e.counters()
     e.close()
     if not same_on_all_ranks:
         raise SystemExit(f"bench.py: rank {rank} holds link volumes {vol_sha[:16]}.. that differ from another rank's")
@@ -334,7 +340,10 @@ def run_engine_arm(args, rank, world, local_rank):
                          "kernel_ms_per_launch": sssp_ms_launch},
             "sssp_gteps": gteps,
             # the other kernels of a step against the same HBM peak (algorithmic bytes of SURVEY.md 8d; this rank's share)
-            "other_kernels": other_kernels(tm, ctr, K, p, peak),
+            "other_kernels": other_kernels(tm1, ctr1, 3, p, peak),
+            "other_kernels_note": "three extra iterations with every kernel on one stream (inside the timed steps the scatter and its "
+                                  "all-reduce run on a second stream beside K1: phase_ms_per_step['scatter'] is that overlapped duration)",
+            "one_stream_ms_per_step": tm1["ms"]["iteration"] / 3,
             "wall_ms_per_step": wall / K * 1e3,
             "phase_ms_per_step": {k_: v / K for k_, v in tm["ms"].items()},
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},

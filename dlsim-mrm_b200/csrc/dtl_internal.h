@@ -206,8 +206,10 @@ struct ColumnLaunch {
     double* least_contrib;             // [n_od]
     int* error_flag;                   // bit0 arena overflow, bit1 column slots exhausted
     unsigned long long* path_nodes;    // counter
+    int* path_len;                     // [n_od] nodes of the path found for the cell (may be null): key of sort_cells_by_path_length
 };
 void launch_backtrace(const ColumnLaunch& a, cudaStream_t st);
+void sort_cells_by_path_length(const int* path_len, int* cells, const int* cell_ptr, int first, int n_tasks, cudaStream_t st);
 
 struct ScatterLaunch {
     int L, T, AT;

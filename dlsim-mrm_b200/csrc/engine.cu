@@ -14,6 +14,7 @@
 #include <cstring>
 #include <future>
 #include <map>
+#include <set>
 #include <numeric>
 #include <chrono>
 #include <thread>
@@ -88,6 +89,11 @@ struct DevBuf {
 struct dtl_engine {
     int dev = 0, sm_count = 148;
     cudaStream_t st = nullptr;
+    // side stream of the assignment loop: the column -> link-volume scatter of iteration k (+ its all-reduce) only feeds the VDF
+    // pass of iteration k+1, so it runs beside the shortest-path search of iteration k, on the SMs the search leaves free
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false, overlap = true;
     int N = 0, L = 0, Z = 0, AT = 1, T = 1, B = 1;
     int rank = 0, world = 1;
     dtl_options opt{};
@@ -102,6 +108,9 @@ struct dtl_engine {
     std::vector<int> task_at, task_tau, task_zone;
     std::vector<int> task_cell_ptr; // [n_tasks+1] into d_task_cells
     int *d_task_origin = nullptr, *d_task_zone = nullptr, *d_task_cells = nullptr;
+    // OD cells of a batch ordered by path length for the back-trace (sort_cells_by_path_length), once per batch
+    int *d_path_len = nullptr, *d_task_cell_ptr = nullptr;
+    std::set<int> sorted_batches; // first task of the batches whose cells are sorted
     unsigned char* d_task_skip = nullptr;
     // OD cells owned by this rank
     std::vector<int> cell_global; // local -> global OD index
@@ -256,17 +265,24 @@ struct dtl_engine {
         cudaEventCreate(&e);
         return e;
     }
-    int phase_begin(int cls)
+    int phase_begin(int cls, cudaStream_t on = nullptr)
     {
         cudaEvent_t a = get_event(), b = get_event();
-        cudaEventRecord(a, st);
+        cudaEventRecord(a, on ? on : st);
         pending.push_back({ cls, { a, b } });
         return (int)pending.size() - 1;
     }
-    void phase_end(int handle, int n_launches = 1)
+    void phase_end(int handle, int n_launches = 1, cudaStream_t on = nullptr)
     {
-        cudaEventRecord(pending[handle].second.second, st);
+        cudaEventRecord(pending[handle].second.second, on ? on : st);
         launches[pending[handle].first] += n_launches;
+    }
+    // the main stream waits for what was put on the side stream (no-op when nothing is pending)
+    void join_side()
+    {
+        if (!side_pending) return;
+        cudaStreamWaitEvent(st, ev_join, 0);
+        side_pending = false;
     }
     void resolve_timing()
     {
@@ -465,13 +481,14 @@ int sync_stream(dtl_engine* e)
     }
 }
 
-int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum)
+int all_reduce(dtl_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum, cudaStream_t on = nullptr)
 {
     if (e->world <= 1 || e->local_shard) return 0;
     if (!e->comm) { set_err("world_size > 1 but dtl_comm_init was not called (or the communicator was aborted after a failure)"); return -1; }
-    const int ph = e->phase_begin(6);
-    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, op, e->comm, e->st);
-    e->phase_end(ph);
+    if (!on) on = e->st;
+    const int ph = e->phase_begin(6, on);
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, op, e->comm, on);
+    e->phase_end(ph, 1, on);
     if (r != ncclSuccess) { set_err("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return -1; }
     return 0;
 }
@@ -486,6 +503,7 @@ int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_ove
     a.block_sums = e->d_block_sums; a.sys_tt = e->d_scalars + 0;
     a.volume_override = volume_override;
     a.detail = detail; a.write_cost = write_cost; a.error_flag = e->d_error_flag;
+    e->join_side();
     const int ph = e->phase_begin(0);
     launch_vdf(a, e->st);
     e->phase_end(ph, 2);
@@ -493,12 +511,20 @@ int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_ove
     return 0;
 }
 
-int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false)
+// side: on the side stream, after everything the main stream holds so far; the main stream picks the result up with join_side()
+int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false, bool side = false)
 {
     const size_t TL = (size_t)e->T * e->L;
-    const int ph = e->phase_begin(1);
-    CK(cudaMemsetAsync(e->ls.pce_fix, 0, TL * sizeof(unsigned long long), e->st));
-    if (person) CK(cudaMemsetAsync(e->ls.person_fix, 0, TL * (1 + e->AT) * sizeof(unsigned long long), e->st));
+    e->join_side();
+    cudaStream_t on = e->st;
+    if (side && e->overlap && e->st2) {
+        on = e->st2;
+        CK(cudaEventRecord(e->ev_fork, e->st));
+        CK(cudaStreamWaitEvent(on, e->ev_fork, 0));
+    }
+    const int ph = e->phase_begin(1, on);
+    CK(cudaMemsetAsync(e->ls.pce_fix, 0, TL * sizeof(unsigned long long), on));
+    if (person) CK(cudaMemsetAsync(e->ls.person_fix, 0, TL * (1 + e->AT) * sizeof(unsigned long long), on));
     ScatterLaunch a{};
     a.L = e->L; a.T = e->T; a.AT = e->AT; a.pool = e->pool;
     a.od_at = e->d_od_at; a.od_tau = e->d_od_tau; a.pce = e->d_pce; a.occ = e->d_occ;
@@ -506,11 +532,15 @@ int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false)
     a.pce_fix = e->ls.pce_fix; a.person_fix = person ? e->ls.person_fix : nullptr;
     a.decay_k = decay_k; a.link_refs = e->d_counters + 0;
     a.decay_at = sa ? e->d_sa_decay_at : nullptr;
-    launch_scatter(a, e->st);
-    e->phase_end(ph, 1);
+    launch_scatter(a, on);
+    e->phase_end(ph, 1, on);
     CK(cudaGetLastError());
-    if (all_reduce(e, e->ls.pce_fix, TL, ncclUint64)) return -1;
-    if (person && all_reduce(e, e->ls.person_fix, TL * (1 + e->AT), ncclUint64)) return -1;
+    if (all_reduce(e, e->ls.pce_fix, TL, ncclUint64, ncclSum, on)) return -1;
+    if (person && all_reduce(e, e->ls.person_fix, TL * (1 + e->AT), ncclUint64, ncclSum, on)) return -1;
+    if (on != e->st) {
+        CK(cudaEventRecord(e->ev_join, on));
+        e->side_pending = true;
+    }
     return 0;
 }
 
@@ -785,7 +815,9 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - plan_t0).count());
     b.bundle_counter = e->d_bundle_counter;
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
-    if (b.fuse_pred) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid)); // CTAs without a bundle run the predecessor pass
+    // CTAs without a bundle run the predecessor pass -- unless the side stream holds work (the scatter of this iteration): then the
+    // SMs without a bundle are left to it, and the predecessor pass is done by the searching CTAs as they finish
+    if (b.fuse_pred && !e->side_pending) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid));
     return 0;
 }
 
@@ -1002,9 +1034,13 @@ void dtl_destroy(dtl_engine* e)
     if (!e) return;
     if (e->embed_thread.joinable()) e->embed_thread.join();
     cudaSetDevice(e->dev);
+    if (e->st2) cudaStreamSynchronize(e->st2);
     if (e->st) cudaStreamSynchronize(e->st);
     e->resolve_timing();
     for (cudaEvent_t ev : e->free_events) cudaEventDestroy(ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->st2) cudaStreamDestroy(e->st2);
     // e->comm is shared and lives as long as the process (see dtl_comm_init)
     for (void* p : e->allocs) cudaFree(p);
     if (e->st) cudaStreamDestroy(e->st);
@@ -1038,7 +1074,18 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     CK(cudaGetDevice(&e->dev));
     DTL_TRACE("device selected");
     CK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->dev)); // (cudaGetDeviceProperties costs milliseconds)
-    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    {
+        // the main stream (shortest-path search) gets its CTAs placed before the side stream's
+        int pr_least = 0, pr_greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        CK(cudaStreamCreateWithPriority(&e->st, cudaStreamNonBlocking, pr_greatest));
+        e->overlap = !getenv("DTL_NO_OVERLAP");
+        {
+            CK(cudaStreamCreateWithPriority(&e->st2, cudaStreamNonBlocking, pr_least));
+            CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        }
+    }
     DTL_TRACE("stream");
     e->h_scalars = e->h_scalars_buf; // pageable: a 16-byte read-back per iteration does not pay for pinning memory (2.7 ms)
 
@@ -1236,6 +1283,10 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
+    if (!getenv("DTL_NO_CELL_SORT")) {
+        if (e->alloc(&e->d_path_len, std::max<size_t>(1, task_cells.size()))) return -1;
+        if (e->upload(&e->d_task_cell_ptr, e->task_cell_ptr.data(), e->task_cell_ptr.size())) return -1;
+    }
     DTL_TRACE("OD cells uploaded");
 
     stars_future.wait();
@@ -1454,12 +1505,14 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
         c.task_skip_backtrace = e->d_task_skip;
         c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
+        c.path_len = e->d_path_len;
         bool done = false;
         if (bs.slim) {
             // back-trace on the node-major trees; the kernel does nothing when the label -> tree pass flagged a tie or an
             // overflowed bundle, and the batch is then redone through the per-tree path below
             ColumnLaunch cs = c;
             cs.bl = bs.b.bl; cs.bp = bs.b.bp; cs.task_slot = bs.d_slots; cs.B = bs.b.B; cs.batch_flag = e->d_batch_flag;
+            e->join_side(); // the scatter's MSA decay of the column volumes comes before this iteration's share is added
             const int ph = e->phase_begin(4);
             launch_backtrace(cs, e->st);
             e->phase_end(ph, 1);
@@ -1471,6 +1524,12 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
                 done = true;
                 e->tasks_done += nb;
                 if (want_count) { launch_count_edges_nm(bs.b, e->st); CK(cudaGetLastError()); } // counted on the node-major labels
+                if (e->d_path_len && !e->sorted_batches.count(t0)) {
+                    e->sorted_batches.insert(t0);
+                    sort_cells_by_path_length(e->d_path_len, e->d_task_cells + e->task_cell_ptr[t0], e->d_task_cell_ptr + t0,
+                                              e->task_cell_ptr[t0], nb, e->st);
+                    CK(cudaGetLastError());
+                }
             }
             else {
                 bs.b.slim = 0; bs.slim = false;
@@ -1482,6 +1541,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         }
         if (!done) {
             if (sssp_complete_batch(e, bs, nb, want_count)) return -1;
+            e->join_side();
             const int ph = e->phase_begin(4);
             launch_backtrace(c, e->st);
             e->phase_end(ph, 1);
@@ -1498,10 +1558,11 @@ static int iteration_impl(dtl_engine* e, int k, double row[5])
     CK(cudaSetDevice(e->dev));
     const int ph7 = e->phase_begin(7);
     if (do_vdf(e, false, true, nullptr)) return -1;                    // main_api.cpp:606
-    if (do_scatter(e, k, false)) return -1;                            // main_api.cpp:618
+    if (do_scatter(e, k, false, false, true)) return -1;               // main_api.cpp:618 (side stream: joined before the back-trace)
     const bool want_count = e->counted_edges_cached < 0;
     if (want_count) CK(cudaMemsetAsync(&e->d_stats->counted_edges, 0, 8, e->st));
     if (trees_and_columns(e, k, want_count)) return -1;                // main_api.cpp:647-699
+    e->join_side();
     launch_sum(e->d_least, e->n_cells, 1, e->d_scalars + 1, e->st);
     CK(cudaGetLastError());
     if (all_reduce(e, e->d_scalars + 1, 1, ncclFloat64)) return -1;
@@ -2282,6 +2343,13 @@ int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pr
         }
     }
     return 0;
+}
+
+int dtl_set_overlap(dtl_engine* e, int on)
+{
+    const int was = e->overlap ? 1 : 0;
+    e->overlap = on != 0 && e->st2 != nullptr;
+    return was;
 }
 
 int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset)

@@ -213,6 +213,11 @@ int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pr
  * ms[0]=VDF  ms[1]=scatter  ms[2]=SSSP  ms[3]=tie replay  ms[4]=backtrace/columns  ms[5]=column pool
  * ms[6]=all-reduce  ms[7]=whole iterations;  counts[i] = kernel launches in each class */
 int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset);
+/* The assignment loop runs the scatter of iteration k (+ its all-reduce) on a second stream beside the shortest-path search of
+ * the same iteration (the scatter only feeds the VDF pass of iteration k+1; main_api.cpp:606-699 has no such dependency either,
+ * it is simply serial).  on = 0 puts every kernel back on one stream -- same results; for per-kernel timing (ms[1] is the
+ * duration of the scatter ALONE only then).  Returns the previous setting. */
+int dtl_set_overlap(dtl_engine* e, int on);
 /* work counters since the last reset: { counted edges (Graph500 convention), relaxations, queue pops,
  * SSSP rounds, SSSP tasks, replayed origins, column-link references scattered, back-traced path nodes,
  * trees re-run with worst-case queues, tie candidates observed } */

@@ -16,11 +16,13 @@ static double dmin(double a, double b) { return a < b ? a : b; }
 typedef struct {
     int node_sum, seq_no, n_links, n_nodes;
     double volume, cost, time, toll;
+    int impacted;   /* impacted_path_flag, DTA.h:523 */
     int* links; /* origin -> destination order, DTA.h:551-559 */
 } orc_column;
 
 typedef struct {
     int n, cap;
+    int info_type;  /* CColumnVector::information_type, DTA.h:698 */
     orc_column* c; /* ascending node_sum == std::map iteration order */
 } orc_colvec;
 
@@ -67,6 +69,10 @@ struct orc_state {
     int* ub_flag;              /* [T][L] upper_bound_flag (default 1, VDF.h:60) */
     double* est_dev;           /* [T][L] est_count_dev */
     float *at_pce, *at_occ;    /* [AT] agent-type PCE / OCC as the ODME scatter uses them (float, assignment.h:308-309) */
+    /* dms scenario rows (scenario_API.h:165-188) */
+    int* info_zone;            /* [Z] 1 = information zone (zone_seq_no_2_info_mapping) */
+    int* dms_zone;             /* [T][L] zone seq no of the to-node of a dms link (-1: none / not a zone of the model) */
+    int* dms_has_zone;         /* [T][L] the to-node of the dms link carries a zone id (node_seq_no_2_zone_id_mapping) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -378,6 +384,10 @@ orc_state* orc_create(const orc_problem* p)
     s->ub_flag = (int*)malloc(sizeof(int) * (TL + 1));
     for (size_t i = 0; i < TL; ++i) s->ub_flag[i] = 1;
     s->est_dev = (double*)calloc(TL + 1, sizeof(double));
+    s->info_zone = (int*)calloc(Z > 0 ? Z : 1, sizeof(int));
+    s->dms_zone = (int*)malloc(sizeof(int) * (TL + 1));
+    s->dms_has_zone = (int*)calloc(TL + 1, sizeof(int));
+    for (size_t i = 0; i < TL; ++i) s->dms_zone[i] = -1;
     s->at_pce = (float*)calloc(AT > 0 ? AT : 1, sizeof(float));
     s->at_occ = (float*)calloc(AT > 0 ? AT : 1, sizeof(float));
     for (int at = 0; at < AT; ++at) { s->at_pce[at] = 1; s->at_occ[at] = 1; }
@@ -403,6 +413,7 @@ void orc_destroy(orc_state* s)
     free(s->label); free(s->pred_node); free(s->pred_link); free(s->status); free(s->next);
     free(s->tmp_nodes); free(s->tmp_links); free(s->n_out_unfiltered);
     free(s->m_fftt); free(s->m_cap); free(s->m_nlanes); free(s->rt_info); free(s->sa_lanes); free(s->design_flag); free(s->od_impact);
+    free(s->info_zone); free(s->dms_zone); free(s->dms_has_zone);
     free(s->obs_count); free(s->ub_flag); free(s->est_dev); free(s->at_pce); free(s->at_occ);
     free(s);
 }
@@ -470,8 +481,8 @@ static void scatter_pass_sa(orc_state* s, int iteration_index, int self_reducing
                 }
                 /* :150-176 in the SA stage only users with real-time information are re-routed: a column of an agent type
                    without information keeps its volume, and so does a DMS user's whose origin is not an information zone
-                   (information zones come with dms scenario rows, which this restatement does not cover) */
-                if (sa && s->rt_info[at] != 1) continue;
+                   */
+                if (sa && !(s->rt_info[at] == 1 || (s->rt_info[at] == 2 && s->info_zone[p->od_o[i]]))) continue;
                 if (self_reducing)                                                        /* :182-186 */
                     c->volume = c->volume * ((double)iteration_index / (double)(iteration_index + 1));
             }
@@ -573,7 +584,7 @@ static double sp_region(orc_state* s, int k, int sa, long long* counted_out)
             float vot = p->vot[n->at];
             for (int oi = 0; oi < n->n_origins; ++oi) {
                 int oz = n->zones[oi];
-                if (sa && s->rt_info[n->at] != 1) continue;                               /* main_api.cpp:987-994 */
+                if (sa && !(s->rt_info[n->at] == 1 || (s->rt_info[n->at] == 2 && s->info_zone[oz]))) continue; /* main_api.cpp:987-994 */
                 /* UpdateGeneralizedLinkCost, routing.h:229-231 */
                 for (int l = 0; l < L; ++l) {
                     size_t a = ((size_t)n->tau * AT + n->at) * L + l;
@@ -717,6 +728,131 @@ void orc_sa_iteration(orc_state* s, int it, double row[3])
     double least_total = sp_region(s, it, 1, NULL);                                       /* :966-1018 */
     float denom = 1 > p->total_demand_volume ? (float)1 : p->total_demand_volume;         /* :1027 */
     row[0] = sysTT; row[1] = sysTT / denom; row[2] = least_total;
+}
+
+/* a supply_side_scenario.csv row of type "dms", scenario_API.h:165-188: has_zone = the to-node of the link carries a zone id,
+ * zone = its zone seq no (-1 when that id is not a zone of the model) */
+void orc_sa_dms_link(orc_state* s, int tau, int link, int has_zone, int zone)
+{
+    size_t a = (size_t)tau * s->L + link;
+    s->design_flag[a] = 2;
+    s->dms_has_zone[a] = has_zone;
+    s->dms_zone[a] = zone;
+    if (zone >= 0) s->info_zone[zone] = 1;
+}
+
+static orc_column* colvec_insert(orc_colvec* cv, int node_sum, int* existed)
+{
+    int pos = 0;
+    while (pos < cv->n && cv->c[pos].node_sum < node_sum) ++pos;
+    if (pos < cv->n && cv->c[pos].node_sum == node_sum) { *existed = 1; return &cv->c[pos]; }
+    if (cv->n == cv->cap) {
+        cv->cap = cv->cap ? cv->cap * 2 : 4;
+        cv->c = (orc_column*)realloc(cv->c, sizeof(orc_column) * cv->cap);
+    }
+    memmove(&cv->c[pos + 1], &cv->c[pos], sizeof(orc_column) * (cv->n - pos));
+    memset(&cv->c[pos], 0, sizeof(orc_column));
+    cv->c[pos].node_sum = node_sum;
+    cv->n++;
+    *existed = 0;
+    return &cv->c[pos];
+}
+
+/* g_column_pool_route_modification, assignment.h:1077-1383 (one thread: the travel times of the information-zone columns are
+ * accumulated in visiting order, :1219).  Returns the number of columns that were split. */
+int orc_sa_route_modification(orc_state* s)
+{
+    const orc_problem* p = s->p;
+    const int L = s->L, Z = s->Z, AT = s->AT, T = s->T;
+    int n_split = 0;
+    int* seq = (int*)malloc(sizeof(int) * (size_t)(2 * s->N + 8));
+    for (int o = 0; o < Z; ++o)
+        for (int d = 0; d < Z; ++d)
+            for (int at = 0; at < AT; ++at) {
+                if (s->rt_info[at] != 2) continue;                                        /* :1110 */
+                for (int tau = 0; tau < T; ++tau) {
+                    int cell = find_od(s, o, d, at, tau);
+                    if (cell < 0) continue;                                               /* od_volume > 0, :1115 */
+                    orc_colvec* cv = &s->pool[cell];
+                    const signed char* flag = s->design_flag + (size_t)tau * L;
+                    /* the std::map is walked in key order while g_add_new_column inserts into it: a new column with a larger
+                       key is visited later in the same walk */
+                    int have_key = 0, last_key = 0;
+                    for (;;) {
+                        int j = -1;
+                        for (int q = 0; q < cv->n; ++q)
+                            if (!have_key || cv->c[q].node_sum > last_key) { j = q; break; }
+                        if (j < 0) break;
+                        have_key = 1; last_key = cv->c[j].node_sum;
+                        if (cv->c[j].volume < 0.00001) continue;                          /* :1136 */
+                        int passing_info = 0, new_orig = -1, passing_cap = 0, n_seq = 0;
+                        for (int nl = 0; nl < cv->c[j].n_links; ++nl) {                   /* :1141 */
+                            int l = cv->c[j].links[nl];
+                            size_t a = (size_t)tau * L + l;
+                            if (!passing_info && flag[l] == 2 && s->dms_has_zone[a]) {    /* :1146-1150 */
+                                s->od_impact[cell] = 1;                                   /* :1153-1154 */
+                                if (s->dms_zone[a] < 0) continue;                         /* :1158-1159 */
+                                passing_info = 1; new_orig = s->dms_zone[a];
+                                n_seq = 0;
+                                for (int nl2 = 0; nl2 <= nl; ++nl2) seq[n_seq++] = cv->c[j].links[nl2]; /* :1166-1170 */
+                            }
+                            if (flag[l] == -1) { passing_cap = 1; cv->c[j].impacted = 1; } /* :1176-1180 */
+                        }
+                        if (!(passing_cap && passing_info)) continue;                     /* :1184 */
+                        int cell2 = find_od(s, new_orig, d, at, tau);
+                        if (cell2 < 0 || s->pool[cell2].n == 0) { free(seq); return -1; } /* :1203-1208 the reference stops here */
+                        orc_colvec* cv2 = &s->pool[cell2];
+                        float non_div = 999999;                                           /* :1214 */
+                        for (int q = 0; q < cv2->n; ++q) {                                /* :1215-1236 */
+                            orc_column* c2 = &cv2->c[q];
+                            for (int nl2 = 1; nl2 < c2->n_links; ++nl2) c2->time += s->tt[tau][c2->links[nl2]]; /* accumulates, :1219 */
+                            int div = 1;
+                            for (int nl2 = 1; nl2 < c2->n_links; ++nl2)
+                                if (flag[c2->links[nl2]] <= -1) div = 0;
+                            if (!div) {
+                                float abs_br = 3, ratio_br = 0.15;
+                                if (c2->time < non_div - abs_br && c2->time < (non_div * (1 - ratio_br))) non_div = c2->time;
+                            }
+                        }
+                        int found = 0;
+                        for (int q = 0; q < cv2->n; ++q) {                                /* :1238-1262 */
+                            orc_column* c2 = &cv2->c[q];
+                            int div = 1;
+                            for (int nl2 = 1; nl2 < c2->n_links; ++nl2)
+                                if (flag[c2->links[nl2]] <= -1) div = 0;
+                            if (div && !found && c2->time < non_div) {
+                                for (int nl2 = 1; nl2 < c2->n_links; ++nl2) seq[n_seq++] = c2->links[nl2];
+                                found = 1;
+                            }
+                        }
+                        if (found) {                                                      /* :1264, optional detour :1298-1325 */
+                            float base_tt = 0, alt_tt = 0;
+                            for (int nl0 = 0; nl0 < cv->c[j].n_links; ++nl0) base_tt += s->tt[tau][cv->c[j].links[nl0]];
+                            for (int nl3 = 1; nl3 < n_seq; ++nl3) alt_tt += s->tt[tau][seq[nl3]];
+                            float beta = -0.1;
+                            float prob_base = expf(beta * base_tt) / (expf(beta * base_tt) + expf(beta * alt_tt));
+                            float base_volume = cv->c[j].volume;
+                            cv->c[j].volume = base_volume * prob_base;
+                            /* g_add_new_column, assignment.h:1012-1045 */
+                            int node_sum = 0;
+                            for (int q = 0; q < n_seq; ++q) node_sum = (int)((unsigned)node_sum + (unsigned)seq[q] + (unsigned)p->link_to[seq[q]]);
+                            int size_before = cv->n, existed = 0;
+                            orc_column* nc = colvec_insert(cv, node_sum, &existed);
+                            nc->seq_no = existed ? size_before : size_before + 1;        /* map.size() after operator[] created the entry */
+                            free(nc->links);
+                            nc->links = (int*)malloc(sizeof(int) * (size_t)(n_seq > 0 ? n_seq : 1));
+                            memcpy(nc->links, seq, sizeof(int) * (size_t)n_seq);
+                            nc->n_links = n_seq; nc->n_nodes = n_seq + 1;
+                            nc->volume = base_volume * (1 - prob_base);
+                            nc->impacted = 3;                                             /* :1322 */
+                            ++n_split;
+                        }
+                        cv2->info_type = 1;                                               /* :1360 */
+                    }
+                }
+            }
+    free(seq);
+    return n_split;
 }
 
 /* g_update_gradient_cost_and_assigned_flow_in_column_pool with the SA flag (main_api.cpp:1040, assignment.h:565-928) */

@@ -74,6 +74,10 @@ double orc_finalize(orc_state* s, int K);
  * orc_sa_iteration(0..S), orc_sa_column_update(0..S-1). ---- */
 void orc_sa_configure(orc_state* s, const int* rt_info /* [AT] real_time_information: 0 none, 1 rt, 2 dms */);
 void orc_sa_lane_change(orc_state* s, int tau, int link, double lanes);
+void orc_sa_dms_link(orc_state* s, int tau, int link, int has_zone, int zone); /* "dms" row: information zone of the link's to-node */
+int orc_sa_route_modification(orc_state* s); /* g_column_pool_route_modification (assignment.h:1077-1383), after the last orc_sa_iteration */
+/* per column in orc_get_columns order: impacted_path_flag; per column: information_type of its pool, od-impact flag of its cell */
+void orc_get_column_flags(const orc_state* s, int* impacted, int* info_type, int* od_impact);
 double orc_sa_begin(orc_state* s);
 void orc_sa_iteration(orc_state* s, int it, double row[3]); /* { sysTT, avg travel time, least system TT of the re-routed origins } */
 void orc_sa_column_update(orc_state* s, int n, double row[4]);
