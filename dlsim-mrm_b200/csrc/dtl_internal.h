@@ -170,7 +170,8 @@ struct BundleLaunch {
     int slim;                // 1: the label -> tree pass leaves predecessors node-major in bp and writes no per-tree arrays
     int fuse_pred;           // slim + async: the search kernel runs the label -> predecessor pass itself -- every CTA that has no
                              // (more) bundle to search takes tiles of the bundles that are finished (work[] below)
-    int* work;               // fuse_pred: [1 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters}
+    int* work;               // fuse_pred: [2 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters,
+                             // resident CTAs of the search kernel}
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
     int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
 };
@@ -178,6 +179,7 @@ void launch_count_edges_nm(const BundleLaunch& a, cudaStream_t st);     // Graph
 void launch_sssp_bundle(const BundleLaunch& a, cudaStream_t st);        // search + label -> tree pass
 void launch_sssp_bundle_finish(const BundleLaunch& a, cudaStream_t st); // the label -> tree pass alone
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st);
+void launch_bundle_pred_helpers(const BundleLaunch& a, int grid, cudaStream_t st); // extra CTAs for the fused label -> predecessor pass
 size_t bundle_async_smem_bytes(int N, int ring);
 size_t bundle_smem_bytes(int N, int cap_near); // dynamic shared memory of one CTA: two queue bits per node + two near queues
 void sssp_occupancy(int block, int* max_ctas_per_sm, int* regs);

@@ -801,7 +801,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     }
     b.fuse_pred = slim && b.async && !getenv("DTL_NO_FUSED_PRED") ? 1 : 0;
     if (b.fuse_pred) {
-        const size_t n_work = 1 + 2 * (size_t)b.n_bundles;
+        const size_t n_work = 2 + 2 * (size_t)b.n_bundles;
         if (e->bundle_work_cap < n_work) {
             if (e->alloc(&e->d_bundle_work, n_work)) return -1;
             e->bundle_work_cap = n_work;
@@ -817,7 +817,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
     // CTAs without a bundle run the predecessor pass -- unless the side stream holds work (the scatter of this iteration): then the
     // SMs without a bundle are left to it, and the predecessor pass is done by the searching CTAs as they finish
-    if (b.fuse_pred && !e->side_pending) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid));
+    if (b.fuse_pred && !e->side_pending && !getenv("DTL_BUNDLE_NO_HELPERS")) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid));
     return 0;
 }
 
@@ -902,9 +902,22 @@ int sssp_launch_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const in
         if (b.fuse_pred) {
             CK(cudaMemsetAsync(b.work, 0, sizeof(int), e->st));
             CK(cudaMemsetAsync(b.work + 1, 0xff, sizeof(int) * b.n_bundles, e->st));
-            CK(cudaMemsetAsync(b.work + 1 + b.n_bundles, 0, sizeof(int) * b.n_bundles, e->st));
+            CK(cudaMemsetAsync(b.work + 1 + b.n_bundles, 0, sizeof(int) * (b.n_bundles + 1), e->st));
+        }
+        // the search kernel got no CTAs beyond its bundles (make_bundle_launch: the side stream holds the scatter): when that is
+        // through, the SMs without a bundle run helper CTAs for the label -> predecessor pass, like the search kernel's own idle
+        // CTAs would have (7.7 against 8.1 ms per 2 000 trees with / without them)
+        const int max_grid = e->sm_count * b.ctas_per_sm;
+        const bool helpers = b.fuse_pred && e->side_pending && b.grid < max_grid && !getenv("DTL_BUNDLE_NO_HELPERS");
+        if (helpers) {
+            CK(cudaEventRecord(e->ev_fork, e->st)); // after the resets of b.work, before the search kernel
+            CK(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
         }
         launch_sssp_bundle(b, e->st);
+        if (helpers) {
+            launch_bundle_pred_helpers(b, max_grid - b.grid, e->st2);
+            CK(cudaEventRecord(e->ev_join, e->st2));
+        }
         if (b.async) e->last_sssp_variant = 3;
         e->phase_end(ph, 2);
     } else {

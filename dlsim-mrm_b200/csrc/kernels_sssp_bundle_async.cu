@@ -27,6 +27,58 @@ namespace dtl {
 #define BND_ASYNC_SLEEP 40 /* ns an idle warp sleeps between two polls of its ring slots */
 #endif
 
+// The label -> predecessor pass of the finished bundles (fuse_pred): bundles are taken in the order they finished, tiles of a
+// bundle from a counter.  Run by the CTAs of the search kernel that have nothing (left) to search and by the CTAs of
+// bundle_pred_helper_kernel; s_bundle / s_head are two shared ints of the calling CTA.
+template <int BLOCK, int B>
+__device__ __forceinline__ void bundle_pred_loop(const BundleLaunch& a, int* s_bundle, int* s_head)
+{
+    constexpr int TILE = BLOCK / (B / 2) * 8;
+    const int tid = threadIdx.x;
+    const int N = a.s.N;
+    const int n_tiles = (N + TILE - 1) / TILE;
+    int* const done = a.work + 1;
+    int* const tile_counter = a.work + 1 + a.n_bundles;
+    for (int i = 0; i < a.n_bundles; ++i) {
+        __syncthreads();
+        if (tid == 0) {
+            int b;
+            while ((b = *reinterpret_cast<volatile int*>(&done[i])) < 0) __nanosleep(400);
+            *s_bundle = b;
+        }
+        __syncthreads();
+        const int b = *s_bundle;
+        __threadfence();
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) *s_head = atomicAdd(&tile_counter[b], 1);
+            __syncthreads();
+            const int tile = *s_head;
+            if (tile >= n_tiles) break;
+            bundle_pred_nodes<B, BLOCK, true>(a, b, tile * TILE, min(N, (tile + 1) * TILE), tile == 0);
+        }
+    }
+}
+
+// Helper CTAs for the label -> predecessor pass of a RUNNING search kernel (launched on another stream when the search kernel was
+// given only as many CTAs as it has bundles, so that the SMs without a bundle can first serve that stream's other work -- the
+// link-volume scatter).  A helper only joins in when every CTA of the search kernel is resident (work[1 + 2 * n_bundles] counts
+// them): it then cannot keep a search CTA from being placed, and the search cannot wait for it.
+template <int BLOCK, int B>
+__global__ void __launch_bounds__(BLOCK, 1) bundle_pred_helper_kernel(BundleLaunch a)
+{
+    __shared__ int s_bundle, s_head, s_go;
+    if (threadIdx.x == 0) {
+        const volatile int* started = a.work + 1 + 2 * a.n_bundles;
+        int go = 0;
+        for (int spin = 0; spin < 256 && !(go = *started >= a.grid); ++spin) __nanosleep(200);
+        s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    bundle_pred_loop<BLOCK, B>(a, &s_bundle, &s_head);
+}
+
 // EPL = out-edges relaxed per lane and pass (4, 2 or 1).  A ring entry (one node) is served by a group of
 // G = (B / 2) * (4 / EPL) lanes: lane (es, op) of the group relaxes edges es*EPL .. es*EPL+EPL-1 of the node for origins 2*op and
 // 2*op+1.  Only EPL = 4 is instantiated: on average a warp pass serves 0.9 nodes at the bench configuration (24.5 M passes for
@@ -67,6 +119,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
     int2* q_far2 = q_far + CAPF;
     unsigned long long c_relax = 0;
     unsigned c_pops = 0, c_rounds = 0;
+    if (a.fuse_pred && tid == 0) atomicAdd(&a.work[1 + 2 * a.n_bundles], 1); // resident (see bundle_pred_helper_kernel)
 
     // publish one entry into the ring (any thread)
     auto push_near = [&](int node, int2 row) {
@@ -366,32 +419,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
     }
     // ---- label -> predecessor pass of the finished bundles, by every CTA that has nothing left to search: the CTAs beyond
     // the number of bundles from the start, the others as their bundle finishes (bundles differ by some 10 % in search time).
-    // Bundles are taken in the order they finished, tiles of a bundle from a counter.
-    if (a.fuse_pred) {
-        constexpr int TILE = BLOCK / (B / 2) * 8;
-        const int n_tiles = (N + TILE - 1) / TILE;
-        int* const done = a.work + 1;
-        int* const tile_counter = a.work + 1 + a.n_bundles;
-        for (int i = 0; i < a.n_bundles; ++i) {
-            __syncthreads();
-            if (tid == 0) {
-                int b;
-                while ((b = *reinterpret_cast<volatile int*>(&done[i])) < 0) __nanosleep(400);
-                s_bundle = b;
-            }
-            __syncthreads();
-            const int b = s_bundle;
-            __threadfence();
-            for (;;) {
-                __syncthreads();
-                if (tid == 0) s_head = atomicAdd(&tile_counter[b], 1);
-                __syncthreads();
-                const int tile = s_head;
-                if (tile >= n_tiles) break;
-                bundle_pred_nodes<B, BLOCK, true>(a, b, tile * TILE, min(N, (tile + 1) * TILE), tile == 0);
-            }
-        }
-    }
+    if (a.fuse_pred) bundle_pred_loop<BLOCK, B>(a, &s_bundle, &s_head);
     for (int o = 16; o > 0; o >>= 1) {
         c_relax += __shfl_xor_sync(0xffffffffu, c_relax, o);
         c_pops += __shfl_xor_sync(0xffffffffu, c_pops, o);
@@ -443,6 +471,25 @@ static void async_launch_b(const BundleLaunch& a, size_t smem, cudaStream_t st)
     case 7681: async_launch<768, B, EPL, 1>(a, smem, st); break;
     default: async_launch<1024, B, EPL, 1>(a, smem, st); break;
     }
+}
+
+template <int B>
+static void helper_launch_b(const BundleLaunch& a, int grid, cudaStream_t st)
+{
+    switch (a.block) {
+    case 512: bundle_pred_helper_kernel<512, B><<<grid, 512, 0, st>>>(a); break;
+    case 768: bundle_pred_helper_kernel<768, B><<<grid, 768, 0, st>>>(a); break;
+    default: bundle_pred_helper_kernel<1024, B><<<grid, 1024, 0, st>>>(a); break;
+    }
+}
+
+// `grid` helper CTAs for the fused label -> predecessor pass of the search kernel launched with `a` (same CTA size: the tiles are
+// shared); a.work must have been reset before either kernel starts
+void launch_bundle_pred_helpers(const BundleLaunch& a, int grid, cudaStream_t st)
+{
+    if (!a.fuse_pred || a.n_bundles == 0 || grid <= 0) return;
+    if (a.B == 8) helper_launch_b<8>(a, grid, st);
+    else helper_launch_b<16>(a, grid, st);
 }
 
 void launch_sssp_bundle_async_search(const BundleLaunch& a, cudaStream_t st)
