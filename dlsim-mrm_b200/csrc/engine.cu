@@ -1574,8 +1574,31 @@ static int iteration_impl(dtl_engine* e, int k, double row[5])
     if (do_scatter(e, k, false, false, true)) return -1;               // main_api.cpp:618 (side stream: joined before the back-trace)
     const bool want_count = e->counted_edges_cached < 0;
     if (want_count) CK(cudaMemsetAsync(&e->d_stats->counted_edges, 0, 8, e->st));
+    static const bool k1_timeline = getenv("DTL_K1_TIMELINE") != nullptr; // -DSSSP_PROFILE build: globaltimer stamps of the bundle search
+    if (k1_timeline) {
+        SsspStats z{};
+        CK(cudaMemcpyAsync(&z, e->d_stats, sizeof(z), cudaMemcpyDeviceToHost, e->st));
+        if (sync_stream(e)) return -1;
+        z.stage[4] = ~0ULL; z.stage[7] = ~0ULL; z.stage[5] = 0; z.stage[6] = 0; z.stage[3] = 0;
+        for (int j = 0; j < 8; ++j) z.prof[j] = 0;
+        CK(cudaMemcpyAsync(e->d_stats, &z, sizeof(z), cudaMemcpyHostToDevice, e->st));
+        if (sync_stream(e)) return -1;
+    }
     if (trees_and_columns(e, k, want_count)) return -1;                // main_api.cpp:647-699
     e->join_side();
+    if (k1_timeline) {
+        SsspStats z{};
+        CK(cudaMemcpyAsync(&z, e->d_stats, sizeof(z), cudaMemcpyDeviceToHost, e->st));
+        if (sync_stream(e)) return -1;
+        if (z.stage[3] > 0)
+            fprintf(stderr, "K1 bundle search, thread-0 cycles per bundle: init+seed %.4g, window minimum %.4g, window distribute %.4g, drain %.4g | "
+                            "windows per bundle %.1f, far entries scanned per window %.0f\n",
+                    (double)z.prof[1] / z.stage[3], (double)z.prof[2] / z.stage[3], (double)z.prof[3] / z.stage[3], (double)z.prof[4] / z.stage[3],
+                    (double)z.prof[6] / z.stage[3], (double)z.prof[5] / std::max(1.0, (double)z.prof[6]));
+        if (z.stage[6] > 0)
+            fprintf(stderr, "K1 timeline, iteration %d: first search ended %.3f ms after the first CTA started, last search %.3f ms, last CTA left %.3f ms\n", k,
+                    (double)(z.stage[7] - z.stage[4]) * 1e-6, (double)(z.stage[5] - z.stage[4]) * 1e-6, (double)(z.stage[6] - z.stage[4]) * 1e-6);
+    }
     launch_sum(e->d_least, e->n_cells, 1, e->d_scalars + 1, e->st);
     CK(cudaGetLastError());
     if (all_reduce(e, e->d_scalars + 1, 1, ncclFloat64)) return -1;

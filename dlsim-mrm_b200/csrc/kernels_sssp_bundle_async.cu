@@ -120,6 +120,13 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
     unsigned long long c_relax = 0;
     unsigned c_pops = 0, c_rounds = 0;
     if (a.fuse_pred && tid == 0) atomicAdd(&a.work[1 + 2 * a.n_bundles], 1); // resident (see bundle_pred_helper_kernel)
+#ifdef SSSP_PROFILE
+    if (tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(&a.s.stats->stage[4], now);
+    }
+#endif
 
     // publish one entry into the ring (any thread)
     auto push_near = [&](int node, int2 row) {
@@ -146,6 +153,10 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
         if (bundle >= a.n_bundles) break;
 #ifdef SSSP_PROFILE
         const long long pf_start = clock64(); // per-bundle search time: stage[1] = max, stage[2] = sum, stage[3] = bundles
+        long long pf_t = pf_start, pf_fill = 0, pf_min = 0, pf_dist = 0, pf_drain = 0, pf_nfar = 0; // thread 0's cycles per phase
+#define APF(x_) do { const long long n_ = clock64(); x_ += n_ - pf_t; pf_t = n_; } while (0)
+#else
+#define APF(x_) do { } while (0)
 #endif
         int zone[LPT];
         unsigned has_task = 0;
@@ -202,6 +213,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
         __syncthreads();
         unsigned thr = 0u;
         bool failed = false;
+        APF(pf_fill);
 
         for (;;) {
             // ---- open the next label window from the far pile (block-wide, like the round-synchronous kernel) ----
@@ -213,6 +225,10 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
                 if ((s_state[ST_WORD(q.x)] >> ST_SHIFT(q.x)) & 2u) mm = min(mm, (unsigned)q.y);
             }
             mm = block_min_u32<BLOCK>(mm, s_red);
+#ifdef SSSP_PROFILE
+            pf_nfar += n_far;
+#endif
+            APF(pf_min);
             if (mm == BND_DEAD_KEY) break;
             thr = key_of((unsigned long long)__double_as_longlong(__hiloint2double((int)mm, 0) + a.s.delta));
             if (thr <= mm) thr = mm + 1;
@@ -252,6 +268,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
             int2* t2 = q_far; q_far = q_far2; q_far2 = t2;
             ++c_rounds;
             __syncthreads();
+            APF(pf_dist);
             if (s_overflow) { failed = true; break; }
 
             // ---- drain the window: every group consumes ring entries until nothing is queued or in flight ----
@@ -345,7 +362,8 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
                         for (int t = 0; t < LPT; ++t)
                             old[j][t] = atom_min_if(p + t, (unsigned long long)__double_as_longlong(lu[t] + cost[j]), ok[t]); // routing.h:804,816
                     }
-                    // the edge this lane queues: its head and the head's forward-star row (fetched in the shadow of the atomics)
+                    // the edge this lane queues: its head and the head's forward-star row (requesting the row before the atomics
+                    // instead -- so that it arrives in their shadow -- measured no difference: 7.869 against 7.873 ms)
                     const int je = op / OWN; // index among this lane's EPL edges
                     int myto = to[0];
 #pragma unroll
@@ -393,14 +411,28 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
                 if (have && g == 0) atomicSub(&s_pt, PT_ONE_PENDING); // after every push of this expansion
             }
             __syncthreads();
+            APF(pf_drain);
             if (s_overflow) { failed = true; break; }
         }
 #ifdef SSSP_PROFILE
         if (tid == 0) {
+            atomicAdd(&a.s.stats->prof[1], (unsigned long long)pf_fill);
+            atomicAdd(&a.s.stats->prof[2], (unsigned long long)pf_min);
+            atomicAdd(&a.s.stats->prof[3], (unsigned long long)pf_dist);
+            atomicAdd(&a.s.stats->prof[4], (unsigned long long)pf_drain);
+            atomicAdd(&a.s.stats->prof[5], (unsigned long long)pf_nfar);
+            atomicAdd(&a.s.stats->prof[6], (unsigned long long)c_rounds);
             const unsigned long long dt = (unsigned long long)(clock64() - pf_start);
             atomicMax(&a.s.stats->stage[1], dt);
             atomicAdd(&a.s.stats->stage[2], dt);
             atomicAdd(&a.s.stats->stage[3], 1ULL);
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            atomicMax(&a.s.stats->stage[5], now); // the last search of the launch ended
+            atomicMin(&a.s.stats->stage[7], now); // the first search ended
+#ifdef BUNDLE_DUMP
+            printf("bundle %d cycles %llu windows %u origin0 %d\n", bundle, dt, c_rounds, a.s.task_origin[a.bundle_tasks[bundle * B]]);
+#endif
         }
 #endif
         if (failed) {
@@ -420,6 +452,13 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
     // ---- label -> predecessor pass of the finished bundles, by every CTA that has nothing left to search: the CTAs beyond
     // the number of bundles from the start, the others as their bundle finishes (bundles differ by some 10 % in search time).
     if (a.fuse_pred) bundle_pred_loop<BLOCK, B>(a, &s_bundle, &s_head);
+#ifdef SSSP_PROFILE
+    if (tid == 0) { // stage[4] = first CTA started, [7] = first search ended, [5] = last search ended, [6] = last CTA left (ns, globaltimer)
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(&a.s.stats->stage[6], now);
+    }
+#endif
     for (int o = 16; o > 0; o >>= 1) {
         c_relax += __shfl_xor_sync(0xffffffffu, c_relax, o);
         c_pops += __shfl_xor_sync(0xffffffffu, c_pops, o);
