@@ -15,7 +15,7 @@ timeout 900 python bench.py > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_ncu_launches_bench.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 # --set full of the per-iteration kernels, 11th occurrence of each (iteration 10)
-ncu --set full --import-source on --clock-control none -k regex:'scatter_kernel|sssp_bundle_async_kernel|backtrace|vdf_kernel' -s 40 -c 4 -f \
+ncu --set full --import-source on --clock-control none -k regex:'scatter_kernel|sssp_bundle_async_kernel|backtrace|vdf_kernel|bundle_pred_helper' -s 50 -c 5 -f \
     -o gpurun_out/${tag}_ncu_iter python bench.py --steps 8 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_ncu_iter.log 2>&1
 tail -2 gpurun_out/${tag}_ncu_iter.log
 ncu -i gpurun_out/${tag}_ncu_iter.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_iter_raw.csv 2>/dev/null
