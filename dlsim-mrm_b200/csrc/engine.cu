@@ -94,6 +94,17 @@ struct dtl_engine {
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_pending = false, overlap = true;
+    // pipelined iterations (dtl_iterations): the back-trace of iteration k runs beside the search of iteration k+1, whose trees go to a
+    // second set of buffers; expect_side / defer_helpers tell the launch code that side-stream work will follow the launch
+    bool expect_side = false, defer_helpers = false, pipelined = false;
+    cudaEvent_t ev_k1[2] = { nullptr, nullptr }, ev_vdf = nullptr, ev_done = nullptr;
+    struct TreeSet {
+        unsigned long long* d_bl = nullptr; size_t bl_cap = 0;
+        int2* d_bp = nullptr; size_t bp_cap = 0;
+        unsigned long long* d_labels = nullptr; int* d_pred = nullptr;
+        int* d_tie_nodes = nullptr; int* d_batch_flag = nullptr;
+    } alt;
+    bool alt_ready = false;
     int N = 0, L = 0, Z = 0, AT = 1, T = 1, B = 1;
     int rank = 0, world = 1;
     dtl_options opt{};
@@ -283,6 +294,13 @@ struct dtl_engine {
         if (!side_pending) return;
         cudaStreamWaitEvent(st, ev_join, 0);
         side_pending = false;
+    }
+    void flip_trees()
+    {
+        std::swap(d_bl, alt.d_bl); std::swap(bl_cap, alt.bl_cap);
+        std::swap(d_bp, alt.d_bp); std::swap(bp_cap, alt.bp_cap);
+        std::swap(d_labels, alt.d_labels); std::swap(d_pred, alt.d_pred);
+        std::swap(d_tie_nodes, alt.d_tie_nodes); std::swap(d_batch_flag, alt.d_batch_flag);
     }
     void resolve_timing()
     {
@@ -512,15 +530,20 @@ int do_vdf(dtl_engine* e, bool detail, bool write_cost, const double* volume_ove
 }
 
 // side: on the side stream, after everything the main stream holds so far; the main stream picks the result up with join_side()
-int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false, bool side = false)
+// (after != null: after that event only -- the pipelined loop, whose main stream already holds the next search)
+int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false, bool side = false, cudaEvent_t after = nullptr)
 {
     const size_t TL = (size_t)e->T * e->L;
-    e->join_side();
+    if (!after) e->join_side();
     cudaStream_t on = e->st;
     if (side && e->overlap && e->st2) {
         on = e->st2;
-        CK(cudaEventRecord(e->ev_fork, e->st));
-        CK(cudaStreamWaitEvent(on, e->ev_fork, 0));
+        if (after) {
+            CK(cudaStreamWaitEvent(on, after, 0));
+        } else {
+            CK(cudaEventRecord(e->ev_fork, e->st));
+            CK(cudaStreamWaitEvent(on, e->ev_fork, 0));
+        }
     }
     const int ph = e->phase_begin(1, on);
     CK(cudaMemsetAsync(e->ls.pce_fix, 0, TL * sizeof(unsigned long long), on));
@@ -817,7 +840,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
     // CTAs without a bundle run the predecessor pass -- unless the side stream holds work (the scatter of this iteration): then the
     // SMs without a bundle are left to it, and the predecessor pass is done by the searching CTAs as they finish
-    if (b.fuse_pred && !e->side_pending && !getenv("DTL_BUNDLE_NO_HELPERS")) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid));
+    if (b.fuse_pred && !e->side_pending && !e->expect_side && !getenv("DTL_BUNDLE_NO_HELPERS")) b.grid = std::max(b.grid, std::min(max_grid, e->bundle_grid));
     return 0;
 }
 
@@ -883,6 +906,7 @@ struct BatchState {
     BundleLaunch b{};
     const int* d_slots = nullptr;
     bool bundle = false, slim = false;
+    int helper_grid = 0; // pipelined iterations: helper CTAs to launch once the side stream's scatter is enqueued
 };
 
 int sssp_launch_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, int tree_off,
@@ -908,7 +932,9 @@ int sssp_launch_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const in
         // through, the SMs without a bundle run helper CTAs for the label -> predecessor pass, like the search kernel's own idle
         // CTAs would have (7.7 against 8.1 ms per 2 000 trees with / without them)
         const int max_grid = e->sm_count * b.ctas_per_sm;
-        const bool helpers = b.fuse_pred && e->side_pending && b.grid < max_grid && !getenv("DTL_BUNDLE_NO_HELPERS");
+        const bool want_helpers = b.fuse_pred && b.grid < max_grid && !getenv("DTL_BUNDLE_NO_HELPERS");
+        bs.helper_grid = want_helpers && e->defer_helpers ? max_grid - b.grid : 0;
+        const bool helpers = want_helpers && e->side_pending && !e->defer_helpers;
         if (helpers) {
             CK(cudaEventRecord(e->ev_fork, e->st)); // after the resets of b.work, before the search kernel
             CK(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
@@ -939,6 +965,13 @@ int sssp_complete_batch(dtl_engine* e, BatchState& bs, int n_tasks, bool count_e
     std::vector<int> rerun;
     for (int i = 0; i < n_tasks; ++i)
         if (e->h_tie_nodes[i] < 0) rerun.push_back(i);
+    if (e->pipelined) {
+        bool any = !rerun.empty();
+        for (int i = 0; i < n_tasks && !any; ++i) any = e->h_tie_nodes[i] > 0;
+        // the re-run and replay kernels share counters and workspaces with the NEXT iteration's search, which is already running on the
+        // other stream (e->st2 here: the streams are swapped while an iteration is completed): let it finish first
+        if (any) CK(cudaStreamSynchronize(e->st2));
+    }
     if (!rerun.empty()) { // frontier outgrew the regular queues: recompute those trees with worst-case capacities
         if (!e->d_ws_big) {
             if (e->alloc(&e->d_ws_big, (size_t)e->big_grid * e->ws_big_stride)) return -1;
@@ -1490,6 +1523,8 @@ int dtl_comm_init(dtl_engine* e, const unsigned char id128[128])
 }
 
 // -------------------------------------------------------------------------------------------------
+static int columns_of_batch(dtl_engine* e, BatchState& bs, int t0, int t1, int tree_off, int k, bool want_count);
+
 static int trees_and_columns(dtl_engine* e, int k, bool want_count)
 {
     const int n_tasks = (int)e->task_at.size();
@@ -1508,6 +1543,18 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         if (sssp_launch_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, tree_off, e->h_task_origin.data() + t0, t0,
                               !e->opt.keep_trees, bs))
             return -1;
+        if (columns_of_batch(e, bs, t0, t1, tree_off, k, want_count)) return -1;
+        t0 = t1;
+    }
+    e->trees_valid = e->opt.keep_trees != 0;
+    return 0;
+}
+
+// the tail of a batch: flags of the search (ties, abandoned bundles, overflowed queues -> redone / replayed), then the back-trace
+static int columns_of_batch(dtl_engine* e, BatchState& bs, int t0, int t1, int tree_off, int k, bool want_count)
+{
+    const int nb = t1 - t0;
+    {
         ColumnLaunch c{};
         c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
         c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
@@ -1560,9 +1607,7 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
             e->phase_end(ph, 1);
             CK(cudaGetLastError());
         }
-        t0 = t1;
     }
-    e->trees_valid = e->opt.keep_trees != 0;
     return 0;
 }
 

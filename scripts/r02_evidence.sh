@@ -9,7 +9,7 @@ if [ -z "$SKIP_TESTS" ]; then
   timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc $?" | tee -a gpurun_out/${tag}_pytest.log
   tail -4 gpurun_out/${tag}_pytest.log
 fi
-timeout 900 python bench.py > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err; rc=$?; echo "bench rc $rc"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err; rc=$?; echo "bench rc $rc"
 [ $rc -ne 0 ] && exit 1
 # launch list (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_ncu_launches_bench.csv \
