@@ -251,15 +251,14 @@ def run_engine_arm(args, rank, world, local_rank):
 
     # ---- device-resident throughput: inputs already in HBM when the timed region starts ----
     e = make_engine()
-    for k in range(W):
-        e.iteration(k)
+    e.iterations(0, W)
     e.timing(reset=True); e.counters(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
         sampler.start()
     t0 = time.perf_counter()
-    rows = [e.iteration(W + k) for k in range(K)]
+    rows = e.iterations(W, K)   # dtl_iterations: the K steps issued as a pipeline (back-trace of step k beside the search of step k+1)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier()
@@ -307,8 +306,7 @@ def run_engine_arm(args, rank, world, local_rank):
     e2 = make_engine()
     torch.cuda.synchronize()
     create_s = time.perf_counter() - t0
-    for k in range(K):
-        e2.iteration(k)
+    e2.iterations(0, K)
     e2.finalize(K)
     st = e2.link_state(0, fields=("tt", "pce_volume"))   # the result of the assignment: link travel times and volumes
     torch.cuda.synchronize()

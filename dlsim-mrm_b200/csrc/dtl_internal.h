@@ -172,6 +172,8 @@ struct BundleLaunch {
                              // (more) bundle to search takes tiles of the bundles that are finished (work[] below)
     int* work;               // fuse_pred: [2 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters,
                              // resident CTAs of the search kernel}
+    unsigned* started_word;  // fuse_pred, optional: the CTA that completes the resident count writes started_tag here (pipelined loop:
+    unsigned started_tag;    // the back-trace of the previous iteration waits for it on the side stream)
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)
     int* batch_flag;         // slim: bit 0 = an order-dependent tie was found, bit 1 = a bundle overflowed
 };
@@ -211,6 +213,7 @@ struct ColumnLaunch {
     int* path_len;                     // [n_od] nodes of the path found for the cell (may be null): key of sort_cells_by_path_length
 };
 void launch_backtrace(const ColumnLaunch& a, cudaStream_t st);
+void launch_set_go(const int* flags, int n, unsigned* go, unsigned* start, unsigned tag, int start_when_clean, cudaStream_t st);
 void sort_cells_by_path_length(const int* path_len, int* cells, const int* cell_ptr, int first, int n_tasks, cudaStream_t st);
 
 struct ScatterLaunch {

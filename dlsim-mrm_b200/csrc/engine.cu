@@ -105,6 +105,13 @@ struct dtl_engine {
         int* d_tie_nodes = nullptr; int* d_batch_flag = nullptr;
     } alt;
     bool alt_ready = false;
+    // stream memory operations of the driver API (cuStreamWaitValue32 / cuStreamWriteValue32): the gate of the pipelined loop
+    void *fn_wait_value = nullptr, *fn_write_value = nullptr;
+    unsigned* d_go = nullptr;  // [0..1] per tree set: tag of the iteration whose search raised no flag (0 = it did); [2..3]: tag of the
+                               // iteration whose back-trace may start (the next search is resident, or will not come before a redo)
+    unsigned pipe_tag = 0;
+    unsigned* next_started_word = nullptr; // handed to the next origin-bundle launch (BundleLaunch::started_word)
+    unsigned next_started_tag = 0;
     int N = 0, L = 0, Z = 0, AT = 1, T = 1, B = 1;
     int rank = 0, world = 1;
     dtl_options opt{};
@@ -304,6 +311,20 @@ struct dtl_engine {
     }
     void resolve_timing()
     {
+        static const bool gap_trace = getenv("DTL_GAP_TRACE") != nullptr; // idle time of the main stream between two searches
+        if (gap_trace) {
+            const std::pair<cudaEvent_t, cudaEvent_t>* prev = nullptr;
+            double gap = 0, vdf = 0;
+            int n = 0;
+            for (auto& p : pending) {
+                if (p.first == 0 && prev) { float t = 0; if (cudaEventElapsedTime(&t, p.second.first, p.second.second) == cudaSuccess) vdf += t; }
+                if (p.first != 2) continue;
+                float t = 0;
+                if (prev && cudaEventElapsedTime(&t, prev->second, p.second.first) == cudaSuccess) { gap += t; ++n; }
+                prev = &p.second;
+            }
+            if (n) fprintf(stderr, "main stream between two searches: %.3f ms on average over %d gaps (of which VDF pass %.3f ms)\n", gap / n, n, vdf / n);
+        }
         for (auto& p : pending) {
             float t = 0;
             if (cudaEventElapsedTime(&t, p.second.first, p.second.second) == cudaSuccess) ms[p.first] += t;
@@ -837,6 +858,8 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
         fprintf(stderr, "bundle launch set up (plan + buffers): %.3f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - plan_t0).count());
     b.bundle_counter = e->d_bundle_counter;
+    b.started_word = b.fuse_pred ? e->next_started_word : nullptr;
+    b.started_tag = e->next_started_tag;
     b.grid = std::max(1, std::min(std::min(max_grid, e->bundle_grid), b.n_bundles));
     // CTAs without a bundle run the predecessor pass -- unless the side stream holds work (the scatter of this iteration): then the
     // SMs without a bundle are left to it, and the predecessor pass is done by the searching CTAs as they finish
@@ -907,12 +930,14 @@ struct BatchState {
     const int* d_slots = nullptr;
     bool bundle = false, slim = false;
     int helper_grid = 0; // pipelined iterations: helper CTAs to launch once the side stream's scatter is enqueued
+    bool backtrace_issued = false; // pipelined iterations: the node-major back-trace was already put on the main stream
 };
 
 int sssp_launch_batch(dtl_engine* e, const ForwardStar& f, int n_tasks, const int* d_origin, const int* d_zone, int tree_off,
                       const int* h_origin, int plan_key, bool want_slim, BatchState& bs)
 {
     SsspLaunch& a = bs.a;
+    bs.backtrace_issued = false; bs.helper_grid = 0; // (a BatchState is reused by the pipelined loop)
     a = make_sssp_launch(e, f, n_tasks, d_origin, d_zone, tree_off);
     e->last_sssp_variant = a.smq;
     bs.bundle = a.smq == 2;
@@ -1037,8 +1062,15 @@ int check_flags(dtl_engine* e, bool collective = false)
     int flag = 0;
     SsspStats s{};
     // inside the assignment loop every rank sees the worst flag of any rank and stops at the same point (integer max: exact)
-    if (collective && all_reduce(e, e->d_error_flag, 1, ncclInt32, ncclMax)) return -1;
-    CK(cudaMemcpyAsync(&flag, e->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+    int* d_flag = e->d_error_flag;
+    if (collective && e->pipelined && e->world > 1 && !e->local_shard) {
+        // the next iteration's kernels are running on the other stream and may set bits: reduce a copy (the bits stay in d_error_flag
+        // and are seen one iteration later at the latest)
+        d_flag = reinterpret_cast<int*>(e->d_counters + 3);
+        CK(cudaMemcpyAsync(d_flag, e->d_error_flag, sizeof(int), cudaMemcpyDeviceToDevice, e->st));
+    }
+    if (collective && all_reduce(e, d_flag, 1, ncclInt32, ncclMax)) return -1;
+    CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
     CK(cudaMemcpyAsync(&s, e->d_stats, sizeof(s), cudaMemcpyDeviceToHost, e->st));
     if (sync_stream(e)) return -1;
     if (flag & 1) { set_err("column arena exhausted (%lld path links): raise dtl_options.column_arena_bytes", e->pool.arena_cap); return -1; }
@@ -1551,32 +1583,45 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
 }
 
 // the tail of a batch: flags of the search (ties, abandoned bundles, overflowed queues -> redone / replayed), then the back-trace
+static ColumnLaunch make_column_launch(dtl_engine* e, int t0, int t1, int tree_off, int k)
+{
+    ColumnLaunch c{};
+    c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
+    c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
+    c.od_vol = e->d_od_vol; c.link_from = e->d_link_from;
+    c.labels = e->d_labels + (size_t)tree_off * e->N; c.pred_link = e->d_pred + (size_t)tree_off * e->N;
+    c.task_first = t0; c.task_count = t1 - t0;
+    c.batch_cells = e->d_task_cells + e->task_cell_ptr[t0];
+    c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
+    c.task_skip_backtrace = e->d_task_skip;
+    c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
+    c.path_len = e->d_path_len;
+    return c;
+}
+
+// back-trace on the node-major trees of a bundle batch (on e->st); the kernel does nothing when the label -> tree pass flagged a tie
+// or an overflowed bundle, and the batch is then redone through the per-tree path (columns_of_batch)
+static int issue_slim_backtrace(dtl_engine* e, BatchState& bs, int t0, int t1, int tree_off, int k)
+{
+    ColumnLaunch cs = make_column_launch(e, t0, t1, tree_off, k);
+    cs.bl = bs.b.bl; cs.bp = bs.b.bp; cs.task_slot = bs.d_slots; cs.B = bs.b.B; cs.batch_flag = bs.b.batch_flag;
+    e->join_side(); // the scatter's MSA decay of the column volumes comes before this iteration's share is added
+    const int ph = e->phase_begin(4);
+    launch_backtrace(cs, e->st);
+    e->phase_end(ph, 1);
+    CK(cudaGetLastError());
+    bs.backtrace_issued = true;
+    return 0;
+}
+
 static int columns_of_batch(dtl_engine* e, BatchState& bs, int t0, int t1, int tree_off, int k, bool want_count)
 {
     const int nb = t1 - t0;
     {
-        ColumnLaunch c{};
-        c.N = e->N; c.L = e->L; c.T = e->T; c.AT = e->AT; c.pool = e->pool;
-        c.od_dest_node = e->d_od_dest; c.od_at = e->d_od_at; c.od_tau = e->d_od_tau; c.od_task = e->d_od_task;
-        c.od_vol = e->d_od_vol; c.link_from = e->d_link_from;
-        c.labels = e->d_labels + (size_t)tree_off * e->N; c.pred_link = e->d_pred + (size_t)tree_off * e->N;
-        c.task_first = t0; c.task_count = nb;
-        c.batch_cells = e->d_task_cells + e->task_cell_ptr[t0];
-        c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
-        c.task_skip_backtrace = e->d_task_skip;
-        c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
-        c.path_len = e->d_path_len;
+        ColumnLaunch c = make_column_launch(e, t0, t1, tree_off, k);
         bool done = false;
         if (bs.slim) {
-            // back-trace on the node-major trees; the kernel does nothing when the label -> tree pass flagged a tie or an
-            // overflowed bundle, and the batch is then redone through the per-tree path below
-            ColumnLaunch cs = c;
-            cs.bl = bs.b.bl; cs.bp = bs.b.bp; cs.task_slot = bs.d_slots; cs.B = bs.b.B; cs.batch_flag = e->d_batch_flag;
-            e->join_side(); // the scatter's MSA decay of the column volumes comes before this iteration's share is added
-            const int ph = e->phase_begin(4);
-            launch_backtrace(cs, e->st);
-            e->phase_end(ph, 1);
-            CK(cudaGetLastError());
+            if (!bs.backtrace_issued && issue_slim_backtrace(e, bs, t0, t1, tree_off, k)) return -1;
             int flag = 0;
             CK(cudaMemcpyAsync(&flag, e->d_batch_flag, sizeof(int), cudaMemcpyDeviceToHost, e->st));
             if (sync_stream(e)) return -1;
@@ -1610,6 +1655,8 @@ static int columns_of_batch(dtl_engine* e, BatchState& bs, int t0, int t1, int t
     }
     return 0;
 }
+
+static void iteration_row(const dtl_engine* e, double sysTT, double least, double row[5]);
 
 static int iteration_impl(dtl_engine* e, int k, double row[5])
 {
@@ -1663,15 +1710,226 @@ static int iteration_impl(dtl_engine* e, int k, double row[5])
     e->phase_end(ph7, 0);
     if (check_flags(e, true)) return -1;
     e->resolve_timing();
-    const double sysTT = e->h_scalars[0], least = e->h_scalars[1];
-    if (row) {
-        row[0] = sysTT;
-        row[1] = least;
-        row[2] = (sysTT - least) / std::max(0.00001, least);           // main_api.cpp:711
-        const float denom = 1 > e->total_demand ? (float)1 : e->total_demand; // main_api.cpp:716
-        row[3] = sysTT / denom;
-        row[4] = e->counted_edges_cached;
+    if (row) iteration_row(e, e->h_scalars[0], e->h_scalars[1], row);
+    return 0;
+}
+
+// ---- pipelined iterations --------------------------------------------------------------------------------------------------
+// The back-trace of iteration k (and its sums, scalar all-reduce and flag checks) only feeds the scatter of iteration k+1, and the
+// search of iteration k+1 only needs the link volumes the scatter of iteration k left -- so a run of iterations is issued as
+//     main stream:  K4(k) K1(k)            K4(k+1) K1(k+1)                    K4(k+2) K1(k+2) ...
+//     side stream:        K3(k) helpers(k)         K2a(k) sums(k) K3(k+1) helpers(k+1)        K2a(k+1) ...
+// with the trees of consecutive iterations in two sets of buffers (dtl_engine::flip_trees).  The host checks the flags of iteration k
+// (ties, abandoned bundles, errors) while K1(k+1) runs and only then issues K3(k+1), so a batch that has to be redone is redone
+// before anything reads its columns.  Same kernels on the same data in an order that respects every dependency: the results are
+// those of dtl_iteration called n times (tests/test_engine_gpu.py::test_pipelined_iterations_*).
+static bool pipeline_possible(const dtl_engine* e)
+{
+    if (!e->overlap || !e->st2 || e->opt.keep_trees || e->sa_mode || e->counted_edges_cached < 0 || getenv("DTL_NO_PIPELINE")) return false;
+    const int n_tasks = (int)e->task_at.size();
+    if (n_tasks == 0 || n_tasks > e->batch_tasks) return false;
+    const int fsi = e->task_at[0] * e->T + e->task_tau[0];
+    for (int t = 1; t < n_tasks; ++t)
+        if (e->task_at[t] * e->T + e->task_tau[t] != fsi) return false; // one batch per iteration only
+    return true;
+}
+
+static void iteration_row(const dtl_engine* e, double sysTT, double least, double row[5])
+{
+    row[0] = sysTT;
+    row[1] = least;
+    row[2] = (sysTT - least) / std::max(0.00001, least);           // main_api.cpp:711
+    const float denom = 1 > e->total_demand ? (float)1 : e->total_demand; // main_api.cpp:716
+    row[3] = sysTT / denom;
+    row[4] = e->counted_edges_cached;
+}
+
+static int iterations_impl(dtl_engine* e, int k0, int n, double* rows)
+{
+    CK(cudaSetDevice(e->dev));
+    int k = k0;
+    const int k_end = k0 + n;
+    // one at a time until the pipeline can start (the first iteration of an engine counts the edges of its trees)
+    while (k < k_end && !(k_end - k >= 2 && pipeline_possible(e))) {
+        if (iteration_impl(e, k, rows ? rows + (size_t)(k - k0) * 5 : nullptr)) return -1;
+        ++k;
     }
+    if (k >= k_end) return 0;
+
+    const int n_tasks = (int)e->task_at.size();
+    const int fsi = fs_index(e, e->task_at[0], e->task_tau[0]);
+    const ForwardStar& f = e->fs[fsi];
+    if (!e->alt_ready) {
+        for (auto& ev : e->ev_k1) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_vdf, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+        // the second set of tree buffers: node-major labels / predecessor records are allocated by the launch that needs them; per-tree
+        // arrays only when the searches write them (the single-origin kernels: an origin shard of a multi-GPU run) -- a bundle batch
+        // touches them only when it is redone, and that happens with the main stream drained of anything that uses them
+        SsspLaunch probe = make_sssp_launch(e, f, n_tasks, e->d_task_origin, e->d_task_zone, 0);
+        const bool slim = probe.smq == 2 && !getenv("DTL_NO_SLIM_TREES");
+        if (slim) {
+            e->alt.d_labels = e->d_labels; e->alt.d_pred = e->d_pred;
+        } else {
+            if (e->alloc(&e->alt.d_labels, (size_t)e->batch_tasks * e->N)) return -1;
+            if (e->alloc(&e->alt.d_pred, (size_t)e->batch_tasks * e->N)) return -1;
+        }
+        if (e->alloc(&e->alt.d_tie_nodes, e->batch_tasks)) return -1;
+        if (e->alloc(&e->d_go, 4)) return -1;
+        CK(cudaMemset(e->d_go, 0, 4 * sizeof(unsigned)));
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &e->fn_wait_value, cudaEnableDefault, &q1) != cudaSuccess || q1 != cudaDriverEntryPointSuccess)
+            e->fn_wait_value = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &e->fn_write_value, cudaEnableDefault, &q2) != cudaSuccess || q2 != cudaDriverEntryPointSuccess)
+            e->fn_write_value = nullptr;
+        cudaGetLastError();
+        e->alt_ready = true;
+    }
+    struct Guard { // whatever happens, the engine leaves this function in its one-iteration-at-a-time state
+        dtl_engine* e; cudaStream_t st, st2;
+        ~Guard() { e->st = st; e->st2 = st2; e->pipelined = e->expect_side = e->defer_helpers = false; }
+    } guard{ e, e->st, e->st2 };
+    e->pipelined = e->expect_side = e->defer_helpers = true;
+    const int ph7 = e->phase_begin(7);
+    BatchState bs[2];
+    auto helpers_and_join = [&](BatchState& b) -> int { // on the side stream, behind the scatter
+        if (b.helper_grid > 0) {
+            launch_bundle_pred_helpers(b.b, b.helper_grid, e->st2);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e->ev_join, e->st2));
+        }
+        return 0;
+    };
+    auto vdf_and_search = [&](int kk, BatchState& b, int slot) -> int { // on the main stream: K4(kk), K1(kk)
+        if (do_vdf(e, false, true, nullptr)) return -1;                                        // main_api.cpp:606 (joins the side stream)
+        CK(cudaMemcpyAsync(e->d_scalars + 10 + slot, e->d_scalars, sizeof(double), cudaMemcpyDeviceToDevice, e->st)); // system TT of kk
+        CK(cudaEventRecord(e->ev_vdf, e->st));
+        if (sssp_launch_batch(e, f, n_tasks, e->d_task_origin, e->d_task_zone, 0, e->h_task_origin.data(), 0, true, b)) return -1;
+        CK(cudaEventRecord(e->ev_k1[slot], e->st));
+        (void)kk;
+        return 0;
+    };
+    // prologue: K4(k), K1(k) on the main stream, K3(k) + helpers on the side stream
+    if (vdf_and_search(k, bs[0], 0)) return -1;
+    if (do_scatter(e, k, false, false, true, e->ev_vdf)) return -1;                            // main_api.cpp:618
+    if (helpers_and_join(bs[0])) return -1;
+    // The slow paths of a batch (an order-dependent tie, an abandoned bundle, overflowed queues) re-read the link costs of iteration k,
+    // which K4(k+1) rewrites.  So everything of iteration k+1 is issued behind a GATE on the main stream: a one-block kernel behind
+    // K1(k) writes the iteration's tag into a device word when the search raised no flag (0 otherwise) and the stream waits for that
+    // value (cuStreamWaitValue32) -- no host round trip between two searches (measured: 0.29-0.44 ms of an 8.7 ms iteration with the
+    // host in between).  When a flag was raised the main stream stays parked at the gate while the side stream redoes the batch with
+    // the costs of iteration k, and the write that ends the completion of iteration k (cuStreamWriteValue32) opens it.  Without stream
+    // memory operations the host looks at the flags itself before it issues iteration k+1.
+    typedef int (*stream_value_fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+    const stream_value_fn wait_value = (stream_value_fn)e->fn_wait_value, write_value = (stream_value_fn)e->fn_write_value;
+    const bool gated = wait_value && write_value && e->d_go && !getenv("DTL_PIPELINE_HOST_GATE");
+    std::vector<int> h_flags;
+    for (int cur = 0; k < k_end; ++k, cur ^= 1) {
+        const bool last = k + 1 == k_end;
+        const unsigned tag = ++e->pipe_tag ? e->pipe_tag : ++e->pipe_tag;
+        bool clean = false;
+        // An origin-bundle search leaves the side stream only the SMs without a bundle, and there the scatter alone lasts most of a
+        // search: the node-major back-trace then stays on the MAIN stream, between K1(k) and the gate (it does nothing when the
+        // search raised a flag), and only its sums and checks go to the side stream.  (With it on the side stream the side
+        // stream is as long as the search: 8.80 ms per iteration against 9.03 without the pipeline.)
+        // (bundles of 16 = 8 and more trees per SM, the whole demand on one GPU: measured 8.82 / 8.80 ms per iteration with the back-trace
+        // on the main / side stream; a rank of 2, bundles of 8: 6.12 / 5.79 ms -- there the side stream has room)
+        const bool bt_on_main = gated && bs[cur].slim && bs[cur].b.B >= 16 && !getenv("DTL_PIPELINE_BT_ON_SIDE");
+        if (bt_on_main) {
+            if (issue_slim_backtrace(e, bs[cur], 0, n_tasks, 0, k)) return -1;
+            CK(cudaEventRecord(e->ev_k1[cur], e->st)); // what the side stream waits for is now the back-trace
+        }
+        bool side_waits = false; // the back-trace of iteration k waits until the search of iteration k+1 is resident
+        if (!last && gated) {
+            // (an origin-bundle search needs a whole SM per CTA: started at the end of K1(k), the back-trace's CTAs sit on every SM
+            // when K1(k+1) arrives, and the VDF pass in between takes 0.24 instead of 0.04 ms)
+            side_waits = !bt_on_main && bs[cur].bundle && bs[cur].b.fuse_pred && !getenv("DTL_PIPELINE_NO_START_ORDER");
+            launch_set_go(bs[cur].slim ? e->d_batch_flag : e->d_tie_nodes, bs[cur].slim ? 1 : n_tasks, e->d_go + cur, e->d_go + 2 + cur, tag,
+                          side_waits ? 0 : 1, e->st);
+            CK(cudaGetLastError());
+            e->next_started_word = side_waits ? e->d_go + 2 + cur : nullptr;
+            e->next_started_tag = tag;
+            if (wait_value(e->st, (unsigned long long)(uintptr_t)(e->d_go + cur), tag, 1u /* CU_STREAM_WAIT_VALUE_EQ */) != 0) {
+                set_err("cuStreamWaitValue32 failed");
+                return -1;
+            }
+            clean = true; // as far as issuing goes: what follows on the main stream runs only when the gate opens
+        } else if (!last) {
+            CK(cudaEventSynchronize(e->ev_k1[cur]));
+            if (bs[cur].slim) {
+                h_flags.assign(1, 0);
+                CK(cudaMemcpy(h_flags.data(), e->d_batch_flag, sizeof(int), cudaMemcpyDeviceToHost));
+            } else {
+                h_flags.assign(n_tasks, 0);
+                CK(cudaMemcpy(h_flags.data(), e->d_tie_nodes, sizeof(int) * n_tasks, cudaMemcpyDeviceToHost));
+            }
+            clean = true;
+            for (int v : h_flags) clean = clean && v == 0;
+        }
+        if (!last && clean) {
+            e->flip_trees();
+            const int rc = vdf_and_search(k + 1, bs[cur ^ 1], cur ^ 1);
+            e->flip_trees();
+            e->next_started_word = nullptr;
+            if (rc) return -1;
+            if (side_waits && !bs[cur ^ 1].b.started_word) side_waits = false; // the next launch is not one that announces itself
+        }
+        // ---- iteration k is completed on the side stream (the helper code below issues on e->st)
+        std::swap(e->st, e->st2);
+        e->side_pending = false;
+        // re-run / replay kernels share counters with a search of iteration k+1 that is already running: only possible with the host
+        // gate (behind the device gate nothing of iteration k+1 runs while a batch is redone)
+        e->pipelined = clean && !gated;
+        int rc = 0;
+        do {
+            if (cudaStreamWaitEvent(e->st, e->ev_k1[cur], 0) != cudaSuccess) { set_err("cudaStreamWaitEvent failed"); rc = -1; break; }
+            if (side_waits && wait_value(e->st, (unsigned long long)(uintptr_t)(e->d_go + 2 + cur), tag, 1u) != 0) {
+                set_err("cuStreamWaitValue32 failed"); rc = -1; break;
+            }
+            if ((rc = columns_of_batch(e, bs[cur], 0, n_tasks, 0, k, false))) break;           // main_api.cpp:647-699
+            if (!last && gated && write_value(e->st, (unsigned long long)(uintptr_t)(e->d_go + cur), tag, 0u) != 0) {
+                set_err("cuStreamWriteValue32 failed"); rc = -1; break;
+            }
+            launch_sum(e->d_least, e->n_cells, 1, e->d_scalars + 1, e->st);
+            if ((rc = all_reduce(e, e->d_scalars + 1, 1, ncclFloat64))) break;
+            if (cudaMemcpyAsync(e->h_scalars + 1, e->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, e->st) != cudaSuccess ||
+                cudaMemcpyAsync(e->h_scalars, e->d_scalars + 10 + cur, sizeof(double), cudaMemcpyDeviceToHost, e->st) != cudaSuccess) {
+                set_err("cudaMemcpyAsync failed"); rc = -1; break;
+            }
+            rc = check_flags(e, true);
+        } while (0);
+        std::swap(e->st, e->st2);
+        e->pipelined = true;
+        if (rc) {
+            // leave nothing parked at a gate that will never open
+            if (gated && !last) {
+                write_value(e->st2, (unsigned long long)(uintptr_t)(e->d_go + 2 + cur), tag, 0u);
+                write_value(e->st2, (unsigned long long)(uintptr_t)(e->d_go + cur), tag, 0u);
+            }
+            return -1;
+        }
+        if (rows) iteration_row(e, e->h_scalars[0], e->h_scalars[1], rows + (size_t)(k - k0) * 5);
+        if (!last && !clean) { // the batch was redone with the costs of iteration k: only now may they be rewritten
+            CK(cudaEventRecord(e->ev_done, e->st2));
+            CK(cudaStreamWaitEvent(e->st, e->ev_done, 0));
+            e->flip_trees();
+            const int rc2 = vdf_and_search(k + 1, bs[cur ^ 1], cur ^ 1);
+            e->flip_trees();
+            if (rc2) return -1;
+        }
+        if (!last) {
+            if (do_scatter(e, k + 1, false, false, true, e->ev_vdf)) return -1;                // behind K2a(k) on the side stream, after K4(k+1)
+            if (helpers_and_join(bs[cur ^ 1])) return -1;
+            e->flip_trees(); // the set of iteration k+1 is the current one from here on
+        }
+    }
+    CK(cudaEventRecord(e->ev_done, e->st2));
+    CK(cudaStreamWaitEvent(e->st, e->ev_done, 0));
+    e->side_pending = false;
+    e->phase_end(ph7, 0);
+    if (sync_stream(e)) return -1;
+    e->resolve_timing();
+    e->trees_valid = false;
     return 0;
 }
 
@@ -1679,6 +1937,13 @@ static int iteration_impl(dtl_engine* e, int k, double row[5])
 int dtl_iteration(dtl_engine* e, int k, double row[5])
 {
     const int rc = iteration_impl(e, k, row);
+    if (rc) comm_abort(e);
+    return rc;
+}
+
+int dtl_iterations(dtl_engine* e, int k0, int n, double* rows)
+{
+    const int rc = iterations_impl(e, k0, n, rows);
     if (rc) comm_abort(e);
     return rc;
 }
@@ -2038,11 +2303,7 @@ int dtl_sa_column_update(dtl_engine* e, int n, double row[4])
 }
 int dtl_run_assignment(dtl_engine* e, int K, int CU, double* iter_rows, double* cu_rows)
 {
-    for (int k = 0; k < K; ++k) {
-        double row[5];
-        if (dtl_iteration(e, k, row)) return -1;
-        if (iter_rows) memcpy(iter_rows + (size_t)k * 5, row, sizeof(row));
-    }
+    if (dtl_iterations(e, 0, K, iter_rows)) return -1;
     for (int n = 0; n < CU; ++n) {
         double row[4];
         if (dtl_column_update(e, n, row)) return -1;

@@ -1496,9 +1496,10 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     summary << ",# of nodes = ," << g->prob.n_nodes << std::endl;
     summary << ",# of links =," << g->prob.n_links << std::endl;
     summary << ",# of zones =," << g->prob.n_zones << std::endl;
-    for (int k = 0; k < column_generation_iterations; ++k) {      // main_api.cpp:589-728
-        double row[5];
-        if (dtl_iteration(e, k, row)) fail(dtl_last_error());
+    std::vector<double> iter_rows((size_t)std::max(1, column_generation_iterations) * 5);
+    if (dtl_iterations(e, 0, column_generation_iterations, iter_rows.data())) fail(dtl_last_error()); // main_api.cpp:589-728, pipelined
+    for (int k = 0; k < column_generation_iterations; ++k) {
+        const double* row = iter_rows.data() + (size_t)k * 5;
         if (k == 0) summary << "Iteration, CPU Running Time, # of agents, Avg Travel Time(min),  Avg UE gap %" << std::endl;
         summary << k << "," << 0.0 << "," << g->prob.total_demand_volume << "," << row[3] << "," << row[2] * 100 << std::endl;
         printf("iteration: %d,systemTT: %g, least system TT:%g,gap=%g\n", k, row[0], row[1], row[2]);

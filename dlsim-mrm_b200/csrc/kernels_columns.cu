@@ -212,6 +212,26 @@ void sort_cells_by_path_length(const int* path_len, int* cells, const int* cell_
     cell_sort_in_task_kernel<<<n_tasks, 256, 0, st>>>(path_len, cells, cell_ptr, first);
 }
 
+// gates of the pipelined loop (engine.cu: iterations_impl).  *go = tag when none of the n flag words of a search is set, else 0 (the
+// main stream waits for tag before it rewrites the link costs).  *start = tag lets the side stream begin the back-trace: at once when
+// a flag is set (the batch is redone first, nothing of the next iteration will run meanwhile) or when the next search does not
+// announce itself (start_when_clean); otherwise the next search writes it when all its CTAs are resident.
+__global__ void __launch_bounds__(256) set_go_kernel(const int* flags, int n, unsigned* go, unsigned* start, unsigned tag, int start_when_clean)
+{
+    int any = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) any |= flags[i] != 0;
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (any || start_when_clean) *reinterpret_cast<volatile unsigned*>(start) = tag;
+        *reinterpret_cast<volatile unsigned*>(go) = any ? 0u : tag;
+    }
+}
+void launch_set_go(const int* flags, int n, unsigned* go, unsigned* start, unsigned tag, int start_when_clean, cudaStream_t st)
+{
+    set_go_kernel<<<1, 256, 0, st>>>(flags, n, go, start, tag, start_when_clean);
+}
+
 void launch_backtrace(const ColumnLaunch& a, cudaStream_t st)
 {
     if (a.n_batch_cells == 0) return;

@@ -119,7 +119,13 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
     int2* q_far2 = q_far + CAPF;
     unsigned long long c_relax = 0;
     unsigned c_pops = 0, c_rounds = 0;
-    if (a.fuse_pred && tid == 0) atomicAdd(&a.work[1 + 2 * a.n_bundles], 1); // resident (see bundle_pred_helper_kernel)
+    if (a.fuse_pred && tid == 0) { // resident (see bundle_pred_helper_kernel); the last one to arrive tells whoever waits for it
+        const int r = atomicAdd(&a.work[1 + 2 * a.n_bundles], 1);
+        if (a.started_word && r == (int)gridDim.x - 1) {
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(a.started_word) = a.started_tag;
+        }
+    }
 #ifdef SSSP_PROFILE
     if (tid == 0) {
         unsigned long long now;

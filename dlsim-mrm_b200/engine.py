@@ -275,6 +275,14 @@ class Engine:
         self._ck(self.lib.dtl_iteration(self.h, int(k), _ptr(row)))
         return dict(sysTT=row[0], least=row[1], gap=row[2], avg_tt=row[3], counted_edges=row[4])
 
+    def iterations(self, k0: int, n: int) -> list:
+        """Iterations k0 .. k0+n-1 in one call (pipelined on the device: dtl_iterations); the rows of iteration()."""
+        rows = np.zeros((max(n, 1), 5))
+        self.lib.dtl_iterations.restype = C.c_int
+        self.lib.dtl_iterations.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self._ck(self.lib.dtl_iterations(self.h, int(k0), int(n), _ptr(rows)))
+        return [dict(sysTT=r[0], least=r[1], gap=r[2], avg_tt=r[3], counted_edges=r[4]) for r in rows[:n]]
+
     def column_update(self, n: int) -> dict:
         row = np.zeros(4)
         self._ck(self.lib.dtl_column_update(self.h, int(n), _ptr(row)))

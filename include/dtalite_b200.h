@@ -110,6 +110,12 @@ int dtl_get_tasks(const dtl_engine* e, int* at, int* tau, int* zone);
  * Replaces the loop body main_api.cpp:589-728.
  * row = { systemTT, least_systemTT, relative_gap, avg_travel_time, counted_edges } */
 int dtl_iteration(dtl_engine* e, int k, double row[5]);
+/* n iterations k0 .. k0+n-1 in one call: the same results as n calls of dtl_iteration (rows: [n][5], may be NULL), issued as a pipeline
+ * -- the back-trace, sums and checks of iteration k run on a second stream beside the shortest-path search of iteration k+1, whose
+ * trees go to a second set of buffers (main_api.cpp:589-728 is a plain loop; nothing in it forbids the overlap: the search of k+1
+ * reads the link travel times, the back-trace of k writes the column pool).  Falls back to one iteration at a time where the pipeline
+ * does not apply (kept trees, the SA stage, several tree batches per iteration). */
+int dtl_iterations(dtl_engine* e, int k0, int n, double* rows);
 /* One column-pool gradient-projection iteration; replaces
  * g_update_gradient_cost_and_assigned_flow_in_column_pool (assignment.h:565).
  * row = { avg_travel_time, total_gap, relative_gap_percent, total_system_demand } */

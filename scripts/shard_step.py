@@ -13,11 +13,9 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 p = D.read_gmns(ensure_workload("grid100k"), 8)
 with D.Engine(p, rank=0, world_size=world, max_columns_per_od=K + 4) as e:
     e.comm_init(None)
-    for k in range(3):
-        e.iteration(k)
+    e.iterations(0, 3)
     e.timing(reset=True)
-    for k in range(3, K):
-        e.iteration(k)
+    e.iterations(3, K - 3)   # dtl_iterations: pipelined (DTL_NO_PIPELINE=1: one iteration at a time)
     t = e.timing()
     n = K - 3
     print(f"world {world} kernel {os.environ.get('DTL_SSSP_KERNEL', 'auto')} block {os.environ.get('DTL_SSSP_SMQ_BLOCK', 'auto')}:",

@@ -431,3 +431,57 @@ def test_node_major_trees_fall_back_on_ties_and_overflow(D, oracle_mod, monkeypa
     monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "4")
     c, _ = _loop_vs_oracle(D, oracle_mod, problems("corridor_101"), 3)
     assert c["reruns"] > 0
+
+
+# ------------------------------------------------------------------------------------------------ pipelined iterations
+def _pipelined_vs_sequential(D, oracle_mod, p, K, expect_pipeline=True):
+    """dtl_iterations (back-trace of iteration k beside the search of iteration k+1, two sets of tree buffers) must leave exactly what
+    K calls of dtl_iteration leave: the same rows, the same Q31.32 link volumes, the same columns -- and both match the oracle."""
+    o = oracle_mod.Oracle(p)
+    rows_o = [o.iteration(k) for k in range(K)]
+    o.finalize(K)
+    with D.Engine(p, keep_trees=False, max_columns_per_od=K + 4) as e1, D.Engine(p, keep_trees=False, max_columns_per_od=K + 4) as e2:
+        rows1 = [e1.iteration(k) for k in range(K)]
+        rows2 = e2.iterations(0, 2) + e2.iterations(2, K - 2)      # two calls: the pipeline is entered and left twice
+        for k, (r1, r2, ro) in enumerate(zip(rows1, rows2, rows_o)):
+            assert r1 == r2, (k, r1, r2)                             # deterministic sums: the same bits
+            for key in ("sysTT", "least"):
+                assert abs(r2[key] - ro[key]) <= TOL * max(1e-9, abs(ro[key])), (k, key, r2, ro)
+        assert np.array_equal(e1.volume_fixed(0), e2.volume_fixed(0))
+        e1.finalize(K); e2.finalize(K)
+        s1, s2, so = e1.link_state(0), e2.link_state(0), o.link_state(0)
+        assert np.array_equal(s1["tt"], s2["tt"]) and np.array_equal(s1["pce_volume"], s2["pce_volume"])
+        assert rel_err(s2["tt"], so["tt"]) <= TOL and rel_err(s2["pce_volume"], so["pce_volume"], floor=1e-3) <= TOL
+        _compare_columns(e2.columns(), o.columns())
+        c1, c2 = e1.counters(), e2.counters()
+        assert c1["replayed"] == c2["replayed"] and c1["reruns"] == c2["reruns"] and c1["tasks"] == c2["tasks"]
+        return c2, e2.sssp_kernel
+
+
+@pytest.mark.parametrize("workload,kernel", [("grid2k", "smq"), ("grid2k", "gq"), ("grid2k", "bundle"), ("grid10k", "bundle16"), ("grid10k", "smq")])
+def test_pipelined_iterations_match_sequential_and_oracle(D, oracle_mod, tmp_path, monkeypatch, workload, kernel):
+    _force_kernel(monkeypatch, kernel)
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
+    p = D.read_gmns(str(tmp_path), 8)
+    c, used = _pipelined_vs_sequential(D, oracle_mod, p, 6)
+    assert c["replayed"] == 0 and c["reruns"] == 0
+
+
+@pytest.mark.parametrize("kernel", ["bundle16", "smq"])
+def test_pipelined_iterations_redo_batches_with_ties_and_overflows(D, oracle_mod, monkeypatch, tmp_path, kernel):
+    """the slow paths inside the pipeline: order-dependent ties (replay) and queues that overflow (worst-case re-run)"""
+    _force_kernel(monkeypatch, kernel)
+    c, _ = _pipelined_vs_sequential(D, oracle_mod, _tie_grid(), 5)
+    assert c["replayed"] > 0
+    monkeypatch.setenv("DTL_SSSP_QUEUE_CAP", "4")
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS["grid2k"])
+    c, _ = _pipelined_vs_sequential(D, oracle_mod, D.read_gmns(str(tmp_path), 8), 4)
+    assert c["reruns"] > 0
+
+
+@pytest.mark.parametrize("name", ["corridor_101", "corridor_3_2p"])
+def test_iterations_call_on_several_forward_stars(D, problems, oracle_mod, name):
+    """several agent types / periods: more than one tree batch per iteration, dtl_iterations runs them one iteration at a time"""
+    _pipelined_vs_sequential(D, oracle_mod, problems(name), 5)
