@@ -15,7 +15,7 @@ os.makedirs(out_dir, exist_ok=True)
 # template kernels: the instantiation that runs by default (engine.cu: make_bundle_launch / choose_sssp_variant)
 PREFER = {
     "sssp_bundle_async_kernel": "<768, 16, 4, false, 1>", "sssp_bundle_kernel": "<1024, 16, 2>", "bundle_finish_kernel": "<16, 64, false>",
-    "bundle_pred_kernel": "<16>", "sssp_kernel": "<128, 4>", "sssp_smq_kernel": "<512, 2, 2>", "scatter_kernel": None, "vdf_kernel": None,
+    "bundle_pred_kernel": "<16>", "bundle_pred_helper_kernel": "<768, 16>", "sssp_kernel": "<128, 4>", "sssp_smq_kernel": "<512, 2, 2>", "scatter_kernel": None, "vdf_kernel": None,
 }
 txt = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, check=True).stdout.decode()
 blocks = re.split(r"\n\s*Function : ", txt)[1:]
