@@ -294,6 +294,7 @@ def run_engine_arm(args, rank, world, local_rank):
     for k in range(3):
         e.iteration(W + K + k)
     tm1, ctr1 = e.timing(), e.counters()
+    k1_alone_ms = tm1["ms"]["sssp"] / max(1, tm1["launches"]["sssp"] // k1_kernels_per_launch)
     e.close()
     if not same_on_all_ranks:
         raise SystemExit(f"bench.py: rank {rank} holds link volumes {vol_sha[:16]}.. that differ from another rank's")
@@ -335,7 +336,10 @@ def run_engine_arm(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": k1_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": k1_traffic(world), "peak_source": peak_src,
                          "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": edges_rank / launches_per_iter,
-                         "kernel_ms_per_launch": sssp_ms_launch},
+                         "kernel_ms_per_launch": sssp_ms_launch,
+                         # the same kernel without the scatter beside it (the three one-stream iterations behind the timed steps)
+                         "kernel_ms_per_launch_alone": k1_alone_ms,
+                         "frac_alone": BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (k1_alone_ms / 1e3) / 1e9 / peak if k1_alone_ms else None},
             "sssp_gteps": gteps,
             # the other kernels of a step against the same HBM peak (algorithmic bytes of SURVEY.md 8d; this rank's share)
             "other_kernels": other_kernels(tm1, ctr1, 3, p, peak),

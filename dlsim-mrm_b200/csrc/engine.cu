@@ -810,7 +810,7 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
         if (const char* env = getenv("DTL_BUNDLE_ASYNC_BLOCK")) { // experiment hook: "<threads>" or "<threads>x<CTAs per SM>"
             int t = 1024, c = 1;
             sscanf(env, "%dx%d", &t, &c);
-            const int ok[4][2] = { { 1024, 1 }, { 768, 1 }, { 512, 1 }, { 512, 2 } };
+            const int ok[6][2] = { { 1024, 1 }, { 896, 1 }, { 832, 1 }, { 768, 1 }, { 512, 1 }, { 512, 2 } };
             for (const auto& o2 : ok)
                 if (o2[0] == t && o2[1] == c) { b.block = t; ctas_per_sm = c; }
         }
@@ -820,7 +820,9 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
         b.cap_near = ring; // far more slots than the 128 tickets the groups of a CTA can hold: a ticket never meets the slot of an older lap
         b.near_limit = ring;
         if (const char* env = getenv("DTL_SSSP_QUEUE_CAP")) b.near_limit = std::min(ring, std::max(8, atoi(env))); // test hook for the re-run path
-        if (!(e->opt.sssp_delta_factor > 0)) b.s.delta *= 1.5; // windows of 12 mean link costs: fewer block-wide re-bucketing steps
+        // windows of 10.4 mean link costs (measured per 2 000 trees: 5 / 6 / 7 / 8 / 9 / 10.5 / 12 / 14 / 16 mean link costs ->
+        // 8.17 / 8.04 / 7.99 / 7.93 / 7.79 / 7.80 / 7.87 / 7.99 / 8.15 ms: wider windows re-expand more nodes, narrower ones drain more tails)
+        if (!(e->opt.sssp_delta_factor > 0)) b.s.delta *= 1.3;
     }
     const int max_grid = e->sm_count * ctas_per_sm;
     b.ctas_per_sm = ctas_per_sm;

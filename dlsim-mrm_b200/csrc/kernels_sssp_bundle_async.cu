@@ -514,6 +514,8 @@ static void async_launch_b(const BundleLaunch& a, size_t smem, cudaStream_t st)
     case 5122: async_launch<512, B, EPL, 2>(a, smem, st); break;
     case 5121: async_launch<512, B, EPL, 1>(a, smem, st); break;
     case 7681: async_launch<768, B, EPL, 1>(a, smem, st); break;
+    case 8961: async_launch<896, B, EPL, 1>(a, smem, st); break;
+    case 8321: async_launch<832, B, EPL, 1>(a, smem, st); break;
     default: async_launch<1024, B, EPL, 1>(a, smem, st); break;
     }
 }
@@ -524,6 +526,8 @@ static void helper_launch_b(const BundleLaunch& a, int grid, cudaStream_t st)
     switch (a.block) {
     case 512: bundle_pred_helper_kernel<512, B><<<grid, 512, 0, st>>>(a); break;
     case 768: bundle_pred_helper_kernel<768, B><<<grid, 768, 0, st>>>(a); break;
+    case 832: bundle_pred_helper_kernel<832, B><<<grid, 832, 0, st>>>(a); break;
+    case 896: bundle_pred_helper_kernel<896, B><<<grid, 896, 0, st>>>(a); break;
     default: bundle_pred_helper_kernel<1024, B><<<grid, 1024, 0, st>>>(a); break;
     }
 }
