@@ -1118,6 +1118,8 @@ void dtl_destroy(dtl_engine* e)
     if (e->st) cudaStreamSynchronize(e->st);
     e->resolve_timing();
     for (cudaEvent_t ev : e->free_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : { e->ev_k1[0], e->ev_k1[1], e->ev_vdf, e->ev_done })
+        if (ev) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->st2) cudaStreamDestroy(e->st2);
@@ -1788,9 +1790,19 @@ static int iterations_impl(dtl_engine* e, int k0, int n, double* rows)
         e->alt_ready = true;
     }
     struct Guard { // whatever happens, the engine leaves this function in its one-iteration-at-a-time state
-        dtl_engine* e; cudaStream_t st, st2;
-        ~Guard() { e->st = st; e->st2 = st2; e->pipelined = e->expect_side = e->defer_helpers = false; }
-    } guard{ e, e->st, e->st2 };
+        dtl_engine* e; cudaStream_t st, st2; bool ok;
+        ~Guard()
+        {
+            e->st = st; e->st2 = st2; e->pipelined = e->expect_side = e->defer_helpers = false;
+            e->next_started_word = nullptr;
+            if (!ok && e->fn_write_value && e->d_go) {
+                // a failure may have left a stream parked at a gate that nobody will open any more: open them all (the latest tag is
+                // the only one a wait can still be parked on), so that dtl_destroy can drain the streams
+                typedef int (*stream_value_fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+                for (int i = 0; i < 4; ++i) ((stream_value_fn)e->fn_write_value)(st2, (unsigned long long)(uintptr_t)(e->d_go + i), e->pipe_tag, 0u);
+            }
+        }
+    } guard{ e, e->st, e->st2, false };
     e->pipelined = e->expect_side = e->defer_helpers = true;
     const int ph7 = e->phase_begin(7);
     BatchState bs[2];
@@ -1929,6 +1941,7 @@ static int iterations_impl(dtl_engine* e, int k0, int n, double* rows)
     CK(cudaStreamWaitEvent(e->st, e->ev_done, 0));
     e->side_pending = false;
     e->phase_end(ph7, 0);
+    guard.ok = true;
     if (sync_stream(e)) return -1;
     e->resolve_timing();
     e->trees_valid = false;

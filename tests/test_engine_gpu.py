@@ -485,3 +485,20 @@ def test_pipelined_iterations_redo_batches_with_ties_and_overflows(D, oracle_mod
 def test_iterations_call_on_several_forward_stars(D, problems, oracle_mod, name):
     """several agent types / periods: more than one tree batch per iteration, dtl_iterations runs them one iteration at a time"""
     _pipelined_vs_sequential(D, oracle_mod, problems(name), 5)
+
+
+@pytest.mark.parametrize("kernel", ["bundle16", "smq"])
+def test_pipelined_iterations_fail_cleanly(D, tmp_path, monkeypatch, kernel):
+    """an error inside the pipeline (one column slot per OD cell: the second new path of a cell does not fit) comes back as an error,
+    leaves no stream parked at a gate -- the engine can be closed -- and a fresh engine works afterwards"""
+    _force_kernel(monkeypatch, kernel)
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS["grid2k"])
+    p = D.read_gmns(str(tmp_path), 8)
+    e = D.Engine(p, keep_trees=False, max_columns_per_od=1)
+    with pytest.raises(D.EngineError, match="columns"):
+        e.iterations(0, 8)
+    e.close()
+    with D.Engine(p, keep_trees=False, max_columns_per_od=12) as e2:
+        rows = e2.iterations(0, 4)
+        assert len(rows) == 4 and all(r["least"] > 0 for r in rows)
