@@ -376,6 +376,7 @@ struct dtl_gmns {
     int sa_iterations = 0;
     // supply_side_scenario.csv rows of type "sa" (scenario_API.h:152-160): lanes of (period, link) during the sensitivity analysis
     std::vector<int> sa_tau, sa_link;
+    std::vector<int> dms_tau, dms_link, dms_zone; // "dms" rows: period, link, zone seq no of the link's to-node (-1: its zone id is no zone of the model)
     std::vector<double> sa_lanes;
     // measurement.csv rows of type "link" (ODME.h:100-178), one entry per (row, period) in file order
     std::vector<int> ms_tau, ms_link, ms_ub;
@@ -910,7 +911,9 @@ void bind_problem(dtl_gmns& g, int blocks)
 }
 
 // g_load_supply_side_scenario_file, scenario_API.h:53-190: rows of type "sa" change the lanes of a link for the
-// sensitivity-analysis stage; "dms" rows (information zones, route splicing) are not supported.
+// sensitivity-analysis stage; "dms" rows (scenario_API.h:165-188) mark a link as a message sign and the zone of its to-node as an
+// information zone.  The reader keeps them (dtl_gmns_dms; the oracle's restatement of g_column_pool_route_modification is pinned with
+// them); the engine has no route modification yet, so network_assignment() stops on them.
 void read_scenario(dtl_gmns& g)
 {
     Csv p;
@@ -942,7 +945,14 @@ void read_scenario(dtl_gmns& g)
             if (g.design_flag.empty()) g.design_flag.assign(g.periods.size() * g.link_from.size(), 0);
             g.design_flag[(size_t)tau * g.link_from.size() + li->second] = -1;
         } else if (type == "dms") {
-            stop("supply_side_scenario.csv: scenario_type dms (information zones, route modification) is not supported");
+            const int zid = g.node_zone_org[ti->second];
+            if (zid < 1) stop("supply_side_scenario.csv: information zone has not been defined!"); // scenario_API.h:170-175
+            int zone = -1;
+            for (size_t z = 0; z < g.zone_id.size(); ++z)
+                if (g.zone_id[z] == zid) zone = (int)z;                                   // g_zoneid_to_zone_seq_no_mapping, :179-182
+            if (g.design_flag.empty()) g.design_flag.assign(g.periods.size() * g.link_from.size(), 0);
+            g.design_flag[(size_t)tau * g.link_from.size() + li->second] = 2;
+            g.dms_tau.push_back(tau); g.dms_link.push_back(li->second); g.dms_zone.push_back(zone);
         }
     }
 }
@@ -1037,6 +1047,18 @@ int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link
         if (sa_tau) sa_tau[i] = g->sa_tau[i];
         if (sa_link) sa_link[i] = g->sa_link[i];
         if (sa_lanes) sa_lanes[i] = g->sa_lanes[i];
+    }
+    return n;
+}
+
+int dtl_gmns_dms(const dtl_gmns* g, int* dms_tau, int* dms_link, int* dms_zone, int capacity)
+{
+    if (!g) return -1;
+    const int n = (int)g->dms_link.size();
+    for (int i = 0; i < std::min(n, capacity); ++i) {
+        if (dms_tau) dms_tau[i] = g->dms_tau[i];
+        if (dms_link) dms_link[i] = g->dms_link[i];
+        if (dms_zone) dms_zone[i] = g->dms_zone[i];
     }
     return n;
 }
@@ -1480,6 +1502,8 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     // information, a supply-side scenario changes lanes, or SA iterations are asked for
     bool any_rt = false;
     for (const AgentType& a : g->agents) any_rt = any_rt || a.rt_info == 1;
+    if (!g->dms_link.empty())
+        fail("supply_side_scenario.csv: scenario_type dms (information zones, g_column_pool_route_modification) is not supported by the engine yet");
     const bool sa_stage = any_rt || !g->sa_link.empty() || S > 0;
     dtl_options opt;
     dtl_default_options(&opt);

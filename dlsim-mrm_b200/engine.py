@@ -183,6 +183,12 @@ def read_gmns(directory: str, memory_blocks: int = 4) -> Problem:
         L.dtl_gmns_scenario(h, None, _ptr(sa_tau), _ptr(sa_link), _ptr(sa_lanes), n_sa)
         q.rt_info = rt[:A].copy()
         q.sa_changes = [(int(sa_tau[i]), int(sa_link[i]), float(sa_lanes[i])) for i in range(n_sa)]
+        L.dtl_gmns_dms.restype = C.c_int
+        L.dtl_gmns_dms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        n_dms = L.dtl_gmns_dms(h, None, None, None, 0)
+        d_tau = np.zeros(max(1, n_dms), np.int32); d_link = np.zeros(max(1, n_dms), np.int32); d_zone = np.zeros(max(1, n_dms), np.int32)
+        L.dtl_gmns_dms(h, _ptr(d_tau), _ptr(d_link), _ptr(d_zone), n_dms)
+        q.dms_links = [(int(d_tau[i]), int(d_link[i]), int(d_zone[i])) for i in range(n_dms)]
         # ODME inputs: agent-type PCE / occupancy (float) and the link rows of measurement.csv
         pce, occ = np.zeros(max(A, 1), np.float32), np.zeros(max(A, 1), np.float32)
         n_ms = L.dtl_gmns_measurements(h, _ptr(pce), _ptr(occ), None, None, None, None, 0)

@@ -57,6 +57,7 @@ class Problem:
     # sensitivity-analysis inputs (not part of dtl_problem): real_time_info per agent type, "sa" lane changes (tau, link, lanes)
     rt_info: np.ndarray | None = None
     sa_changes: list | None = None
+    dms_links: list | None = None   # "dms" rows of supply_side_scenario.csv: (period, link, information zone seq no or -1)
     # ODME inputs: agent-type PCE / occupancy as floats, measurement.csv link rows (tau, link, count, upper_bound_flag)
     at_pce: np.ndarray | None = None
     at_occ: np.ndarray | None = None

@@ -251,6 +251,10 @@ int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id);
  * 0 none, 1 real-time information, 2 dms) and the "sa" rows of supply_side_scenario.csv (scenario_API.h:152-160) as
  * (period, link, lanes) triples.  Returns the number of sa rows (at most `capacity` are copied) or -1. */
 int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link, double* sa_lanes, int capacity);
+/* the "dms" rows of supply_side_scenario.csv (scenario_API.h:165-188): period, link and the zone seq no of the link's to-node (the
+ * information zone; -1 when its zone id is no zone of the model).  Returns their number.  network_assignment() stops on them: the
+ * engine has no g_column_pool_route_modification (assignment.h:1077-1383) yet. */
+int dtl_gmns_dms(const dtl_gmns* g, int* dms_tau, int* dms_link, int* dms_zone, int capacity);
 /* ODME inputs: the agent types' PCE / person occupancy as floats (assignment.h:308-309) and the "link" rows of measurement.csv
  * (ODME.h:100-178), one entry per (row, demand period) in file order: (period, link, count, upper_bound_flag).  Returns the
  * number of entries (at most `capacity` are copied) or -1. */

@@ -246,11 +246,21 @@ class Oracle:
         return label, pn, pl, int(pops), int(relax.value)
 
     # ---- sensitivity-analysis stage (main_api.cpp:771-1042) ----
-    def sa_configure(self, rt_info, changes=()):
+    def sa_configure(self, rt_info, changes=(), dms=()):
         rt = np.ascontiguousarray(rt_info, np.int32)
         self.lib.orc_sa_configure(self.h, _ptr(rt))
         for tau, link, lanes in changes:
             self.lib.orc_sa_lane_change(self.h, int(tau), int(link), float(lanes))
+        self.lib.orc_sa_dms_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        for tau, link, zone in dms or ():  # "dms" rows: the reader only keeps links whose to-node carries a zone id
+            self.lib.orc_sa_dms_link(self.h, int(tau), int(link), 1, int(zone))
+
+    def sa_route_modification(self) -> int:
+        """g_column_pool_route_modification (assignment.h:1077-1383), between the SA iterations and the SA column-pool iterations;
+        returns the number of columns that were split (-1: the reference would have stopped)"""
+        self.lib.orc_sa_route_modification.restype = C.c_int
+        self.lib.orc_sa_route_modification.argtypes = [C.c_void_p]
+        return int(self.lib.orc_sa_route_modification(self.h))
 
     def sa_begin(self) -> float:
         return float(self.lib.orc_sa_begin(self.h))

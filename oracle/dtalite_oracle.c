@@ -723,6 +723,11 @@ double orc_sa_begin(orc_state* s)
 void orc_sa_iteration(orc_state* s, int it, double row[3])
 {
     const orc_problem* p = s->p;
+    /* induced delay, main_api.cpp:877-891: links without a scenario whose degree of congestion of the last VDF pass exceeds 3 get
+       network_design_flag -2; the flag only matters where the code asks for "<= -1" (g_column_pool_route_modification) */
+    for (int tau = 0; tau < s->T; ++tau)
+        for (int l = 0; l < s->L; ++l)
+            if (s->design_flag[(size_t)tau * s->L + l] == 0 && s->doc[tau][l] > 3) s->design_flag[(size_t)tau * s->L + l] = -2;
     double sysTT = vdf_pass(s);                                                           /* :897 */
     scatter_pass_sa(s, it, 1, 1);                                                         /* :913 */
     double least_total = sp_region(s, it, 1, NULL);                                       /* :966-1018 */
@@ -838,7 +843,11 @@ int orc_sa_route_modification(orc_state* s)
                             for (int q = 0; q < n_seq; ++q) node_sum = (int)((unsigned)node_sum + (unsigned)seq[q] + (unsigned)p->link_to[seq[q]]);
                             int size_before = cv->n, existed = 0;
                             orc_column* nc = colvec_insert(cv, node_sum, &existed);
-                            nc->seq_no = existed ? size_before : size_before + 1;        /* map.size() after operator[] created the entry */
+                            (void)existed;
+                            nc->seq_no = size_before; /* "map[key].path_seq_no = map.size()", assignment.h:1042: the right operand is evaluated
+                                                         first (C++17), i.e. BEFORE operator[] creates the entry -- two columns of a cell can
+                                                         end up with the same path_seq_no, and the column-pool update then treats both as
+                                                         "the least-cost path" (assignment.h:775) */
                             free(nc->links);
                             nc->links = (int*)malloc(sizeof(int) * (size_t)(n_seq > 0 ? n_seq : 1));
                             memcpy(nc->links, seq, sizeof(int) * (size_t)n_seq);

@@ -17,6 +17,10 @@ import pytest
 from conftest import FIXTURES, GOLDEN, ROOT, rel_err
 
 CASES = [("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0), ("corridor_101", 20, 5, 2)]
+# "dms" rows (information zones, g_column_pool_route_modification, assignment.h:1077-1383): the dataset's own supply_side_scenario.csv
+# (one "sa" row that closes a motorway link, one "dms" row); reference dumps from ONE OpenMP thread -- the route modification
+# accumulates path travel times on columns that several origins share inside a parallel loop.  Oracle only: the engine stops on them.
+DMS_CASES = [("corridor_101+dms", 20, 5, 0), ("corridor_101+dms", 20, 5, 2)]
 REL = 1e-6  # link volumes, travel times, column volumes (SURVEY.md 8d parity gates)
 
 
@@ -27,7 +31,10 @@ def sa():
 
 def _run(x, p, K, CU, S):
     """the whole entry-point sequence on an oracle or an engine (same method names)"""
-    x.sa_configure(p.rt_info, p.sa_changes)
+    if p.dms_links:
+        x.sa_configure(p.rt_info, p.sa_changes, p.dms_links)
+    else:
+        x.sa_configure(p.rt_info, p.sa_changes)
     for k in range(K):
         x.iteration(k)
     for n in range(CU):
@@ -35,6 +42,8 @@ def _run(x, p, K, CU, S):
     x.finalize(K)
     x.sa_begin()
     rows = [x.sa_iteration(it) for it in range(S + 1)]
+    if p.dms_links:
+        assert x.sa_route_modification() > 0     # main_api.cpp:1036
     cu = [x.sa_column_update(n) for n in range(S)]
     return rows, cu
 
@@ -62,7 +71,17 @@ def test_reader_scenario_inputs(problems, sa, name, K, CU, S):
         assert np.float32(lanes) == np.float32(sa[f"{key}:sa_lanes"][l])
 
 
-@pytest.mark.parametrize("name,K,CU,S", CASES)
+def test_reader_keeps_dms_rows_and_the_drop_in_refuses_them(problems, native, tmp_path):
+    p = problems("corridor_101+dms")
+    assert p.dms_links == [(0, 395, 98)] and [(t, l) for t, l, _ in p.sa_changes] == [(0, 3898)]   # links 107201->107300, 63702->93601
+    from conftest import stage_fixture
+    stage_fixture("corridor_101+dms", str(tmp_path))
+    r = subprocess.run([native.EXE_PATH if hasattr(native, "EXE_PATH") else os.path.join(ROOT, "dlsim-mrm_b200", "lib", "DTALite_b200")],
+                       cwd=str(tmp_path), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 2 and b"dms" in r.stdout and b"Program stops" in r.stdout
+
+
+@pytest.mark.parametrize("name,K,CU,S", CASES + DMS_CASES)
 def test_oracle_sa_stage_matches_the_reference(problems, oracle_mod, sa, name, K, CU, S):
     p = problems(name)
     key = f"{name}:S={S}"
@@ -91,6 +110,8 @@ def test_oracle_sa_stage_matches_the_reference(problems, oracle_mod, sa, name, K
     # the re-routing did something: columns of the agent types with information carry the SA flag
     if np.any(p.rt_info == 1):
         assert np.count_nonzero(sa[f"{key}:col_sa_flag"]) > 0
+    if p.dms_links:  # and the route modification split columns of the message-sign users (impacted_path_flag 3 = diverted, new column)
+        assert np.count_nonzero(sa[f"{key}:col_impacted_path_flag"] == 3) > 50 and len(oc["node_sum"]) == len(sa[f"{key}:col_node_sum"])
 
 
 @pytest.mark.gpu
