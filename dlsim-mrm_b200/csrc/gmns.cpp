@@ -912,8 +912,8 @@ void bind_problem(dtl_gmns& g, int blocks)
 
 // g_load_supply_side_scenario_file, scenario_API.h:53-190: rows of type "sa" change the lanes of a link for the
 // sensitivity-analysis stage; "dms" rows (scenario_API.h:165-188) mark a link as a message sign and the zone of its to-node as an
-// information zone.  The reader keeps them (dtl_gmns_dms; the oracle's restatement of g_column_pool_route_modification is pinned with
-// them); the engine has no route modification yet, so network_assignment() stops on them.
+// information zone.  The reader keeps them (dtl_gmns_dms); the engine has no g_column_pool_route_modification (assignment.h:1077-1383)
+// yet, so network_assignment() stops on them.
 void read_scenario(dtl_gmns& g)
 {
     Csv p;
