@@ -78,6 +78,8 @@ struct ColumnPool {     // column CSR with fixed slots per OD cell
     double* volume;     // [n_od*cap]
     double* cost;       // [n_od*cap] path_gradient_cost
     double* time;       // [n_od*cap] path_travel_time
+    int* seq;           // [n_od*cap] or null: path_seq_no of a column where it is not its slot index (only g_add_new_column of the
+                        // route modification makes them differ, assignment.h:1042)
     int* arena;         // path links, origin -> destination order
     long long arena_cap = 0;
     unsigned long long* arena_used; // device bump pointer
@@ -213,6 +215,8 @@ struct ColumnLaunch {
     int* path_len;                     // [n_od] nodes of the path found for the cell (may be null): key of sort_cells_by_path_length
 };
 void launch_backtrace(const ColumnLaunch& a, cudaStream_t st);
+// induced delay, main_api.cpp:877-891: links without a scenario whose degree of congestion exceeds 3 get network_design_flag -2
+void launch_induced_delay_flags(signed char* design_flag, const double* doc, size_t n, cudaStream_t st);
 void launch_set_go(const int* flags, int n, unsigned* go, unsigned* start, unsigned tag, int start_when_clean, cudaStream_t st);
 void sort_cells_by_path_length(const int* path_len, int* cells, const int* cell_ptr, int first, int n_tasks, cudaStream_t st);
 
@@ -227,6 +231,8 @@ struct ScatterLaunch {
     int decay_k;                    // <0: none
     const unsigned char* decay_at;  // [AT] or null: the decay applies only to columns of agent types with a non-zero entry (SA
                                     // stage: only users with real-time information are re-routed, assignment.h:150-176)
+    const unsigned char* decay_cell; // [n_od] or null: the same per OD cell (message-sign users are only re-routed from an
+                                    // information zone, assignment.h:160-170); takes precedence over decay_at
     unsigned long long* link_refs;  // counter
     int cell_stride;                // set by launch_scatter: warp w handles cell (w * cell_stride) % n_od
 };

@@ -143,6 +143,12 @@ struct dtl_engine {
     std::vector<double> sa_lanes;
     bool sa_mode = false;                  // trees_and_columns only visits the agent types with real-time information
     unsigned char *d_sa_decay_at = nullptr, *d_od_impact = nullptr;
+    // "dms" scenario rows (dtl_sa_set_dms): message signs, information zones, and what follows from them in the SA stage
+    std::vector<int> dms_tau, dms_link, dms_zone;
+    std::vector<char> info_zone;                 // [Z]
+    unsigned char *d_sa_decay_cell = nullptr, *d_sa_task_skip = nullptr; // [n_cells] / [n_tasks], see sa_set_dms_impl
+    std::vector<int> h_od_at, h_od_tau, h_od_task, h_od_dzone; // [n_cells] host copies (route modification)
+    std::vector<unsigned char> h_task_skip;     // [n_tasks] origin has no physical out-link (routing.h:428)
     signed char* d_design_flag = nullptr;
     int* d_rt_info = nullptr;
     std::vector<std::vector<double>> sa_hist_time, sa_hist_volume; // per SA column-pool iteration: path time / volume of every slot
@@ -576,6 +582,7 @@ int do_scatter(dtl_engine* e, int decay_k, bool person, bool sa = false, bool si
     a.pce_fix = e->ls.pce_fix; a.person_fix = person ? e->ls.person_fix : nullptr;
     a.decay_k = decay_k; a.link_refs = e->d_counters + 0;
     a.decay_at = sa ? e->d_sa_decay_at : nullptr;
+    a.decay_cell = sa ? e->d_sa_decay_cell : nullptr;
     launch_scatter(a, on);
     e->phase_end(ph, 1, on);
     CK(cudaGetLastError());
@@ -1228,7 +1235,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     // origin has no task never get columns in the reference either.  The partition (with more than one rank: four breadth-first
     // searches), the task list and the cell arrays (two passes over the OD rows: count per task, then fill) are put together by
     // a second worker thread while this thread uploads the link arrays; they are uploaded when it is done.
-    std::vector<int> owner, task_of, origin, od_dest, od_at, od_tau, od_task, task_cells;
+    std::vector<int> owner, task_of, origin, od_dest, od_at, od_tau, od_task, task_cells, od_dzone;
     std::vector<unsigned char> skip;
     std::vector<double> od_vol;
     int bad_od_row = -1, n_tasks = 0;
@@ -1273,7 +1280,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         for (int t = 0; t < n_tasks; ++t) e->task_cell_ptr[t + 1] += e->task_cell_ptr[t];
         std::vector<int> cur(e->task_cell_ptr.begin(), e->task_cell_ptr.end() - 1);
         e->cell_global.resize(n_keep); od_dest.resize(n_keep); od_at.resize(n_keep); od_tau.resize(n_keep); od_task.resize(n_keep);
-        od_vol.resize(n_keep); task_cells.resize(n_keep);
+        od_vol.resize(n_keep); task_cells.resize(n_keep); od_dzone.resize(n_keep);
         int c = 0;
         for (int i = 0; i < p->n_od; ++i) {
             const int t = task_i_of[i];
@@ -1281,6 +1288,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
             e->cell_global[c] = i;
             od_dest[c] = p->zone_centroid[p->od_d[i]];
             od_at[c] = p->od_at[i]; od_tau[c] = p->od_tau[i]; od_task[c] = t; od_vol[c] = p->od_vol[i];
+            od_dzone[c] = p->od_d[i];
             task_cells[cur[t]++] = c;
             ++c;
         }
@@ -1358,11 +1366,13 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_task_origin, origin.data(), n_tasks)) return -1;
     if (e->upload(&e->d_task_zone, e->task_zone.data(), n_tasks)) return -1;
     if (e->upload(&e->d_task_skip, skip.data(), n_tasks)) return -1;
+    e->h_task_skip = skip;
     e->n_cells = (int)e->cell_global.size();
     if (e->upload(&e->d_od_dest, od_dest.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_at, od_at.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_tau, od_tau.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
+    e->h_od_at = od_at; e->h_od_tau = od_tau; e->h_od_task = od_task; e->h_od_dzone = od_dzone;
     if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
     if (!getenv("DTL_NO_CELL_SORT")) {
@@ -1571,7 +1581,13 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         int t1 = t0;
         while (t1 < n_tasks && t1 - t0 < e->batch_tasks && fs_index(e, e->task_at[t1], e->task_tau[t1]) == fsi) ++t1;
         const int nb = t1 - t0;
-        if (e->sa_mode && e->sa_rt_info[e->task_at[t0]] != 1) { t0 = t1; continue; } // main_api.cpp:987-994
+        if (e->sa_mode) {                                                 // main_api.cpp:984-994
+            const int rt = e->sa_rt_info[e->task_at[t0]];
+            bool any = rt == 1;
+            if (rt == 2) // message-sign users: only the origins that are information zones (the other trees of the batch are not back-traced)
+                for (int t = t0; t < t1 && !any; ++t) any = !e->info_zone.empty() && e->info_zone[e->task_zone[t]];
+            if (!any) { t0 = t1; continue; }
+        }
         const int tree_off = e->opt.keep_trees ? t0 : 0; // keep_trees: the batch buffer holds every task
         // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept:
         // dtl_get_tree reads the per-tree arrays)
@@ -1597,7 +1613,7 @@ static ColumnLaunch make_column_launch(dtl_engine* e, int t0, int t1, int tree_o
     c.task_first = t0; c.task_count = t1 - t0;
     c.batch_cells = e->d_task_cells + e->task_cell_ptr[t0];
     c.n_batch_cells = e->task_cell_ptr[t1] - e->task_cell_ptr[t0];
-    c.task_skip_backtrace = e->d_task_skip;
+    c.task_skip_backtrace = e->sa_mode && e->d_sa_task_skip ? e->d_sa_task_skip : e->d_task_skip;
     c.k = k; c.least_contrib = e->d_least; c.error_flag = e->d_error_flag; c.path_nodes = e->d_counters + 1;
     c.path_len = e->d_path_len;
     return c;
@@ -2031,6 +2047,43 @@ static int sa_configure_impl(dtl_engine* e, const int* rt_info, int n_changes, c
     CK(cudaMemcpy(e->d_rt_info, e->sa_rt_info.data(), sizeof(int) * e->AT, cudaMemcpyHostToDevice));
     CK(cudaMemset(e->d_od_impact, 0, (size_t)std::max(1, e->n_cells)));
     e->sa_hist_time.clear(); e->sa_hist_volume.clear();
+    e->dms_tau.clear(); e->dms_link.clear(); e->dms_zone.clear(); e->info_zone.clear();
+    e->d_sa_decay_cell = nullptr; e->d_sa_task_skip = nullptr; // (slab memory: the arrays of an earlier configuration stay allocated)
+    return 0;
+}
+
+// "dms" rows of supply_side_scenario.csv (scenario_API.h:165-188), after dtl_sa_configure: the link becomes a message sign
+// (network_design_flag 2), the zone of its to-node an information zone.  In the SA stage a message-sign user (real_time_information 2)
+// is re-routed -- MSA decay of its columns, new shortest path -- only from an origin that is an information zone
+// (assignment.h:160-170, main_api.cpp:990-994): that is a per-cell / per-task predicate, not a per-agent-type one.
+static int sa_set_dms_impl(dtl_engine* e, int n, const int* tau, const int* link, const int* zone)
+{
+    CK(cudaSetDevice(e->dev));
+    if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
+    if (e->world > 1 && !e->local_shard) {
+        set_err("dms scenario rows need the whole column pool on one GPU (the route modification splices columns of other origins)");
+        return -1;
+    }
+    for (int i = 0; i < n; ++i)
+        if (tau[i] < 0 || tau[i] >= e->T || link[i] < 0 || link[i] >= e->L || zone[i] >= e->Z) { set_err("dms row %d: period, link or zone out of range", i); return -1; }
+    e->dms_tau.assign(tau, tau + n); e->dms_link.assign(link, link + n); e->dms_zone.assign(zone, zone + n);
+    e->info_zone.assign(std::max(1, e->Z), 0);
+    for (int i = 0; i < n; ++i) {
+        const signed char two = 2;
+        CK(cudaMemcpy(e->d_design_flag + (size_t)tau[i] * e->L + link[i], &two, 1, cudaMemcpyHostToDevice));
+        if (zone[i] >= 0) e->info_zone[zone[i]] = 1;
+    }
+    const int n_tasks = (int)e->task_at.size();
+    std::vector<unsigned char> decay(std::max(1, e->n_cells), 0), skip(std::max(1, n_tasks), 0);
+    for (int c = 0; c < e->n_cells; ++c) {
+        const int rt = e->sa_rt_info[e->h_od_at[c]];
+        decay[c] = rt == 1 || (rt == 2 && e->info_zone[e->task_zone[e->h_od_task[c]]]);
+    }
+    for (int t = 0; t < n_tasks; ++t)
+        skip[t] = e->h_task_skip[t] || (e->sa_rt_info[e->task_at[t]] == 2 && !e->info_zone[e->task_zone[t]]);
+    if (e->alloc(&e->d_sa_decay_cell, decay.size()) || e->alloc(&e->d_sa_task_skip, skip.size())) return -1;
+    CK(cudaMemcpy(e->d_sa_decay_cell, decay.data(), decay.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_sa_task_skip, skip.data(), skip.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -2066,6 +2119,8 @@ static int sa_iteration_impl(dtl_engine* e, int it, double row[2])
     CK(cudaSetDevice(e->dev));
     if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
     const int ph7 = e->phase_begin(7);
+    launch_induced_delay_flags(e->d_design_flag, e->ls.doc, (size_t)e->T * e->L, e->st); // main_api.cpp:877-891 (DOC of the last VDF pass)
+    CK(cudaGetLastError());
     // (person volumes and the detail outputs of the VDF are refreshed too: with S = 0 this is the state the writers print)
     if (do_vdf(e, true, true, nullptr)) return -1;                     // main_api.cpp:897
     if (do_scatter(e, it, true, true)) return -1;                      // :913
@@ -2082,6 +2137,199 @@ static int sa_iteration_impl(dtl_engine* e, int it, double row[2])
         row[0] = e->h_scalars[0];
         row[1] = e->h_scalars[0] / denom;
     }
+    return 0;
+}
+
+struct PoolHost {
+    std::vector<int> count, node_sum, n_links, n_nodes;
+    std::vector<long long> offset;
+    std::vector<double> volume, cost, time;
+    std::vector<int> seq; // path_seq_no: the slot index unless the pool carries its own array
+};
+static int pool_to_host(dtl_engine* e, PoolHost& h)
+{
+    const size_t n = e->n_cells, s = n * e->pool.cap;
+    h.count.resize(n); h.node_sum.resize(s); h.n_links.resize(s); h.n_nodes.resize(s); h.offset.resize(s);
+    h.volume.resize(s); h.cost.resize(s); h.time.resize(s);
+    if (!n) return 0;
+    CK(cudaMemcpyAsync(h.count.data(), e->pool.count, n * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.node_sum.data(), e->pool.node_sum, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.n_links.data(), e->pool.n_links, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.n_nodes.data(), e->pool.n_nodes, s * 4, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.offset.data(), e->pool.offset, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.volume.data(), e->pool.volume, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.cost.data(), e->pool.cost, s * 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(h.time.data(), e->pool.time, s * 8, cudaMemcpyDeviceToHost, e->st));
+    h.seq.resize(s);
+    if (e->pool.seq) CK(cudaMemcpyAsync(h.seq.data(), e->pool.seq, s * 4, cudaMemcpyDeviceToHost, e->st));
+    if (sync_stream(e)) return -1;
+    if (!e->pool.seq)
+        for (size_t i = 0; i < s; ++i) h.seq[i] = (int)(i % (size_t)e->pool.cap);
+    return 0;
+}
+
+// g_column_pool_route_modification (assignment.h:1077-1383), stage II of the SA stage (main_api.cpp:1036): a column of a message-sign
+// user that passes a message sign AND a link with a lane change is split -- a share exp(-0.1 t_base) / (exp(-0.1 t_base) + exp(-0.1 t_alt))
+// stays, the rest goes to a new column: the old path up to the sign, then the first column of (information zone -> same destination)
+// that avoids every impacted link and beats the non-diverted time.  The reference walks std::maps that it inserts into while it
+// iterates, accumulates path times on the information zone's columns across ALL origins (assignment.h:1229: "+=", never reset) and
+// numbers new columns with the map size before the insertion: an order-dependent serial pass over a few thousand columns, done once.
+// It runs on the host over the downloaded column pool -- there is nothing here for a GPU -- and uploads what changed.  Float
+// arithmetic where the reference uses float.  n_split: columns that were split.
+static int sa_route_modification_impl(dtl_engine* e, int* n_split)
+{
+    CK(cudaSetDevice(e->dev));
+    if (n_split) *n_split = 0;
+    if (e->sa_rt_info.empty()) { set_err("dtl_sa_configure has not been called"); return -1; }
+    if (e->dms_link.empty()) return 0;
+    const int L = e->L, Z = e->Z, AT = e->AT, T = e->T, cap = e->pool.cap;
+    const size_t TL = (size_t)T * L, slots = (size_t)e->n_cells * cap;
+    PoolHost h;
+    if (pool_to_host(e, h)) return -1;
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, e->pool.arena_used, 8, cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (unsigned long long)e->pool.arena_cap);
+    std::vector<int> arena((size_t)used + 4);
+    CK(cudaMemcpy(arena.data(), e->pool.arena, sizeof(int) * (size_t)used, cudaMemcpyDeviceToHost));
+    const size_t used0 = (size_t)used;
+    std::vector<double> tt(TL);
+    std::vector<signed char> flag(TL);
+    std::vector<unsigned char> od_impact(std::max(1, e->n_cells));
+    CK(cudaMemcpy(tt.data(), e->ls.tt, TL * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(flag.data(), e->d_design_flag, TL, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(od_impact.data(), e->d_od_impact, (size_t)e->n_cells, cudaMemcpyDeviceToHost));
+    std::map<std::pair<int, int>, int> dms_zone_of; // (period, link) -> information zone (-1: not a zone of the model)
+    for (size_t i = 0; i < e->dms_link.size(); ++i) dms_zone_of[{ e->dms_tau[i], e->dms_link[i] }] = e->dms_zone[i];
+    std::map<std::tuple<int, int, int, int>, int> cell_of; // (origin zone, destination zone, agent type, period) -> cell
+    for (int c = 0; c < e->n_cells; ++c) cell_of[std::make_tuple(e->task_zone[e->h_od_task[c]], e->h_od_dzone[c], e->h_od_at[c], e->h_od_tau[c])] = c;
+    auto by_key = [&](int cell) { // the cell's slots in std::map order (ascending node_sum)
+        std::vector<int> o(h.count[cell]);
+        std::iota(o.begin(), o.end(), 0);
+        const size_t base = (size_t)cell * cap;
+        std::sort(o.begin(), o.end(), [&](int x, int y) { return h.node_sum[base + x] < h.node_sum[base + y]; });
+        return o;
+    };
+    int splits = 0;
+    std::vector<int> seq;
+    for (int o = 0; o < Z; ++o)
+        for (int d = 0; d < Z; ++d)
+            for (int at = 0; at < AT; ++at) {
+                if (e->sa_rt_info[at] != 2) continue;                                       // :1110
+                for (int tau = 0; tau < T; ++tau) {
+                    auto ci = cell_of.find(std::make_tuple(o, d, at, tau));
+                    if (ci == cell_of.end()) continue;                                      // od_volume > 0, :1115
+                    const int cell = ci->second;
+                    const size_t base = (size_t)cell * cap;
+                    const signed char* fl = flag.data() + (size_t)tau * L;
+                    const double* t_link = tt.data() + (size_t)tau * L;
+                    bool have_key = false;
+                    int last_key = 0;
+                    for (;;) { // the std::map walk: a column inserted with a larger key is met later in the same walk
+                        int j = -1;
+                        for (int q = 0; q < h.count[cell]; ++q) {
+                            const int k = h.node_sum[base + q];
+                            if ((!have_key || k > last_key) && (j < 0 || k < h.node_sum[base + j])) j = q;
+                        }
+                        if (j < 0) break;
+                        have_key = true; last_key = h.node_sum[base + j];
+                        if (h.volume[base + j] < 0.00001) continue;                         // :1136
+                        bool passing_info = false, passing_cap = false;
+                        int new_orig = -1;
+                        seq.clear();
+                        const int* links = arena.data() + h.offset[base + j];
+                        for (int nl = 0; nl < h.n_links[base + j]; ++nl) {                  // :1141
+                            const int l = links[nl];
+                            if (!passing_info && fl[l] == 2) {                              // :1146-1150 (a message sign's to-node carries a zone id: the reader insists)
+                                od_impact[cell] = 1;                                        // :1153-1154
+                                const auto z = dms_zone_of.find({ tau, l });
+                                if (z == dms_zone_of.end() || z->second < 0) continue;     // :1158-1159
+                                passing_info = true; new_orig = z->second;
+                                seq.assign(links, links + nl + 1);                          // :1166-1170
+                            }
+                            if (fl[l] == -1) passing_cap = true;                            // :1176-1180
+                        }
+                        if (!(passing_cap && passing_info)) continue;                       // :1184
+                        auto c2i = cell_of.find(std::make_tuple(new_orig, d, at, tau));
+                        if (c2i == cell_of.end() || h.count[c2i->second] == 0) {            // :1203-1208 (the reference stops)
+                            set_err("route modification: no column from the information zone %d to zone %d in the column pool", new_orig, d);
+                            return -1;
+                        }
+                        const int cell2 = c2i->second;
+                        const size_t base2 = (size_t)cell2 * cap;
+                        const std::vector<int> order2 = by_key(cell2);
+                        float non_div = 999999;                                             // :1223
+                        auto diverts = [&](int q) {
+                            const int* l2 = arena.data() + h.offset[base2 + q];
+                            for (int nl2 = 1; nl2 < h.n_links[base2 + q]; ++nl2)
+                                if (fl[l2[nl2]] <= -1) return false;                        // :1238 (incl. induced delay, -2)
+                            return true;
+                        };
+                        for (int q : order2) {                                              // :1225-1250
+                            const int* l2 = arena.data() + h.offset[base2 + q];
+                            for (int nl2 = 1; nl2 < h.n_links[base2 + q]; ++nl2) h.time[base2 + q] += t_link[l2[nl2]]; // accumulates, :1229
+                            if (!diverts(q)) {
+                                const float abs_br = 3, ratio_br = 0.15;
+                                if (h.time[base2 + q] < non_div - abs_br && h.time[base2 + q] < (non_div * (1 - ratio_br))) non_div = (float)h.time[base2 + q];
+                            }
+                        }
+                        bool found = false;
+                        for (int q : order2) {                                              // :1254-1287
+                            if (found || !diverts(q) || !(h.time[base2 + q] < non_div)) continue;
+                            const int* l2 = arena.data() + h.offset[base2 + q];
+                            seq.insert(seq.end(), l2 + 1, l2 + h.n_links[base2 + q]);
+                            found = true;
+                        }
+                        if (!found) continue;
+                        float base_tt = 0, alt_tt = 0;                                      // optional detour, :1329-1356
+                        for (int nl0 = 0; nl0 < h.n_links[base + j]; ++nl0) base_tt += t_link[links[nl0]];
+                        for (size_t nl3 = 1; nl3 < seq.size(); ++nl3) alt_tt += t_link[seq[nl3]];
+                        const float beta = -0.1;
+                        const float prob_base = expf(beta * base_tt) / (expf(beta * base_tt) + expf(beta * alt_tt));
+                        const float base_volume = (float)h.volume[base + j];
+                        h.volume[base + j] = base_volume * prob_base;
+                        int node_sum = 0;                                                   // g_add_new_column, :1020-1053
+                        for (int l : seq) node_sum = (int)((unsigned)node_sum + (unsigned)l + (unsigned)e->h_link_to[l]);
+                        const int size_before = h.count[cell];
+                        int slot = -1;
+                        for (int q = 0; q < size_before; ++q)
+                            if (h.node_sum[base + q] == node_sum) slot = q;
+                        if (slot < 0) {
+                            if (size_before >= cap) { set_err("an OD cell needs more than %d columns: raise dtl_options.max_columns_per_od", cap); return -1; }
+                            slot = size_before;
+                            h.count[cell] = size_before + 1;
+                            h.node_sum[base + slot] = node_sum;
+                            h.cost[base + slot] = 0; h.time[base + slot] = 0;
+                        }
+                        h.seq[base + slot] = size_before; // "map[key].path_seq_no = map.size()": the size is taken before the entry is created
+                        const size_t need = (seq.size() + 3) & ~(size_t)3; // columns stay 16-byte aligned and padded with -1
+                        if ((long long)(used + need) > e->pool.arena_cap) { set_err("column arena exhausted (%lld path links): raise dtl_options.column_arena_bytes", e->pool.arena_cap); return -1; }
+                        arena.resize((size_t)used + need + 4, -1);
+                        std::copy(seq.begin(), seq.end(), arena.begin() + (size_t)used);
+                        std::fill(arena.begin() + (size_t)used + seq.size(), arena.begin() + (size_t)used + need, -1);
+                        h.offset[base + slot] = (long long)used;
+                        used += need;
+                        h.n_links[base + slot] = (int)seq.size();
+                        h.n_nodes[base + slot] = (int)seq.size() + 1;
+                        h.volume[base + slot] = base_volume * (1 - prob_base);
+                        ++splits;
+                    }
+                }
+            }
+    // upload what changed
+    if (!e->pool.seq && e->alloc(&e->pool.seq, std::max<size_t>(1, slots))) return -1;
+    CK(cudaMemcpy(e->pool.seq, h.seq.data(), slots * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.count, h.count.data(), (size_t)e->n_cells * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.node_sum, h.node_sum.data(), slots * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.n_links, h.n_links.data(), slots * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.n_nodes, h.n_nodes.data(), slots * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.offset, h.offset.data(), slots * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.volume, h.volume.data(), slots * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.cost, h.cost.data(), slots * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.time, h.time.data(), slots * 8, cudaMemcpyHostToDevice));
+    if ((size_t)used > used0) CK(cudaMemcpy(e->pool.arena + used0, arena.data() + used0, sizeof(int) * ((size_t)used - used0), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pool.arena_used, &used, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_od_impact, od_impact.data(), (size_t)e->n_cells, cudaMemcpyHostToDevice));
+    if (n_split) *n_split = splits;
     return 0;
 }
 
@@ -2310,6 +2558,16 @@ int dtl_sa_iteration(dtl_engine* e, int it, double row[2])
     if (rc) comm_abort(e);
     return rc;
 }
+int dtl_sa_set_dms(dtl_engine* e, int n, const int* dms_tau, const int* dms_link, const int* dms_zone)
+{
+    return sa_set_dms_impl(e, n, dms_tau, dms_link, dms_zone);
+}
+int dtl_sa_route_modification(dtl_engine* e, int* n_split)
+{
+    const int rc = sa_route_modification_impl(e, n_split);
+    if (rc) comm_abort(e);
+    return rc;
+}
 int dtl_sa_column_update(dtl_engine* e, int n, double row[4])
 {
     const int rc = sa_column_update_impl(e, n, row);
@@ -2417,29 +2675,6 @@ int dtl_get_gen_cost(dtl_engine* e, int at, int tau, double* cost)
 }
 
 // ---- column pool read-back ---------------------------------------------------------------------
-struct PoolHost {
-    std::vector<int> count, node_sum, n_links, n_nodes;
-    std::vector<long long> offset;
-    std::vector<double> volume, cost, time;
-};
-static int pool_to_host(dtl_engine* e, PoolHost& h)
-{
-    const size_t n = e->n_cells, s = n * e->pool.cap;
-    h.count.resize(n); h.node_sum.resize(s); h.n_links.resize(s); h.n_nodes.resize(s); h.offset.resize(s);
-    h.volume.resize(s); h.cost.resize(s); h.time.resize(s);
-    if (!n) return 0;
-    CK(cudaMemcpyAsync(h.count.data(), e->pool.count, n * 4, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.node_sum.data(), e->pool.node_sum, s * 4, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.n_links.data(), e->pool.n_links, s * 4, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.n_nodes.data(), e->pool.n_nodes, s * 4, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.offset.data(), e->pool.offset, s * 8, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.volume.data(), e->pool.volume, s * 8, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.cost.data(), e->pool.cost, s * 8, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaMemcpyAsync(h.time.data(), e->pool.time, s * 8, cudaMemcpyDeviceToHost, e->st));
-    if (sync_stream(e)) return -1;
-    return 0;
-}
-
 long long dtl_num_columns(dtl_engine* e)
 {
     if (cudaSetDevice(e->dev) != cudaSuccess) return -1;
@@ -2484,7 +2719,7 @@ int dtl_get_columns(dtl_engine* e, int* od_index, int* node_sum, int* seq_no, in
         for (int j : order) { // std::map order of the reference: ascending node_sum
             if (od_index) od_index[c_out] = e->cell_global[c];
             if (node_sum) node_sum[c_out] = h.node_sum[base + j];
-            if (seq_no) seq_no[c_out] = j; // slots are filled in insertion order == path_seq_no
+            if (seq_no) seq_no[c_out] = h.seq[base + j]; // slots are filled in insertion order == path_seq_no (but see ColumnPool::seq)
             if (n_links) n_links[c_out] = h.n_links[base + j];
             if (n_nodes) n_nodes[c_out] = h.n_nodes[base + j];
             if (volume) volume[c_out] = h.volume[base + j];

@@ -912,8 +912,8 @@ void bind_problem(dtl_gmns& g, int blocks)
 
 // g_load_supply_side_scenario_file, scenario_API.h:53-190: rows of type "sa" change the lanes of a link for the
 // sensitivity-analysis stage; "dms" rows (scenario_API.h:165-188) mark a link as a message sign and the zone of its to-node as an
-// information zone.  The reader keeps them (dtl_gmns_dms); the engine has no g_column_pool_route_modification (assignment.h:1077-1383)
-// yet, so network_assignment() stops on them.
+// information zone.  The reader keeps them (dtl_gmns_dms -> dtl_sa_set_dms / dtl_sa_route_modification); network_assignment() still
+// stops on them: its writers do not print the message-sign columns yet.
 void read_scenario(dtl_gmns& g)
 {
     Csv p;
@@ -1503,7 +1503,8 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     bool any_rt = false;
     for (const AgentType& a : g->agents) any_rt = any_rt || a.rt_info == 1;
     if (!g->dms_link.empty())
-        fail("supply_side_scenario.csv: scenario_type dms (information zones, g_column_pool_route_modification) is not supported by the engine yet");
+        fail("supply_side_scenario.csv: scenario_type dms (information zones, g_column_pool_route_modification) is not supported by this entry point yet: "
+             "the engine API has it (dtl_sa_set_dms, dtl_sa_route_modification), the file writers do not print the message-sign columns");
     const bool sa_stage = any_rt || !g->sa_link.empty() || S > 0;
     dtl_options opt;
     dtl_default_options(&opt);

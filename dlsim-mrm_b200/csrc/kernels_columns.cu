@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) backtrace_kernel(ColumnLaunch a)
         if (off + need > P.arena_cap) { atomicOr(a.error_flag, 1); return; }
         slot = cnt;
         P.node_sum[base + slot] = key;
+        if (P.seq) P.seq[base + slot] = slot;
         P.n_links[base + slot] = n_links;
         P.n_nodes[base + slot] = n_nodes;
         P.offset[base + slot] = off;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(128) backtrace_nm_kernel(ColumnLaunch a)
         if (off + need > P.arena_cap) { atomicOr(a.error_flag, 1); return; }
         slot = cnt;
         P.node_sum[base + slot] = key;
+        if (P.seq) P.seq[base + slot] = slot;
         P.n_links[base + slot] = n_links;
         P.n_nodes[base + slot] = n_nodes;
         P.offset[base + slot] = off;
@@ -210,6 +212,16 @@ void sort_cells_by_path_length(const int* path_len, int* cells, const int* cell_
 {
     if (n_tasks <= 0) return;
     cell_sort_in_task_kernel<<<n_tasks, 256, 0, st>>>(path_len, cells, cell_ptr, first);
+}
+
+__global__ void __launch_bounds__(256) induced_delay_kernel(signed char* design_flag, const double* doc, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && design_flag[i] == 0 && doc[i] > 3) design_flag[i] = -2;
+}
+void launch_induced_delay_flags(signed char* design_flag, const double* doc, size_t n, cudaStream_t st)
+{
+    if (n) induced_delay_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(design_flag, doc, n);
 }
 
 // gates of the pipelined loop (engine.cu: iterations_impl).  *go = tag when none of the n flag words of a search is set, else 0 (the
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(256, PERSON ? 3 : SCATTER_MIN_BLOCKS) scatter_
             vol_l = P.volume[base + j0 + lane];
             n_l = P.n_links[base + j0 + lane];
             off_l = P.offset[base + j0 + lane];
-            if (a.decay_k >= 0 && (!a.decay_at || a.decay_at[at]))   // assignment.h:182-186 MSA self-reduction (:150-176 in the SA stage)
+            if (a.decay_k >= 0 && (a.decay_cell ? a.decay_cell[cell] != 0 : (!a.decay_at || a.decay_at[at]))) // assignment.h:182-186 MSA self-reduction (:150-176 in the SA stage)
                 P.volume[base + j0 + lane] = vol_l * ((double)a.decay_k / (double)(a.decay_k + 1));
         }
         // four columns per step: their link groups are requested together (a warp otherwise has ONE load in flight per column
@@ -477,7 +489,7 @@ __global__ void __launch_bounds__(128) pool_update_kernel(PoolUpdateLaunch a)
                     if ((first || k2 > prev_key) && (j < 0 || k2 < key)) { j = c2; key = k2; }
                 }
                 prev_key = key; first = false;
-                if (j == least) continue;                                // :775
+                if (P.seq && least >= 0 ? P.seq[base + j] == P.seq[base + least] : j == least) continue; // :775 (path_seq_no != least path_seq_no)
                 const double c = P.cost[base + j];
                 const double v = P.volume[base + j];
                 const double diff = c - least_cost;

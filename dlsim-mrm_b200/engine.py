@@ -415,12 +415,26 @@ class Engine:
         return dict(obs_count=obs, upper_bound_flag=ub, est_count_dev=dev)
 
     # ---- sensitivity-analysis stage (main_api.cpp:771-1042) ----
-    def sa_configure(self, rt_info, changes=()):
+    def sa_configure(self, rt_info, changes=(), dms=()):
         rt = np.ascontiguousarray(rt_info, np.int32)
         tau = np.ascontiguousarray([c[0] for c in changes] or [0], np.int32)
         link = np.ascontiguousarray([c[1] for c in changes] or [0], np.int32)
         lanes = np.ascontiguousarray([c[2] for c in changes] or [0.0], np.float64)
         self._ck(self.lib.dtl_sa_configure(self.h, _ptr(rt), len(changes), _ptr(tau), _ptr(link), _ptr(lanes)))
+        if dms:  # "dms" rows of supply_side_scenario.csv: (period, link, information zone)
+            d = np.ascontiguousarray(dms, np.int32).reshape(-1, 3)
+            cols = [np.ascontiguousarray(d[:, i]) for i in range(3)]
+            self.lib.dtl_sa_set_dms.restype = C.c_int
+            self.lib.dtl_sa_set_dms.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            self._ck(self.lib.dtl_sa_set_dms(self.h, len(d), _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2])))
+
+    def sa_route_modification(self) -> int:
+        """g_column_pool_route_modification between the SA iterations and the SA column-pool iterations; returns the columns split"""
+        n = C.c_int(0)
+        self.lib.dtl_sa_route_modification.restype = C.c_int
+        self.lib.dtl_sa_route_modification.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.dtl_sa_route_modification(self.h, C.byref(n)))
+        return n.value
 
     def sa_begin(self) -> float:
         s = C.c_double(0)

@@ -178,11 +178,20 @@ int dtl_odme_get(dtl_engine* e, int tau, double* obs_count, int* upper_bound_fla
  *   dtl_sa_iteration     one column re-generation iteration (:864-1034): K4, K3 (only columns of agent types with real-time
  *                        information are decayed, assignment.h:150-176), K1 + K2a for their origins; row = { sysTT, avg travel time }
  *   dtl_sa_column_update one column-pool iteration under the SA rules (assignment.h:699-713, 828-846); row as dtl_column_update
- *   dtl_sa_get_columns   per column, in dtl_get_columns order: the cell's impact flag and the per-iteration path time / volume */
+ *   dtl_sa_get_columns   per column, in dtl_get_columns order: the cell's impact flag and the per-iteration path time / volume
+ * "dms" scenario rows (scenario_API.h:165-188; one GPU only):
+ *   dtl_sa_set_dms       after dtl_sa_configure: n message signs (period, link, information zone = zone seq no of the link's
+ *                        to-node, -1 if it is no zone of the model).  Message-sign users (rt_info 2) are then re-routed in the SA
+ *                        stage from origins that are information zones (assignment.h:160-170, main_api.cpp:990-994)
+ *   dtl_sa_route_modification   g_column_pool_route_modification (assignment.h:1077-1383, main_api.cpp:1036), between the last
+ *                        dtl_sa_iteration and the first dtl_sa_column_update: splits the columns of message-sign users that pass a
+ *                        sign and a lane change; *n_split (may be NULL) = columns that were split */
 int dtl_sa_configure(dtl_engine* e, const int* rt_info, int n_changes, const int* sa_tau, const int* sa_link, const double* sa_lanes);
 int dtl_sa_begin(dtl_engine* e, double* sys_tt);
 int dtl_sa_iteration(dtl_engine* e, int it, double row[2]);
 int dtl_sa_column_update(dtl_engine* e, int n, double row[4]);
+int dtl_sa_set_dms(dtl_engine* e, int n, const int* dms_tau, const int* dms_link, const int* dms_zone);
+int dtl_sa_route_modification(dtl_engine* e, int* n_split);
 int dtl_sa_get_columns(dtl_engine* e, unsigned char* od_impact, int* n_iterations, double* hist_time, double* hist_volume);
 
 /* ---- kernel-level entry points (known-answer tests, benchmarks) ---- */
@@ -252,8 +261,7 @@ int dtl_gmns_ids(const dtl_gmns* g, int* node_id, int* zone_id);
  * (period, link, lanes) triples.  Returns the number of sa rows (at most `capacity` are copied) or -1. */
 int dtl_gmns_scenario(const dtl_gmns* g, int* rt_info, int* sa_tau, int* sa_link, double* sa_lanes, int capacity);
 /* the "dms" rows of supply_side_scenario.csv (scenario_API.h:165-188): period, link and the zone seq no of the link's to-node (the
- * information zone; -1 when its zone id is no zone of the model).  Returns their number.  network_assignment() stops on them: the
- * engine has no g_column_pool_route_modification (assignment.h:1077-1383) yet. */
+ * information zone; -1 when its zone id is no zone of the model).  Returns their number (feed them to dtl_sa_set_dms). */
 int dtl_gmns_dms(const dtl_gmns* g, int* dms_tau, int* dms_link, int* dms_zone, int capacity);
 /* ODME inputs: the agent types' PCE / person occupancy as floats (assignment.h:308-309) and the "link" rows of measurement.csv
  * (ODME.h:100-178), one entry per (row, demand period) in file order: (period, link, count, upper_bound_flag).  Returns the
