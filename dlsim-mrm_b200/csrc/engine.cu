@@ -149,6 +149,8 @@ struct dtl_engine {
     unsigned char *d_sa_decay_cell = nullptr, *d_sa_task_skip = nullptr; // [n_cells] / [n_tasks], see sa_set_dms_impl
     std::vector<int> h_od_at, h_od_tau, h_od_task, h_od_dzone; // [n_cells] host copies (route modification)
     std::vector<unsigned char> h_task_skip;     // [n_tasks] origin has no physical out-link (routing.h:428)
+    std::vector<unsigned char> sa_slot_impact;  // [n_cells * cap] impacted_path_flag the route modification set (1 impacted, 3 diverted new column)
+    std::vector<unsigned char> sa_cell_info;    // [n_cells] CColumnVector::information_type (1: a detour was looked for in this cell's columns)
     signed char* d_design_flag = nullptr;
     int* d_rt_info = nullptr;
     std::vector<std::vector<double>> sa_hist_time, sa_hist_volume; // per SA column-pool iteration: path time / volume of every slot
@@ -2048,6 +2050,7 @@ static int sa_configure_impl(dtl_engine* e, const int* rt_info, int n_changes, c
     CK(cudaMemset(e->d_od_impact, 0, (size_t)std::max(1, e->n_cells)));
     e->sa_hist_time.clear(); e->sa_hist_volume.clear();
     e->dms_tau.clear(); e->dms_link.clear(); e->dms_zone.clear(); e->info_zone.clear();
+    e->sa_slot_impact.clear(); e->sa_cell_info.clear();
     e->d_sa_decay_cell = nullptr; e->d_sa_task_skip = nullptr; // (slab memory: the arrays of an earlier configuration stay allocated)
     return 0;
 }
@@ -2211,6 +2214,8 @@ static int sa_route_modification_impl(dtl_engine* e, int* n_split)
     };
     int splits = 0;
     std::vector<int> seq;
+    e->sa_slot_impact.assign(std::max<size_t>(1, slots), 0);
+    e->sa_cell_info.assign(std::max(1, e->n_cells), 0);
     for (int o = 0; o < Z; ++o)
         for (int d = 0; d < Z; ++d)
             for (int at = 0; at < AT; ++at) {
@@ -2246,7 +2251,7 @@ static int sa_route_modification_impl(dtl_engine* e, int* n_split)
                                 passing_info = true; new_orig = z->second;
                                 seq.assign(links, links + nl + 1);                          // :1166-1170
                             }
-                            if (fl[l] == -1) passing_cap = true;                            // :1176-1180
+                            if (fl[l] == -1) { passing_cap = true; e->sa_slot_impact[base + j] = 1; } // :1176-1180
                         }
                         if (!(passing_cap && passing_info)) continue;                       // :1184
                         auto c2i = cell_of.find(std::make_tuple(new_orig, d, at, tau));
@@ -2256,6 +2261,7 @@ static int sa_route_modification_impl(dtl_engine* e, int* n_split)
                         }
                         const int cell2 = c2i->second;
                         const size_t base2 = (size_t)cell2 * cap;
+                        e->sa_cell_info[cell2] = 1;                                         // :1360
                         const std::vector<int> order2 = by_key(cell2);
                         float non_div = 999999;                                             // :1223
                         auto diverts = [&](int q) {
@@ -2311,6 +2317,7 @@ static int sa_route_modification_impl(dtl_engine* e, int* n_split)
                         h.n_links[base + slot] = (int)seq.size();
                         h.n_nodes[base + slot] = (int)seq.size() + 1;
                         h.volume[base + slot] = base_volume * (1 - prob_base);
+                        e->sa_slot_impact[base + slot] = 3;                                 // :1356
                         ++splits;
                     }
                 }
@@ -2561,6 +2568,27 @@ int dtl_sa_iteration(dtl_engine* e, int it, double row[2])
 int dtl_sa_set_dms(dtl_engine* e, int n, const int* dms_tau, const int* dms_link, const int* dms_zone)
 {
     return sa_set_dms_impl(e, n, dms_tau, dms_link, dms_zone);
+}
+// per column, in dtl_get_columns order: impacted_path_flag as the route modification left it, and the information_type of its cell
+int dtl_sa_get_route_flags(dtl_engine* e, unsigned char* path_impact, unsigned char* info_type)
+{
+    CK(cudaSetDevice(e->dev));
+    PoolHost h;
+    if (pool_to_host(e, h)) return -1;
+    long long c_out = 0;
+    std::vector<int> order;
+    for (int c = 0; c < e->n_cells; ++c) {
+        const size_t base = (size_t)c * e->pool.cap;
+        order.resize(h.count[c]);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return h.node_sum[base + x] < h.node_sum[base + y]; });
+        for (int j : order) {
+            if (path_impact) path_impact[c_out] = e->sa_slot_impact.size() > base + j ? e->sa_slot_impact[base + j] : 0;
+            if (info_type) info_type[c_out] = e->sa_cell_info.size() > (size_t)c ? e->sa_cell_info[c] : 0;
+            ++c_out;
+        }
+    }
+    return 0;
 }
 int dtl_sa_route_modification(dtl_engine* e, int* n_split)
 {

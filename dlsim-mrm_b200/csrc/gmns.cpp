@@ -912,8 +912,7 @@ void bind_problem(dtl_gmns& g, int blocks)
 
 // g_load_supply_side_scenario_file, scenario_API.h:53-190: rows of type "sa" change the lanes of a link for the
 // sensitivity-analysis stage; "dms" rows (scenario_API.h:165-188) mark a link as a message sign and the zone of its to-node as an
-// information zone.  The reader keeps them (dtl_gmns_dms -> dtl_sa_set_dms / dtl_sa_route_modification); network_assignment() still
-// stops on them: its writers do not print the message-sign columns yet.
+// information zone (dtl_gmns_dms -> dtl_sa_set_dms / dtl_sa_route_modification).
 void read_scenario(dtl_gmns& g)
 {
     Csv p;
@@ -1271,7 +1270,7 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                 }
                 appendf(out, "%.3f,", sum / std::max(1, cnt));
             }
-            appendf(out, "%s,", !g.design_flag.empty() && g.design_flag[k] == -1 ? "sa" : "");
+            appendf(out, "%s,", g.design_flag.empty() ? "" : g.design_flag[k] == -1 ? "sa" : g.design_flag[k] == 2 ? "dms" : ""); // scenario_code, scenario_API.h:160,168
             // base case / after the sensitivity-analysis stage (g_record_corridor_performance_summary, output.h:52-98): the
             // "before" record is taken between the assignment and the stage (network_assignment below), the "after" record is
             // the state being written.  Without the stage both are the final state and the differences are zero.
@@ -1346,10 +1345,18 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
     // Rows are formatted in parallel and written in order: the file is ~2.5 KB per column (node, link and coordinate
     // sequences), gigabytes on a regional network, and one fprintf stream made it the longest phase of the whole run.
     // Per-node / per-link text is formatted once; the row prefix keeps the reference's printf format (output.h:1248-1445).
+    // message signs ("dms" rows): the route modification's impacted_path_flag per column and information_type per cell -- a cell with
+    // information_type 1 is printed from its first physical node on (no virtual first link is stripped) and without its columns
+    // below 0.1 (output.h:1219-1226)
+    std::vector<unsigned char> route_impact(od_index.size(), 0), info_type(od_index.size(), 0);
+    const bool with_dms = g.sa_stage && !g.dms_link.empty();
+    if (with_dms && dtl_sa_get_route_flags(e, route_impact.data(), info_type.data())) { fclose(f); return -1; }
     std::vector<long long> kept; // columns that are written, in output order: more than two physical nodes (output.h:1239)
     kept.reserve(order.size());
-    for (long long oc : order)
-        if (n_nodes[oc] - 2 > 2) kept.push_back(oc);
+    for (long long oc : order) {
+        if (info_type[oc] && volume[oc] < 0.1) continue;
+        if (n_nodes[oc] - (info_type[oc] ? 1 : 2) > 2) kept.push_back(oc);
+    }
     const int N = g.prob.n_nodes;
     std::vector<std::string> node_seq(N), node_xy(N), link_seq(L);
     {
@@ -1394,6 +1401,9 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
                     path_impact[c] = 1;
                 }
             }
+        if (with_dms) // the flags as g_column_pool_route_modification set them (on the volumes of that moment), incl. 3 = diverted new column
+            for (long long c = 0; c < nc; ++c)
+                if (g.agents[g.od_at[od_index[c]]].rt_info == 2) path_impact[c] = route_impact[c];
     }
     auto format_row = [&](long long oc, int count, std::string& out) {
         const int cell = od_index[oc];
@@ -1415,16 +1425,19 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         const double vol = std::max(0.001, volume[oc]);
         char b[1024];
         const int nb = snprintf(b, sizeof b, ",%d,%d,%d,%d,%d,%d->%d,%d,%d,%s,%s,%d,%s,%s,%.4f,%d,%d,%d,%d,%d,%.1f,%d,%.1f,%.4f,%.4f,%.4f,%.4f,%.4f,",
-                                count, g.zone_id[o], g.zone_id[d], o, d, g.zone_id[o], g.zone_id[d], seq[oc], seq[oc] + 1, "", "", 0,
+                                count, g.zone_id[o], g.zone_id[d], o, d, g.zone_id[o], g.zone_id[d], seq[oc], seq[oc] + 1, "", "", (int)info_type[oc],
                                 g.agents[at].name.c_str(), g.periods[tau].name.c_str(), vol, 0, 0,
                                 g.sa_stage && od_impact_regular.count(std::make_tuple(o, d, tau)) ? 1 : 0, (int)at_impact[oc], (int)path_impact[oc],
-                                path_toll, m_nodes - 2,
+                                path_toll, m_nodes - (info_type[oc] ? 1 : 2),
                                 (double)path_tt, path_tt, path_tt_no_access, dist, dist_km, dist_ml);
         out.append(b, std::min<size_t>(nb > 0 ? nb : 0, sizeof b - 1));
-        // nodes: origin centroid, then the head of every link; the virtual first/last connector is stripped
+        // nodes: origin centroid, then the head of every link; the virtual first/last connector is stripped (the first one is kept
+        // for a cell with information_type 1: virtual_first_link_delta = 0, output.h:1222-1226)
+        const int first_delta = info_type[oc] ? 0 : 1;
+        if (!first_delta && m_links > 0) out += node_seq[g.link_from[pl[0]]];
         for (int q = 0; q + 1 < m_links; ++q) out += node_seq[g.link_to[pl[q]]];
         out += ',';
-        for (int q = 1; q + 1 < m_links; ++q) out += link_seq[pl[q]];
+        for (int q = first_delta; q + 1 < m_links; ++q) out += link_seq[pl[q]];
         out += ',';
         if (n_hist == 0) out += sa_cols;
         else {                                                        // output.h:1367-1390
@@ -1443,6 +1456,7 @@ int dtl_gmns_write_outputs(const dtl_gmns* gp, dtl_engine* e, const char* dir_c)
         }
         if (volume[oc] >= 5 || count < 3000) {
             out += "\"LINESTRING (";
+            if (!first_delta && m_links > 0) { out += node_xy[g.link_from[pl[0]]]; if (m_links > 1) out += ", "; }
             for (int q = 0; q + 1 < m_links; ++q) {
                 out += node_xy[g.link_to[pl[q]]];
                 if (q + 2 < m_links) out += ", ";
@@ -1502,13 +1516,10 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
     // information, a supply-side scenario changes lanes, or SA iterations are asked for
     bool any_rt = false;
     for (const AgentType& a : g->agents) any_rt = any_rt || a.rt_info == 1;
-    if (!g->dms_link.empty())
-        fail("supply_side_scenario.csv: scenario_type dms (information zones, g_column_pool_route_modification) is not supported by this entry point yet: "
-             "the engine API has it (dtl_sa_set_dms, dtl_sa_route_modification), the file writers do not print the message-sign columns");
-    const bool sa_stage = any_rt || !g->sa_link.empty() || S > 0;
+    const bool sa_stage = any_rt || !g->sa_link.empty() || !g->dms_link.empty() || S > 0;
     dtl_options opt;
     dtl_default_options(&opt);
-    opt.max_columns_per_od = std::max(4, column_generation_iterations + 4) + (sa_stage ? S + 1 : 0);
+    opt.max_columns_per_od = std::max(4, column_generation_iterations + 4) + (sa_stage ? S + 1 : 0) + (g->dms_link.empty() ? 0 : 8);
     const auto t_create = clk::now();
     dtl_engine* e = dtl_create(dtl_gmns_problem(g), &opt);
     if (!e) fail(dtl_last_error());
@@ -1606,6 +1617,9 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
         std::vector<int> rt(AT);
         for (int at = 0; at < AT; ++at) rt[at] = g->agents[at].rt_info;
         if (dtl_sa_configure(e, rt.data(), (int)g->sa_link.size(), g->sa_tau.data(), g->sa_link.data(), g->sa_lanes.data())) fail(dtl_last_error());
+        if (!g->dms_link.empty() &&                                     // scenario_API.h:165-188
+            dtl_sa_set_dms(e, (int)g->dms_link.size(), g->dms_tau.data(), g->dms_link.data(), g->dms_zone.data()))
+            fail(dtl_last_error());
         if (dtl_sa_begin(e, nullptr)) fail(dtl_last_error());          // main_api.cpp:779-794, 857
         for (size_t i = 0; i < g->sa_link.size(); ++i) {               // the same lane changes on the host image the writers print
             bool later = false;
@@ -1623,6 +1637,7 @@ double network_assignment(int assignment_mode, int column_generation_iterations,
             if (it == 0) summary << "Sensitivity analysis stage" << std::endl << ",Iteration,Avg Travel Time(min)" << std::endl;
             summary << it << "," << row[1] << "," << std::endl;
         }
+        if (!g->dms_link.empty() && dtl_sa_route_modification(e, nullptr)) fail(dtl_last_error()); // main_api.cpp:1036
         summary << "column updating" << std::endl;                    // main_api.cpp:1040, assignment.h:1057
         for (int n = 0; n < S; ++n) {
             double row[4];

@@ -192,6 +192,9 @@ int dtl_sa_iteration(dtl_engine* e, int it, double row[2]);
 int dtl_sa_column_update(dtl_engine* e, int n, double row[4]);
 int dtl_sa_set_dms(dtl_engine* e, int n, const int* dms_tau, const int* dms_link, const int* dms_zone);
 int dtl_sa_route_modification(dtl_engine* e, int* n_split);
+/* per column, in dtl_get_columns order: impacted_path_flag as dtl_sa_route_modification left it (1 = passes a lane change, 3 = the new,
+ * diverted column; assignment.h:1179,1356) and the information_type of its OD cell (assignment.h:1360); either may be NULL */
+int dtl_sa_get_route_flags(dtl_engine* e, unsigned char* path_impact, unsigned char* info_type);
 int dtl_sa_get_columns(dtl_engine* e, unsigned char* od_impact, int* n_iterations, double* hist_time, double* hist_volume);
 
 /* ---- kernel-level entry points (known-answer tests, benchmarks) ---- */

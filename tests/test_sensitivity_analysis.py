@@ -19,9 +19,7 @@ from conftest import FIXTURES, GOLDEN, ROOT, rel_err
 CASES = [("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0), ("corridor_101", 20, 5, 2)]
 # "dms" rows (information zones, g_column_pool_route_modification, assignment.h:1077-1383): the dataset's own supply_side_scenario.csv
 # (one "sa" row that closes a motorway link, one "dms" row); reference dumps from ONE OpenMP thread -- the route modification
-# accumulates path travel times on columns that several origins share inside a parallel loop.  The engine API covers them
-# (dtl_sa_set_dms, dtl_sa_route_modification); the drop-in entry point still stops on them (its writers do not print the
-# message-sign columns).
+# accumulates path travel times on columns that several origins share inside a parallel loop.
 DMS_CASES = [("corridor_101+dms", 20, 5, 0), ("corridor_101+dms", 20, 5, 2)]
 REL = 1e-6  # link volumes, travel times, column volumes (SURVEY.md 8d parity gates)
 
@@ -73,14 +71,9 @@ def test_reader_scenario_inputs(problems, sa, name, K, CU, S):
         assert np.float32(lanes) == np.float32(sa[f"{key}:sa_lanes"][l])
 
 
-def test_reader_keeps_dms_rows_and_the_drop_in_refuses_them(problems, native, tmp_path):
+def test_reader_keeps_dms_rows(problems):
     p = problems("corridor_101+dms")
     assert p.dms_links == [(0, 395, 98)] and [(t, l) for t, l, _ in p.sa_changes] == [(0, 3898)]   # links 107201->107300, 63702->93601
-    from conftest import stage_fixture
-    stage_fixture("corridor_101+dms", str(tmp_path))
-    r = subprocess.run([native.EXE_PATH if hasattr(native, "EXE_PATH") else os.path.join(ROOT, "dlsim-mrm_b200", "lib", "DTALite_b200")],
-                       cwd=str(tmp_path), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    assert r.returncode == 2 and b"dms" in r.stdout and b"Program stops" in r.stdout
 
 
 @pytest.mark.parametrize("name,K,CU,S", CASES + DMS_CASES)
@@ -158,15 +151,15 @@ assert lib.network_assignment(1, int(sys.argv[2]), int(sys.argv[3]), 0, int(sys.
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,K,CU,S", [("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0)])
+@pytest.mark.parametrize("name,K,CU,S", [("sa_corridor", 20, 5, 3), ("sa_corridor", 20, 5, 0), ("corridor_101", 20, 5, 0),
+                                         ("corridor_101+dms", 20, 5, 0)])
 def test_output_files_with_sa_stage(native, tmp_path, name, K, CU, S):
     """network_assignment(1, K, CU, 0, S, 0, 4) through the C ABI: link_performance.csv (before / after columns, scenario code),
     route_assignment.csv (re-routed columns, impact flags, per-iteration records) and the summary rows of the stage"""
     from test_output_files_gpu import _compare_csv
     lib = os.path.join(ROOT, "dlsim-mrm_b200", "lib", "libdtalite_b200.so")
-    src = os.path.join(FIXTURES, name)
-    for f in os.listdir(src):
-        shutil.copy(os.path.join(src, f), tmp_path)
+    from conftest import stage_fixture
+    stage_fixture(name, str(tmp_path))
     r = subprocess.run([sys.executable, "-c", CALL, lib, str(K), str(CU), str(S)], cwd=tmp_path, stdin=subprocess.DEVNULL,
                        capture_output=True, timeout=900)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
