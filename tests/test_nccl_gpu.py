@@ -94,3 +94,58 @@ def test_a_failing_rank_stops_every_rank(tmp_path):
     assert all(str(q["error"]) != "" for q in parts), "both ranks must report the failure"
     assert int(parts[0]["failed_at"]) == int(parts[1]["failed_at"]) >= 0, "and stop in the same iteration"
     assert "max_columns_per_od" in str(parts[1]["error"])
+
+
+def _worker_grid(rank, world, out_dir, grid_dir, mode):
+    """one agent type, one batch of trees per iteration: dtl_iterations runs as a pipeline (collectives on the side stream)"""
+    sys.path.insert(0, ROOT)
+    os.environ["DTL_NCCL_TIMEOUT_S"] = "30"
+    import dlsim_mrm_b200 as D
+    p = D.read_gmns(grid_dir, 8)
+    uid = _exchange_id(rank, os.path.join(out_dir, f"id_{mode}"), D)
+    cap = 1 if (mode == "pfail" and rank == 1) else 12
+    res = {"error": ""}
+    with D.Engine(p, device=rank, rank=rank, world_size=world, max_columns_per_od=cap) as e:
+        e.comm_init(uid)
+        try:
+            rows = e.iterations(0, 6)
+            res["least"] = np.array([r["least"] for r in rows])
+            res["volume"] = e.volume_fixed(0)
+        except D.EngineError as ex:
+            res["error"] = str(ex)
+    np.savez(os.path.join(out_dir, f"{mode}_rank{rank}.npz"), **res)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_pipelined_iterations_over_nccl(tmp_path):
+    """dtl_iterations on two ranks: the same rows and the same Q31.32 link volumes as one GPU running dtl_iteration six times"""
+    import torch.multiprocessing as mp
+    import dlsim_mrm_b200 as D
+    from dlsim_mrm_b200 import synth
+    grid = str(tmp_path / "grid")
+    os.makedirs(grid)
+    synth.write_grid(grid, **synth.WORKLOADS["grid2k"])
+    mp.spawn(_worker_grid, args=(2, str(tmp_path), grid, "pipe"), nprocs=2, join=True)
+    parts = [np.load(tmp_path / f"pipe_rank{r}.npz") for r in range(2)]
+    assert all(str(q["error"]) == "" for q in parts), [str(q["error"]) for q in parts]
+    p = D.read_gmns(grid, 8)
+    with D.Engine(p, device=0, max_columns_per_od=12) as e:
+        rows = [e.iteration(k) for k in range(6)]
+        whole = e.volume_fixed(0)
+    for q in parts:
+        assert np.array_equal(q["volume"], whole)
+        assert np.allclose(q["least"], [r["least"] for r in rows], rtol=1e-12)   # an all-reduced FP64 sum of two partial sums
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_a_failing_rank_stops_every_rank_inside_the_pipeline(tmp_path):
+    import torch.multiprocessing as mp
+    from dlsim_mrm_b200 import synth
+    grid = str(tmp_path / "grid")
+    os.makedirs(grid)
+    synth.write_grid(grid, **synth.WORKLOADS["grid2k"])
+    t0 = time.time()
+    mp.spawn(_worker_grid, args=(2, str(tmp_path), grid, "pfail"), nprocs=2, join=True)
+    assert time.time() - t0 < 150, "a rank was left waiting in a collective"
+    parts = [np.load(tmp_path / f"pfail_rank{r}.npz") for r in range(2)]
+    assert all(str(q["error"]) != "" for q in parts), "both ranks must report the failure"
