@@ -301,6 +301,24 @@ def run_engine_arm(args, rank, world, local_rank):
     if golden_sha is not None and golden_sha != vol_sha:
         raise SystemExit(f"bench.py: link volumes after {W + K} iterations ({vol_sha[:16]}..) differ from the single-GPU golden ({golden_sha[:16]}..)")
 
+    # ---- the same steps with the destination-bounded search (dtl_set_bounded_search; off by default: the headline `value` runs the
+    # reference's complete one-to-all trees).  Exact -- the link volumes must carry the same digest -- and reported as an extra key.
+    barrier()
+    e3 = make_engine()
+    e3.set_bounded_search(True)
+    e3.iterations(0, W)
+    e3.timing(reset=True)
+    barrier()
+    e3.iterations(W, K)
+    torch.cuda.synchronize()
+    tm3 = e3.timing()
+    bounded_s = max_over_ranks(tm3["ms"]["iteration"] / 1e3)
+    bounded_sha = hashlib.sha256(e3.volume_fixed(0).tobytes()).hexdigest()
+    bounded_k1_ms = tm3["ms"]["sssp"] / max(1, tm3["launches"]["sssp"] // k1_kernels_per_launch)
+    e3.close()
+    if bounded_sha != vol_sha:
+        raise SystemExit(f"bench.py: the destination-bounded search changed the link volumes ({bounded_sha[:16]}.. instead of {vol_sha[:16]}..)")
+
     # ---- end to end through the C ABI with host buffers: image upload + K iterations + result read-back ----
     barrier()
     t0 = time.perf_counter()
@@ -346,6 +364,11 @@ def run_engine_arm(args, rank, world, local_rank):
             "other_kernels_note": "three extra iterations with every kernel on one stream (inside the timed steps the scatter and its "
                                   "all-reduce run on a second stream beside K1: phase_ms_per_step['scatter'] is that overlapped duration)",
             "one_stream_ms_per_step": tm1["ms"]["iteration"] / 3,
+            "destination_bounded": {"value": K / bounded_s, "unit": UNIT, "ms_per_step": bounded_s / K * 1e3, "k1_ms_per_launch": bounded_k1_ms,
+                                    "same_link_volume_digest": True,
+                                    "what": "the same K steps with dtl_set_bounded_search(1): an origin-bundle search stops when nothing queued can "
+                                            "still improve a destination with demand (exact: same columns, volumes, gaps); NOT the headline -- "
+                                            "`value` computes the reference's complete one-to-all trees"},
             "wall_ms_per_step": wall / K * 1e3,
             "phase_ms_per_step": {k_: v / K for k_, v in tm["ms"].items()},
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},

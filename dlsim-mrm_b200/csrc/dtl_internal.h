@@ -174,6 +174,12 @@ struct BundleLaunch {
                              // (more) bundle to search takes tiles of the bundles that are finished (work[] below)
     int* work;               // fuse_pred: [2 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters,
                              // resident CTAs of the search kernel}
+    // destination-bounded search (optional, dtl_set_bounded_search): a bundle's search stops as soon as no queued node can still
+    // improve the label of a destination the bundle's origins have demand to; labels beyond that bound are not final and the
+    // label -> predecessor pass treats them as unreached
+    const int* dest_ptr;     // [n_bundles + 1] into dest_idx, or null: every search runs to the end
+    const int* dest_idx;     // node * B + slot of every (origin, destination with demand) of a bundle
+    unsigned* bundle_bound;  // [n_bundles] out: scheduling key (high word of the label) below which the labels of the bundle are final
     unsigned* started_word;  // fuse_pred, optional: the CTA that completes the resident count writes started_tag here (pipelined loop:
     unsigned started_tag;    // the back-trace of the previous iteration waits for it on the side stream)
     int2* bp;                // [n_bundles][N][B] {predecessor link, predecessor node}, node-major (slim)

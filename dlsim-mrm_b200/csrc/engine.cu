@@ -214,7 +214,16 @@ struct dtl_engine {
     int2* d_bfar = nullptr;
     int bundle_grid = 0, bundle_cap_far = 0;
     int* d_bundle_counter = nullptr;
-    struct BundlePlan { int B = 0, n_bundles = 0; int* d_tasks = nullptr; int* d_slots = nullptr; };
+    struct BundlePlan {
+        int B = 0, n_bundles = 0; int* d_tasks = nullptr; int* d_slots = nullptr;
+        std::vector<int> h_tasks;                         // [n_bundles * B] batch-local task of every slot (-1 = empty)
+        int *d_dest_ptr = nullptr, *d_dest_idx = nullptr; // destination-bounded search: node * B + slot of every destination with demand
+    };
+    // destination-bounded search (dtl_set_bounded_search): off by default -- the trees then are the reference's complete trees
+    bool bounded = false, count_pass = false;
+    unsigned* d_bundle_bound = nullptr;
+    size_t bundle_bound_cap = 0;
+    std::vector<int> h_task_cells, h_od_dest;             // [n_cells] cells grouped by task (creation order) / destination centroid of a cell
     std::map<std::tuple<int, int, int, int>, BundlePlan> bundle_plans; // (forward star, first task, tasks, B)
     int* d_bundle_tmp = nullptr;
     size_t bundle_tmp_cap = 0;
@@ -784,6 +793,7 @@ static int plan_bundles(dtl_engine* e, const ForwardStar& f, int n_tasks, const 
         if (e->alloc(&d, out.size())) return -1;
         dtl_engine::BundlePlan pl;
         pl.B = B; pl.n_bundles = nb; pl.d_tasks = d; pl.d_slots = d + n_out;
+        pl.h_tasks.assign(out.begin(), out.begin() + n_out);
         e->bundle_plans[key] = pl;
     } else {
         if (e->bundle_tmp_cap < out.size()) {
@@ -885,6 +895,35 @@ static int make_bundle_launch(dtl_engine* e, const ForwardStar& f, const SsspLau
     if (getenv("DTL_CREATE_TRACE"))
         fprintf(stderr, "bundle launch set up (plan + buffers): %.3f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - plan_t0).count());
+    b.dest_ptr = nullptr; b.dest_idx = nullptr; b.bundle_bound = nullptr;
+    if (e->bounded && !e->count_pass && b.fuse_pred && plan_key >= 0 && b.block == 768 && ctas_per_sm == 1) {
+        // destination-bounded search: the (node, slot) of every destination the origins of a bundle have demand to, per bundle
+        const int fsi = (int)(&f - e->fs.data());
+        auto it = e->bundle_plans.find(std::make_tuple(fsi, plan_key, n, B));
+        if (it != e->bundle_plans.end()) {
+            dtl_engine::BundlePlan& pl = it->second;
+            if (!pl.d_dest_ptr) {
+                std::vector<int> ptr(pl.n_bundles + 1, 0), idx;
+                for (int bi = 0; bi < pl.n_bundles; ++bi) {
+                    for (int sl = 0; sl < B; ++sl) {
+                        const int t = pl.h_tasks[(size_t)bi * B + sl];
+                        if (t < 0) continue;
+                        const int tg = plan_key + t; // plan_key is the first task of the batch
+                        for (int q = e->task_cell_ptr[tg]; q < e->task_cell_ptr[tg + 1]; ++q)
+                            idx.push_back(e->h_od_dest[e->h_task_cells[q]] * B + sl);
+                    }
+                    ptr[bi + 1] = (int)idx.size();
+                }
+                if (idx.empty()) idx.push_back(0);
+                if (e->upload(&pl.d_dest_ptr, ptr.data(), ptr.size()) || e->upload(&pl.d_dest_idx, idx.data(), idx.size())) return -1;
+            }
+            if (e->bundle_bound_cap < (size_t)pl.n_bundles) {
+                if (e->alloc(&e->d_bundle_bound, (size_t)pl.n_bundles)) return -1;
+                e->bundle_bound_cap = (size_t)pl.n_bundles;
+            }
+            b.dest_ptr = pl.d_dest_ptr; b.dest_idx = pl.d_dest_idx; b.bundle_bound = e->d_bundle_bound;
+        }
+    }
     b.bundle_counter = e->d_bundle_counter;
     b.started_word = b.fuse_pred ? e->next_started_word : nullptr;
     b.started_tag = e->next_started_tag;
@@ -1189,6 +1228,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
         CK(cudaStreamCreateWithPriority(&e->st, cudaStreamNonBlocking, pr_greatest));
         e->overlap = !getenv("DTL_NO_OVERLAP");
+        e->bounded = getenv("DTL_BOUNDED_SEARCH") != nullptr; // experiment hook; the API is dtl_set_bounded_search
         {
             CK(cudaStreamCreateWithPriority(&e->st2, cudaStreamNonBlocking, pr_least));
             CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -1411,6 +1451,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->upload(&e->d_od_tau, od_tau.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_od_task, od_task.data(), e->n_cells)) return -1;
     e->h_od_at = od_at; e->h_od_tau = od_tau; e->h_od_task = od_task; e->h_od_dzone = od_dzone;
+    e->h_task_cells = task_cells; e->h_od_dest = od_dest;
     if (e->upload(&e->d_od_vol, od_vol.data(), e->n_cells)) return -1;
     if (e->upload(&e->d_task_cells, task_cells.data(), task_cells.size())) return -1;
     if (!getenv("DTL_NO_CELL_SORT")) {
@@ -1735,7 +1776,10 @@ static int iteration_impl(dtl_engine* e, int k, double row[5])
         CK(cudaMemcpyAsync(e->d_stats, &z, sizeof(z), cudaMemcpyHostToDevice, e->st));
         if (sync_stream(e)) return -1;
     }
-    if (trees_and_columns(e, k, want_count)) return -1;                // main_api.cpp:647-699
+    e->count_pass = want_count; // (the edge count of the trees is that of complete trees)
+    const int rc_tc = trees_and_columns(e, k, want_count);             // main_api.cpp:647-699
+    e->count_pass = false;
+    if (rc_tc) return -1;
     e->join_side();
     if (k1_timeline) {
         SsspStats z{};
@@ -3000,6 +3044,13 @@ int dtl_get_tree(dtl_engine* e, int task, double* label, int* pred_node, int* pr
         }
     }
     return 0;
+}
+
+int dtl_set_bounded_search(dtl_engine* e, int on)
+{
+    const int was = e->bounded ? 1 : 0;
+    e->bounded = on != 0;
+    return was;
 }
 
 int dtl_set_overlap(dtl_engine* e, int on)

@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(BLOCK, 1) bundle_pred_helper_kernel(BundleLaun
 // 21.7 M expansions), which suggested spreading a node over more lanes to shorten the serial instruction stream of a pass, but
 // the ready nodes come in bursts and the number of GROUPS a CTA has is what counts then -- measured per 2 000 trees with 1 024
 // threads: EPL = 4 (128 groups) 7.3 ms, EPL = 2 (64 groups) 7.7 ms, EPL = 1 (32 groups, one node per warp) 12.2 ms.
-template <int BLOCK, int B, int EPL, bool TAGS, int CPS>
+// BOUNDED: destination-bounded search (BundleLaunch::dest_ptr) -- after every window opening the smallest FRESH key of anything still
+// queued is a lower bound on every label that can still change; when all destinations with demand lie below it the search stops.
+template <int BLOCK, int B, int EPL, bool TAGS, int CPS, bool BOUNDED>
 __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLaunch a)
 {
     constexpr int LPT = 2;
@@ -183,7 +185,10 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
         }
         for (int i = tid; i < n_words; i += BLOCK) s_state[i] = 0u;
         for (int i = tid; i < RING; i += BLOCK) s_q[i] = 0;
-        if (tid == 0) { s_head = 0; s_pt = 0u; s_n_far = 0; s_n_far2 = 0; s_overflow = 0; }
+        if (tid == 0) {
+            s_head = 0; s_pt = 0u; s_n_far = 0; s_n_far2 = 0; s_overflow = 0;
+            if (a.bundle_bound) a.bundle_bound[bundle] = BND_DEAD_KEY; // unless the search stops early, every label is final
+        }
         __syncthreads();
         if (tid < B) { // seed: every origin relaxes its own (unhidden) row once with label 0; the heads wait in the far pile
             const int task = __ldg(&a.bundle_tasks[bundle * B + tid]);
@@ -240,6 +245,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
             if (thr <= mm) thr = mm + 1;
             if (tid == 0) { s_head = 0; s_pt = 0u; } // the ring is empty here: every published entry was consumed and finished
             __syncthreads();
+            unsigned lb = BND_DEAD_KEY; // BOUNDED: smallest fresh key of the live entries
             // one far entry per OPL lanes (the lanes of a group's first edge subgroup suffice: a label row is OPL 16-byte loads)
             for (int base = 0; base < n_far; base += BLOCK / OPL) {
                 if (base + (tid & ~31) / OPL >= n_far) continue;
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
                     k = min(key_of(lab.x), key_of(lab.y));
                 }
                 const unsigned key = group_min_u32<OPL>(k);
+                if (BOUNDED && live) lb = min(lb, key);
                 if (live && op == 0) {
                     if (key < thr) {
                         const unsigned o2 = atomicOr(&s_state[w], 1u << sh);
@@ -276,6 +283,18 @@ __global__ void __launch_bounds__(BLOCK, CPS) sssp_bundle_async_kernel(BundleLau
             __syncthreads();
             APF(pf_dist);
             if (s_overflow) { failed = true; break; }
+            if (BOUNDED && a.dest_ptr) {
+                lb = block_min_u32<BLOCK>(lb, s_red);
+                unsigned far_dest = 0; // largest key of a destination label (an unreached destination keeps the search going)
+                const int d1 = __ldg(&a.dest_ptr[bundle + 1]);
+                for (int i = __ldg(&a.dest_ptr[bundle]) + tid; i < d1; i += BLOCK)
+                    far_dest = max(far_dest, key_of(__ldcg(&bl[__ldg(&a.dest_idx[i])])));
+                far_dest = ~block_min_u32<BLOCK>(~far_dest, s_red);
+                if (far_dest < lb) { // nothing queued can reach below lb: every destination label is final
+                    if (tid == 0) a.bundle_bound[bundle] = lb;
+                    break;
+                }
+            }
 
             // ---- drain the window: every group consumes ring entries until nothing is queued or in flight ----
             int ticket = -1; // this group's claim on a ring position (leader's register, broadcast when needed)
@@ -482,33 +501,43 @@ size_t bundle_async_smem_bytes(int N, int ring)
     return words * sizeof(unsigned) + (size_t)ring * (sizeof(int2) + sizeof(int));
 }
 
-template <int BLOCK, int B, int EPL, int CPS>
-static void async_launch(const BundleLaunch& a, size_t smem, cudaStream_t st)
+template <int BLOCK, int B, int EPL, int CPS, bool BOUNDED>
+static void async_launch_bd(const BundleLaunch& a, size_t smem, cudaStream_t st)
 {
     // a.tagged: some node outside the hidden centroid rows has a zone-tagged out-link (routing.h:779-786 then has to be
     // evaluated inside the edge loop); ordinary networks only tag the connectors that leave a centroid
     if (a.tagged) {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS><<<a.grid, BLOCK, smem, st>>>(a);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS, BOUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS, BOUNDED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        sssp_bundle_async_kernel<BLOCK, B, EPL, true, CPS, BOUNDED><<<a.grid, BLOCK, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS, BOUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS, BOUNDED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         static bool said = false;
         if (!said && getenv("DTL_BUNDLE_DEBUG")) {
             said = true;
             int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS>, BLOCK, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS, BOUNDED>, BLOCK, smem);
             fprintf(stderr, "async bundle search: %d threads x %d CTAs/SM asked, %d edges per lane, occupancy %d CTAs/SM, %zu B dynamic smem, grid %d, %d bundles of %d\n",
                     BLOCK, CPS, EPL, occ, smem, a.grid, a.n_bundles, B);
         }
-        sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS><<<a.grid, BLOCK, smem, st>>>(a);
+        sssp_bundle_async_kernel<BLOCK, B, EPL, false, CPS, BOUNDED><<<a.grid, BLOCK, smem, st>>>(a);
     }
+}
+
+template <int BLOCK, int B, int EPL, int CPS>
+static void async_launch(const BundleLaunch& a, size_t smem, cudaStream_t st)
+{
+    async_launch_bd<BLOCK, B, EPL, CPS, false>(a, smem, st);
 }
 
 template <int B, int EPL>
 static void async_launch_b(const BundleLaunch& a, size_t smem, cudaStream_t st)
 {
+    if (a.dest_ptr && a.block == 768 && a.ctas_per_sm == 1) { // the destination-bounded search exists for the default CTA shape only
+        async_launch_bd<768, B, EPL, 1, true>(a, smem, st);
+        return;
+    }
     // CTA size x resident CTAs per SM: one big CTA per SM, or two smaller ones (each with its own bundle, ring and queue bits)
     switch (a.block * 10 + a.ctas_per_sm) {
     case 5122: async_launch<512, B, EPL, 2>(a, smem, st); break;

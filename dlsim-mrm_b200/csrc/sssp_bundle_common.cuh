@@ -113,6 +113,8 @@ __device__ __forceinline__ void bundle_pred_nodes(const BundleLaunch& a, int bun
     if (bad && report_overflow && tid < G) atomicOr(a.batch_flag, 2);
     const ulonglong2* const bl2 = reinterpret_cast<const ulonglong2*>(a.bl + (size_t)bundle * N * B) + g;
     int4* const out = reinterpret_cast<int4*>(a.bp + (size_t)bundle * N * B) + g;
+    // destination-bounded search: labels whose key is not below the bundle's bound are not final (treated as unreached)
+    const unsigned bound = a.bundle_bound ? (SAME_LAUNCH ? __ldcg(&a.bundle_bound[bundle]) : __ldg(&a.bundle_bound[bundle])) : BND_DEAD_KEY;
     bool tie = false;
     for (int v = v_begin + tid / G; v < v_end; v += NODES) {
         const ulonglong2 lvb = ld_row(bl2 + (size_t)v * G);
@@ -131,8 +133,8 @@ __device__ __forceinline__ void bundle_pred_nodes(const BundleLaunch& a, int bun
                 ed[q] = __ldg(reinterpret_cast<const int4*>(&a.s.edges[eidx[q]]));
             }
         }
-        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0];
-        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1];
+        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0] && key_of(lvb.x) < bound;
+        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1] && key_of(lvb.y) < bound;
         const double lv0 = __longlong_as_double((long long)lvb.x), lv1 = __longlong_as_double((long long)lvb.y);
         int first0 = -1, first1 = -1, link0 = DTL_NO_PRED, link1 = DTL_NO_PRED;
         auto consider = [&](int u, double cost, int link, bool tagged, ulonglong2 lu) {

@@ -482,6 +482,12 @@ class Engine:
         self._ck(self.lib.dtl_get_timing(self.h, _ptr(ms), _ptr(cnt), int(reset)))
         return {"ms": dict(zip(self.TIMING_CLASSES, ms.tolist())), "launches": dict(zip(self.TIMING_CLASSES, cnt.tolist()))}
 
+    def set_bounded_search(self, on: bool) -> bool:
+        """Destination-bounded origin-bundle search inside the assignment loop (exact; off by default); returns the old setting."""
+        self.lib.dtl_set_bounded_search.restype = C.c_int
+        self.lib.dtl_set_bounded_search.argtypes = [C.c_void_p, C.c_int]
+        return bool(self.lib.dtl_set_bounded_search(self.h, int(bool(on))))
+
     def set_overlap(self, on: bool) -> bool:
         """Scatter of an iteration beside its shortest-path search (default) or everything on one stream; returns the old setting."""
         self.lib.dtl_set_overlap.restype = C.c_int

@@ -502,3 +502,30 @@ def test_pipelined_iterations_fail_cleanly(D, tmp_path, monkeypatch, kernel):
     with D.Engine(p, keep_trees=False, max_columns_per_od=12) as e2:
         rows = e2.iterations(0, 4)
         assert len(rows) == 4 and all(r["least"] > 0 for r in rows)
+
+
+@pytest.mark.parametrize("workload,pipelined", [("grid2k", False), ("grid10k", True), ("grid10k", False)])
+def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, tmp_path, monkeypatch, workload, pipelined):
+    """dtl_set_bounded_search(1): an origin-bundle search stops when no queued node can still improve a destination with demand --
+    rows, Q31.32 link volumes and columns are the same bits as with complete trees, and both match the oracle"""
+    _force_kernel(monkeypatch, "bundle16")
+    from dlsim_mrm_b200 import synth
+    synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
+    p = D.read_gmns(str(tmp_path), 8)
+    K = 6
+    o = oracle_mod.Oracle(p)
+    rows_o = [o.iteration(k) for k in range(K)]
+    with D.Engine(p, max_columns_per_od=K + 4) as e1, D.Engine(p, max_columns_per_od=K + 4) as e2:
+        assert e2.set_bounded_search(True) is False
+        rows1 = [e1.iteration(k) for k in range(K)]
+        rows2 = e2.iterations(0, K) if pipelined else [e2.iteration(k) for k in range(K)]
+        for k, (r1, r2, ro) in enumerate(zip(rows1, rows2, rows_o)):
+            assert r1 == r2, (k, r1, r2)
+            assert abs(r2["least"] - ro["least"]) <= TOL * abs(ro["least"])
+        assert np.array_equal(e1.volume_fixed(0), e2.volume_fixed(0))
+        c1, c2 = e1.columns(), e2.columns()
+        for key in ("od_index", "node_sum", "seq_no", "links", "volume"):
+            assert np.array_equal(c1[key], c2[key]), key
+        _compare_columns(c2, o.columns())
+        k1, k2 = e1.counters(), e2.counters()
+        assert k2["pops"] < k1["pops"] and k2["replayed"] == 0 and k2["reruns"] == 0   # and it did stop early
