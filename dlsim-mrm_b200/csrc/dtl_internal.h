@@ -139,6 +139,11 @@ struct SsspLaunch {
     int cap_smem;            // shared-memory-queue variant: entries per near queue (two buffers, 28 B per entry)
     int smq;                 // 1: launch the shared-memory-queue variant (few trees per SM)
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
+    // destination-bounded search of the shared-memory-queue kernel (optional, see BundleLaunch::dest_ptr): the destinations with demand
+    // of batch-local task i are od_dest[cells[k]] for k in [cell_ptr[i], cell_ptr[i + 1])
+    const int* bd_cell_ptr;  // null: every search runs to the end
+    const int* bd_cells;
+    const int* bd_dest;
     int* tie_cand;           // [grid][tie_cap]
     int tie_cap;
     int* task_counter;       // device int, zeroed before launch

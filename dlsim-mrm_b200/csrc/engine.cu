@@ -220,7 +220,7 @@ struct dtl_engine {
         int *d_dest_ptr = nullptr, *d_dest_idx = nullptr; // destination-bounded search: node * B + slot of every destination with demand
     };
     // destination-bounded search (dtl_set_bounded_search): off by default -- the trees then are the reference's complete trees
-    bool bounded = false, count_pass = false;
+    bool bounded = false, count_pass = false, in_loop = false; // in_loop: the trees of this launch are only back-traced
     unsigned* d_bundle_bound = nullptr;
     size_t bundle_bound_cap = 0;
     std::vector<int> h_task_cells, h_od_dest;             // [n_cells] cells grouped by task (creation order) / destination centroid of a cell
@@ -985,6 +985,11 @@ SsspLaunch make_sssp_launch(dtl_engine* e, const ForwardStar& f, int n_tasks, co
     a.tie_cand = e->d_tie_cand; a.tie_cap = e->tie_cap; a.task_counter = e->d_task_counter; a.stats = e->d_stats;
     a.grid = std::min(e->sssp_grid, std::max(1, n_tasks)); a.block = e->sssp_block;
     choose_sssp_variant(e, a);
+    a.bd_cell_ptr = nullptr; a.bd_cells = nullptr; a.bd_dest = nullptr;
+    if (e->bounded && e->in_loop && !e->count_pass && a.smq == 1 && !e->opt.keep_trees && e->d_task_cell_ptr) {
+        const int t0 = (int)(d_origin - e->d_task_origin); // first task of the batch
+        a.bd_cell_ptr = e->d_task_cell_ptr + t0; a.bd_cells = e->d_task_cells; a.bd_dest = e->d_od_dest;
+    }
     return a;
 }
 
@@ -1672,9 +1677,11 @@ static int trees_and_columns(dtl_engine* e, int k, bool want_count)
         // the loop only back-traces the trees: an origin-bundle batch may leave them node-major (not when the trees are kept:
         // dtl_get_tree reads the per-tree arrays)
         BatchState bs;
-        if (sssp_launch_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, tree_off, e->h_task_origin.data() + t0, t0,
-                              !e->opt.keep_trees, bs))
-            return -1;
+        e->in_loop = true;
+        const int rc_l = sssp_launch_batch(e, e->fs[fsi], nb, e->d_task_origin + t0, e->d_task_zone + t0, tree_off, e->h_task_origin.data() + t0, t0,
+                                           !e->opt.keep_trees, bs);
+        e->in_loop = false;
+        if (rc_l) return -1;
         if (columns_of_batch(e, bs, t0, t1, tree_off, k, want_count)) return -1;
         t0 = t1;
     }
@@ -1917,7 +1924,10 @@ static int iterations_impl(dtl_engine* e, int k0, int n, double* rows)
         if (do_vdf(e, false, true, nullptr)) return -1;                                        // main_api.cpp:606 (joins the side stream)
         CK(cudaMemcpyAsync(e->d_scalars + 10 + slot, e->d_scalars, sizeof(double), cudaMemcpyDeviceToDevice, e->st)); // system TT of kk
         CK(cudaEventRecord(e->ev_vdf, e->st));
-        if (sssp_launch_batch(e, f, n_tasks, e->d_task_origin, e->d_task_zone, 0, e->h_task_origin.data(), 0, true, b)) return -1;
+        e->in_loop = true;
+        const int rc_l = sssp_launch_batch(e, f, n_tasks, e->d_task_origin, e->d_task_zone, 0, e->h_task_origin.data(), 0, true, b);
+        e->in_loop = false;
+        if (rc_l) return -1;
         CK(cudaEventRecord(e->ev_k1[slot], e->st));
         (void)kk;
         return 0;

@@ -33,7 +33,9 @@ namespace dtl {
 #endif
 #define SMQ_MIN_CTAS(BLOCK) (1024 / (BLOCK)) /* 64 registers per thread: 1024 threads per SM */
 
-template <int BLOCK, int G, int U>
+// BOUNDED: destination-bounded search (SsspLaunch::bd_cell_ptr) -- when a label window is opened the smallest live label of the far
+// pile bounds every label that can still change from below; the search stops when all destinations with demand lie below it.
+template <int BLOCK, int G, int U, bool BOUNDED>
 __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(SsspLaunch a)
 {
     extern __shared__ int4 s_dyn[];
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
         __syncthreads();
         PF(1);
         int n_near = 1;
+        double bound = 2.0 * DTL_MAX_LABEL_COST; // BOUNDED: labels at or beyond it are not final when the search stopped early
         int buf = 0; // near-queue buffer read this round
         int ci = 0;  // s_cnt[ci] counted this round's entries, pushes count into s_cnt[ci+1], s_cnt[ci+2] is cleared
         double thr = a.delta;
@@ -307,6 +310,14 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
             }
             m = block_min<BLOCK>(m, s_red);
             if (!(m < DTL_MAX_LABEL_COST)) break; // every far entry is dead
+            if (BOUNDED && a.bd_cell_ptr) {
+                double far_dest = 0.0; // an unreached destination (1e15) keeps the search going
+                const int c1 = __ldg(&a.bd_cell_ptr[task + 1]);
+                for (int i = __ldg(&a.bd_cell_ptr[task]) + tid; i < c1; i += BLOCK)
+                    far_dest = fmax(far_dest, ld_label(&lab[__ldg(&a.bd_dest[__ldg(&a.bd_cells[i])])]));
+                far_dest = -block_min<BLOCK>(-far_dest, s_red);
+                if (far_dest < m) { bound = m; break; } // nothing queued can get below m: every destination label is final
+            }
             thr = m + a.delta;
             for (int i = tid; i < n_far; i += BLOCK) {
                 const QEntry q = ld_entry(&q_far[i]);
@@ -351,7 +362,7 @@ __global__ void __launch_bounds__(BLOCK, SMQ_MIN_CTAS(BLOCK)) sssp_smq_kernel(Ss
                 const int w = all_nodes ? i : tie_cand[i];
                 if (w == origin) continue;
                 const double lw = ld_label(&lab[w]);
-                if (!(lw < DTL_MAX_LABEL_COST)) continue;
+                if (!(lw < DTL_MAX_LABEL_COST) || !(lw < bound)) continue;
                 int first_u = -1, best_e = 0x7fffffff;
                 bool multi = false;
                 for (int j = a.in_ptr[w]; j < a.in_ptr[w + 1]; ++j) {
@@ -408,8 +419,13 @@ template <int BLOCK>
 static void smq_launch(const SsspLaunch& a, cudaStream_t st)
 {
     const size_t smem = smq_smem_bytes(a.cap_smem);
-    cudaFuncSetAttribute(sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U><<<a.grid, BLOCK, smem, st>>>(a);
+    if (a.bd_cell_ptr) {
+        cudaFuncSetAttribute(sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U, true><<<a.grid, BLOCK, smem, st>>>(a);
+        return;
+    }
+    cudaFuncSetAttribute(sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sssp_smq_kernel<BLOCK, SMQ_G, SMQ_U, false><<<a.grid, BLOCK, smem, st>>>(a);
 }
 
 void launch_sssp_smq(const SsspLaunch& a, cudaStream_t st)

@@ -504,11 +504,12 @@ def test_pipelined_iterations_fail_cleanly(D, tmp_path, monkeypatch, kernel):
         assert len(rows) == 4 and all(r["least"] > 0 for r in rows)
 
 
-@pytest.mark.parametrize("workload,pipelined", [("grid2k", False), ("grid10k", True), ("grid10k", False)])
-def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, tmp_path, monkeypatch, workload, pipelined):
-    """dtl_set_bounded_search(1): an origin-bundle search stops when no queued node can still improve a destination with demand --
-    rows, Q31.32 link volumes and columns are the same bits as with complete trees, and both match the oracle"""
-    _force_kernel(monkeypatch, "bundle16")
+@pytest.mark.parametrize("workload,pipelined,kernel", [("grid2k", False, "bundle16"), ("grid10k", True, "bundle16"), ("grid10k", False, "bundle16"),
+                                                       ("grid10k", True, "smq"), ("grid2k", False, "smq")])
+def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, tmp_path, monkeypatch, workload, pipelined, kernel):
+    """dtl_set_bounded_search(1): a search (origin bundles, shared-memory queues) stops when no queued node can still improve a
+    destination with demand -- rows, Q31.32 link volumes and columns are the same bits as with complete trees, and both match the oracle"""
+    _force_kernel(monkeypatch, kernel)
     from dlsim_mrm_b200 import synth
     synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
     p = D.read_gmns(str(tmp_path), 8)
