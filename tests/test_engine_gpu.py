@@ -529,4 +529,6 @@ def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, 
             assert np.array_equal(c1[key], c2[key]), key
         _compare_columns(c2, o.columns())
         k1, k2 = e1.counters(), e2.counters()
-        assert k2["pops"] < k1["pops"] and k2["replayed"] == 0 and k2["reruns"] == 0   # and it did stop early
+        assert k2["replayed"] == 0 and k2["reruns"] == 0
+        if workload == "grid10k":   # and it did stop early (on the 2 000-node grid the destinations reach the far side: nothing to save,
+            assert k2["pops"] < k1["pops"]   # and the expansion counts of two runs of the asynchronous search differ by a few hundred)
