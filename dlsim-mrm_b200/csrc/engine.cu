@@ -235,23 +235,6 @@ struct dtl_engine {
     int last_sssp_variant = -1;
     double counted_edges_cached = -1;
     std::thread embed_thread;        // landmark embeddings of the forward stars (bundle planner), computed behind dtl_create
-    // The big buffers of the origin-bundle search (node-major labels and predecessor records of both tree sets, the far piles) used to
-    // be allocated by the first two searches (1.2-12 ms of cudaMalloc in iterations 0 and 1); when the shape of the problem says
-    // that bundles will run, a worker allocates them behind the rest of dtl_create.  adopt_prealloc() hands them to the engine.
-    std::thread prealloc_thread;
-    struct Prealloc { void* p[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; size_t words = 0, far_elems = 0; int grid = 0, cap_far = 0; } pre;
-    void adopt_prealloc()
-    {
-        if (!prealloc_thread.joinable()) return;
-        prealloc_thread.join();
-        for (void* q : pre.p)
-            if (q) allocs.push_back(q);
-        if (pre.p[0]) { d_bl = (unsigned long long*)pre.p[0]; bl_cap = pre.words; dev_bytes += pre.words * 8; }
-        if (pre.p[1]) { d_bp = (int2*)pre.p[1]; bp_cap = pre.words; dev_bytes += pre.words * 8; }
-        if (pre.p[2]) { alt.d_bl = (unsigned long long*)pre.p[2]; alt.bl_cap = pre.words; dev_bytes += pre.words * 8; }
-        if (pre.p[3]) { alt.d_bp = (int2*)pre.p[3]; alt.bp_cap = pre.words; dev_bytes += pre.words * 8; }
-        if (pre.p[4]) { d_bfar = (int2*)pre.p[4]; bundle_grid = pre.grid; bundle_cap_far = pre.cap_far; dev_bytes += pre.far_elems * sizeof(int2); }
-    }
     std::vector<float> h_embed_all;  // embedding of the whole network when the zone partition needed one (world_size > 1)
 
     // timing
@@ -1183,7 +1166,6 @@ void dtl_destroy(dtl_engine* e)
 {
     if (!e) return;
     if (e->embed_thread.joinable()) e->embed_thread.join();
-    e->adopt_prealloc();
     cudaSetDevice(e->dev);
     if (e->st2) cudaStreamSynchronize(e->st2);
     if (e->st) cudaStreamSynchronize(e->st);
@@ -1246,24 +1228,6 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     e->N = p->n_nodes; e->L = p->n_links; e->Z = p->n_zones; e->AT = p->n_agent_types; e->T = p->n_periods;
     e->B = std::max(1, p->memory_blocks);
     e->rank = o.rank; e->world = std::max(1, o.world_size);
-    if (e->AT * e->T == 1 && !o.keep_trees && !getenv("DTL_NO_PREALLOC") && !getenv("DTL_BUNDLE_B") && !getenv("DTL_SSSP_KERNEL")) {
-        // one forward star: every iteration is one batch of at most ceil(Z / world) trees; from 4 trees per SM on they run as origin
-        // bundles (choose_sssp_variant, make_bundle_launch), of 16 from 8 trees per SM
-        const int tasks_ub = (e->Z + e->world - 1) / e->world;
-        if (tasks_ub >= 4 * e->sm_count) {
-            const int Bn = tasks_ub < 8 * e->sm_count ? 8 : 16;
-            e->pre.words = (size_t)((tasks_ub + Bn - 1) / Bn) * Bn * e->N;
-            e->pre.grid = e->sm_count; e->pre.cap_far = 2 * e->N + 1024;
-            e->pre.far_elems = (size_t)e->pre.grid * 2 * e->pre.cap_far;
-            dtl_engine* eng = e;
-            e->prealloc_thread = std::thread([eng]() {
-                if (cudaSetDevice(eng->dev) != cudaSuccess) return;
-                for (int i = 0; i < 4; ++i)
-                    if (cudaMalloc(&eng->pre.p[i], eng->pre.words * 8) != cudaSuccess) { eng->pre.p[i] = nullptr; cudaGetLastError(); }
-                if (cudaMalloc(&eng->pre.p[4], eng->pre.far_elems * sizeof(int2)) != cudaSuccess) { eng->pre.p[4] = nullptr; cudaGetLastError(); }
-            });
-        }
-    }
     e->total_demand = p->total_demand_volume;
     const int N = e->N, L = e->L, Z = e->Z, AT = e->AT, T = e->T;
     if (N <= 0 || L < 0 || Z <= 0 || AT <= 0 || T <= 0) { set_err("empty problem"); return -1; }
@@ -1546,7 +1510,6 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
     if (e->alloc(&e->d_ws, (size_t)e->sssp_grid * e->ws_stride)) return -1;
     if (e->alloc(&e->d_tie_cand, (size_t)e->sssp_grid * e->tie_cap)) return -1;
 
-    e->adopt_prealloc(); // (before the free memory is looked at)
     DTL_TRACE("path-link arena: what is left, bounded b");
     // ---- path-link arena: what is left, bounded by the option ----
     CK(cudaMemGetInfo(&free_b, &total_b));
