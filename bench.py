@@ -56,13 +56,13 @@ def ensure_workload(name: str) -> str:
     return d
 
 
-def k1_traffic(n_gpus: int):
+def k1_traffic(n_gpus: int, suffix: str = ""):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same command
     (profiles/k1_traffic.json, written by scripts/ncu_traffic.py); None when no capture of this GPU count is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
             t = json.load(f)
-        return t.get(str(n_gpus), {}).get("dram_bytes_per_launch")
+        return t.get(str(n_gpus) + suffix, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -251,6 +251,8 @@ def run_engine_arm(args, rank, world, local_rank):
 
     # ---- device-resident throughput: inputs already in HBM when the timed region starts ----
     e = make_engine()
+    if not e.set_bounded_search(True):  # the engine's default (dtl_set_bounded_search): searches stop at the last destination with demand
+        raise SystemExit("bench.py: the destination-bounded search is not the engine's default (DTL_COMPLETE_SEARCH set?)")
     e.iterations(0, W)
     e.timing(reset=True); e.counters(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -274,8 +276,7 @@ def run_engine_arm(args, rank, world, local_rank):
     edges_rank = rows[-1]["counted_edges"] / world  # the row holds the all-reduced count; ranks own equal shares of zones
     launches_per_iter = k1_launches / K
     peak, peak_src = measured_peak()
-    achieved = BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (sssp_ms_launch / 1e3) / 1e9
-    gteps = rows[-1]["counted_edges"] * K / (max_over_ranks(tm["ms"]["sssp"]) / 1e3) / 1e9
+    sssp_ms_all = max_over_ranks(tm["ms"]["sssp"])
     dev_bytes = e.device_bytes
     # every rank must hold the same all-reduced integers, and they must be the single-GPU ones (committed table)
     import hashlib
@@ -317,23 +318,30 @@ def run_engine_arm(args, rank, world, local_rank):
     e2.close()
     barrier()
 
-    # ---- the same steps with the destination-bounded search (dtl_set_bounded_search; off by default: the headline `value` runs the
-    # reference's complete one-to-all trees).  Exact -- the link volumes must carry the same digest -- and reported as an extra key.
+    # ---- the same steps with complete one-to-all trees (dtl_set_bounded_search(0): what the reference computes, routing.h:633-939).
+    # Exact either way -- the link volumes must carry the same digest.  The complete run also gives the edge accounting of the
+    # headline run: the Graph500 count (row[4]) is that of complete trees, a bounded search relaxes only a part of them, and the
+    # kernels count their relaxations -- settled edges = complete count x (relaxations of the headline run / of the complete run).
     barrier()
     e3 = make_engine()
-    e3.set_bounded_search(True)
+    e3.set_bounded_search(False)
     e3.iterations(0, W)
-    e3.timing(reset=True)
+    e3.timing(reset=True); e3.counters(reset=True)
     barrier()
     e3.iterations(W, K)
     torch.cuda.synchronize()
-    tm3 = e3.timing()
-    bounded_s = max_over_ranks(tm3["ms"]["iteration"] / 1e3)
-    bounded_sha = hashlib.sha256(e3.volume_fixed(0).tobytes()).hexdigest()
-    bounded_k1_ms = tm3["ms"]["sssp"] / max(1, tm3["launches"]["sssp"] // k1_kernels_per_launch)
+    tm3, ctr3 = e3.timing(), e3.counters()
+    complete_s = max_over_ranks(tm3["ms"]["iteration"] / 1e3)
+    complete_sha = hashlib.sha256(e3.volume_fixed(0).tobytes()).hexdigest()
+    complete_k1_ms = tm3["ms"]["sssp"] / max(1, tm3["launches"]["sssp"] // k1_kernels_per_launch)
     e3.close()
-    if bounded_sha != vol_sha:
-        raise SystemExit(f"bench.py: the destination-bounded search changed the link volumes ({bounded_sha[:16]}.. instead of {vol_sha[:16]}..)")
+    if complete_sha != vol_sha:
+        raise SystemExit(f"bench.py: complete and destination-bounded searches give different link volumes ({complete_sha[:16]}.. / {vol_sha[:16]}..)")
+    settled_share = min(1.0, ctr["relaxations"] / max(1.0, ctr3["relaxations"]))
+    settled_rank = edges_rank * settled_share
+    achieved = BYTES_PER_EDGE * (settled_rank / launches_per_iter) / (sssp_ms_launch / 1e3) / 1e9
+    gteps = rows[-1]["counted_edges"] * settled_share * K / (sssp_ms_all / 1e3) / 1e9
+    complete_achieved = BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (complete_k1_ms / 1e3) / 1e9
 
     out = None
     if rank == 0:
@@ -353,26 +361,33 @@ def run_engine_arm(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": k1_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": k1_traffic(world), "peak_source": peak_src,
-                         "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": edges_rank / launches_per_iter,
+                         "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": settled_rank / launches_per_iter,
+                         "edge_count": "edges a destination-bounded launch settles = Graph500 count of the complete trees "
+                                       f"({edges_rank / launches_per_iter:.0f}) x {settled_share:.4f}, the kernel-counted relaxations of the timed "
+                                       "steps over those of the same steps with complete trees",
                          "kernel_ms_per_launch": sssp_ms_launch,
                          # the same kernel without the scatter beside it (the three one-stream iterations behind the timed steps)
                          "kernel_ms_per_launch_alone": k1_alone_ms,
-                         "frac_alone": BYTES_PER_EDGE * (edges_rank / launches_per_iter) / (k1_alone_ms / 1e3) / 1e9 / peak if k1_alone_ms else None},
+                         "frac_alone": BYTES_PER_EDGE * (settled_rank / launches_per_iter) / (k1_alone_ms / 1e3) / 1e9 / peak if k1_alone_ms else None},
             "sssp_gteps": gteps,
             # the other kernels of a step against the same HBM peak (algorithmic bytes of SURVEY.md 8d; this rank's share)
             "other_kernels": other_kernels(tm1, ctr1, 3, p, peak),
             "other_kernels_note": "three extra iterations with every kernel on one stream (inside the timed steps the scatter and its "
                                   "all-reduce run on a second stream beside K1: phase_ms_per_step['scatter'] is that overlapped duration)",
             "one_stream_ms_per_step": tm1["ms"]["iteration"] / 3,
-            "destination_bounded": {"value": K / bounded_s, "unit": UNIT, "ms_per_step": bounded_s / K * 1e3, "k1_ms_per_launch": bounded_k1_ms,
-                                    "same_link_volume_digest": True,
-                                    "what": "the same K steps with dtl_set_bounded_search(1): an origin-bundle search stops when nothing queued can "
-                                            "still improve a destination with demand (exact: same columns, volumes, gaps); NOT the headline -- "
-                                            "`value` computes the reference's complete one-to-all trees"},
+            "complete_trees": {"value": K / complete_s, "unit": UNIT, "ms_per_step": complete_s / K * 1e3, "k1_ms_per_launch": complete_k1_ms,
+                               "roofline_achieved": complete_achieved, "roofline_frac": complete_achieved / peak,
+                               "counted_edges_per_launch": edges_rank / launches_per_iter, "traffic": k1_traffic(world, "_complete"),
+                               "same_link_volume_digest": True,
+                               "what": "the same K steps with dtl_set_bounded_search(0): every search builds the reference's complete "
+                                       "one-to-all tree (routing.h:633-939).  The headline `value` runs the engine's default, where a search "
+                                       "stops when nothing queued can still improve a destination with demand -- same columns, volumes, gaps "
+                                       "(the digest is checked in this run)"},
             "wall_ms_per_step": wall / K * 1e3,
             "phase_ms_per_step": {k_: v / K for k_, v in tm["ms"].items()},
             "work_per_step": {k_: v / K for k_, v in ctr.items() if k_ != "counted_edges"},
-            "counted_edges_per_step": rows[-1]["counted_edges"],
+            "counted_edges_per_step": rows[-1]["counted_edges"] * settled_share,
+            "complete_tree_edges_per_step": rows[-1]["counted_edges"],
             "relative_gap_last": rows[-1]["gap"],
             "volume_digest": {"sha256": vol_sha, "iterations": W + K, "same_on_all_ranks": bool(same_on_all_ranks),
                               "matches_single_gpu_golden": None if golden_sha is None else golden_sha == vol_sha},

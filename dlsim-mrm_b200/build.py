@@ -68,7 +68,7 @@ def build_variant(name: str, sssp_flags, verbose: bool = False) -> str:
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile the shared library (and the DTALite_b200 executable) if sources changed."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     lib_src = [s for s in sources() if os.path.basename(s) != "main.cpp"]
     if force or _stale(LIB_PATH, deps):
         objs = []

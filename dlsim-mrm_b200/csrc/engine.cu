@@ -219,8 +219,9 @@ struct dtl_engine {
         std::vector<int> h_tasks;                         // [n_bundles * B] batch-local task of every slot (-1 = empty)
         int *d_dest_ptr = nullptr, *d_dest_idx = nullptr; // destination-bounded search: node * B + slot of every destination with demand
     };
-    // destination-bounded search (dtl_set_bounded_search): off by default -- the trees then are the reference's complete trees
-    bool bounded = false, count_pass = false, in_loop = false; // in_loop: the trees of this launch are only back-traced
+    // destination-bounded search (dtl_set_bounded_search): on by default -- searches whose trees are only back-traced stop at the last
+    // destination with demand; off (or DTL_COMPLETE_SEARCH=1): every search builds the reference's complete tree
+    bool bounded = true, count_pass = false, in_loop = false; // in_loop: the trees of this launch are only back-traced
     unsigned* d_bundle_bound = nullptr;
     size_t bundle_bound_cap = 0;
     std::vector<int> h_task_cells, h_od_dest;             // [n_cells] cells grouped by task (creation order) / destination centroid of a cell
@@ -1215,7 +1216,7 @@ static int create_impl(dtl_engine* e, const dtl_problem* p, const dtl_options* o
         CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
         CK(cudaStreamCreateWithPriority(&e->st, cudaStreamNonBlocking, pr_greatest));
         e->overlap = !getenv("DTL_NO_OVERLAP");
-        e->bounded = getenv("DTL_BOUNDED_SEARCH") != nullptr; // experiment hook; the API is dtl_set_bounded_search
+        e->bounded = getenv("DTL_COMPLETE_SEARCH") == nullptr; // the API is dtl_set_bounded_search
         {
             CK(cudaStreamCreateWithPriority(&e->st2, cudaStreamNonBlocking, pr_least));
             CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));

@@ -120,6 +120,12 @@ __device__ __forceinline__ void bundle_pred_nodes(const BundleLaunch& a, int bun
         const ulonglong2 lvb = ld_row(bl2 + (size_t)v * G);
         const int4 r01 = __ldg(reinterpret_cast<const int4*>(a.s.rin4 + (size_t)v * 4));
         const int4 r23 = __ldg(reinterpret_cast<const int4*>(a.s.rin4 + (size_t)v * 4) + 1);
+        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0] && key_of(lvb.x) < bound;
+        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1] && key_of(lvb.y) < bound;
+        // a search that stopped early: a node beyond the bound for both origins of this lane gets no record at all (nothing is requested,
+        // nothing written -- the row keeps whatever an earlier iteration left there).  The back-trace never comes by: it walks from
+        // destinations below the bound (that is when the search stopped) towards smaller labels.  The origin rows are always written.
+        if (bound != BND_DEAD_KEY && !need0 && !need1 && v != origin[0] && v != origin[1]) continue;
         const int from[4] = { r01.x, r01.z, r23.x, r23.z };
         const int eidx[4] = { r01.y, r01.w, r23.y, r23.w & 0x3fffffff };
         ulonglong2 lub[4];
@@ -133,8 +139,6 @@ __device__ __forceinline__ void bundle_pred_nodes(const BundleLaunch& a, int bun
                 ed[q] = __ldg(reinterpret_cast<const int4*>(&a.s.edges[eidx[q]]));
             }
         }
-        const bool need0 = task[0] >= 0 && lvb.x < INF_BITS && v != origin[0] && key_of(lvb.x) < bound;
-        const bool need1 = task[1] >= 0 && lvb.y < INF_BITS && v != origin[1] && key_of(lvb.y) < bound;
         const double lv0 = __longlong_as_double((long long)lvb.x), lv1 = __longlong_as_double((long long)lvb.y);
         int first0 = -1, first1 = -1, link0 = DTL_NO_PRED, link1 = DTL_NO_PRED;
         auto consider = [&](int u, double cost, int link, bool tagged, ulonglong2 lu) {

@@ -483,7 +483,7 @@ class Engine:
         return {"ms": dict(zip(self.TIMING_CLASSES, ms.tolist())), "launches": dict(zip(self.TIMING_CLASSES, cnt.tolist()))}
 
     def set_bounded_search(self, on: bool) -> bool:
-        """Destination-bounded origin-bundle search inside the assignment loop (exact; off by default); returns the old setting."""
+        """Destination-bounded origin-bundle search inside the assignment loop (exact; on by default, False = the reference's complete trees); returns the old setting."""
         self.lib.dtl_set_bounded_search.restype = C.c_int
         self.lib.dtl_set_bounded_search.argtypes = [C.c_void_p, C.c_int]
         return bool(self.lib.dtl_set_bounded_search(self.h, int(bool(on))))

@@ -236,12 +236,13 @@ int dtl_get_timing(dtl_engine* e, double ms[8], long long counts[8], int reset);
  * it is simply serial).  on = 0 puts every kernel back on one stream -- same results; for per-kernel timing (ms[1] is the
  * duration of the scatter ALONE only then).  Returns the previous setting. */
 int dtl_set_overlap(dtl_engine* e, int on);
-/* Destination-bounded shortest-path search, OFF by default.  The reference computes every one-to-all tree to the end
- * (routing.h:633-939) although the assignment loop only back-traces the destinations an origin has demand to (routing.h:428-520).
- * on = 1: inside the assignment loop an origin-bundle search stops as soon as nothing that is still queued can improve the label of
- * such a destination -- exact: the paths, columns, link volumes and gaps are the same bits; only the labels beyond the bound (which
- * nothing reads) are not final.  Calls that hand out trees (dtl_sssp_trees, keep_trees) always run complete searches.  Returns the
- * previous setting. */
+/* Destination-bounded shortest-path search, ON by default (DTL_COMPLETE_SEARCH=1 in the environment or on = 0 turns it off).  The
+ * reference computes every one-to-all tree to the end (routing.h:633-939) although the assignment loop only back-traces the
+ * destinations an origin has demand to (routing.h:428-520).  on = 1: inside the assignment loop a search (origin bundles, shared-memory
+ * queues) stops as soon as nothing that is still queued can improve the label of such a destination -- exact: the paths, columns, link
+ * volumes and gaps are the same bits; only the labels beyond the bound (which nothing reads) are not final.  on = 0: every search runs
+ * to the end.  Calls that hand out trees (dtl_sssp_trees, keep_trees), the Graph500 edge count of the first iteration, the global-queue
+ * kernel and the overflow re-runs always run complete searches.  Returns the previous setting. */
 int dtl_set_bounded_search(dtl_engine* e, int on);
 /* work counters since the last reset: { counted edges (Graph500 convention), relaxations, queue pops,
  * SSSP rounds, SSSP tasks, replayed origins, column-link references scattered, back-traced path nodes,

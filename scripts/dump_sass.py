@@ -14,8 +14,9 @@ out_dir = os.path.join(ROOT, "profiles", "sass")
 os.makedirs(out_dir, exist_ok=True)
 # template kernels: the instantiation that runs by default (engine.cu: make_bundle_launch / choose_sssp_variant)
 PREFER = {
-    "sssp_bundle_async_kernel": "<768, 16, 4, false, 1>", "sssp_bundle_kernel": "<1024, 16, 2>", "bundle_finish_kernel": "<16, 64, false>",
-    "bundle_pred_kernel": "<16>", "bundle_pred_helper_kernel": "<768, 16>", "sssp_kernel": "<128, 4>", "sssp_smq_kernel": "<512, 2, 2>", "scatter_kernel": None, "vdf_kernel": None,
+    # (the destination-bounded instantiation is the default inside the loop, the complete one runs the count pass and dtl_set_bounded_search(0))
+    "sssp_bundle_async_kernel": ("<768, 16, 4, false, 1, true>", "<768, 16, 4, false, 1, false>"), "sssp_bundle_kernel": "<1024, 16, 2>", "bundle_finish_kernel": "<16, 64, false>",
+    "bundle_pred_kernel": "<16>", "bundle_pred_helper_kernel": "<768, 16>", "sssp_kernel": "<128, 4>", "sssp_smq_kernel": ("<512, 2, 2, true>", "<512, 2, 2, false>"), "scatter_kernel": None, "vdf_kernel": None,
 }
 txt = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, check=True).stdout.decode()
 blocks = re.split(r"\n\s*Function : ", txt)[1:]
@@ -28,7 +29,8 @@ for b in blocks:
     short = re.sub(r"\(.*$", "", short).replace("dtl::", "")
     family = short.split("<")[0]
     targs = short[len(family):]
-    if family in PREFER and PREFER[family] is not None and targs.replace("(bool)", "").replace("(int)", "") != PREFER[family]:
+    want = PREFER.get(family)
+    if want is not None and targs.replace("(bool)", "").replace("(int)", "") not in ((want,) if isinstance(want, str) else want):
         continue
     lines = [l for l in b.split("\n")[1:] if re.search(r"/\*[0-9a-f]{4}\*/", l)]
     ops = collections.Counter()

@@ -507,8 +507,9 @@ def test_pipelined_iterations_fail_cleanly(D, tmp_path, monkeypatch, kernel):
 @pytest.mark.parametrize("workload,pipelined,kernel", [("grid2k", False, "bundle16"), ("grid10k", True, "bundle16"), ("grid10k", False, "bundle16"),
                                                        ("grid10k", True, "smq"), ("grid2k", False, "smq")])
 def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, tmp_path, monkeypatch, workload, pipelined, kernel):
-    """dtl_set_bounded_search(1): a search (origin bundles, shared-memory queues) stops when no queued node can still improve a
-    destination with demand -- rows, Q31.32 link volumes and columns are the same bits as with complete trees, and both match the oracle"""
+    """The engine's default (dtl_set_bounded_search(1)): a search (origin bundles, shared-memory queues) stops when no queued node can still
+    improve a destination with demand -- rows, Q31.32 link volumes and columns are the same bits as with the reference's complete trees
+    (dtl_set_bounded_search(0)), and both match the oracle"""
     _force_kernel(monkeypatch, kernel)
     from dlsim_mrm_b200 import synth
     synth.write_grid(str(tmp_path), **synth.WORKLOADS[workload])
@@ -517,7 +518,8 @@ def test_destination_bounded_search_changes_nothing_but_the_time(D, oracle_mod, 
     o = oracle_mod.Oracle(p)
     rows_o = [o.iteration(k) for k in range(K)]
     with D.Engine(p, max_columns_per_od=K + 4) as e1, D.Engine(p, max_columns_per_od=K + 4) as e2:
-        assert e2.set_bounded_search(True) is False
+        assert e1.set_bounded_search(False) is True    # e1: complete trees; the setter returns the previous setting (the default: on)
+        assert e2.set_bounded_search(True) is True
         rows1 = [e1.iteration(k) for k in range(K)]
         rows2 = e2.iterations(0, K) if pipelined else [e2.iteration(k) for k in range(K)]
         for k, (r1, r2, ro) in enumerate(zip(rows1, rows2, rows_o)):
