@@ -338,6 +338,7 @@ def run_engine_arm(args, rank, world, local_rank):
     if complete_sha != vol_sha:
         raise SystemExit(f"bench.py: complete and destination-bounded searches give different link volumes ({complete_sha[:16]}.. / {vol_sha[:16]}..)")
     settled_share = min(1.0, ctr["relaxations"] / max(1.0, ctr3["relaxations"]))
+    pops_share = min(1.0, ctr["pops"] / max(1.0, ctr3["pops"]))  # the same ratio on node expansions (cross-check of the share above)
     settled_rank = edges_rank * settled_share
     achieved = BYTES_PER_EDGE * (settled_rank / launches_per_iter) / (sssp_ms_launch / 1e3) / 1e9
     gteps = rows[-1]["counted_edges"] * settled_share * K / (sssp_ms_all / 1e3) / 1e9
@@ -364,7 +365,7 @@ def run_engine_arm(args, rank, world, local_rank):
                          "algorithmic_bytes_per_edge": BYTES_PER_EDGE, "counted_edges_per_launch": settled_rank / launches_per_iter,
                          "edge_count": "edges a destination-bounded launch settles = Graph500 count of the complete trees "
                                        f"({edges_rank / launches_per_iter:.0f}) x {settled_share:.4f}, the kernel-counted relaxations of the timed "
-                                       "steps over those of the same steps with complete trees",
+                                       f"steps over those of the same steps with complete trees (node expansions: x {pops_share:.4f})",
                          "kernel_ms_per_launch": sssp_ms_launch,
                          # the same kernel without the scatter beside it (the three one-stream iterations behind the timed steps)
                          "kernel_ms_per_launch_alone": k1_alone_ms,
