@@ -66,7 +66,8 @@ typedef struct dtl_problem {
 typedef struct dtl_options {
     int device;                   /* CUDA device ordinal; -1 = current device */
     int max_columns_per_od;       /* capacity of each OD cell's column set (>= number of CG iterations) */
-    int rank, world_size;         /* origin zones are sharded  zone % world_size == rank */
+    int rank, world_size;         /* origin zones are sharded over world_size ranks in spatially contiguous blocks (any partition gives
+                                   * the same integer link-volume sums; DTL_SHARD=mod selects the reference's zone % blocks rule) */
     double sssp_delta_factor;     /* label window of the SSSP kernel in units of the mean link cost; <=0 = default */
     int sssp_block_threads;       /* 0 = default */
     int sssp_ctas_per_sm;         /* 0 = default */
@@ -91,7 +92,7 @@ int dtl_comm_get_unique_id(unsigned char id128[128]);
  * volumes itself (used to check the sharding on one GPU). */
 int dtl_comm_init(dtl_engine* e, const unsigned char id128[128]);
 /* Host-only: the (agent type, period, zone) shortest-path tasks rank `rank` of `world_size` owns, in canonical
- * order (g_assign_computing_tasks_to_memory_blocks, main_api.cpp:201-275, then zone % world_size == rank).
+ * order (g_assign_computing_tasks_to_memory_blocks, main_api.cpp:201-275, then the rank's block of zones).
  * Returns the number of tasks (may exceed capacity; only `capacity` entries are written). */
 int dtl_plan_tasks(const dtl_problem* p, int rank, int world_size, int* at, int* tau, int* zone, int capacity);
 
@@ -168,8 +169,9 @@ int dtl_odme_run(dtl_engine* e, int n_iterations, double* rows, int* n_done);
 int dtl_odme_get(dtl_engine* e, int tau, double* obs_count, int* upper_bound_flag, double* est_count_dev);
 
 /* ---- sensitivity-analysis stage: stage II of network_assignment, main_api.cpp:771-1042 ----
- * Covered: supply-side "sa" lane changes (scenario_API.h:152-160) and the re-routing of the agent types with real-time
- * information; dms scenario rows / information zones / route modification and demand-side scenario factors are not.
+ * Covered: supply-side "sa" lane changes (scenario_API.h:152-160), the re-routing of the agent types with real-time
+ * information, and "dms" scenario rows with their information zones and the route modification (below); demand-side
+ * scenario factors are not.
  * Call order: dtl_sa_configure (any time after dtl_create), the assignment (dtl_iteration..., dtl_finalize), dtl_sa_begin,
  * dtl_sa_iteration(0..S), dtl_sa_column_update(0..S-1).
  *   dtl_sa_configure     rt_info [AT] = real_time_information of the agent types (0 none, 1 real-time, 2 dms; DTA.h:486);
