@@ -65,10 +65,16 @@ def build_variant(name: str, sssp_flags, verbose: bool = False) -> str:
     return lib
 
 
+def dependencies():
+    """Every file the library is built from: sources plus the headers they include (.h and .cuh of csrc/, include/*.h)."""
+    return (sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+            + glob.glob(os.path.join(INCLUDE, "*.h")))
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile the shared library (and the DTALite_b200 executable) if sources changed."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    deps = dependencies()
     lib_src = [s for s in sources() if os.path.basename(s) != "main.cpp"]
     if force or _stale(LIB_PATH, deps):
         objs = []

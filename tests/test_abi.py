@@ -38,3 +38,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.lower(), f"{f} mentions the oracle: the product path must not depend on it"
+
+
+def test_every_included_header_is_a_build_dependency():
+    """A header that only some .cu files include (e.g. csrc/*.cuh) must make the library stale when it changes: the build is
+    in-tree and the .so travels to the GPU box as built here."""
+    from dlsim_mrm_b200 import build
+    deps = {os.path.realpath(d) for d in build.dependencies()}
+    csrc = os.path.join(ROOT, "dlsim-mrm_b200", "csrc")
+    inc = os.path.join(ROOT, "include")
+    for src in build.dependencies():
+        for name in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(src).read(), re.M):
+            for base in (csrc, inc):
+                path = os.path.realpath(os.path.join(base, name))
+                if os.path.exists(path):
+                    assert path in deps, f"{os.path.basename(src)} includes {name}, which the build does not watch"
