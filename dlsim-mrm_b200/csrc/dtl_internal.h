@@ -139,7 +139,7 @@ struct SsspLaunch {
     int cap_smem;            // shared-memory-queue variant: entries per near queue (two buffers, 28 B per entry)
     int smq;                 // 1: launch the shared-memory-queue variant (few trees per SM)
     int far_trigger;         // far-pile size above which dead entries are dropped between rounds
-    // destination-bounded search of the shared-memory-queue kernel (optional, see BundleLaunch::dest_ptr): the destinations with demand
+    // destination-bounded search of the shared-memory-queue kernel (the loop's default; null pointers = complete search; see BundleLaunch::dest_ptr): the destinations with demand
     // of batch-local task i are od_dest[cells[k]] for k in [cell_ptr[i], cell_ptr[i + 1])
     const int* bd_cell_ptr;  // null: every search runs to the end
     const int* bd_cells;
@@ -179,7 +179,7 @@ struct BundleLaunch {
                              // (more) bundle to search takes tiles of the bundles that are finished (work[] below)
     int* work;               // fuse_pred: [2 + 2 * n_bundles] {finished count, finished bundles in order (-1 = not yet), tile counters,
                              // resident CTAs of the search kernel}
-    // destination-bounded search (optional, dtl_set_bounded_search): a bundle's search stops as soon as no queued node can still
+    // destination-bounded search (the loop's default, dtl_set_bounded_search; dest_ptr null = complete search): a bundle's search stops as soon as no queued node can still
     // improve the label of a destination the bundle's origins have demand to; labels beyond that bound are not final and the
     // label -> predecessor pass treats them as unreached
     const int* dest_ptr;     // [n_bundles + 1] into dest_idx, or null: every search runs to the end
